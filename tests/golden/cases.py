@@ -1,0 +1,118 @@
+"""Seeded input construction shared by ``make_golden.py`` (which runs the unmodified
+reference in the build container) and the parity tests (which re-create the very
+same inputs and compare against the committed ``*.npz`` outputs).
+
+Pure numpy (``RandomState`` is bit-stable across platforms); no torch, no reference.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def window_of(kind, win_length, dtype):
+    if kind is None:
+        return None
+    n = np.arange(win_length, dtype=np.float64)
+    if kind == "hann":      # periodic hann == torch.hann_window(win_length)
+        w = 0.5 - 0.5 * np.cos(2 * np.pi * n / win_length)
+    elif kind == "hamming":
+        w = 0.54 - 0.46 * np.cos(2 * np.pi * n / win_length)
+    elif kind == "sqrthann":
+        w = np.sqrt(0.5 - 0.5 * np.cos(2 * np.pi * n / win_length))
+    else:
+        raise ValueError(kind)
+    return w.astype(dtype)
+
+
+def make_case_inputs(case):
+    """Returns dict(mag, C, kwargs) for a case description.
+
+    mag is a smooth-ish positive random magnitude of the right shape (it does not
+    need to be a consistent spectrogram), C = mag * exp(i*phi) the complex start."""
+    rs = np.random.RandomState(case["seed"])
+    dtype = np.dtype(case["dtype"])
+    n_fft = case["n_fft"]
+    onesided = case.get("onesided", True)
+    F = n_fft // 2 + 1 if onesided else n_fft
+    T = case["T"]
+    B = case["B"]
+    mag = np.abs(rs.randn(B, F, T) + 1j * rs.randn(B, F, T)) * (0.5 + rs.rand(B, 1, T))
+    phi = 2 * np.pi * rs.rand(B, F, T)
+    mag = mag.astype(dtype)
+    cdt = np.complex64 if dtype == np.float32 else np.complex128
+    C = (mag.astype(np.float64) * np.exp(1j * phi)).astype(cdt)
+    kwargs = {}
+    wl = case.get("win_length")
+    wk = case.get("window")
+    if wl is not None:
+        kwargs["win_length"] = wl
+    if wk is not None:
+        kwargs["window"] = window_of(wk, wl or n_fft, dtype)
+    for key in ("hop_length", "center", "pad_mode", "normalized"):
+        if key in case:
+            kwargs[key] = case[key]
+    if "onesided" in case:
+        kwargs["onesided"] = case["onesided"]
+    if case.get("squeeze"):
+        mag, C = mag[0], C[0]
+    return {"mag": mag, "C": C, "kwargs": kwargs}
+
+
+def _c(name, **kw):
+    d = dict(name=name, seed=1234, dtype="float64", B=2, T=21, n_fft=128)
+    d.update(kw)
+    return d
+
+
+# Griffin-Lim / ADMM single- and multi-iteration cases -------------------------
+ITER_CASES = [
+    _c("hann128_f64", window="hann", hop_length=32),
+    _c("hann128_f32", window="hann", hop_length=32, dtype="float32", seed=11),
+    _c("default_rect_f64", seed=5),                                  # all-default kwargs
+    _c("default_rect_f32", seed=6, dtype="float32", n_fft=256, T=13),
+    _c("hann256_hop64_f32", window="hann", hop_length=64, n_fft=256, T=17, dtype="float32", seed=7),
+    _c("hann512_hop128_f32", window="hann", hop_length=128, n_fft=512, T=12, dtype="float32", seed=8),
+    _c("short_win_hann_f64", n_fft=128, win_length=75, window="hann", hop_length=32, seed=9),
+    _c("short_win_rect_f64", n_fft=128, win_length=75, hop_length=32, seed=10),
+    _c("nocenter_hamming_f64", window="hamming", hop_length=32, center=False, seed=12),
+    _c("normalized_f64", window="hann", hop_length=32, normalized=True, seed=13),
+    _c("pad_constant_f64", window="hann", hop_length=32, pad_mode="constant", seed=14),
+    _c("pad_replicate_f64", window="hann", hop_length=32, pad_mode="replicate", seed=15),
+    _c("pad_circular_f64", window="hann", hop_length=32, pad_mode="circular", seed=16),
+    _c("twosided_f64", window="hann", hop_length=32, onesided=False, seed=17),
+    _c("twosided_norm_f32", window="hann", hop_length=32, onesided=False, normalized=True,
+       dtype="float32", seed=18),
+    _c("odd_hop_f64", window="hann", hop_length=24, seed=19),
+    _c("hop_half_sqrthann_f64", window="sqrthann", hop_length=64, seed=20),
+    _c("squeeze2d_f32", window="hann", hop_length=32, dtype="float32", B=1, squeeze=True, seed=21),
+    _c("b1_keepdim_f32", window="hann", hop_length=32, dtype="float32", B=1, seed=22),
+    _c("hann1024_hop256_f32", window="hann", hop_length=256, n_fft=1024, T=9, dtype="float32", seed=23),
+    _c("hann2048_hop512_f32", window="hann", hop_length=512, n_fft=2048, T=7, B=1, dtype="float32", seed=24),
+]
+
+GL_ALPHAS = [0.99, 0.3, 0.0]
+ADMM_RHOS = [0.1, 1.0]
+ITER_COUNTS = [1, 2, 3]
+
+# RTISI-LA full runs (small) ------------------------------------------------------
+RTISI_CASES = [
+    dict(_c("rtisi_hann128_f64", window="hann", hop_length=32, T=9), look_ahead=-1, asym=False, max_iter=3, alpha=0.99),
+    dict(_c("rtisi_hann128_la0_f64", window="hann", hop_length=32, T=9), look_ahead=0, asym=False, max_iter=3, alpha=0.99),
+    dict(_c("rtisi_hann128_la2_f64", window="hann", hop_length=32, T=9), look_ahead=2, asym=False, max_iter=2, alpha=0.5),
+    dict(_c("rtisi_hann128_asym_f64", window="hann", hop_length=32, T=9), look_ahead=-1, asym=True, max_iter=3, alpha=0.99),
+    dict(_c("rtisi_hann128_asym_la2_f64", window="hann", hop_length=32, T=9), look_ahead=2, asym=True, max_iter=2, alpha=0.0),
+    dict(_c("rtisi_rect_default_f64", T=9), look_ahead=-1, asym=False, max_iter=2, alpha=0.99),
+    dict(_c("rtisi_nocenter_f64", window="hamming", hop_length=32, T=9, center=False), look_ahead=-1, asym=False, max_iter=2, alpha=0.99),
+    dict(_c("rtisi_norm_f64", window="hann", hop_length=32, T=9, normalized=True), look_ahead=1, asym=True, max_iter=2, alpha=0.99),
+    dict(_c("rtisi_twosided_f64", window="hann", hop_length=32, T=9, onesided=False), look_ahead=-1, asym=False, max_iter=2, alpha=0.99),
+    dict(_c("rtisi_shortwin_f64", window="hann", win_length=75, hop_length=32, T=9), look_ahead=-1, asym=True, max_iter=2, alpha=0.99),
+    dict(_c("rtisi_hann256_f32", window="hann", hop_length=64, n_fft=256, T=8, dtype="float32"), look_ahead=3, asym=False, max_iter=2, alpha=0.99),
+    dict(_c("rtisi_squeeze_f64", window="hann", hop_length=32, T=9, B=1, squeeze=True), look_ahead=-1, asym=False, max_iter=2, alpha=0.99),
+]
+
+# early-stop behaviour of the host loop ----------------------------------------------
+LOOP_CASES = [
+    dict(_c("loop_tol1e-1", window="hann", hop_length=32, T=33), tol=1e-1, eva_iter=3, max_iter=60, metric="sc"),
+    dict(_c("loop_tol1e-2", window="hann", hop_length=32, T=33), tol=1e-2, eva_iter=5, max_iter=80, metric="snr"),
+    dict(_c("loop_tol0", window="hann", hop_length=32, T=33), tol=0.0, eva_iter=4, max_iter=10, metric="ser"),
+]
