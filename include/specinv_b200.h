@@ -1,0 +1,125 @@
+/*
+ * specinv_b200 -- C ABI of the B200-native (sm_100a) iterative STFT/ISTFT
+ * phase-retrieval hot path: Griffin-Lim / fast Griffin-Lim, ADMM, RTISI-LA and the
+ * spectral metrics of torch_specinv 0.2.1.
+ *
+ * The reference (yoyololicon/spectrogram-inversion) is pure Python on top of
+ * PyTorch ops and has no FFI of its own; the boundary it offers is its Python
+ * signatures (torch_specinv/methods.py:193, :273, :415; metrics.py:4,17,32).  This
+ * header is the C level directly below them: every entry point replaces the
+ * PyTorch-op sequence of one reference code region (cited per function) with
+ * hand-written CUDA kernels.  INTEGRATION.md shows the ctypes binding a maintainer
+ * of the reference would add.
+ *
+ * Conventions
+ *  - plain C, no torch types; every pointer is a DEVICE pointer unless the name
+ *    ends in _host; the caller owns and allocates every buffer;
+ *  - every call is asynchronous on the given CUDA stream (a cudaStream_t passed
+ *    as void*); nothing synchronises, nothing allocates, no global state;
+ *  - return value: 0 = ok, negative = SPECINV_ERR_*, positive = cudaError_t;
+ *  - real type is float (SPECINV_F32) or double (SPECINV_F64); complex values are
+ *    interleaved (re, im) pairs of that type.
+ *
+ * Internal ("split, frame-major") spectrum layout used by all kernels
+ *    main : [batch][n_frames][row]  complex, row = n_fft/2 (onesided) or n_fft
+ *    nyq  : [batch][n_frames]       complex, the k = n_fft/2 bin (onesided only)
+ *  magnitudes use the same two arrays with real elements.  Splitting the Nyquist
+ *  bin off keeps every frame row 16-byte aligned (n_fft/2 * 8 B) for vector / bulk
+ *  loads; specinv_pack_* / specinv_unpack_* convert from / to the reference's
+ *  strided (batch, freq, time) tensors.
+ */
+#ifndef SPECINV_B200_H
+#define SPECINV_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPECINV_ABI_VERSION 1
+
+enum {
+    SPECINV_OK = 0,
+    SPECINV_ERR_INVALID = -1,      /* bad argument (null pointer, non power-of-two n_fft, ...) */
+    SPECINV_ERR_UNSUPPORTED = -2,  /* valid in the reference but not implemented by these kernels */
+    SPECINV_ERR_NO_DEVICE = -3     /* no sm_100 device / kernel image not loadable */
+};
+
+enum { SPECINV_F32 = 0, SPECINV_F64 = 1 };
+
+/* torch.stft pad_mode (methods.py:38) */
+enum { SPECINV_PAD_REFLECT = 0, SPECINV_PAD_CONSTANT = 1, SPECINV_PAD_REPLICATE = 2, SPECINV_PAD_CIRCULAR = 3 };
+
+/* Normalised STFT description == the output of the reference's _args_helper
+ * (methods.py:21-91) plus the problem size. */
+typedef struct specinv_desc {
+    int32_t n_fft;       /* power of two, 16..8192 */
+    int32_t hop;         /* hop_length, 1..n_fft */
+    int32_t n_frames;    /* T */
+    int32_t batch;       /* B */
+    int32_t center;      /* 0/1 (methods.py:37) */
+    int32_t pad_mode;    /* SPECINV_PAD_* (only used when center) */
+    int32_t normalized;  /* 0/1: N^-1/2 on both transforms (methods.py:143) */
+    int32_t onesided;    /* 0/1 (methods.py:59-68) */
+    int32_t dtype;       /* SPECINV_F32 / SPECINV_F64 */
+    int32_t reserved[7]; /* must be zero */
+} specinv_desc;
+
+int specinv_abi_version(void);
+const char* specinv_error_string(int code);
+
+/* Output length of the overlap-add, (T-1)*hop + n_fft - 2*pad  (methods.py:127-128,148). */
+int specinv_signal_length(const specinv_desc* d, int64_t* length);
+
+/* ---- plan: twiddles, scaled analysis/synthesis windows, 1/envelope ------------------
+ * Replaces _get_ola_weight (methods.py:94-96) and the one-shot envelope
+ * conv_transpose1d (methods.py:129-131).  `window` is the n_fft-long window already
+ * zero-padded by the host exactly like methods.py:79-83.  inv_env = 1/sum_t w^2 with NO
+ * epsilon: a zero envelope gives inf, like the reference's division (methods.py:132). */
+int specinv_plan_bytes(const specinv_desc* d, size_t* bytes);
+int specinv_plan_init(const specinv_desc* d, const void* window, void* plan, void* stream);
+/* copies the length-L envelope (not its inverse) out of the plan */
+int specinv_plan_envelope(const specinv_desc* d, const void* plan, void* env_out, void* stream);
+
+/* ---- layout conversion (strides in ELEMENTS of the (batch, freq, time) tensor) ---------- */
+int specinv_pack_complex(const specinv_desc* d, const void* spec, int64_t sb, int64_t sf, int64_t st,
+                         void* main_out, void* nyq_out, void* stream);
+int specinv_pack_real(const specinv_desc* d, const void* mag, int64_t sb, int64_t sf, int64_t st,
+                      void* main_out, void* nyq_out, void* stream);
+int specinv_unpack_complex(const specinv_desc* d, const void* main_in, const void* nyq_in,
+                           void* spec_out, int64_t sb, int64_t sf, int64_t st, void* stream);
+
+/* ---- primitives ---------------------------------------------------------------------------
+ * specinv_stft  : torch.stft as called at methods.py:241, :464  (x (B,L) -> spectrum)
+ * specinv_istft : _istft, methods.py:135-150 (spectrum -> x (B,L)), envelope from the plan */
+int specinv_stft(const specinv_desc* d, const void* plan, const void* x, void* main_out, void* nyq_out,
+                 void* stream);
+int specinv_istft(const specinv_desc* d, const void* plan, const void* main_in, const void* nyq_in,
+                  void* x_out, void* stream);
+
+/* ---- fused iterations ---------------------------------------------------------------------
+ * specinv_gl_iter : one closure call of griffin_lim, methods.py:237-250:
+ *      s = STFT(x_in); q_out = s - lr*q_in; x_out = ISTFT(q_out*mag/(|q_out|+1e-16))
+ *   q_in/q_out and x_in/x_out must not alias (neighbouring tiles re-read the old state).
+ *   sums (may be NULL): two doubles to which sum (|s|-mag)^2 and sum |s|^2 over all
+ *   B*F*T bins are ADDED (the fused metric epilogue for methods.py:181-182).
+ * specinv_admm_iter : one closure call of ADMM, methods.py:458-483 with Y == X + U:
+ *      R = STFT(x_in); Z = (rho*(X+U)+R)/(1+rho); U' = U+X-Z; X' = proj(Z-U'); x_out = ISTFT(X'+U') */
+int specinv_gl_iter(const specinv_desc* d, const void* plan, const void* x_in, void* x_out,
+                    const void* q_in_main, const void* q_in_nyq, void* q_out_main, void* q_out_nyq,
+                    const void* mag_main, const void* mag_nyq, double lr, double* sums, void* stream);
+int specinv_admm_iter(const specinv_desc* d, const void* plan, const void* x_in, void* x_out,
+                      const void* X_in_main, const void* X_in_nyq, const void* U_in_main, const void* U_in_nyq,
+                      void* X_out_main, void* X_out_nyq, void* U_out_main, void* U_out_nyq,
+                      const void* mag_main, const void* mag_nyq, double rho, double* sums, void* stream);
+
+/* ---- metrics (metrics.py:4-43, F.mse_loss at methods.py:182) ---------------------------------
+ * out[0] += sum (a-b)^2, out[1] += sum a^2, out[2] += sum b^2 over n contiguous reals. */
+int specinv_metric_sums(int dtype, const void* a, const void* b, int64_t n, double* out3, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPECINV_B200_H */

@@ -1,0 +1,94 @@
+"""ctypes binding of libspecinv_b200.so (include/specinv_b200.h).
+
+There is deliberately no fallback: if the CUDA library is missing or a call fails, a
+RuntimeError is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "lib", "libspecinv_b200.so")
+
+F32, F64 = 0, 1
+PAD_MODES = {"reflect": 0, "constant": 1, "replicate": 2, "circular": 3}
+ERR_UNSUPPORTED = -2
+
+EXPORTS = (
+    "specinv_abi_version", "specinv_error_string", "specinv_signal_length",
+    "specinv_plan_bytes", "specinv_plan_init", "specinv_plan_envelope",
+    "specinv_pack_complex", "specinv_pack_real", "specinv_unpack_complex",
+    "specinv_stft", "specinv_istft", "specinv_gl_iter", "specinv_admm_iter",
+    "specinv_metric_sums",
+)
+
+
+class Desc(C.Structure):
+    """struct specinv_desc"""
+    _fields_ = [("n_fft", C.c_int32), ("hop", C.c_int32), ("n_frames", C.c_int32), ("batch", C.c_int32),
+                ("center", C.c_int32), ("pad_mode", C.c_int32), ("normalized", C.c_int32),
+                ("onesided", C.c_int32), ("dtype", C.c_int32), ("reserved", C.c_int32 * 7)]
+
+
+_lib: Optional[C.CDLL] = None
+
+
+def _declare(lib: C.CDLL) -> None:
+    vp, i64, dbl = C.c_void_p, C.c_int64, C.c_double
+    dp = C.POINTER(Desc)
+    lib.specinv_abi_version.restype = C.c_int
+    lib.specinv_abi_version.argtypes = []
+    lib.specinv_error_string.restype = C.c_char_p
+    lib.specinv_error_string.argtypes = [C.c_int]
+    sigs = {
+        "specinv_signal_length": [dp, C.POINTER(i64)],
+        "specinv_plan_bytes": [dp, C.POINTER(C.c_size_t)],
+        "specinv_plan_init": [dp, vp, vp, vp],
+        "specinv_plan_envelope": [dp, vp, vp, vp],
+        "specinv_pack_complex": [dp, vp, i64, i64, i64, vp, vp, vp],
+        "specinv_pack_real": [dp, vp, i64, i64, i64, vp, vp, vp],
+        "specinv_unpack_complex": [dp, vp, vp, vp, i64, i64, i64, vp],
+        "specinv_stft": [dp, vp, vp, vp, vp, vp],
+        "specinv_istft": [dp, vp, vp, vp, vp, vp],
+        "specinv_gl_iter": [dp, vp, vp, vp, vp, vp, vp, vp, vp, vp, dbl, vp, vp],
+        "specinv_admm_iter": [dp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, dbl, vp, vp],
+        "specinv_metric_sums": [C.c_int, vp, vp, i64, vp, vp],
+    }
+    for name, args in sigs.items():
+        fn = getattr(lib, name)
+        fn.restype = C.c_int
+        fn.argtypes = args
+
+
+def lib() -> C.CDLL:
+    """Load (once) and return the CUDA library; raise loudly when it is not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m spectrogram_inversion_b200.build` "
+                "(there is no CPU / PyTorch fallback for this path)")
+        handle = C.CDLL(LIB_PATH)
+        _declare(handle)
+        if handle.specinv_abi_version() != 1:
+            raise RuntimeError("libspecinv_b200.so ABI version mismatch")
+        _lib = handle
+    return _lib
+
+
+def check(code: int, what: str = "") -> None:
+    if code != 0:
+        msg = lib().specinv_error_string(code).decode()
+        exc = NotImplementedError if code == ERR_UNSUPPORTED else RuntimeError
+        raise exc(f"specinv_b200 {what} failed: {msg} (code {code})")
+
+
+def make_desc(n_fft: int, hop: int, n_frames: int, batch: int, center: bool, pad_mode: int,
+              normalized: bool, onesided: bool, dtype: int) -> Desc:
+    d = Desc()
+    d.n_fft, d.hop, d.n_frames, d.batch = int(n_fft), int(hop), int(n_frames), int(batch)
+    d.center, d.pad_mode, d.normalized, d.onesided = int(bool(center)), int(pad_mode), int(bool(normalized)), int(bool(onesided))
+    d.dtype = int(dtype)
+    return d

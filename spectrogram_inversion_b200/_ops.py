@@ -1,0 +1,125 @@
+"""torch.library custom ops: thin wrappers that hand raw device pointers and the current CUDA
+stream to the C ABI of libspecinv_b200.so.  No computation happens in Python/PyTorch here."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+from torch import Tensor
+
+from . import _lib
+
+_DT = {torch.float32: _lib.F32, torch.float64: _lib.F64, torch.complex64: _lib.F32, torch.complex128: _lib.F64}
+
+
+def _p(t: Tensor):
+    return C.c_void_p(t.data_ptr()) if t.numel() else None
+
+
+def _stream(t: Tensor):
+    return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _desc(ref: Tensor, n_fft: int, hop: int, n_frames: int, batch: int, center: bool, pad_mode: int,
+          normalized: bool, onesided: bool):
+    return _lib.make_desc(n_fft, hop, n_frames, batch, center, pad_mode, normalized, onesided, _DT[ref.dtype])
+
+
+def _need_cuda(*ts: Tensor) -> None:
+    for t in ts:
+        if t.numel() and not t.is_cuda:
+            raise RuntimeError("specinv_b200 ops only run on CUDA tensors (no CPU fallback)")
+        if t.numel() and not t.is_contiguous():
+            raise RuntimeError("specinv_b200 ops need contiguous buffers")
+
+
+@torch.library.custom_op("specinv_b200::plan_init", mutates_args=("plan",), device_types="cuda")
+def plan_init(plan: Tensor, window: Tensor, n_fft: int, hop: int, n_frames: int, batch: int, center: bool,
+              pad_mode: int, normalized: bool, onesided: bool) -> None:
+    _need_cuda(plan, window)
+    d = _desc(window, n_fft, hop, n_frames, batch, center, pad_mode, normalized, onesided)
+    with torch.cuda.device(plan.device):
+        _lib.check(_lib.lib().specinv_plan_init(C.byref(d), _p(window), _p(plan), _stream(plan)), "plan_init")
+
+
+@torch.library.custom_op("specinv_b200::stft", mutates_args=("out_main", "out_nyq"), device_types="cuda")
+def stft(plan: Tensor, x: Tensor, out_main: Tensor, out_nyq: Tensor, n_fft: int, hop: int, center: bool,
+         pad_mode: int, normalized: bool, onesided: bool) -> None:
+    _need_cuda(plan, x, out_main, out_nyq)
+    d = _desc(x, n_fft, hop, out_main.shape[1], out_main.shape[0], center, pad_mode, normalized, onesided)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().specinv_stft(C.byref(d), _p(plan), _p(x), _p(out_main), _p(out_nyq), _stream(x)), "stft")
+
+
+@torch.library.custom_op("specinv_b200::istft", mutates_args=("x_out",), device_types="cuda")
+def istft(plan: Tensor, in_main: Tensor, in_nyq: Tensor, x_out: Tensor, n_fft: int, hop: int, center: bool,
+          pad_mode: int, normalized: bool, onesided: bool) -> None:
+    _need_cuda(plan, in_main, in_nyq, x_out)
+    d = _desc(x_out, n_fft, hop, in_main.shape[1], in_main.shape[0], center, pad_mode, normalized, onesided)
+    with torch.cuda.device(x_out.device):
+        _lib.check(_lib.lib().specinv_istft(C.byref(d), _p(plan), _p(in_main), _p(in_nyq), _p(x_out), _stream(x_out)),
+                   "istft")
+
+
+@torch.library.custom_op("specinv_b200::gl_iter",
+                         mutates_args=("x_out", "q_out_main", "q_out_nyq", "sums"), device_types="cuda")
+def gl_iter(plan: Tensor, x_in: Tensor, x_out: Tensor, q_in_main: Tensor, q_in_nyq: Tensor, q_out_main: Tensor,
+            q_out_nyq: Tensor, mag_main: Tensor, mag_nyq: Tensor, sums: Tensor, lr: float, n_fft: int, hop: int,
+            center: bool, pad_mode: int, normalized: bool, onesided: bool) -> None:
+    _need_cuda(plan, x_in, x_out, q_in_main, q_in_nyq, q_out_main, q_out_nyq, mag_main, mag_nyq, sums)
+    d = _desc(x_in, n_fft, hop, q_in_main.shape[1], q_in_main.shape[0], center, pad_mode, normalized, onesided)
+    with torch.cuda.device(x_in.device):
+        _lib.check(_lib.lib().specinv_gl_iter(
+            C.byref(d), _p(plan), _p(x_in), _p(x_out), _p(q_in_main), _p(q_in_nyq), _p(q_out_main), _p(q_out_nyq),
+            _p(mag_main), _p(mag_nyq), float(lr), _p(sums), _stream(x_in)), "gl_iter")
+
+
+@torch.library.custom_op("specinv_b200::admm_iter",
+                         mutates_args=("x_out", "X_out_main", "X_out_nyq", "U_out_main", "U_out_nyq", "sums"),
+                         device_types="cuda")
+def admm_iter(plan: Tensor, x_in: Tensor, x_out: Tensor, X_in_main: Tensor, X_in_nyq: Tensor, U_in_main: Tensor,
+              U_in_nyq: Tensor, X_out_main: Tensor, X_out_nyq: Tensor, U_out_main: Tensor, U_out_nyq: Tensor,
+              mag_main: Tensor, mag_nyq: Tensor, sums: Tensor, rho: float, n_fft: int, hop: int, center: bool,
+              pad_mode: int, normalized: bool, onesided: bool) -> None:
+    _need_cuda(plan, x_in, x_out, X_in_main, X_in_nyq, U_in_main, U_in_nyq, X_out_main, X_out_nyq, U_out_main,
+               U_out_nyq, mag_main, mag_nyq, sums)
+    d = _desc(x_in, n_fft, hop, X_in_main.shape[1], X_in_main.shape[0], center, pad_mode, normalized, onesided)
+    with torch.cuda.device(x_in.device):
+        _lib.check(_lib.lib().specinv_admm_iter(
+            C.byref(d), _p(plan), _p(x_in), _p(x_out), _p(X_in_main), _p(X_in_nyq), _p(U_in_main), _p(U_in_nyq),
+            _p(X_out_main), _p(X_out_nyq), _p(U_out_main), _p(U_out_nyq), _p(mag_main), _p(mag_nyq), float(rho),
+            _p(sums), _stream(x_in)), "admm_iter")
+
+
+@torch.library.custom_op("specinv_b200::pack", mutates_args=("out_main", "out_nyq"), device_types="cuda")
+def pack(spec: Tensor, out_main: Tensor, out_nyq: Tensor, n_fft: int, onesided: bool) -> None:
+    """(B, F, T) strided real or complex tensor -> split frame-major layout."""
+    if not spec.is_cuda:
+        raise RuntimeError("specinv_b200 ops only run on CUDA tensors (no CPU fallback)")
+    B, Fb, T = spec.shape
+    d = _desc(spec, n_fft, 1, T, B, True, 0, False, onesided)
+    sb, sf, st = spec.stride()
+    fn = _lib.lib().specinv_pack_complex if spec.is_complex() else _lib.lib().specinv_pack_real
+    with torch.cuda.device(spec.device):
+        _lib.check(fn(C.byref(d), _p(spec), sb, sf, st, _p(out_main), _p(out_nyq), _stream(spec)), "pack")
+
+
+@torch.library.custom_op("specinv_b200::unpack", mutates_args=("spec_out",), device_types="cuda")
+def unpack(in_main: Tensor, in_nyq: Tensor, spec_out: Tensor, n_fft: int, onesided: bool) -> None:
+    B, Fb, T = spec_out.shape
+    d = _desc(spec_out, n_fft, 1, T, B, True, 0, False, onesided)
+    sb, sf, st = spec_out.stride()
+    with torch.cuda.device(spec_out.device):
+        _lib.check(_lib.lib().specinv_unpack_complex(C.byref(d), _p(in_main), _p(in_nyq), _p(spec_out), sb, sf, st,
+                                                      _stream(spec_out)), "unpack")
+
+
+@torch.library.custom_op("specinv_b200::metric_sums", mutates_args=("out3",), device_types="cuda")
+def metric_sums(a: Tensor, b: Tensor, out3: Tensor) -> None:
+    """out3[0] += sum (a-b)^2, out3[1] += sum a^2, out3[2] += sum b^2."""
+    _need_cuda(a, b, out3)
+    if a.numel() != b.numel() or a.dtype != b.dtype:
+        raise RuntimeError("metric_sums: shape/dtype mismatch")
+    with torch.cuda.device(a.device):
+        _lib.check(_lib.lib().specinv_metric_sums(_DT[a.dtype], _p(a), _p(b), a.numel(), _p(out3), _stream(a)),
+                   "metric_sums")

@@ -1,0 +1,260 @@
+// extern "C" entry points of libspecinv_b200.so (see include/specinv_b200.h), the plan
+// initialisation kernels, layout conversion and the standalone metric reduction.
+#include "specinv_common.cuh"
+
+namespace specinv {
+
+// implemented in specinv_generic.cu
+int generic_stft(const specinv_desc*, const void*, const void*, void*, void*, void*);
+int generic_istft(const specinv_desc*, const void*, const void*, const void*, void*, void*);
+int generic_gl_iter(const specinv_desc*, const void*, const void*, void*, const void*, const void*, void*, void*,
+                    const void*, const void*, double, double*, void*);
+int generic_admm_iter(const specinv_desc*, const void*, const void*, void*, const void*, const void*, const void*,
+                      const void*, void*, void*, void*, void*, const void*, const void*, double, double*, void*);
+// implemented in specinv_gl1024.cu (fast path); returns SPECINV_ERR_UNSUPPORTED when not applicable
+int fast_gl_iter(const specinv_desc*, const void*, const void*, void*, const void*, const void*, void*, void*,
+                 const void*, const void*, double, double*, void*);
+
+// ---------------------------------------------------------------- plan
+template <typename T>
+__global__ void plan_tables_kernel(int N, int M, int normalized, const T* __restrict__ window,
+                                   cx_t<T>* tw, cx_t<T>* twr, T* wa, T* ws) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < M) {
+        double s, c;
+        sincospi(2.0 * i / M, &s, &c);
+        tw[i] = mk<T>((T)c, (T)(-s));
+    }
+    if (i <= M / 2) {
+        double s, c;
+        sincospi(2.0 * i / N, &s, &c);
+        twr[i] = mk<T>((T)c, (T)(-s));
+    }
+    if (i < N) {
+        // forward: 1 (or N^-1/2 when normalized); inverse: 1/N (or N^-1/2), methods.py:143
+        const double fs = normalized ? rsqrt((double)N) : 1.0;
+        const double is = normalized ? rsqrt((double)N) : 1.0 / N;
+        wa[i] = (T)((double)window[i] * fs);
+        ws[i] = (T)((double)window[i] * is);
+    }
+}
+
+// env[m] = sum_t w^2[m + P - t*hop]  (methods.py:129-131), inv_env = 1/env without epsilon.
+template <typename T>
+__global__ void plan_envelope_kernel(Dims dm, const T* __restrict__ window, T* env, T* inv_env) {
+    const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= dm.L) return;
+    const long long pp = m + dm.P;
+    long long tlo = pp >= dm.N ? (pp - dm.N) / dm.hop + 1 : 0;
+    long long thi = pp / dm.hop;
+    if (thi > dm.T - 1) thi = dm.T - 1;
+    T acc = T(0);
+    for (long long t = tlo; t <= thi; ++t) {
+        const T w = window[pp - t * dm.hop];
+        acc += w * w;
+    }
+    env[m] = acc;
+    inv_env[m] = T(1) / acc;
+}
+
+template <typename T>
+static int plan_init_t(const Dims& dm, const specinv_desc* d, const void* window, void* plan, cudaStream_t st) {
+    const PlanLayout pl = plan_layout(dm, d->dtype);
+    char* p = (char*)plan;
+    const int n = dm.N;
+    plan_tables_kernel<T><<<(n + 255) / 256, 256, 0, st>>>(dm.N, dm.M, d->normalized, (const T*)window,
+                                                           (cx_t<T>*)(p + pl.tw), (cx_t<T>*)(p + pl.twr),
+                                                           (T*)(p + pl.wa), (T*)(p + pl.ws));
+    plan_envelope_kernel<T><<<(unsigned)((dm.L + 255) / 256), 256, 0, st>>>(dm, (const T*)window, (T*)(p + pl.env),
+                                                                            (T*)(p + pl.inv_env));
+    return (int)cudaGetLastError();
+}
+
+// ---------------------------------------------------------------- layout conversion
+// 32x32 tile transpose between the reference's (batch, freq, time) tensor (arbitrary element
+// strides) and the split frame-major layout.  TO_INTERNAL: coalesced along the smaller of the two
+// source strides when reading, along freq when writing.
+template <typename V, bool TO_INTERNAL>
+__global__ void convert_kernel(Dims dm, int F, V* main, V* nyq, V* ext, long long sb, long long sf, long long st) {
+    __shared__ V tile[32][33];
+    const int b = blockIdx.z;
+    const int fbase = blockIdx.x * 32, tbase = blockIdx.y * 32;
+    const bool time_fast = st <= sf;   // which external index should follow threadIdx.x
+    auto internal = [&](int f, int t) -> V* {
+        const long long fr = (long long)b * dm.T + t;
+        if (dm.onesided && f == dm.M) return nyq + fr;
+        return main + fr * dm.row + f;
+    };
+    if (TO_INTERNAL) {
+        for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+            const int f = time_fast ? fbase + j : fbase + threadIdx.x;
+            const int t = time_fast ? tbase + threadIdx.x : tbase + j;
+            if (f < F && t < dm.T) {
+                const V v = ext[b * sb + f * sf + t * st];
+                if (time_fast) tile[j][threadIdx.x] = v; else tile[threadIdx.x][j] = v;
+            }
+        }
+        __syncthreads();
+        for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+            const int f = fbase + threadIdx.x, t = tbase + j;
+            if (f < F && t < dm.T) *internal(f, t) = tile[threadIdx.x][j];
+        }
+    } else {
+        for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+            const int f = fbase + threadIdx.x, t = tbase + j;
+            if (f < F && t < dm.T) tile[threadIdx.x][j] = *internal(f, t);
+        }
+        __syncthreads();
+        for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+            const int f = time_fast ? fbase + j : fbase + threadIdx.x;
+            const int t = time_fast ? tbase + threadIdx.x : tbase + j;
+            if (f < F && t < dm.T) ext[b * sb + f * sf + t * st] = time_fast ? tile[j][threadIdx.x] : tile[threadIdx.x][j];
+        }
+    }
+}
+
+template <typename V, bool TO_INTERNAL>
+static int convert(const Dims& dm, V* main, V* nyq, V* ext, long long sb, long long sf, long long st, cudaStream_t s) {
+    const int F = dm.onesided ? dm.M + 1 : dm.N;
+    dim3 grid((F + 31) / 32, (dm.T + 31) / 32, dm.B), block(32, 8);
+    if (grid.y > 65535 || grid.z > 65535) return SPECINV_ERR_UNSUPPORTED;
+    convert_kernel<V, TO_INTERNAL><<<grid, block, 0, s>>>(dm, F, main, nyq, ext, sb, sf, st);
+    return (int)cudaGetLastError();
+}
+
+// ---------------------------------------------------------------- metric sums
+template <typename T>
+__global__ void metric_sums_kernel(const T* __restrict__ a, const T* __restrict__ b, long long n, double* out3) {
+    double d = 0, e = 0, g = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double x = (double)a[i], y = (double)b[i];
+        d += (x - y) * (x - y); e += x * x; g += y * y;
+    }
+    __shared__ double red[3][8];
+    for (int o = 16; o > 0; o >>= 1) {
+        d += __shfl_xor_sync(0xffffffffu, d, o);
+        e += __shfl_xor_sync(0xffffffffu, e, o);
+        g += __shfl_xor_sync(0xffffffffu, g, o);
+    }
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = d; red[1][threadIdx.x >> 5] = e; red[2][threadIdx.x >> 5] = g; }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        double s = 0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += red[threadIdx.x][i];
+        atomicAdd(out3 + threadIdx.x, s);
+    }
+}
+
+}  // namespace specinv
+
+using namespace specinv;
+
+extern "C" {
+
+int specinv_abi_version(void) { return SPECINV_ABI_VERSION; }
+
+const char* specinv_error_string(int code) {
+    switch (code) {
+        case SPECINV_OK: return "ok";
+        case SPECINV_ERR_INVALID: return "invalid argument";
+        case SPECINV_ERR_UNSUPPORTED: return "configuration not supported by the sm_100a kernels";
+        case SPECINV_ERR_NO_DEVICE: return "no usable CUDA device";
+        default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "unknown error";
+    }
+}
+
+int specinv_signal_length(const specinv_desc* d, int64_t* length) {
+    Dims dm; int rc = make_dims(d, &dm); if (rc) return rc;
+    if (!length) return SPECINV_ERR_INVALID;
+    *length = dm.L;
+    return SPECINV_OK;
+}
+
+int specinv_plan_bytes(const specinv_desc* d, size_t* bytes) {
+    Dims dm; int rc = make_dims(d, &dm); if (rc) return rc;
+    if (!bytes) return SPECINV_ERR_INVALID;
+    *bytes = plan_layout(dm, d->dtype).total;
+    return SPECINV_OK;
+}
+
+int specinv_plan_init(const specinv_desc* d, const void* window, void* plan, void* stream) {
+    Dims dm; int rc = make_dims(d, &dm); if (rc) return rc;
+    if (!window || !plan) return SPECINV_ERR_INVALID;
+    return d->dtype == SPECINV_F64 ? plan_init_t<double>(dm, d, window, plan, (cudaStream_t)stream)
+                                   : plan_init_t<float>(dm, d, window, plan, (cudaStream_t)stream);
+}
+
+int specinv_plan_envelope(const specinv_desc* d, const void* plan, void* env_out, void* stream) {
+    Dims dm; int rc = make_dims(d, &dm); if (rc) return rc;
+    if (!plan || !env_out) return SPECINV_ERR_INVALID;
+    const PlanLayout pl = plan_layout(dm, d->dtype);
+    const size_t es = d->dtype == SPECINV_F64 ? 8 : 4;
+    return (int)cudaMemcpyAsync(env_out, (const char*)plan + pl.env, (size_t)dm.L * es, cudaMemcpyDeviceToDevice,
+                                (cudaStream_t)stream);
+}
+
+int specinv_pack_complex(const specinv_desc* d, const void* spec, int64_t sb, int64_t sf, int64_t st,
+                         void* main_out, void* nyq_out, void* stream) {
+    Dims dm; int rc = make_dims(d, &dm); if (rc) return rc;
+    if (!spec || !main_out || (dm.onesided && !nyq_out)) return SPECINV_ERR_INVALID;
+    if (d->dtype == SPECINV_F64)
+        return convert<double2, true>(dm, (double2*)main_out, (double2*)nyq_out, (double2*)spec, sb, sf, st, (cudaStream_t)stream);
+    return convert<float2, true>(dm, (float2*)main_out, (float2*)nyq_out, (float2*)spec, sb, sf, st, (cudaStream_t)stream);
+}
+
+int specinv_pack_real(const specinv_desc* d, const void* mag, int64_t sb, int64_t sf, int64_t st,
+                      void* main_out, void* nyq_out, void* stream) {
+    Dims dm; int rc = make_dims(d, &dm); if (rc) return rc;
+    if (!mag || !main_out || (dm.onesided && !nyq_out)) return SPECINV_ERR_INVALID;
+    if (d->dtype == SPECINV_F64)
+        return convert<double, true>(dm, (double*)main_out, (double*)nyq_out, (double*)mag, sb, sf, st, (cudaStream_t)stream);
+    return convert<float, true>(dm, (float*)main_out, (float*)nyq_out, (float*)mag, sb, sf, st, (cudaStream_t)stream);
+}
+
+int specinv_unpack_complex(const specinv_desc* d, const void* main_in, const void* nyq_in,
+                           void* spec_out, int64_t sb, int64_t sf, int64_t st, void* stream) {
+    Dims dm; int rc = make_dims(d, &dm); if (rc) return rc;
+    if (!spec_out || !main_in || (dm.onesided && !nyq_in)) return SPECINV_ERR_INVALID;
+    if (d->dtype == SPECINV_F64)
+        return convert<double2, false>(dm, (double2*)main_in, (double2*)nyq_in, (double2*)spec_out, sb, sf, st, (cudaStream_t)stream);
+    return convert<float2, false>(dm, (float2*)main_in, (float2*)nyq_in, (float2*)spec_out, sb, sf, st, (cudaStream_t)stream);
+}
+
+int specinv_stft(const specinv_desc* d, const void* plan, const void* x, void* main_out, void* nyq_out, void* stream) {
+    return generic_stft(d, plan, x, main_out, nyq_out, stream);
+}
+
+int specinv_istft(const specinv_desc* d, const void* plan, const void* main_in, const void* nyq_in, void* x_out,
+                  void* stream) {
+    return generic_istft(d, plan, main_in, nyq_in, x_out, stream);
+}
+
+int specinv_gl_iter(const specinv_desc* d, const void* plan, const void* x_in, void* x_out,
+                    const void* q_in_main, const void* q_in_nyq, void* q_out_main, void* q_out_nyq,
+                    const void* mag_main, const void* mag_nyq, double lr, double* sums, void* stream) {
+    return generic_gl_iter(d, plan, x_in, x_out, q_in_main, q_in_nyq, q_out_main, q_out_nyq, mag_main, mag_nyq, lr,
+                           sums, stream);
+}
+
+int specinv_admm_iter(const specinv_desc* d, const void* plan, const void* x_in, void* x_out,
+                      const void* X_in_main, const void* X_in_nyq, const void* U_in_main, const void* U_in_nyq,
+                      void* X_out_main, void* X_out_nyq, void* U_out_main, void* U_out_nyq,
+                      const void* mag_main, const void* mag_nyq, double rho, double* sums, void* stream) {
+    return generic_admm_iter(d, plan, x_in, x_out, X_in_main, X_in_nyq, U_in_main, U_in_nyq, X_out_main, X_out_nyq,
+                             U_out_main, U_out_nyq, mag_main, mag_nyq, rho, sums, stream);
+}
+
+int specinv_metric_sums(int dtype, const void* a, const void* b, int64_t n, double* out3, void* stream) {
+    if (!a || !b || !out3 || n < 0) return SPECINV_ERR_INVALID;
+    if (dtype != SPECINV_F32 && dtype != SPECINV_F64) return SPECINV_ERR_INVALID;
+    if (n == 0) return SPECINV_OK;
+    long long blocks = (n + 256 * 8 - 1) / (256 * 8);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (dtype == SPECINV_F64)
+        metric_sums_kernel<double><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const double*)a, (const double*)b, n, out3);
+    else
+        metric_sums_kernel<float><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const float*)a, (const float*)b, n, out3);
+    return (int)cudaGetLastError();
+}
+
+}  // extern "C"

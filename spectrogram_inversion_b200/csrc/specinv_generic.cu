@@ -1,0 +1,416 @@
+// Generic (any power-of-two n_fft, any hop, every torch.stft option the reference forwards)
+// fused tile kernels: STFT, ISTFT, one Griffin-Lim iteration, one ADMM iteration.
+//
+// One CTA owns a tile of consecutive frames of one signal and the output samples
+// [t0*hop, t1*hop) of the padded signal.  It (re)computes the K = ceil(N/hop)-1 frames before
+// the tile as a halo so that the overlap-add of its output range needs no other CTA: no
+// atomics, deterministic, and the whole iteration
+//     frame+window -> real FFT -> point-wise update/projection -> inverse real FFT
+//     -> windowed overlap-add -> 1/envelope
+// stays in shared memory.  The real FFT of length N is an N/2-point complex FFT done in place:
+// forward decimation-in-frequency (natural -> bit-reversed), the point-wise stage works directly
+// on bit-reversed positions, inverse decimation-in-time (bit-reversed -> natural), so no
+// reordering pass is ever needed.  Two radix-2 stages are fused per pass (radix-2^2).
+//
+// Replaces, per iteration, torch.stft + ~8 point-wise kernels + fft.irfft + conv_transpose1d with
+// a dense diag(window) weight of the reference (methods.py:241-248, :464-477, :127-132).
+#include "specinv_common.cuh"
+
+namespace specinv {
+
+enum { OP_STFT = 0, OP_ISTFT = 1, OP_GL = 2, OP_ADMM = 3 };
+
+struct TileArgs {
+    const void* x_in;
+    void* x_out;
+    const void* s0_in_main;  const void* s0_in_nyq;   // GL: q_in   ADMM: X_in   ISTFT: spectrum
+    void* s0_out_main;       void* s0_out_nyq;        // GL: q_out  ADMM: X_out  STFT: spectrum
+    const void* s1_in_main;  const void* s1_in_nyq;   // ADMM: U_in
+    void* s1_out_main;       void* s1_out_nyq;        // ADMM: U_out
+    const void* mag_main;    const void* mag_nyq;
+    const void* tw; const void* twr; const void* wa; const void* ws; const void* inv_env;
+    double* sums;
+    double coef;       // GL: lr = alpha/(1+alpha)   ADMM: rho
+    Dims dm;
+    int tile_frames;   // owned frames per tile
+    int Mp;            // padded complex elements per frame in shared memory
+};
+
+__device__ __forceinline__ int padidx(int n) { return n + (n >> 4); }
+
+template <typename T>
+struct BinIO {
+    const TileArgs& a;
+    long long fr;   // b*T + t
+    __device__ BinIO(const TileArgs& a_, long long fr_) : a(a_), fr(fr_) {}
+    __device__ __forceinline__ cx_t<T> ldc(const void* main, const void* nyq, int kk) const {
+        if (a.dm.onesided && kk == a.dm.M) return ((const cx_t<T>*)nyq)[fr];
+        return ((const cx_t<T>*)main)[fr * a.dm.row + kk];
+    }
+    __device__ __forceinline__ void stc(void* main, void* nyq, int kk, cx_t<T> v) const {
+        if (a.dm.onesided && kk == a.dm.M) ((cx_t<T>*)nyq)[fr] = v;
+        else ((cx_t<T>*)main)[fr * a.dm.row + kk] = v;
+    }
+    __device__ __forceinline__ T ldm(int kk) const {
+        if (a.dm.onesided && kk == a.dm.M) return ((const T*)a.mag_nyq)[fr];
+        return ((const T*)a.mag_main)[fr * a.dm.row + kk];
+    }
+};
+
+// Point-wise stage for one frequency bin.  s = STFT bin of the current signal estimate.
+// Returns the spectrum value that goes into the inverse transform.
+template <typename T, int OP>
+__device__ __forceinline__ cx_t<T> bin_update(const TileArgs& a, const BinIO<T>& io, int kk, cx_t<T> s,
+                                              bool owned, bool want_sums, T& dsum, T& esum) {
+    if constexpr (OP == OP_STFT) {
+        io.stc(a.s0_out_main, a.s0_out_nyq, kk, s);
+        return s;
+    } else if constexpr (OP == OP_ISTFT) {
+        return io.ldc(a.s0_in_main, a.s0_in_nyq, kk);
+    } else if constexpr (OP == OP_GL) {
+        // methods.py:243-247
+        const T lr = (T)a.coef;
+        cx_t<T> qp = io.ldc(a.s0_in_main, a.s0_in_nyq, kk);
+        T m = io.ldm(kk);
+        cx_t<T> q = mk<T>(s.x - qp.x * lr, s.y - qp.y * lr);
+        if (owned) {
+            io.stc(a.s0_out_main, a.s0_out_nyq, kk, q);
+            if (want_sums) {
+                T r = fast_sqrt(s.x * s.x + s.y * s.y);
+                dsum += (r - m) * (r - m);
+                esum += r * r;
+            }
+        }
+        return project<T>(q, m);
+    } else {
+        // methods.py:467-475 with Y = X + U
+        const T rho = (T)a.coef;
+        const T inv = T(1) / (T(1) + rho);
+        cx_t<T> X = io.ldc(a.s0_in_main, a.s0_in_nyq, kk);
+        cx_t<T> U = io.ldc(a.s1_in_main, a.s1_in_nyq, kk);
+        T m = io.ldm(kk);
+        cx_t<T> Z = mk<T>((rho * (X.x + U.x) + s.x) * inv, (rho * (X.y + U.y) + s.y) * inv);
+        cx_t<T> Un = mk<T>(U.x + X.x - Z.x, U.y + X.y - Z.y);
+        cx_t<T> Xn = project<T>(mk<T>(Z.x - Un.x, Z.y - Un.y), m);
+        if (owned) {
+            io.stc(a.s0_out_main, a.s0_out_nyq, kk, Xn);
+            io.stc(a.s1_out_main, a.s1_out_nyq, kk, Un);
+            if (want_sums) {
+                T r = fast_sqrt(s.x * s.x + s.y * s.y);
+                dsum += (r - m) * (r - m);
+                esum += r * r;
+            }
+        }
+        return mk<T>(Xn.x + Un.x, Xn.y + Un.y);
+    }
+}
+
+template <typename T, int OP>
+__global__ void __launch_bounds__(256) tile_kernel(const TileArgs a) {
+    using C = cx_t<T>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    C* wb = reinterpret_cast<C*>(smem_raw);
+
+    const Dims& dm = a.dm;
+    const int M = dm.M, N = dm.N, hop = dm.hop, Mp = a.Mp;
+    const int b = blockIdx.y;
+    const int t0 = blockIdx.x * a.tile_frames;
+    const int t1 = min(dm.T, t0 + a.tile_frames);
+    const int f0 = (OP == OP_STFT) ? t0 : max(0, t0 - dm.K);
+    const int nfr = t1 - f0;
+    const int tid = threadIdx.x, NT = blockDim.x;
+
+    const C* tw = (const C*)a.tw;
+    const C* twr = (const C*)a.twr;
+    const T* wa = (const T*)a.wa;
+    const T* ws = (const T*)a.ws;
+
+    // ---- A: frame + analysis window: z[n] = x[2n] w[2n] + i x[2n+1] w[2n+1] ---------------
+    if constexpr (OP != OP_ISTFT) {
+        const T* x = (const T*)a.x_in + (long long)b * dm.L;
+        for (int idx = tid; idx < nfr * M; idx += NT) {
+            const int f = idx / M, n = idx - f * M;
+            const long long pp = (long long)(f0 + f) * hop + 2 * n;
+            const long long i0 = pad_index(pp, dm.P, dm.L, dm.pad_mode);
+            const long long i1 = pad_index(pp + 1, dm.P, dm.L, dm.pad_mode);
+            const T v0 = i0 >= 0 ? x[i0] : T(0);
+            const T v1 = i1 >= 0 ? x[i1] : T(0);
+            wb[f * Mp + padidx(n)] = mk<T>(v0 * wa[2 * n], v1 * wa[2 * n + 1]);
+        }
+        __syncthreads();
+
+        // ---- B: forward DIF passes, spans M, M/4, ... (two radix-2 stages per pass) -------
+        int S = M;
+        for (; S >= 4; S >>= 2) {
+            const int q4 = S >> 2, step = M / S;
+            for (int idx = tid; idx < nfr * (M >> 2); idx += NT) {
+                const int f = idx / (M >> 2), r = idx - f * (M >> 2);
+                const int blk = r / q4, j = r - blk * q4;
+                C* v = wb + f * Mp;
+                const int e0 = blk * S + j;
+                const int i0 = padidx(e0), i1 = padidx(e0 + q4), i2 = padidx(e0 + 2 * q4), i3 = padidx(e0 + 3 * q4);
+                const C v0 = v[i0], v1 = v[i1], v2 = v[i2], v3 = v[i3];
+                const C w1 = tw[j * step], w2 = tw[2 * j * step];
+                const C a0 = cadd(v0, v2), a2 = cmul(csub(v0, v2), w1);
+                const C a1 = cadd(v1, v3), a3 = mul_mi(cmul(csub(v1, v3), w1));
+                v[i0] = cadd(a0, a1);
+                v[i1] = cmul(csub(a0, a1), w2);
+                v[i2] = cadd(a2, a3);
+                v[i3] = cmul(csub(a2, a3), w2);
+            }
+            __syncthreads();
+        }
+        if (S == 2) {  // odd log2(M): one plain radix-2 stage of span 2 (trivial twiddle)
+            for (int idx = tid; idx < nfr * (M >> 1); idx += NT) {
+                const int f = idx / (M >> 1), r = idx - f * (M >> 1);
+                C* v = wb + f * Mp;
+                const int i0 = padidx(2 * r), i1 = padidx(2 * r + 1);
+                const C v0 = v[i0], v1 = v[i1];
+                v[i0] = cadd(v0, v1);
+                v[i1] = csub(v0, v1);
+            }
+            __syncthreads();
+        }
+    }
+
+    // ---- C: real-FFT post-process, point-wise update, inverse pre-process (pairs k, M-k) ----
+    T dsum = T(0), esum = T(0);
+    const bool want_sums = a.sums != nullptr;
+    {
+        const int npair = M / 2 + 1;
+        const int sh = 32 - dm.logM;
+        for (int idx = tid; idx < nfr * npair; idx += NT) {
+            const int f = idx / npair, k = idx - f * npair;
+            const int t = f0 + f;
+            const bool owned = t >= t0;
+            C* v = wb + f * Mp;
+            const int kA = k, kB = M - k;
+            const int pA = padidx((int)(__brev((unsigned)kA) >> sh));
+            const int pB = padidx((int)(__brev((unsigned)(kB & (M - 1))) >> sh));
+            const C w = twr[k];
+            C sA = mk<T>(T(0), T(0)), sB = sA;
+            if constexpr (OP != OP_ISTFT) {
+                const C za = v[pA], zb = v[pB];
+                const T er = T(0.5) * (za.x + zb.x), ei = T(0.5) * (za.y - zb.y);
+                const T orr = T(0.5) * (za.y + zb.y), oi = T(-0.5) * (za.x - zb.x);
+                const T wor = w.x * orr - w.y * oi, woi = w.x * oi + w.y * orr;
+                sA = mk<T>(er + wor, ei + woi);
+                sB = mk<T>(er - wor, -(ei - woi));
+            }
+            const BinIO<T> io(a, (long long)b * dm.T + t);
+            C hA, hB;
+            if (dm.onesided) {
+                hA = bin_update<T, OP>(a, io, kA, sA, owned, want_sums, dsum, esum);
+                hB = (kB != kA) ? bin_update<T, OP>(a, io, kB, sB, owned, want_sums, dsum, esum) : hA;
+            } else {
+                // two-sided: bins kA, kB and their mirrors N-kA, N-kB (= conj of the real-input STFT);
+                // ifft(...).real (methods.py:145-146) == irfft of the Hermitian part (p[k]+conj p[N-k])/2
+                hA = bin_update<T, OP>(a, io, kA, sA, owned, want_sums, dsum, esum);
+                if (kA != 0) {
+                    C m = bin_update<T, OP>(a, io, N - kA, mk<T>(sA.x, -sA.y), owned, want_sums, dsum, esum);
+                    hA = mk<T>(T(0.5) * (hA.x + m.x), T(0.5) * (hA.y - m.y));
+                }
+                if (kB != kA) {
+                    hB = bin_update<T, OP>(a, io, kB, sB, owned, want_sums, dsum, esum);
+                    if (kB != M) {
+                        C m = bin_update<T, OP>(a, io, N - kB, mk<T>(sB.x, -sB.y), owned, want_sums, dsum, esum);
+                        hB = mk<T>(T(0.5) * (hB.x + m.x), T(0.5) * (hB.y - m.y));
+                    }
+                } else {
+                    hB = hA;
+                }
+            }
+            if constexpr (OP != OP_STFT) {
+                if (k == 0) { hA.y = T(0); hB.y = T(0); }  // C2R ignores Im(DC), Im(Nyquist)
+                const T Ar = hA.x + hB.x, Ai = hA.y - hB.y;
+                const T Dr = hA.x - hB.x, Di = hA.y + hB.y;
+                const T Gr = w.x * Dr + w.y * Di, Gi = w.x * Di - w.y * Dr;   // conj(w) * D
+                v[pA] = mk<T>(Ar - Gi, Ai + Gr);
+                if (kB != kA && k != 0) v[pB] = mk<T>(Ar + Gi, Gr - Ai);
+            }
+        }
+    }
+
+    if constexpr (OP == OP_GL || OP == OP_ADMM) {
+        if (want_sums) {   // fused metric epilogue: block reduce, one double atomic pair per CTA
+            __shared__ double red[2][8];
+            double d = (double)dsum, e = (double)esum;
+            for (int o = 16; o > 0; o >>= 1) {
+                d += __shfl_xor_sync(0xffffffffu, d, o);
+                e += __shfl_xor_sync(0xffffffffu, e, o);
+            }
+            if ((tid & 31) == 0) { red[0][tid >> 5] = d; red[1][tid >> 5] = e; }
+            __syncthreads();
+            if (tid == 0) {
+                double dd = 0, ee = 0;
+                for (int i = 0; i < (NT >> 5); ++i) { dd += red[0][i]; ee += red[1][i]; }
+                atomicAdd(a.sums, dd);
+                atomicAdd(a.sums + 1, ee);
+            }
+        }
+    }
+    if constexpr (OP == OP_STFT) return;
+    __syncthreads();
+
+    // ---- D: inverse DIT passes, spans (2), 4*.., conj twiddles --------------------------------
+    {
+        int S = 4;
+        if (dm.logM & 1) {
+            for (int idx = tid; idx < nfr * (M >> 1); idx += NT) {
+                const int f = idx / (M >> 1), r = idx - f * (M >> 1);
+                C* v = wb + f * Mp;
+                const int i0 = padidx(2 * r), i1 = padidx(2 * r + 1);
+                const C v0 = v[i0], v1 = v[i1];
+                v[i0] = cadd(v0, v1);
+                v[i1] = csub(v0, v1);
+            }
+            __syncthreads();
+            S = 8;
+        }
+        for (; S <= M; S <<= 2) {
+            const int q4 = S >> 2, step = M / S;
+            for (int idx = tid; idx < nfr * (M >> 2); idx += NT) {
+                const int f = idx / (M >> 2), r = idx - f * (M >> 2);
+                const int blk = r / q4, j = r - blk * q4;
+                C* v = wb + f * Mp;
+                const int e0 = blk * S + j;
+                const int i0 = padidx(e0), i1 = padidx(e0 + q4), i2 = padidx(e0 + 2 * q4), i3 = padidx(e0 + 3 * q4);
+                const C w1 = tw[j * step], w2 = tw[2 * j * step];
+                const C v0 = v[i0], v1 = cmulc(v[i1], w2), v2 = v[i2], v3 = cmulc(v[i3], w2);
+                const C a0 = cadd(v0, v1), a1 = csub(v0, v1);
+                const C a2 = cmulc(cadd(v2, v3), w1), a3 = mul_pi(cmulc(csub(v2, v3), w1));
+                v[i0] = cadd(a0, a2);
+                v[i2] = csub(a0, a2);
+                v[i1] = cadd(a1, a3);
+                v[i3] = csub(a1, a3);
+            }
+            __syncthreads();
+        }
+    }
+
+    // ---- E: windowed overlap-add of the owned output range (gather), times 1/envelope --------
+    {
+        const long long o0 = (long long)t0 * hop;
+        const long long o1 = (t1 == dm.T) ? dm.Lp : (long long)t1 * hop;
+        T* xo = (T*)a.x_out + (long long)b * dm.L;
+        const T* ienv = (const T*)a.inv_env;
+        const T* wbf = reinterpret_cast<const T*>(wb);
+        for (long long pp = o0 + tid; pp < o1; pp += NT) {
+            const long long m = pp - dm.P;
+            if (m < 0 || m >= dm.L) continue;
+            int tlo = pp >= N ? (int)((pp - N) / hop) + 1 : 0;
+            if (tlo < f0) tlo = f0;
+            int thi = (int)(pp / hop);
+            if (thi > t1 - 1) thi = t1 - 1;
+            T acc = T(0);
+            for (int t = tlo; t <= thi; ++t) {
+                const int i = (int)(pp - (long long)t * hop);
+                acc += wbf[2 * ((t - f0) * Mp + padidx(i >> 1)) + (i & 1)] * ws[i];
+            }
+            xo[m] = acc * ienv[m];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+static int g_smem_optin = -1;
+
+static int smem_optin() {
+    if (g_smem_optin < 0) {
+        int dev = 0, v = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) return 0;
+        g_smem_optin = v;
+    }
+    return g_smem_optin;
+}
+
+template <typename T, int OP>
+static int launch_tile(TileArgs& a, cudaStream_t st) {
+    const Dims& dm = a.dm;
+    const int Mp = dm.M + (dm.M >> 4);
+    const size_t frame_bytes = (size_t)Mp * 2 * sizeof(T);
+    const int halo = (OP == OP_STFT) ? 0 : dm.K;
+    const int optin = smem_optin();
+    if (optin <= 0) return SPECINV_ERR_NO_DEVICE;
+    const size_t big = (size_t)optin - 1024;        // static smem of the reduction + slack
+    size_t budget = big < (size_t)100 * 1024 ? big : (size_t)100 * 1024;   // 2 CTAs / SM when possible
+    int cap = (int)(budget / frame_bytes);
+    if (cap - halo < (halo > 1 ? 2 * halo : 2)) cap = (int)(big / frame_bytes);  // poor owned/halo ratio: one fat CTA
+    int owned = cap - halo;
+    if (owned < 1) return SPECINV_ERR_UNSUPPORTED;  // hop too small for this n_fft: halo does not fit
+    if (owned > dm.T) owned = dm.T;
+    // small problems: prefer enough tiles to cover the 148 SMs
+    while (owned > 4 * (halo > 0 ? halo : 1) && (long long)dm.B * ((dm.T + owned - 1) / owned) < 2 * 148) owned = (owned + 1) / 2;
+    a.tile_frames = owned;
+    a.Mp = Mp;
+    const size_t smem = (size_t)(owned + halo) * frame_bytes;
+    cudaError_t e = cudaFuncSetAttribute(tile_kernel<T, OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    dim3 grid((dm.T + owned - 1) / owned, dm.B);
+    if (grid.y > 65535) return SPECINV_ERR_UNSUPPORTED;
+    tile_kernel<T, OP><<<grid, 256, smem, st>>>(a);
+    return (int)cudaGetLastError();
+}
+
+static void fill_plan(TileArgs& a, const Dims& dm, int dtype, const void* plan) {
+    const PlanLayout pl = plan_layout(dm, dtype);
+    const char* p = (const char*)plan;
+    a.tw = p + pl.tw; a.twr = p + pl.twr; a.wa = p + pl.wa; a.ws = p + pl.ws; a.inv_env = p + pl.inv_env;
+    a.dm = dm;
+}
+
+template <int OP>
+static int dispatch(int dtype, TileArgs& a, cudaStream_t st) {
+    return dtype == SPECINV_F64 ? launch_tile<double, OP>(a, st) : launch_tile<float, OP>(a, st);
+}
+
+int generic_stft(const specinv_desc* d, const void* plan, const void* x, void* main_out, void* nyq_out, void* stream) {
+    Dims dm; int rc = make_dims(d, &dm); if (rc) return rc;
+    if (!plan || !x || !main_out || (dm.onesided && !nyq_out)) return SPECINV_ERR_INVALID;
+    TileArgs a{}; fill_plan(a, dm, d->dtype, plan);
+    a.x_in = x; a.s0_out_main = main_out; a.s0_out_nyq = nyq_out;
+    return dispatch<OP_STFT>(d->dtype, a, (cudaStream_t)stream);
+}
+
+int generic_istft(const specinv_desc* d, const void* plan, const void* main_in, const void* nyq_in, void* x_out, void* stream) {
+    Dims dm; int rc = make_dims(d, &dm); if (rc) return rc;
+    if (!plan || !x_out || !main_in || (dm.onesided && !nyq_in)) return SPECINV_ERR_INVALID;
+    TileArgs a{}; fill_plan(a, dm, d->dtype, plan);
+    a.x_out = x_out; a.s0_in_main = main_in; a.s0_in_nyq = nyq_in;
+    return dispatch<OP_ISTFT>(d->dtype, a, (cudaStream_t)stream);
+}
+
+int generic_gl_iter(const specinv_desc* d, const void* plan, const void* x_in, void* x_out,
+                    const void* q_in_main, const void* q_in_nyq, void* q_out_main, void* q_out_nyq,
+                    const void* mag_main, const void* mag_nyq, double lr, double* sums, void* stream) {
+    Dims dm; int rc = make_dims(d, &dm); if (rc) return rc;
+    if (!plan || !x_in || !x_out || !q_in_main || !q_out_main || !mag_main) return SPECINV_ERR_INVALID;
+    if (dm.onesided && (!q_in_nyq || !q_out_nyq || !mag_nyq)) return SPECINV_ERR_INVALID;
+    if (x_in == x_out || q_in_main == q_out_main) return SPECINV_ERR_INVALID;
+    TileArgs a{}; fill_plan(a, dm, d->dtype, plan);
+    a.x_in = x_in; a.x_out = x_out;
+    a.s0_in_main = q_in_main; a.s0_in_nyq = q_in_nyq; a.s0_out_main = q_out_main; a.s0_out_nyq = q_out_nyq;
+    a.mag_main = mag_main; a.mag_nyq = mag_nyq; a.coef = lr; a.sums = sums;
+    return dispatch<OP_GL>(d->dtype, a, (cudaStream_t)stream);
+}
+
+int generic_admm_iter(const specinv_desc* d, const void* plan, const void* x_in, void* x_out,
+                      const void* X_in_main, const void* X_in_nyq, const void* U_in_main, const void* U_in_nyq,
+                      void* X_out_main, void* X_out_nyq, void* U_out_main, void* U_out_nyq,
+                      const void* mag_main, const void* mag_nyq, double rho, double* sums, void* stream) {
+    Dims dm; int rc = make_dims(d, &dm); if (rc) return rc;
+    if (!plan || !x_in || !x_out || !X_in_main || !U_in_main || !X_out_main || !U_out_main || !mag_main) return SPECINV_ERR_INVALID;
+    if (dm.onesided && (!X_in_nyq || !U_in_nyq || !X_out_nyq || !U_out_nyq || !mag_nyq)) return SPECINV_ERR_INVALID;
+    if (x_in == x_out || X_in_main == X_out_main || U_in_main == U_out_main) return SPECINV_ERR_INVALID;
+    TileArgs a{}; fill_plan(a, dm, d->dtype, plan);
+    a.x_in = x_in; a.x_out = x_out;
+    a.s0_in_main = X_in_main; a.s0_in_nyq = X_in_nyq; a.s0_out_main = X_out_main; a.s0_out_nyq = X_out_nyq;
+    a.s1_in_main = U_in_main; a.s1_in_nyq = U_in_nyq; a.s1_out_main = U_out_main; a.s1_out_nyq = U_out_nyq;
+    a.mag_main = mag_main; a.mag_nyq = mag_nyq; a.coef = rho; a.sums = sums;
+    return dispatch<OP_ADMM>(d->dtype, a, (cudaStream_t)stream);
+}
+
+}  // namespace specinv

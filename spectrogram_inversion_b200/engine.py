@@ -1,0 +1,244 @@
+"""Device-side state and drivers for the fused iterations.
+
+Everything numerical is done by the CUDA kernels behind ``_ops``; this module only owns
+buffers (PyTorch is the allocator / stream provider) and the host loop that the reference
+keeps in ``_training_loop`` (torch_specinv/methods.py:153-190)."""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Callable, List, Optional, Tuple
+
+import torch
+from tqdm import tqdm
+
+from . import _lib, _ops
+from .stft_args import StftArgs, real_dtype_of
+
+_CDT = {torch.float32: torch.complex64, torch.float64: torch.complex128}
+
+
+def require_cuda() -> None:
+    if not torch.cuda.is_available():
+        raise RuntimeError("spectrogram_inversion_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    _lib.lib()
+
+
+def compute_device(t: torch.Tensor) -> torch.device:
+    """CUDA tensors run in place; host tensors are staged through the current CUDA device."""
+    require_cuda()
+    return t.device if t.is_cuda else torch.device("cuda", torch.cuda.current_device())
+
+
+@dataclass
+class SplitSpec:
+    """Split frame-major spectrum: main (B, T, row), nyq (B, T) or empty when two-sided."""
+    main: torch.Tensor
+    nyq: torch.Tensor
+
+    def like(self) -> "SplitSpec":
+        return SplitSpec(torch.empty_like(self.main), torch.empty_like(self.nyq))
+
+    def zeros_like(self) -> "SplitSpec":
+        return SplitSpec(torch.zeros_like(self.main), torch.zeros_like(self.nyq))
+
+
+class StftPlan:
+    """Twiddles, scaled windows and 1/envelope for one (stft args, T, B, dtype, device)."""
+
+    def __init__(self, args: StftArgs, n_frames: int, batch: int, dtype: torch.dtype, device: torch.device):
+        require_cuda()
+        if dtype not in _CDT:
+            raise NotImplementedError(f"dtype {dtype} is not supported (float32 / float64 only)")
+        if args.pad_mode not in _lib.PAD_MODES:
+            raise NotImplementedError(f"pad_mode {args.pad_mode!r} is not supported")
+        n = args.n_fft
+        if n < 16 or n > 8192 or n & (n - 1):
+            raise NotImplementedError(f"n_fft={n}: the sm_100a kernels need a power of two in [16, 8192]")
+        self.args, self.T, self.B, self.dtype, self.device = args, int(n_frames), int(batch), dtype, device
+        self.cdtype = _CDT[dtype]
+        self.pad_mode = _lib.PAD_MODES[args.pad_mode]
+        self.length = args.signal_length(self.T)
+        self.row = n // 2 if args.onesided else n
+        self.n_bins = args.n_bins
+        d = _lib.make_desc(n, args.hop_length, self.T, self.B, args.center, self.pad_mode, args.normalized,
+                           args.onesided, _ops._DT[dtype])
+        nbytes = _lib.C.c_size_t(0)
+        _lib.check(_lib.lib().specinv_plan_bytes(_lib.C.byref(d), _lib.C.byref(nbytes)), "plan_bytes")
+        self.buf = torch.empty(nbytes.value, dtype=torch.uint8, device=device)
+        window = args.window.detach().to(device=device, dtype=dtype).contiguous()
+        _ops.plan_init(self.buf, window, n, args.hop_length, self.T, self.B, args.center, self.pad_mode,
+                       args.normalized, args.onesided)
+        self._k = (n, args.hop_length, args.center, self.pad_mode, args.normalized, args.onesided)
+
+    # ---- buffers ---------------------------------------------------------------------------
+    def empty_spec(self, real: bool = False) -> SplitSpec:
+        dt = self.dtype if real else self.cdtype
+        main = torch.empty(self.B, self.T, self.row, dtype=dt, device=self.device)
+        nyq = torch.empty((self.B, self.T) if self.args.onesided else (0,), dtype=dt, device=self.device)
+        return SplitSpec(main, nyq)
+
+    def empty_signal(self) -> torch.Tensor:
+        return torch.empty(self.B, self.length, dtype=self.dtype, device=self.device)
+
+    # ---- layout ----------------------------------------------------------------------------
+    def pack(self, spec: torch.Tensor) -> SplitSpec:
+        """(B, F, T) tensor with any strides -> split layout (real or complex)."""
+        assert spec.shape == (self.B, self.n_bins, self.T), (spec.shape, (self.B, self.n_bins, self.T))
+        want = self.cdtype if spec.is_complex() else self.dtype
+        spec = spec.detach().to(device=self.device, dtype=want)
+        out = self.empty_spec(real=not spec.is_complex())
+        _ops.pack(spec, out.main, out.nyq, self.args.n_fft, self.args.onesided)
+        return out
+
+    def unpack(self, s: SplitSpec) -> torch.Tensor:
+        """split layout -> (B, F, T) complex with the physical layout torch.stft produces
+        (frame-major: strides (F*T, 1, F))."""
+        out = torch.empty(self.B, self.T, self.n_bins, dtype=self.cdtype, device=self.device).transpose(1, 2)
+        _ops.unpack(s.main, s.nyq, out, self.args.n_fft, self.args.onesided)
+        return out
+
+    # ---- primitives ------------------------------------------------------------------------
+    def stft(self, x: torch.Tensor, out: Optional[SplitSpec] = None) -> SplitSpec:
+        out = out or self.empty_spec()
+        _ops.stft(self.buf, x, out.main, out.nyq, *self._k)
+        return out
+
+    def istft(self, s: SplitSpec, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        out = out if out is not None else self.empty_signal()
+        _ops.istft(self.buf, s.main, s.nyq, out, *self._k)
+        return out
+
+
+def spec_sums(a: SplitSpec, b: SplitSpec) -> torch.Tensor:
+    """3 doubles: sum (a-b)^2, sum a^2, sum b^2 over a real split spectrum pair."""
+    out = torch.zeros(3, dtype=torch.float64, device=a.main.device)
+    _ops.metric_sums(a.main, b.main, out)
+    if a.nyq.numel():
+        _ops.metric_sums(a.nyq, b.nyq, out)
+    return out
+
+
+class _Solver:
+    """Common ping-pong state for the fused iterations."""
+
+    def __init__(self, plan: StftPlan, mag: SplitSpec):
+        self.plan, self.mag = plan, mag
+        self.x = [plan.empty_signal(), plan.empty_signal()]
+        self.cur = 0
+        self.sums = torch.zeros(2, dtype=torch.float64, device=plan.device)
+        self._nosums = torch.empty(0, dtype=torch.float64, device=plan.device)
+        self.n_bins_total = plan.B * plan.n_bins * plan.T
+        self.g = float(spec_sums(mag, mag)[2].item())   # sum mag^2 (constant per call)
+        self.iterations = 0
+
+    @property
+    def signal(self) -> torch.Tensor:
+        return self.x[self.cur]
+
+    def _launch(self, sums: torch.Tensor) -> None:
+        raise NotImplementedError
+
+    def step(self, evaluate: bool = False) -> Optional[Tuple[float, float]]:
+        """One fused iteration.  With ``evaluate`` returns (d, e) = (sum (|s|-mag)^2, sum |s|^2) of
+        the spectrogram the iteration started from -- exactly the ``output`` the reference's closure
+        returns (methods.py:242, :465) -- which costs one device->host sync like the reference's
+        ``.item()`` calls (methods.py:181-182)."""
+        if evaluate:
+            self.sums.zero_()
+            self._launch(self.sums)
+        else:
+            self._launch(self._nosums)
+        self.cur ^= 1
+        self.iterations += 1
+        if evaluate:
+            d, e = self.sums.tolist()
+            return d, e
+        return None
+
+
+class GriffinLimSolver(_Solver):
+    """State machine of griffin_lim (methods.py:225-255): q_0 = C, x_0 = ISTFT(C), then
+    q_n = STFT(x_{n-1}) - lr q_{n-1};  x_n = ISTFT(proj(q_n))."""
+
+    def __init__(self, plan: StftPlan, C: SplitSpec, mag: SplitSpec, alpha: float):
+        super().__init__(plan, mag)
+        self.lr = alpha / (1 + alpha)                     # methods.py:235
+        self.q = [C, C.like()]
+        plan.istft(C, self.x[0])                          # methods.py:233
+
+    def _launch(self, sums: torch.Tensor) -> None:
+        p, i, o = self.plan, self.cur, self.cur ^ 1
+        _ops.gl_iter(p.buf, self.x[i], self.x[o], self.q[i].main, self.q[i].nyq, self.q[o].main, self.q[o].nyq,
+                     self.mag.main, self.mag.nyq, sums, self.lr, *p._k)
+
+    @property
+    def q_state(self) -> SplitSpec:
+        return self.q[self.cur]
+
+
+class ADMMSolver(_Solver):
+    """State machine of ADMM (methods.py:452-490) with the redundant Y = X + U eliminated."""
+
+    def __init__(self, plan: StftPlan, C: SplitSpec, mag: SplitSpec, rho: float):
+        super().__init__(plan, mag)
+        self.rho = float(rho)
+        self.X = [C, C.like()]
+        self.U = [C.zeros_like(), C.like()]
+        plan.istft(C, self.x[0])                          # methods.py:453
+
+    def _launch(self, sums: torch.Tensor) -> None:
+        p, i, o = self.plan, self.cur, self.cur ^ 1
+        _ops.admm_iter(p.buf, self.x[i], self.x[o], self.X[i].main, self.X[i].nyq, self.U[i].main, self.U[i].nyq,
+                       self.X[o].main, self.X[o].nyq, self.U[o].main, self.U[o].nyq, self.mag.main, self.mag.nyq,
+                       sums, self.rho, *p._k)
+
+
+def metric_value(name: str, d: float, e: float, g: float) -> float:
+    """sc / snr / ser from the three sums (metrics.py:14, :28-29, :43)."""
+    def l10(v: float) -> float:
+        return math.log10(v) if v > 0 else -math.inf
+    if name == "SC":
+        return 10.0 * (l10(d) - l10(g))
+    if name == "SNR":
+        return -10.0 * (l10(d) - l10(g))
+    if name == "SER":
+        return 10.0 * (l10(e) - l10(d))
+    raise AssertionError(name)
+
+
+METRIC_NAMES = ("SC", "SNR", "SER")   # methods.py:14-18
+
+
+def training_loop(solver: _Solver, max_iter: int, tol: float, verbose, eva_iter: int, metric: str,
+                  history: Optional[List] = None) -> int:
+    """Host loop with the reference's evaluation cadence and early-stop rule (methods.py:153-190)."""
+    assert eva_iter > 0
+    assert max_iter > 0
+    assert tol >= 0
+    metric = metric.upper()
+    assert metric in METRIC_NAMES
+    bar = {metric: 0}
+    init_loss = None
+    previous_loss = None
+    done = 0
+    with tqdm(total=max_iter, disable=not verbose) as pbar:
+        for i in range(max_iter):
+            if i % eva_iter == eva_iter - 1:
+                d, e = solver.step(evaluate=True)
+                done = i + 1
+                bar[metric] = metric_value(metric, d, e, solver.g)
+                l2_loss = d / solver.n_bins_total
+                if history is not None:
+                    history.append((i, bar[metric], l2_loss))
+                pbar.set_postfix(**bar, loss=l2_loss)
+                pbar.update(eva_iter)
+                if not init_loss:
+                    init_loss = l2_loss
+                elif (previous_loss - l2_loss) / init_loss < tol and previous_loss > l2_loss:
+                    break
+                previous_loss = l2_loss
+            else:
+                solver.step()
+                done = i + 1
+    return done

@@ -1,0 +1,144 @@
+"""Public algorithm API with the reference's signatures (torch_specinv/methods.py:193, :273, :415,
+:572), running on the sm_100a kernels of libspecinv_b200.so.  No CPU / PyTorch fallback."""
+from __future__ import annotations
+
+import math
+from typing import Optional, Tuple
+
+import torch
+
+from .engine import (ADMMSolver, GriffinLimSolver, METRIC_NAMES, SplitSpec, StftPlan, compute_device,
+                     training_loop)
+from .stft_args import StftArgs, args_helper
+
+__all__ = ["griffin_lim", "RTISI_LA", "ADMM", "phase_init"]
+
+pi2 = 2 * math.pi
+
+
+def _pop_aliases(kw: dict, max_iter, eva_iter):
+    """BASELINE.json / the reference README spell these ``maxiter`` / ``evaiter``; the reference code
+    itself only knows max_iter / eva_iter (methods.py:193-200).  Accept both."""
+    if "maxiter" in kw:
+        max_iter = kw.pop("maxiter")
+    if "evaiter" in kw:
+        eva_iter = kw.pop("evaiter")
+    return max_iter, eva_iter
+
+
+def _spec_formatter(spec: torch.Tensor, **stft_kwargs) -> Tuple[torch.Tensor, torch.Tensor]:
+    """methods.py:99-111: 2-D -> 3-D; real input gets a phase from phase_init, complex input is the
+    initial estimate and its modulus the target."""
+    shape = spec.shape
+    assert 4 > len(shape) > 1
+    if len(shape) == 2:
+        spec = spec.unsqueeze(0)
+    if not spec.is_complex():
+        return phase_init(spec, **stft_kwargs), spec
+    return spec, spec.abs()
+
+
+def _setup(spec: torch.Tensor, stft_kwargs: dict):
+    dev = compute_device(spec)
+    work = spec.detach().to(dev)
+    cmplx, target = _spec_formatter(work, **stft_kwargs)
+    args = args_helper(target, **stft_kwargs)
+    B, _, T = target.shape
+    plan = StftPlan(args, T, B, target.dtype, dev)
+    return plan, plan.pack(cmplx), plan.pack(target)
+
+
+def _finish(x: torch.Tensor, spec: torch.Tensor) -> torch.Tensor:
+    """methods.py:267-270: drop the batch dim unless the input was (1, F, T)."""
+    x = x.clone()
+    if not (spec.shape[0] == 1 and len(spec.shape) == 3):
+        x = x.squeeze(0)
+    return x.to(spec.device)
+
+
+def griffin_lim(spec, max_iter=200, tol=1e-6, alpha=0.99, verbose=True, eva_iter=10, metric="sc",
+                **stft_kwargs):
+    r"""Griffin-Lim / fast Griffin-Lim phase reconstruction (drop-in for
+    ``torch_specinv.griffin_lim``, methods.py:193-270).
+
+    Args:
+        spec (Tensor): magnitude (real) or initial complex estimate, ``(F, T)`` or ``(B, F, T)``.
+        max_iter (int): number of iterations.
+        tol (float): early-stop tolerance on the relative MSE decrease. Default ``1e-6``.
+        alpha (float): momentum of fast Griffin-Lim, 0 disables it. Default ``0.99``.
+        verbose (bool): progress bar.
+        eva_iter (int): evaluate the metric every ``eva_iter`` iterations. Default ``10``.
+        metric (str): ``'sc'``, ``'snr'`` or ``'ser'``.
+        **stft_kwargs: the ``torch.stft`` arguments the spectrogram was computed with.
+
+    Returns:
+        the time-domain signal, ``(L,)`` or ``(B, L)``.
+    """
+    assert alpha >= 0
+    max_iter, eva_iter = _pop_aliases(stft_kwargs, max_iter, eva_iter)
+    assert eva_iter > 0
+    assert max_iter > 0
+    assert tol >= 0
+    assert metric.upper() in METRIC_NAMES
+    plan, C, mag = _setup(spec, stft_kwargs)
+    solver = GriffinLimSolver(plan, C, mag, alpha)
+    training_loop(solver, max_iter, tol, verbose, eva_iter, metric)
+    return _finish(solver.signal, spec)
+
+
+def ADMM(spec, max_iter=1000, tol=1e-6, rho=0.1, verbose=1, eva_iter=10, metric="sc", **stft_kwargs):
+    r"""ADMM phase recovery (drop-in for ``torch_specinv.ADMM``, methods.py:415-506)."""
+    max_iter, eva_iter = _pop_aliases(stft_kwargs, max_iter, eva_iter)
+    assert eva_iter > 0
+    assert max_iter > 0
+    assert tol >= 0
+    assert metric.upper() in METRIC_NAMES
+    plan, C, mag = _setup(spec, stft_kwargs)
+    solver = ADMMSolver(plan, C, mag, rho)
+    training_loop(solver, max_iter, tol, verbose, eva_iter, metric)
+    return _finish(solver.signal, spec)
+
+
+def RTISI_LA(spec, look_ahead=-1, asymmetric_window=False, max_iter=25, alpha=0.99, verbose=1, **stft_kwargs):
+    r"""Real-Time Iterative Spectrogram Inversion with Look-Ahead (drop-in for
+    ``torch_specinv.RTISI_LA``, methods.py:273-412)."""
+    assert max_iter > 0
+    assert alpha >= 0
+    assert not spec.is_complex()
+    assert 4 > len(spec.shape) > 1
+    raise NotImplementedError("RTISI_LA: the persistent sm_100a kernel is not built yet")
+
+
+def phase_init(spec, **stft_kwargs):
+    r"""One-shot phase initialiser (simplified SPSI), drop-in for ``torch_specinv.phase_init``
+    (methods.py:572-615): instantaneous frequency of each strict spectral peak (parabolic
+    interpolation) assigned to the peak bin and its two neighbours, integrated over time."""
+    assert not spec.is_complex()
+    shape = spec.shape
+    if len(spec.shape) == 2:
+        spec = spec.unsqueeze(0)
+    assert len(spec.shape) == 3
+    dev = compute_device(spec)
+    m = spec.detach().to(dev)
+    args = args_helper(m, **stft_kwargs)
+    # TODO(kernel): one-shot, off the per-iteration path; runs as device-side tensor ops for now
+    F_, dt = m.shape[1], m.dtype
+    peak = torch.zeros_like(m, dtype=torch.bool)
+    peak[:, 1:-1] = (m[:, 1:-1] > m[:, 2:]) & (m[:, 1:-1] > m[:, :-2])
+    lo = torch.roll(m, 1, 1)
+    hi = torch.roll(m, -1, 1)
+    k = torch.arange(F_, device=dev, dtype=dt).view(1, -1, 1)
+    p = 0.5 * (lo - hi) / (lo - 2 * m + hi)
+    omega = torch.where(peak, pi2 * (k + p) / args.n_fft * args.hop_length, torch.zeros_like(m))
+    up = torch.roll(omega, -1, 1)      # omega of a peak at k+1
+    up[:, -1] = 0
+    down = torch.roll(omega, 1, 1)     # omega of a peak at k-1 (written last in the reference, so it wins)
+    down[:, 0] = 0
+    pk_dn = torch.roll(peak, 1, 1)
+    pk_dn[:, 0] = False
+    pk_up = torch.roll(peak, -1, 1)
+    pk_up[:, -1] = False
+    phase = torch.where(pk_dn, down, torch.where(pk_up, up, omega))
+    phase = torch.cumsum(phase, 2)
+    out = m * torch.exp(phase * 1j)
+    return out.view(shape).to(spec.device)

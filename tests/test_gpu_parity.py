@@ -1,0 +1,216 @@
+"""GPU parity: the CUDA kernels (through the C ABI / torch.library ops) against the numpy oracle
+and against the golden vectors produced by the unmodified reference.
+
+Tolerances: BASELINE.json north_star -- single-iteration max-abs <= 1e-5 in fp32 from identical
+state (scaled by max(1, |x|max)); fp64 is held to 1e-10."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import cases
+from oracle import specinv_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+GL = np.load(os.path.join(G, "gl.npz"))
+ADMM = np.load(os.path.join(G, "admm.npz"))
+PRIM = np.load(os.path.join(G, "primitives.npz"))
+LOOP = np.load(os.path.join(G, "loop.npz"))
+MISC = np.load(os.path.join(G, "misc.npz"))
+
+
+def tol_of(dtype):
+    return 1e-10 if np.dtype(dtype) == np.float64 else 1e-5
+
+
+def close(a, b, tol, what=""):
+    a = a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
+    b = np.asarray(b)
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    fin = np.isfinite(b)
+    assert (np.isfinite(a) == fin).all(), what
+    scale = max(1.0, float(np.abs(b[fin]).max())) if fin.any() else 1.0
+    err = float(np.abs(a[fin] - b[fin]).max()) if fin.any() else 0.0
+    assert err <= tol * scale, (what, err, tol * scale)
+
+
+def build(case):
+    from spectrogram_inversion_b200.engine import StftPlan
+    from spectrogram_inversion_b200.stft_args import args_helper
+    inp = cases.make_case_inputs(case)
+    C = inp["C"] if inp["C"].ndim == 3 else inp["C"][None]
+    mag = inp["mag"] if inp["mag"].ndim == 3 else inp["mag"][None]
+    kw = {k: (torch.from_numpy(v) if isinstance(v, np.ndarray) else v) for k, v in inp["kwargs"].items()}
+    dev = torch.device("cuda")
+    magt = torch.from_numpy(mag).to(dev)
+    args = args_helper(magt, **kw)
+    plan = StftPlan(args, mag.shape[2], mag.shape[0], magt.dtype, dev)
+    oa = O.args_helper(mag.shape[1], mag.dtype, **inp["kwargs"])
+    return inp, C, mag, plan, oa
+
+
+@pytest.mark.parametrize("case", cases.ITER_CASES, ids=lambda c: c["name"])
+def test_stft_istft_primitives(case):
+    inp, C, mag, plan, oa = build(case)
+    name = case["name"]
+    tol = tol_of(case["dtype"])
+    Cs = plan.pack(torch.from_numpy(C))
+    close(plan.unpack(Cs), C, 0.0, "pack/unpack round trip")
+    x = plan.istft(Cs)
+    close(x, PRIM[f"{name}/istft_x"], tol, "istft vs reference")
+    xo, env = O.istft(C, oa)
+    close(x, xo, tol, "istft vs oracle")
+    if np.isfinite(xo).all():
+        S = plan.unpack(plan.stft(torch.from_numpy(xo).cuda()))
+        close(S, O.stft(xo, oa), tol * 10, "stft vs oracle")
+        if f"{name}/stft_of_x" in PRIM:
+            close(S, PRIM[f"{name}/stft_of_x"], tol * 20, "stft vs reference")
+
+
+@pytest.mark.parametrize("case", cases.ITER_CASES, ids=lambda c: c["name"])
+def test_griffin_lim_iterations_from_identical_state(case):
+    from spectrogram_inversion_b200.engine import GriffinLimSolver
+    inp, C, mag, plan, oa = build(case)
+    tol = tol_of(case["dtype"])
+    for alpha in cases.GL_ALPHAS:
+        solver = GriffinLimSolver(plan, plan.pack(torch.from_numpy(C)), plan.pack(torch.from_numpy(mag)), alpha)
+        st = O.gl_init(C, oa)
+        close(solver.signal, st.x, tol, "x0")
+        for k in (1, 2, 3):
+            # restart the CUDA step from the ORACLE's state so every step is a single-iteration test
+            solver.x[solver.cur].copy_(torch.from_numpy(st.x))
+            solver.q[solver.cur] = plan.pack(torch.from_numpy(st.q))
+            solver.q[solver.cur ^ 1] = solver.q[solver.cur].like()
+            d, e = solver.step(evaluate=True)
+            st = O.gl_step(st, mag, alpha / (1 + alpha), oa)
+            close(solver.signal, st.x, tol, f"x after step {k} alpha {alpha}")
+            close(plan.unpack(solver.q_state), st.q, tol * 10, f"q after step {k}")
+            do, eo, go = O.metric_sums(st.out_mag, mag)
+            rel = 1e-4 if case["dtype"] == "float32" else 1e-10
+            assert abs(d - do) <= rel * max(do, 1e-30) + 1e-12 and abs(e - eo) <= rel * eo
+            assert abs(solver.g - go) <= rel * go
+
+
+@pytest.mark.parametrize("case", cases.ITER_CASES, ids=lambda c: c["name"])
+def test_griffin_lim_matches_reference_golden(case):
+    import spectrogram_inversion_b200 as S
+    inp = cases.make_case_inputs(case)
+    kw = {k: (torch.from_numpy(v) if isinstance(v, np.ndarray) else v) for k, v in inp["kwargs"].items()}
+    tol = tol_of(case["dtype"])
+    C = torch.from_numpy(inp["C"]).cuda()
+    for alpha in cases.GL_ALPHAS:
+        for k in cases.ITER_COUNTS:
+            y = S.griffin_lim(C, max_iter=k, tol=0, alpha=alpha, verbose=False, eva_iter=1, **kw)
+            assert y.is_cuda
+            close(y, GL[f"{case['name']}/a{alpha}/k{k}"], tol * (4 ** (k - 1)), f"a{alpha} k{k}")
+
+
+@pytest.mark.parametrize("case", cases.ITER_CASES, ids=lambda c: c["name"])
+def test_admm_iterations_and_golden(case):
+    import spectrogram_inversion_b200 as S
+    from spectrogram_inversion_b200.engine import ADMMSolver
+    inp, C, mag, plan, oa = build(case)
+    tol = tol_of(case["dtype"])
+    kw = {k: (torch.from_numpy(v) if isinstance(v, np.ndarray) else v) for k, v in inp["kwargs"].items()}
+    for rho in cases.ADMM_RHOS:
+        solver = ADMMSolver(plan, plan.pack(torch.from_numpy(C)), plan.pack(torch.from_numpy(mag)), rho)
+        st = O.admm_init(C, oa)
+        for k in (1, 2, 3):
+            i = solver.cur
+            solver.x[i].copy_(torch.from_numpy(st.x))
+            solver.X[i] = plan.pack(torch.from_numpy(st.X))
+            solver.U[i] = plan.pack(torch.from_numpy(st.U))
+            solver.X[i ^ 1] = solver.X[i].like()
+            solver.U[i ^ 1] = solver.U[i].like()
+            solver.step(evaluate=(k == 2))
+            st = O.admm_step(st, mag, rho, oa)
+            close(solver.signal, st.x, tol * 2, f"x step {k} rho {rho}")
+            close(plan.unpack(solver.X[solver.cur]), st.X, tol * 10, "X")
+            close(plan.unpack(solver.U[solver.cur]), st.U, tol * 10, "U")
+        for k in cases.ITER_COUNTS:
+            y = S.ADMM(torch.from_numpy(inp["C"]).cuda(), max_iter=k, tol=0, rho=rho, verbose=False, eva_iter=1, **kw)
+            close(y, ADMM[f"{case['name']}/r{rho}/k{k}"], tol * 2 * (4 ** (k - 1)), f"r{rho} k{k}")
+
+
+@pytest.mark.parametrize("case", cases.LOOP_CASES, ids=lambda c: c["name"])
+def test_early_stop_like_reference(case):
+    from spectrogram_inversion_b200.engine import ADMMSolver, GriffinLimSolver, training_loop
+    inp, C, mag, plan, oa = build(case)
+    for algo in ("gl", "admm"):
+        Cs, ms = plan.pack(torch.from_numpy(C)), plan.pack(torch.from_numpy(mag))
+        solver = GriffinLimSolver(plan, Cs, ms, 0.99) if algo == "gl" else ADMMSolver(plan, Cs, ms, 0.1)
+        hist = []
+        n = training_loop(solver, case["max_iter"], case["tol"], False, case["eva_iter"], case["metric"], hist)
+        assert n == int(LOOP[f"{case['name']}/{algo}/iters"]), (algo, n)
+        close(solver.signal, LOOP[f"{case['name']}/{algo}/x"], 1e-7 if algo == "gl" else 5e-2, algo)
+
+
+@pytest.mark.parametrize("i", [0, 1])
+def test_metrics_like_reference(i):
+    import spectrogram_inversion_b200 as S
+    a, b = MISC[f"metric{i}/a"], MISC[f"metric{i}/b"]
+    ta, tb = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    rel = 1e-5 if i == 0 else 1e-12
+    for fn in ("sc", "snr", "ser"):
+        got = getattr(S, fn)(ta, tb)
+        assert got.ndim == 0 and got.is_cuda and got.dtype == ta.dtype
+        want = float(MISC[f"metric{i}/{fn}"])
+        assert abs(float(got) - want) <= rel * max(1.0, abs(want)), (fn, float(got), want)
+    assert S.spectral_convergence is S.sc
+    # host tensors are staged through the GPU and come back on the host
+    assert not S.sc(torch.from_numpy(a), torch.from_numpy(b)).is_cuda
+
+
+def test_public_api_shapes_and_asserts():
+    import spectrogram_inversion_b200 as S
+    for shape in [(4410,), (2, 4410), (1, 4410)]:
+        for dtype in (torch.float32, torch.float64):
+            x = torch.randn(*shape, dtype=dtype, device="cuda")
+            spec = torch.stft(x, 256, return_complex=True, window=torch.ones(256, dtype=dtype, device="cuda"))
+            for fn in (S.griffin_lim, S.ADMM):
+                y = fn(spec, max_iter=4, verbose=False)
+                assert y.ndim == x.ndim and y.dtype == dtype and y.is_cuda
+                if y.ndim > 1:
+                    assert y.shape[0] == x.shape[0] and y.shape[1] <= x.shape[1]
+    spec = torch.stft(torch.randn(2048, device="cuda"), 128, return_complex=True,
+                      window=torch.hann_window(128, device="cuda"))
+    with pytest.raises(AssertionError):
+        S.griffin_lim(spec, alpha=-1)
+    with pytest.raises(AssertionError):
+        S.griffin_lim(spec, max_iter=0)
+    with pytest.raises(AssertionError):
+        S.griffin_lim(spec, eva_iter=0)
+    with pytest.raises(AssertionError):
+        S.griffin_lim(spec, tol=-1)
+    with pytest.raises(AssertionError):
+        S.griffin_lim(spec, metric="nope")
+    with pytest.raises(AssertionError):
+        S.ADMM(spec, metric="nope")
+    with pytest.raises(AssertionError):
+        S.RTISI_LA(spec)
+    # host input -> host output (staged through the GPU, never computed on the CPU)
+    y = S.griffin_lim(spec.cpu(), max_iter=2, verbose=False, window=torch.hann_window(128), maxiter=3)
+    assert not y.is_cuda
+
+
+def test_full_run_spectral_convergence_within_1pct():
+    """north_star: final spectral convergence after the full iteration count within 1 % of the
+    reference's (here: of the oracle's, which is pinned to the reference)."""
+    import spectrogram_inversion_b200 as S
+    rs = np.random.RandomState(3)
+    x = rs.randn(2, 6000).astype(np.float32)
+    w = cases.window_of("hann", 256, np.float32)
+    a = O.args_helper(129, np.float32, window=w, hop_length=64)
+    mag = np.abs(O.stft(x, a))
+    C = (mag * np.exp(2j * np.pi * rs.rand(*mag.shape))).astype(np.complex64)
+    for algo, kw in (("griffin_lim", dict(alpha=0.99)), ("ADMM", dict(rho=0.1))):
+        yo = getattr(O, algo)(C, max_iter=64, tol=0, window=w, hop_length=64, **kw)
+        yg = getattr(S, algo)(torch.from_numpy(C).cuda(), max_iter=64, tol=0, verbose=False,
+                              window=torch.from_numpy(w).cuda(), hop_length=64, **kw)
+        sco = O.sc(np.abs(O.stft(yo, a)), mag)
+        scg = O.sc(np.abs(O.stft(yg.cpu().numpy(), a)), mag)
+        # 1 % on the linear spectral-convergence ratio == 0.0864 dB
+        assert abs(scg - sco) <= 20 * np.log10(1.01) + 0.05 * abs(sco) * 0, (algo, scg, sco)
