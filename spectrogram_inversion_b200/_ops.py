@@ -9,7 +9,15 @@ from torch import Tensor
 
 from . import _lib
 
+# number of CUDA kernels of libspecinv_b200.so launched through these ops (bench.py reports it)
+LAUNCHES = [0]
+
 _DT = {torch.float32: _lib.F32, torch.float64: _lib.F64, torch.complex64: _lib.F32, torch.complex128: _lib.F64}
+
+
+def _ok(code: int, what: str, kernels: int = 1) -> None:
+    _lib.check(code, what)
+    LAUNCHES[0] += kernels
 
 
 def _p(t: Tensor):
@@ -39,7 +47,7 @@ def plan_init(plan: Tensor, window: Tensor, n_fft: int, hop: int, n_frames: int,
     _need_cuda(plan, window)
     d = _desc(window, n_fft, hop, n_frames, batch, center, pad_mode, normalized, onesided)
     with torch.cuda.device(plan.device):
-        _lib.check(_lib.lib().specinv_plan_init(C.byref(d), _p(window), _p(plan), _stream(plan)), "plan_init")
+        _ok(_lib.lib().specinv_plan_init(C.byref(d), _p(window), _p(plan), _stream(plan)), "plan_init", 2)
 
 
 @torch.library.custom_op("specinv_b200::stft", mutates_args=("out_main", "out_nyq"), device_types="cuda")
@@ -48,7 +56,7 @@ def stft(plan: Tensor, x: Tensor, out_main: Tensor, out_nyq: Tensor, n_fft: int,
     _need_cuda(plan, x, out_main, out_nyq)
     d = _desc(x, n_fft, hop, out_main.shape[1], out_main.shape[0], center, pad_mode, normalized, onesided)
     with torch.cuda.device(x.device):
-        _lib.check(_lib.lib().specinv_stft(C.byref(d), _p(plan), _p(x), _p(out_main), _p(out_nyq), _stream(x)), "stft")
+        _ok(_lib.lib().specinv_stft(C.byref(d), _p(plan), _p(x), _p(out_main), _p(out_nyq), _stream(x)), "stft")
 
 
 @torch.library.custom_op("specinv_b200::istft", mutates_args=("x_out",), device_types="cuda")
@@ -57,7 +65,7 @@ def istft(plan: Tensor, in_main: Tensor, in_nyq: Tensor, x_out: Tensor, n_fft: i
     _need_cuda(plan, in_main, in_nyq, x_out)
     d = _desc(x_out, n_fft, hop, in_main.shape[1], in_main.shape[0], center, pad_mode, normalized, onesided)
     with torch.cuda.device(x_out.device):
-        _lib.check(_lib.lib().specinv_istft(C.byref(d), _p(plan), _p(in_main), _p(in_nyq), _p(x_out), _stream(x_out)),
+        _ok(_lib.lib().specinv_istft(C.byref(d), _p(plan), _p(in_main), _p(in_nyq), _p(x_out), _stream(x_out)),
                    "istft")
 
 
@@ -69,7 +77,7 @@ def gl_iter(plan: Tensor, x_in: Tensor, x_out: Tensor, q_in_main: Tensor, q_in_n
     _need_cuda(plan, x_in, x_out, q_in_main, q_in_nyq, q_out_main, q_out_nyq, mag_main, mag_nyq, sums)
     d = _desc(x_in, n_fft, hop, q_in_main.shape[1], q_in_main.shape[0], center, pad_mode, normalized, onesided)
     with torch.cuda.device(x_in.device):
-        _lib.check(_lib.lib().specinv_gl_iter(
+        _ok(_lib.lib().specinv_gl_iter(
             C.byref(d), _p(plan), _p(x_in), _p(x_out), _p(q_in_main), _p(q_in_nyq), _p(q_out_main), _p(q_out_nyq),
             _p(mag_main), _p(mag_nyq), float(lr), _p(sums), _stream(x_in)), "gl_iter")
 
@@ -85,7 +93,7 @@ def admm_iter(plan: Tensor, x_in: Tensor, x_out: Tensor, X_in_main: Tensor, X_in
                U_out_nyq, mag_main, mag_nyq, sums)
     d = _desc(x_in, n_fft, hop, X_in_main.shape[1], X_in_main.shape[0], center, pad_mode, normalized, onesided)
     with torch.cuda.device(x_in.device):
-        _lib.check(_lib.lib().specinv_admm_iter(
+        _ok(_lib.lib().specinv_admm_iter(
             C.byref(d), _p(plan), _p(x_in), _p(x_out), _p(X_in_main), _p(X_in_nyq), _p(U_in_main), _p(U_in_nyq),
             _p(X_out_main), _p(X_out_nyq), _p(U_out_main), _p(U_out_nyq), _p(mag_main), _p(mag_nyq), float(rho),
             _p(sums), _stream(x_in)), "admm_iter")
@@ -97,20 +105,20 @@ def pack(spec: Tensor, out_main: Tensor, out_nyq: Tensor, n_fft: int, onesided: 
     if not spec.is_cuda:
         raise RuntimeError("specinv_b200 ops only run on CUDA tensors (no CPU fallback)")
     B, Fb, T = spec.shape
-    d = _desc(spec, n_fft, 1, T, B, True, 0, False, onesided)
+    d = _desc(spec, n_fft, 1, T, B, False, 0, False, onesided)
     sb, sf, st = spec.stride()
     fn = _lib.lib().specinv_pack_complex if spec.is_complex() else _lib.lib().specinv_pack_real
     with torch.cuda.device(spec.device):
-        _lib.check(fn(C.byref(d), _p(spec), sb, sf, st, _p(out_main), _p(out_nyq), _stream(spec)), "pack")
+        _ok(fn(C.byref(d), _p(spec), sb, sf, st, _p(out_main), _p(out_nyq), _stream(spec)), "pack")
 
 
 @torch.library.custom_op("specinv_b200::unpack", mutates_args=("spec_out",), device_types="cuda")
 def unpack(in_main: Tensor, in_nyq: Tensor, spec_out: Tensor, n_fft: int, onesided: bool) -> None:
     B, Fb, T = spec_out.shape
-    d = _desc(spec_out, n_fft, 1, T, B, True, 0, False, onesided)
+    d = _desc(spec_out, n_fft, 1, T, B, False, 0, False, onesided)
     sb, sf, st = spec_out.stride()
     with torch.cuda.device(spec_out.device):
-        _lib.check(_lib.lib().specinv_unpack_complex(C.byref(d), _p(in_main), _p(in_nyq), _p(spec_out), sb, sf, st,
+        _ok(_lib.lib().specinv_unpack_complex(C.byref(d), _p(in_main), _p(in_nyq), _p(spec_out), sb, sf, st,
                                                       _stream(spec_out)), "unpack")
 
 
@@ -121,5 +129,5 @@ def metric_sums(a: Tensor, b: Tensor, out3: Tensor) -> None:
     if a.numel() != b.numel() or a.dtype != b.dtype:
         raise RuntimeError("metric_sums: shape/dtype mismatch")
     with torch.cuda.device(a.device):
-        _lib.check(_lib.lib().specinv_metric_sums(_DT[a.dtype], _p(a), _p(b), a.numel(), _p(out3), _stream(a)),
+        _ok(_lib.lib().specinv_metric_sums(_DT[a.dtype], _p(a), _p(b), a.numel(), _p(out3), _stream(a)),
                    "metric_sums")

@@ -50,10 +50,15 @@ def _setup(spec: torch.Tensor, stft_kwargs: dict):
 
 def _finish(x: torch.Tensor, spec: torch.Tensor) -> torch.Tensor:
     """methods.py:267-270: drop the batch dim unless the input was (1, F, T)."""
-    x = x.clone()
     if not (spec.shape[0] == 1 and len(spec.shape) == 3):
         x = x.squeeze(0)
-    return x.to(spec.device)
+    if spec.is_cuda:
+        return x.clone()
+    # host caller: device -> host copy (pinned + asynchronous when the input was pinned)
+    out = torch.empty(x.shape, dtype=x.dtype, pin_memory=spec.is_pinned())
+    out.copy_(x, non_blocking=True)
+    torch.cuda.current_stream(x.device).synchronize()
+    return out
 
 
 def griffin_lim(spec, max_iter=200, tol=1e-6, alpha=0.99, verbose=True, eva_iter=10, metric="sc",

