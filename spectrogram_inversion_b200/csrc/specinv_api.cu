@@ -1,5 +1,7 @@
 // extern "C" entry points of libspecinv_b200.so (see include/specinv_b200.h), the plan
 // initialisation kernels, layout conversion and the standalone metric reduction.
+#include <cstdlib>
+
 #include "specinv_common.cuh"
 
 namespace specinv {
@@ -11,9 +13,17 @@ int generic_gl_iter(const specinv_desc*, const void*, const void*, void*, const 
                     const void*, const void*, double, double*, void*);
 int generic_admm_iter(const specinv_desc*, const void*, const void*, void*, const void*, const void*, const void*,
                       const void*, void*, void*, void*, void*, const void*, const void*, double, double*, void*);
-// implemented in specinv_gl1024.cu (fast path); returns SPECINV_ERR_UNSUPPORTED when not applicable
+// implemented in specinv_gl1024.cu (fast path); return SPECINV_ERR_UNSUPPORTED when not applicable
 int fast_gl_iter(const specinv_desc*, const void*, const void*, void*, const void*, const void*, void*, void*,
                  const void*, const void*, double, double*, void*);
+int fast_admm_iter(const specinv_desc*, const void*, const void*, void*, const void*, const void*, const void*,
+                   const void*, void*, void*, void*, void*, const void*, const void*, double, double*, void*);
+
+// SPECINV_FORCE_GENERIC=1 routes everything through the generic tile kernels (testing / A-B timing)
+static bool force_generic() {
+    const char* e = getenv("SPECINV_FORCE_GENERIC");
+    return e && e[0] == '1';
+}
 
 // ---------------------------------------------------------------- plan
 template <typename T>
@@ -232,6 +242,13 @@ int specinv_istft(const specinv_desc* d, const void* plan, const void* main_in, 
 int specinv_gl_iter(const specinv_desc* d, const void* plan, const void* x_in, void* x_out,
                     const void* q_in_main, const void* q_in_nyq, void* q_out_main, void* q_out_nyq,
                     const void* mag_main, const void* mag_nyq, double lr, double* sums, void* stream) {
+    if (!d || !plan || !x_in || !x_out || !q_in_main || !q_out_main || !mag_main) return SPECINV_ERR_INVALID;
+    if (x_in == x_out || q_in_main == q_out_main) return SPECINV_ERR_INVALID;
+    if (!force_generic() && d->onesided && q_in_nyq && q_out_nyq && mag_nyq) {
+        const int rc = fast_gl_iter(d, plan, x_in, x_out, q_in_main, q_in_nyq, q_out_main, q_out_nyq, mag_main, mag_nyq,
+                                    lr, sums, stream);
+        if (rc != SPECINV_ERR_UNSUPPORTED) return rc;
+    }
     return generic_gl_iter(d, plan, x_in, x_out, q_in_main, q_in_nyq, q_out_main, q_out_nyq, mag_main, mag_nyq, lr,
                            sums, stream);
 }
@@ -240,6 +257,14 @@ int specinv_admm_iter(const specinv_desc* d, const void* plan, const void* x_in,
                       const void* X_in_main, const void* X_in_nyq, const void* U_in_main, const void* U_in_nyq,
                       void* X_out_main, void* X_out_nyq, void* U_out_main, void* U_out_nyq,
                       const void* mag_main, const void* mag_nyq, double rho, double* sums, void* stream) {
+    if (!d || !plan || !x_in || !x_out || !X_in_main || !U_in_main || !X_out_main || !U_out_main || !mag_main)
+        return SPECINV_ERR_INVALID;
+    if (x_in == x_out || X_in_main == X_out_main || U_in_main == U_out_main) return SPECINV_ERR_INVALID;
+    if (!force_generic() && d->onesided && X_in_nyq && U_in_nyq && X_out_nyq && U_out_nyq && mag_nyq) {
+        const int rc = fast_admm_iter(d, plan, x_in, x_out, X_in_main, X_in_nyq, U_in_main, U_in_nyq, X_out_main,
+                                      X_out_nyq, U_out_main, U_out_nyq, mag_main, mag_nyq, rho, sums, stream);
+        if (rc != SPECINV_ERR_UNSUPPORTED) return rc;
+    }
     return generic_admm_iter(d, plan, x_in, x_out, X_in_main, X_in_nyq, U_in_main, U_in_nyq, X_out_main, X_out_nyq,
                              U_out_main, U_out_nyq, mag_main, mag_nyq, rho, sums, stream);
 }

@@ -1,0 +1,270 @@
+// Fast fused iteration kernel for n_fft = 1024, hop = 256 (onesided, fp32): the headline shape.
+//
+// Every half-warp streams through a chunk of consecutive frames of ONE signal:
+//   * the new 256 input samples of each frame arrive by cp.async into a thread-private ring in
+//     shared memory (a hop is 8 of the lane's 32 sample pairs, see gl_fast_core.cuh);
+//   * forward real FFT, point-wise update + projection, inverse real FFT run in registers with one
+//     shared-memory exchange per direction, synchronised by __syncwarp only (no block barrier);
+//   * overlap-add is a register shift-accumulate; a finished 256-sample block is multiplied by
+//     1/envelope and written with coalesced 8-byte stores.
+// A chunk re-computes the 3 frames before it as a halo (state not written, output not stored) so
+// chunks are independent: no atomics, deterministic.  State arrays are ping-ponged (q_in != q_out)
+// because a neighbouring chunk re-reads the old state of its halo frames.
+#include "specinv_common.cuh"
+#include "gl_fast_core.cuh"
+
+namespace specinv {
+namespace fast {
+
+struct FastArgs {
+    const float* x_in; float* x_out;
+    const float2* s0_in;  const float2* s0_in_nyq;  float2* s0_out; float2* s0_out_nyq;
+    const float2* s1_in;  const float2* s1_in_nyq;  float2* s1_out; float2* s1_out_nyq;
+    const float* mag;     const float* mag_nyq;
+    const float2* tw512;  const float2* twr1024;
+    const float* wa; const float* ws; const float* inv_env;
+    double* sums;
+    float coef, coef2;
+    int B, T, P, pad_mode;
+    long long L;
+    int chunks_per_signal, chunk_len, n_chunks;
+};
+
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// Issue the load of block u (padded samples [256 u, 256 u + 256)) of signal x into the lane's ring row.
+__device__ __forceinline__ void load_block(const FastArgs& a, const float* __restrict__ x, int u, int l, float2* ring_row) {
+    const long long base = (long long)u * HOP - a.P;          // unpadded index of the block's first sample
+    const bool interior = base >= 0 && base + HOP <= a.L;
+    if (interior) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            cp_async8(ring_row + ((8 * u + j) & 31), x + base + 32 * j + 2 * l);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const long long pp = (long long)u * HOP + 32 * j + 2 * l;
+            const long long i0 = pad_index(pp, a.P, a.L, a.pad_mode), i1 = pad_index(pp + 1, a.P, a.L, a.pad_mode);
+            ring_row[(8 * u + j) & 31] = f2(i0 >= 0 ? x[i0] : 0.f, i1 >= 0 ? x[i1] : 0.f);
+        }
+    }
+}
+
+// Store a finished block (8 sample pairs per lane) times 1/envelope.
+__device__ __forceinline__ void store_block(const FastArgs& a, float* __restrict__ xo, int u, int l, const float2* blk) {
+    const long long base = (long long)u * HOP - a.P;
+    if (base < 0 || base + HOP > a.L) return;                  // trimmed (centre padding) block
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const long long m = base + 32 * j + 2 * l;
+        const float2 ie = __ldg(reinterpret_cast<const float2*>(a.inv_env + m));
+        *reinterpret_cast<float2*>(xo + m) = f2(blk[j].x * ie.x, blk[j].y * ie.y);
+    }
+}
+
+template <int OP, bool SUMS, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1) fast_iter_kernel(const FastArgs a) {
+    extern __shared__ __align__(16) float2 sm[];
+    float2* s_tw = sm;
+    float2* s_wa = s_tw + TBL;
+    float2* s_ws = s_wa + TBL;
+    float2* s_twr = s_ws + TBL;
+    float2* s_hw = s_twr + 512;
+
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 512; i += WARPS * 32) {
+        const int n2 = i >> 5, k = i & 31;
+        s_tw[n2 * ROW + k] = a.tw512[(n2 * k) & 511];
+        s_wa[n2 * ROW + k] = f2(0.5f * a.wa[32 * k + 2 * n2], 0.5f * a.wa[32 * k + 2 * n2 + 1]);
+        s_ws[n2 * ROW + k] = f2(a.ws[32 * k + 2 * n2], a.ws[32 * k + 2 * n2 + 1]);
+        float2 t;
+        if (i <= 256) t = a.twr1024[i];
+        else { t = a.twr1024[512 - i]; t.x = -t.x; }              // W^k = -conj(W^(512-k))
+        s_twr[i] = t;
+    }
+    __syncthreads();
+
+    const int l = tid & 15;
+    const int hw = tid >> 4;                                       // half-warp slot in the CTA
+    const unsigned hmask = 0xFFFFu << (16 * ((tid >> 4) & 1));
+    float2* ring_row = s_hw + hw * 2 * TBL + l * ROW;
+    float2* exch = s_hw + hw * 2 * TBL + TBL;
+    const Tables tb{s_tw, s_wa, s_ws, s_twr};
+
+    double dacc = 0.0, eacc = 0.0;
+
+    for (int c = hw * gridDim.x + blockIdx.x; c < a.n_chunks; c += gridDim.x * 2 * WARPS) {
+        const int b = c / a.chunks_per_signal, ci = c - b * a.chunks_per_signal;
+        const int t0 = ci * a.chunk_len;
+        const int t1 = min(a.T, t0 + a.chunk_len);
+        if (t0 >= t1) continue;
+        const int tf0 = max(0, t0 - 3);
+        const float* x = a.x_in + (long long)b * a.L;
+        float* xo = a.x_out + (long long)b * a.L;
+
+        float2 acc[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc[i] = f2(0.f, 0.f);
+
+        load_block(a, x, tf0, l, ring_row);
+        load_block(a, x, tf0 + 1, l, ring_row);
+        load_block(a, x, tf0 + 2, l, ring_row);
+        load_block(a, x, tf0 + 3, l, ring_row);
+
+        for (int t = tf0; t < t1; ++t) {
+            cp_async_wait_all();
+            float2 v[32];
+            const int slot0 = (8 * t) & 31;
+            static_for<16>([&](auto ic) {
+                constexpr int n1 = 2 * decltype(ic)::value;
+                const float4 r = *reinterpret_cast<const float4*>(ring_row + ((slot0 + n1) & 31));
+                const float4 w = *reinterpret_cast<const float4*>(s_wa + l * ROW + n1);
+                v[n1] = f2(r.x * w.x, r.y * w.y);
+                v[n1 + 1] = f2(r.z * w.z, r.w * w.w);
+            });
+            // the oldest block's slots are free now: fetch the block frame t+1 will need
+            if (t + 1 < t1) load_block(a, x, t + 4, l, ring_row);
+
+            phase1(l, v, tb, exch);
+            __syncwarp(hmask);
+
+            float2 A[16], Bv[16];
+            phase2_read(l, exch, A, Bv);
+            const long long row = (long long)b * a.T + t;
+            FrameIO io;
+            io.s0_in = a.s0_in + row * M;   io.s0_in_nyq = a.s0_in_nyq + row;
+            io.s0_out = a.s0_out + row * M; io.s0_out_nyq = a.s0_out_nyq + row;
+            if constexpr (OP == OP_ADMM) {
+                io.s1_in = a.s1_in + row * M;   io.s1_in_nyq = a.s1_in_nyq + row;
+                io.s1_out = a.s1_out + row * M; io.s1_out_nyq = a.s1_out_nyq + row;
+            }
+            io.mag = a.mag + row * M; io.mag_nyq = a.mag_nyq + row;
+            io.coef = a.coef; io.coef2 = a.coef2;
+            io.owned = t >= t0;
+            float dsum = 0.f, esum = 0.f;          // per-frame partial sums, folded into doubles below
+            phase2_compute<OP, SUMS>(l, A, Bv, tb, io, dsum, esum);
+            if constexpr (SUMS) { dacc += (double)dsum; eacc += (double)esum; }
+            __syncwarp(hmask);                    // every lane has read its classes: exch may be overwritten
+            phase2_write(l, exch, A, Bv);
+            __syncwarp(hmask);
+            phase3(l, v, tb, exch);
+            __syncwarp(hmask);                    // exch is free for the next frame's phase 1
+
+            // windowed overlap-add in registers: shift by one hop (8 pairs) and accumulate
+            static_for<16>([&](auto ic) {
+                constexpr int n1 = 2 * decltype(ic)::value;
+                const float4 w = *reinterpret_cast<const float4*>(s_ws + l * ROW + n1);
+                if constexpr (n1 < 24) {
+                    acc[n1] = f2(acc[n1 + 8].x + w.x * v[n1].x, acc[n1 + 8].y + w.y * v[n1].y);
+                    acc[n1 + 1] = f2(acc[n1 + 9].x + w.z * v[n1 + 1].x, acc[n1 + 9].y + w.w * v[n1 + 1].y);
+                } else {
+                    acc[n1] = f2(w.x * v[n1].x, w.y * v[n1].y);
+                    acc[n1 + 1] = f2(w.z * v[n1 + 1].x, w.w * v[n1 + 1].y);
+                }
+            });
+            if (t >= t0) store_block(a, xo, t, l, acc);
+        }
+        if (t1 == a.T) {     // tail of the signal: blocks T, T+1, T+2 are complete now
+            store_block(a, xo, a.T, l, acc + 8);
+            store_block(a, xo, a.T + 1, l, acc + 16);
+            store_block(a, xo, a.T + 2, l, acc + 24);
+        }
+    }
+
+    if constexpr (SUMS) {
+        double d = dacc, e = eacc;
+        for (int o = 16; o > 0; o >>= 1) {
+            d += __shfl_xor_sync(0xffffffffu, d, o);
+            e += __shfl_xor_sync(0xffffffffu, e, o);
+        }
+        if ((tid & 31) == 0) { atomicAdd(a.sums, d); atomicAdd(a.sums + 1, e); }
+    }
+}
+
+static int g_sms = 0;
+
+template <int OP, int WARPS>
+static int launch(const FastArgs& a0, cudaStream_t st) {
+    FastArgs a = a0;
+    if (g_sms == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return SPECINV_ERR_NO_DEVICE;
+        if (cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return SPECINV_ERR_NO_DEVICE;
+    }
+    const int grid = g_sms;
+    const int slots = grid * 2 * WARPS;
+    int cps = slots / a.B;
+    if (cps < 1) cps = 1;
+    const int min_len = 24;                       // keep the 3-frame halo below ~12 %
+    if (cps > (a.T + min_len - 1) / min_len) cps = (a.T + min_len - 1) / min_len;
+    if (cps < 1) cps = 1;
+    a.chunk_len = (a.T + cps - 1) / cps;
+    a.chunks_per_signal = (a.T + a.chunk_len - 1) / a.chunk_len;
+    a.n_chunks = a.B * a.chunks_per_signal;
+    const size_t smem = (size_t)(3 * TBL + 512 + 2 * WARPS * 2 * TBL) * sizeof(float2);
+    cudaError_t e;
+    if (a.sums) {
+        e = cudaFuncSetAttribute(fast_iter_kernel<OP, true, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        fast_iter_kernel<OP, true, WARPS><<<grid, WARPS * 32, smem, st>>>(a);
+    } else {
+        e = cudaFuncSetAttribute(fast_iter_kernel<OP, false, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        fast_iter_kernel<OP, false, WARPS><<<grid, WARPS * 32, smem, st>>>(a);
+    }
+    return (int)cudaGetLastError();
+}
+
+}  // namespace fast
+
+// Returns SPECINV_ERR_UNSUPPORTED when the shape is not the one this kernel is specialised for.
+static bool fast_applicable(const specinv_desc* d) {
+    return d->dtype == SPECINV_F32 && d->n_fft == 1024 && d->hop == 256 && d->onesided;
+}
+
+static void fill_common(fast::FastArgs& a, const Dims& dm, const specinv_desc* d, const void* plan) {
+    const PlanLayout pl = plan_layout(dm, d->dtype);
+    const char* p = (const char*)plan;
+    a.tw512 = (const float2*)(p + pl.tw); a.twr1024 = (const float2*)(p + pl.twr);
+    a.wa = (const float*)(p + pl.wa); a.ws = (const float*)(p + pl.ws); a.inv_env = (const float*)(p + pl.inv_env);
+    a.B = dm.B; a.T = dm.T; a.P = dm.P; a.pad_mode = dm.pad_mode; a.L = dm.L;
+}
+
+int fast_gl_iter(const specinv_desc* d, const void* plan, const void* x_in, void* x_out,
+                 const void* q_in_main, const void* q_in_nyq, void* q_out_main, void* q_out_nyq,
+                 const void* mag_main, const void* mag_nyq, double lr, double* sums, void* stream) {
+    if (!fast_applicable(d)) return SPECINV_ERR_UNSUPPORTED;
+    Dims dm; int rc = make_dims(d, &dm); if (rc) return rc;
+    fast::FastArgs a{};
+    fill_common(a, dm, d, plan);
+    a.x_in = (const float*)x_in; a.x_out = (float*)x_out;
+    a.s0_in = (const float2*)q_in_main; a.s0_in_nyq = (const float2*)q_in_nyq;
+    a.s0_out = (float2*)q_out_main; a.s0_out_nyq = (float2*)q_out_nyq;
+    a.mag = (const float*)mag_main; a.mag_nyq = (const float*)mag_nyq;
+    a.coef = (float)lr; a.sums = sums;
+    return fast::launch<fast::OP_GL, 12>(a, (cudaStream_t)stream);
+}
+
+int fast_admm_iter(const specinv_desc* d, const void* plan, const void* x_in, void* x_out,
+                   const void* X_in_main, const void* X_in_nyq, const void* U_in_main, const void* U_in_nyq,
+                   void* X_out_main, void* X_out_nyq, void* U_out_main, void* U_out_nyq,
+                   const void* mag_main, const void* mag_nyq, double rho, double* sums, void* stream) {
+    if (!fast_applicable(d)) return SPECINV_ERR_UNSUPPORTED;
+    Dims dm; int rc = make_dims(d, &dm); if (rc) return rc;
+    fast::FastArgs a{};
+    fill_common(a, dm, d, plan);
+    a.x_in = (const float*)x_in; a.x_out = (float*)x_out;
+    a.s0_in = (const float2*)X_in_main; a.s0_in_nyq = (const float2*)X_in_nyq;
+    a.s0_out = (float2*)X_out_main; a.s0_out_nyq = (float2*)X_out_nyq;
+    a.s1_in = (const float2*)U_in_main; a.s1_in_nyq = (const float2*)U_in_nyq;
+    a.s1_out = (float2*)U_out_main; a.s1_out_nyq = (float2*)U_out_nyq;
+    a.mag = (const float*)mag_main; a.mag_nyq = (const float*)mag_nyq;
+    a.coef = (float)rho; a.coef2 = (float)(1.0 / (1.0 + rho)); a.sums = sums;
+    return fast::launch<fast::OP_ADMM, 12>(a, (cudaStream_t)stream);
+}
+
+}  // namespace specinv

@@ -217,3 +217,88 @@ def test_full_run_spectral_convergence_within_1pct():
         scg = O.sc(np.abs(O.stft(yg.cpu().numpy(), a)), mag)
         # 1 % on the linear spectral-convergence ratio == 0.0864 dB
         assert abs(scg - sco) <= 20 * np.log10(1.01) + 0.05 * abs(sco) * 0, (algo, scg, sco)
+
+
+# ---------------------------------------------------------------------------------------------
+# fast path (n_fft = 1024, hop = 256): many frames, several chunks per signal, every edge mode
+# ---------------------------------------------------------------------------------------------
+FAST_CASES = [
+    dict(B=3, T=101, center=True, pad_mode="reflect", normalized=False, window="hann"),
+    dict(B=2, T=57, center=True, pad_mode="constant", normalized=True, window="hann"),
+    dict(B=2, T=40, center=True, pad_mode="replicate", normalized=False, window="hamming"),
+    dict(B=1, T=333, center=True, pad_mode="circular", normalized=False, window="hann"),
+    dict(B=5, T=64, center=False, pad_mode="reflect", normalized=False, window="hamming"),
+    dict(B=2, T=30, center=True, pad_mode="reflect", normalized=False, window=None, win_length=700),
+]
+
+
+@pytest.mark.parametrize("fc", FAST_CASES, ids=lambda c: f"B{c['B']}_T{c['T']}_{c['pad_mode']}_c{int(c['center'])}")
+def test_fast_path_1024_against_oracle(fc):
+    from spectrogram_inversion_b200.engine import ADMMSolver, GriffinLimSolver, StftPlan
+    from spectrogram_inversion_b200.stft_args import args_helper
+    rs = np.random.RandomState(fc["T"])
+    n_fft, hop = 1024, 256
+    B, T = fc["B"], fc["T"]
+    kw = dict(hop_length=hop, center=fc["center"], pad_mode=fc["pad_mode"], normalized=fc["normalized"])
+    wl = fc.get("win_length", n_fft)
+    if fc["window"] is not None:
+        kw["window"] = cases.window_of(fc["window"], wl, np.float32)
+    if wl != n_fft:
+        kw["win_length"] = wl
+    oa = O.args_helper(n_fft // 2 + 1, np.float32, **kw)
+    mag = (np.abs(rs.randn(B, 513, T) + 1j * rs.randn(B, 513, T)) * 8).astype(np.float32)
+    C = (mag * np.exp(2j * np.pi * rs.rand(B, 513, T))).astype(np.complex64)
+    tkw = {k: (torch.from_numpy(v).cuda() if isinstance(v, np.ndarray) else v) for k, v in kw.items()}
+    magt = torch.from_numpy(mag).cuda()
+    plan = StftPlan(args_helper(magt, **tkw), T, B, torch.float32, torch.device("cuda"))
+
+    # Griffin-Lim, three single steps each restarted from the oracle's state
+    solver = GriffinLimSolver(plan, plan.pack(torch.from_numpy(C)), plan.pack(magt), 0.99)
+    st = O.gl_init(C, oa)
+    for k in range(3):
+        solver.x[solver.cur].copy_(torch.from_numpy(st.x))
+        solver.q[solver.cur] = plan.pack(torch.from_numpy(st.q))
+        solver.q[solver.cur ^ 1] = solver.q[solver.cur].like()
+        out = solver.step(evaluate=(k != 1))
+        st = O.gl_step(st, mag, 0.99 / 1.99, oa)
+        close(solver.signal, st.x, 1e-5, f"fast GL x step {k}")
+        close(plan.unpack(solver.q_state), st.q, 1e-4, f"fast GL q step {k}")
+        if out is not None:
+            do, eo, _ = O.metric_sums(st.out_mag, mag)
+            assert abs(out[0] - do) <= 1e-4 * do and abs(out[1] - eo) <= 1e-4 * eo
+
+    # ADMM
+    solver = ADMMSolver(plan, plan.pack(torch.from_numpy(C)), plan.pack(magt), 0.1)
+    st = O.admm_init(C, oa)
+    for k in range(2):
+        i = solver.cur
+        solver.x[i].copy_(torch.from_numpy(st.x))
+        solver.X[i] = plan.pack(torch.from_numpy(st.X)); solver.U[i] = plan.pack(torch.from_numpy(st.U))
+        solver.X[i ^ 1] = solver.X[i].like(); solver.U[i ^ 1] = solver.U[i].like()
+        solver.step(evaluate=(k == 1))
+        st = O.admm_step(st, mag, 0.1, oa)
+        close(solver.signal, st.x, 2e-5, f"fast ADMM x step {k}")
+        close(plan.unpack(solver.U[solver.cur]), st.U, 1e-3, "fast ADMM U")
+
+
+def test_fast_and_generic_kernels_agree(monkeypatch):
+    """The specialised 1024/256 kernel and the generic tile kernel are two implementations of the
+    same iteration: run 5 free-running iterations with each and compare."""
+    from spectrogram_inversion_b200.engine import GriffinLimSolver, StftPlan
+    from spectrogram_inversion_b200.stft_args import args_helper
+    rs = np.random.RandomState(5)
+    B, T = 4, 200
+    mag = (np.abs(rs.randn(B, 513, T) + 1j * rs.randn(B, 513, T)) * 8).astype(np.float32)
+    C = (mag * np.exp(2j * np.pi * rs.rand(B, 513, T))).astype(np.complex64)
+    w = torch.hann_window(1024, device="cuda")
+    magt = torch.from_numpy(mag).cuda()
+    plan = StftPlan(args_helper(magt, window=w, hop_length=256), T, B, torch.float32, torch.device("cuda"))
+    outs = []
+    for force in ("0", "1"):
+        monkeypatch.setenv("SPECINV_FORCE_GENERIC", force)
+        s = GriffinLimSolver(plan, plan.pack(torch.from_numpy(C)), plan.pack(magt), 0.99)
+        sums = [s.step(evaluate=True) for _ in range(5)]
+        outs.append((s.signal.clone(), sums))
+    close(outs[0][0], outs[1][0].cpu().numpy(), 2e-4, "fast vs generic after 5 iterations")
+    for (d0, e0), (d1, e1) in zip(outs[0][1], outs[1][1]):
+        assert abs(d0 - d1) <= 1e-4 * d1 and abs(e0 - e1) <= 1e-4 * e1
