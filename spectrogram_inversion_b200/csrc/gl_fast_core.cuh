@@ -42,7 +42,8 @@ struct Tables {
 
 // Global-memory view of the current frame (row pointers already offset to the frame).
 struct FrameIO {
-    const float2* s0_in;  const float2* s0_in_nyq;    // GL: q_in      ADMM: X_in
+    const float2* s0_stage;                           // GL: q_in / ADMM: X_in main row, STAGED in shared memory
+    const float2* s0_in_nyq;
     float2* s0_out;       float2* s0_out_nyq;
     const float2* s1_in;  const float2* s1_in_nyq;    // ADMM: U_in
     float2* s1_out;       float2* s1_out_nyq;
@@ -76,8 +77,7 @@ SPX_HD float2 project_fast(float2 q, float mag) {
 // main row (ignored when NYQ: the k = 512 bin lives in the separate nyq arrays).  Returns the value
 // fed to the inverse transform.
 template <int OP, bool SUMS, bool NYQ>
-SPX_HD float2 bin_update_fast(const FrameIO& io, int kk, float2 s, float& dsum, float& esum) {
-    const float m = SPX_LDG(NYQ ? io.mag_nyq : io.mag + kk);
+SPX_HD float2 bin_update_fast(const FrameIO& io, int kk, float2 s, float m, float& dsum, float& esum) {
     if constexpr (SUMS) {
         if (io.owned) {
             const float r = approx_sqrt(s.x * s.x + s.y * s.y);
@@ -86,12 +86,12 @@ SPX_HD float2 bin_update_fast(const FrameIO& io, int kk, float2 s, float& dsum, 
         }
     }
     if constexpr (OP == OP_GL) {
-        const float2 qp = SPX_LDG(NYQ ? io.s0_in_nyq : io.s0_in + kk);
+        const float2 qp = NYQ ? SPX_LDG(io.s0_in_nyq) : io.s0_stage[kk];
         const float2 q = f2(s.x - qp.x * io.coef, s.y - qp.y * io.coef);
         if (io.owned) *(NYQ ? io.s0_out_nyq : io.s0_out + kk) = q;
         return project_fast(q, m);
     } else {
-        const float2 X = SPX_LDG(NYQ ? io.s0_in_nyq : io.s0_in + kk);
+        const float2 X = NYQ ? SPX_LDG(io.s0_in_nyq) : io.s0_stage[kk];
         const float2 U = SPX_LDG(NYQ ? io.s1_in_nyq : io.s1_in + kk);
         const float rho = io.coef, inv = io.coef2;
         const float2 Z = f2((rho * (X.x + U.x) + s.x) * inv, (rho * (X.y + U.y) + s.y) * inv);
@@ -148,32 +148,57 @@ SPX_HD void pre_pair(float2 hP, float2 hQ, float2 w, float2& P, float2& Q) {
     Q = f2(Ar + Gi, Gr - Ai);
 }
 
-// ---- phase 2b: two FFT16, pair processing with the point-wise update, two inverse FFT16 -------------
-template <int OP, bool SUMS>
-SPX_HD void phase2_compute(int p, float2* A, float2* B, const Tables& tb, const FrameIO& io, float& dsum, float& esum) {
+// bin index of the P element of pair slot j for lane p (the Q element is bin 512 - kP; lane 0 slot 0
+// is the special DC / Nyquist / bin-256 slot and uses kP = 0 -> bins 0 and 256)
+template <int J>
+SPX_HD int slot_bin(int p) {
+    if constexpr (J < 8) return p + 32 * J;
+    else return p == 0 ? 16 + 32 * (J - 8) : p + 32 * J;
+}
+
+// Issue the magnitude loads of all 16 pair slots (32 bins) of this lane early, so that their latency is
+// hidden behind the 16-point FFTs.  mP[j] = mag[kP], mQ[j] = mag[512 - kP]; lane 0, slot 0: mag[0], mag[256].
+SPX_HD void load_mags(int p, const float* mag_row, float* mP, float* mQ) {
+    static_for<16>([&](auto jc) {
+        constexpr int j = decltype(jc)::value;
+        const int kP = slot_bin<j>(p);
+        mP[j] = SPX_LDG(mag_row + kP);
+        mQ[j] = SPX_LDG(mag_row + ((j == 0 && p == 0) ? 256 : M - kP));
+    });
+}
+
+// ---- phase 2b: two forward FFT16 ---------------------------------------------------------------------
+SPX_HD void phase2_fft(float2* A, float2* B) {
     fft16<false>(A);     // A[k2] = Zh[ka + 32 k2]
     fft16<false>(B);     // B[k2] = Zh[kb + 32 k2]
+}
+
+// ---- phase 2c: pair processing with the point-wise update, then two inverse FFT16 ---------------------
+template <int OP, bool SUMS>
+SPX_HD void phase2_pointwise(int p, float2* A, float2* B, const Tables& tb, const FrameIO& io, const float* mP,
+                             const float* mQ, float& dsum, float& esum) {
     const bool l0 = p == 0;
-    float2 A2[16], B2[16];
+    // All updates are done in place: a slot's outputs go back to the registers its inputs came from
+    // (which differ between lane 0 and the other lanes, hence the predicated writes).
 
     // slot 0
     if (l0) {
         // lane 0: A[0] = Zh[0] -> DC and Nyquist (both real), A[8] = Zh[256] -> bin 256 = conj(Z[256])
         const float2 z0 = A[0], z8 = A[8];
-        const float2 h0 = bin_update_fast<OP, SUMS, false>(io, 0, f2(2.f * (z0.x + z0.y), 0.f), dsum, esum);
-        const float2 hM = bin_update_fast<OP, SUMS, true>(io, 0, f2(2.f * (z0.x - z0.y), 0.f), dsum, esum);
-        const float2 h8 = bin_update_fast<OP, SUMS, false>(io, 256, f2(2.f * z8.x, -2.f * z8.y), dsum, esum);
-        A2[0] = f2(h0.x + hM.x, h0.x - hM.x);       // C2R ignores Im(DC), Im(Nyquist)
-        A2[8] = f2(2.f * h8.x, -2.f * h8.y);
+        const float2 h0 = bin_update_fast<OP, SUMS, false>(io, 0, f2(2.f * (z0.x + z0.y), 0.f), mP[0], dsum, esum);
+        const float2 hM = bin_update_fast<OP, SUMS, true>(io, 0, f2(2.f * (z0.x - z0.y), 0.f), SPX_LDG(io.mag_nyq), dsum, esum);
+        const float2 h8 = bin_update_fast<OP, SUMS, false>(io, 256, f2(2.f * z8.x, -2.f * z8.y), mQ[0], dsum, esum);
+        A[0] = f2(h0.x + hM.x, h0.x - hM.x);        // C2R ignores Im(DC), Im(Nyquist)
+        A[8] = f2(2.f * h8.x, -2.f * h8.y);
     } else {
         const int kP = p;
         float2 sP, sQ, P, Q;
         const float2 w = tb.twr[kP];
         post_pair(A[0], B[15], w, sP, sQ);
-        const float2 hP = bin_update_fast<OP, SUMS, false>(io, kP, sP, dsum, esum);
-        const float2 hQ = bin_update_fast<OP, SUMS, false>(io, M - kP, sQ, dsum, esum);
+        const float2 hP = bin_update_fast<OP, SUMS, false>(io, kP, sP, mP[0], dsum, esum);
+        const float2 hQ = bin_update_fast<OP, SUMS, false>(io, M - kP, sQ, mQ[0], dsum, esum);
         pre_pair(hP, hQ, w, P, Q);
-        A2[0] = P; B2[15] = Q;
+        A[0] = P; B[15] = Q;
     }
     // slots 1..15.  general lanes: (A[j], B[15-j]), bins (p + 32 j, 512 - p - 32 j)
     //               lane 0, j < 8 : (A[j], A[16-j]),   bins (32 j, 512 - 32 j)
@@ -181,38 +206,35 @@ SPX_HD void phase2_compute(int p, float2* A, float2* B, const Tables& tb, const 
     static_for<15>([&](auto jc) {
         constexpr int j = decltype(jc)::value + 1;
         float2 P, Q;
-        int kP;
+        const int kP = slot_bin<j>(p);
         if constexpr (j < 8) {
             P = A[j];
             Q = l0 ? A[16 - j] : B[15 - j];
-            kP = p + 32 * j;
         } else {
             P = l0 ? B[j - 8] : A[j];
             Q = l0 ? B[23 - j] : B[15 - j];
-            kP = l0 ? 16 + 32 * (j - 8) : p + 32 * j;
         }
         const float2 w = tb.twr[kP];
         float2 sP, sQ;
         post_pair(P, Q, w, sP, sQ);
-        const float2 hP = bin_update_fast<OP, SUMS, false>(io, kP, sP, dsum, esum);
-        const float2 hQ = bin_update_fast<OP, SUMS, false>(io, M - kP, sQ, dsum, esum);
+        const float2 hP = bin_update_fast<OP, SUMS, false>(io, kP, sP, mP[j], dsum, esum);
+        const float2 hQ = bin_update_fast<OP, SUMS, false>(io, M - kP, sQ, mQ[j], dsum, esum);
         pre_pair(hP, hQ, w, P, Q);
         // scatter back (the inverse of the gather above)
         if constexpr (j < 8) {
-            A2[j] = P;
-            if (l0) A2[16 - j] = Q; else B2[15 - j] = Q;
+            A[j] = P;
+            if (l0) A[16 - j] = Q; else B[15 - j] = Q;
         } else {
-            if (l0) { B2[j - 8] = P; B2[23 - j] = Q; } else { A2[j] = P; B2[15 - j] = Q; }
+            if (l0) { B[j - 8] = P; B[23 - j] = Q; } else { A[j] = P; B[15 - j] = Q; }
         }
     });
-    // For general lanes every A2[j] (j = 0..15) and B2[15-j] was written exactly once.
-    // For lane 0: A2[0], A2[8] (slot 0), A2[1..7], A2[9..15] (slots 1..7), B2[0..7], B2[8..15] (slots 8..15).
-    static_for<16>([&](auto jc) { constexpr int j = decltype(jc)::value; A[j] = A2[j]; B[j] = B2[j]; });
+    // General lanes: every A[j] and B[15-j] (j = 0..15) was rewritten exactly once.
+    // Lane 0: A[0], A[8] (slot 0), A[1..7], A[9..15] (slots 1..7), B[0..15] (slots 8..15).
     fft16<true>(A);      // A[n2] = Y_ka[n2]
     fft16<true>(B);
 }
 
-// ---- phase 2c: write the inverse pass-A outputs back to the exchange buffer -------------------------
+// ---- phase 2d: write the inverse pass-A outputs back to the exchange buffer -------------------------
 SPX_HD void phase2_write(int p, float2* exch, const float2* A, const float2* B) {
     const int ka = class_a(p), kb = class_b(p);
     static_for<16>([&](auto nc) {

@@ -10,6 +10,8 @@
 // A chunk re-computes the 3 frames before it as a halo (state not written, output not stored) so
 // chunks are independent: no atomics, deterministic.  State arrays are ping-ponged (q_in != q_out)
 // because a neighbouring chunk re-reads the old state of its halo frames.
+#include <cstdlib>
+
 #include "specinv_common.cuh"
 #include "gl_fast_core.cuh"
 
@@ -35,6 +37,22 @@ __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// Pull the state / magnitude rows of frame `row` into L2 (one 128-byte line per call and lane) so the
+// point-wise stage of that frame hits L2 instead of paying a DRAM round trip in the middle of the frame.
+template <int OP>
+__device__ __forceinline__ void prefetch_rows(const FastArgs& a, long long row, int l) {
+    const char* q = reinterpret_cast<const char*>(a.s0_in + row * M);
+    prefetch_l2(q + 128 * l);
+    prefetch_l2(q + 128 * (l + 16));
+    prefetch_l2(reinterpret_cast<const char*>(a.mag + row * M) + 128 * l);
+    if constexpr (OP == OP_ADMM) {
+        const char* u = reinterpret_cast<const char*>(a.s1_in + row * M);
+        prefetch_l2(u + 128 * l);
+        prefetch_l2(u + 128 * (l + 16));
+    }
+}
 
 // Issue the load of block u (padded samples [256 u, 256 u + 256)) of signal x into the lane's ring row.
 __device__ __forceinline__ void load_block(const FastArgs& a, const float* __restrict__ x, int u, int l, float2* ring_row) {
@@ -66,8 +84,65 @@ __device__ __forceinline__ void store_block(const FastArgs& a, float* __restrict
     }
 }
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+// Named barrier over the warps that share one SM sub-partition (warp_id % 4): they run the frame
+// pipeline in lockstep so that the (large, fully unrolled) instruction stream is fetched once per
+// group instead of once per warp.  It also orders the half-warp exchanges through shared memory.
+template <int THREADS>
+__device__ __forceinline__ void group_barrier(int id) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(THREADS) : "memory");
+}
+
+// ---- tensor memory as a software-managed register extension -------------------------------------------
+// The overlap-add carry (24 sample pairs per lane = 48 words) only matters at the end of every frame but
+// would otherwise pin 48..64 registers through the FFTs.  It lives in TMEM instead: each warp owns the 32
+// TMEM lanes of its sub-partition (32 * (warp % 4)) and a private range of 48 columns, and moves the carry
+// with tcgen05.ld / tcgen05.st (32x32b: one lane per thread, consecutive columns).
+__device__ __forceinline__ void tmem_alloc(unsigned* smem_dst, int ncols) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(d), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(unsigned taddr, int ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(unsigned taddr, float* r) {
+    unsigned* u = reinterpret_cast<unsigned*>(r);
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
+                   "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_st16(unsigned taddr, const float* r) {
+    const unsigned* u = reinterpret_cast<const unsigned*>(r);
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+                 ::"r"(taddr), "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3]), "r"(u[4]), "r"(u[5]), "r"(u[6]), "r"(u[7]),
+                   "r"(u[8]), "r"(u[9]), "r"(u[10]), "r"(u[11]), "r"(u[12]), "r"(u[13]), "r"(u[14]), "r"(u[15])
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_load_carry(unsigned taddr, float2* carry) {
+    float* c = reinterpret_cast<float*>(carry);
+    tmem_ld16(taddr, c); tmem_ld16(taddr + 16, c + 16); tmem_ld16(taddr + 32, c + 32);
+    tmem_wait_ld();
+}
+__device__ __forceinline__ void tmem_store_carry(unsigned taddr, const float2* carry) {
+    const float* c = reinterpret_cast<const float*>(carry);
+    tmem_st16(taddr, c); tmem_st16(taddr + 16, c + 16); tmem_st16(taddr + 32, c + 32);
+    tmem_wait_st();
+}
+constexpr int CARRY = 24;            // sample pairs carried from frame to frame (3 hops)
+constexpr int TMEM_COLS = 256;       // >= (WARPS / 4) * 2 * CARRY, power of two
+
 template <int OP, bool SUMS, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, 1) fast_iter_kernel(const FastArgs a) {
+    static_assert((WARPS / 4) * 2 * CARRY <= TMEM_COLS, "TMEM columns");
+    static_assert(WARPS % 4 == 0, "warps are grouped by SM sub-partition");
+    constexpr int GROUP_THREADS = (WARPS / 4) * 32;
     extern __shared__ __align__(16) float2 sm[];
     float2* s_tw = sm;
     float2* s_wa = s_tw + TBL;
@@ -75,7 +150,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) fast_iter_kernel(const FastArgs
     float2* s_twr = s_ws + TBL;
     float2* s_hw = s_twr + 512;
 
+    __shared__ unsigned s_tmem_base;
     const int tid = threadIdx.x;
+    if (tid < 32) tmem_alloc(&s_tmem_base, TMEM_COLS);
     for (int i = tid; i < 512; i += WARPS * 32) {
         const int n2 = i >> 5, k = i & 31;
         s_tw[n2 * ROW + k] = a.tw512[(n2 * k) & 511];
@@ -86,92 +163,136 @@ __global__ void __launch_bounds__(WARPS * 32, 1) fast_iter_kernel(const FastArgs
         else { t = a.twr1024[512 - i]; t.x = -t.x; }              // W^k = -conj(W^(512-k))
         s_twr[i] = t;
     }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // this warp's TMEM window: lanes 32 * (warp % 4) .. +31, columns 48 * (warp / 4) .. +47
+    const unsigned taddr = s_tmem_base + ((unsigned)(32 * ((tid >> 5) & 3)) << 16) + (unsigned)(2 * CARRY * (tid >> 7));
 
     const int l = tid & 15;
     const int hw = tid >> 4;                                       // half-warp slot in the CTA
-    const unsigned hmask = 0xFFFFu << (16 * ((tid >> 4) & 1));
+    const int bar_id = 1 + ((tid >> 5) & 3);                       // one named barrier per sub-partition
     float2* ring_row = s_hw + hw * 2 * TBL + l * ROW;
     float2* exch = s_hw + hw * 2 * TBL + TBL;
     const Tables tb{s_tw, s_wa, s_ws, s_twr};
 
     double dacc = 0.0, eacc = 0.0;
 
-    for (int c = hw * gridDim.x + blockIdx.x; c < a.n_chunks; c += gridDim.x * 2 * WARPS) {
-        const int b = c / a.chunks_per_signal, ci = c - b * a.chunks_per_signal;
-        const int t0 = ci * a.chunk_len;
-        const int t1 = min(a.T, t0 + a.chunk_len);
-        if (t0 >= t1) continue;
+    const int stride = gridDim.x * 2 * WARPS;
+    const int rounds = (a.n_chunks + stride - 1) / stride;
+    for (int r = 0; r < rounds; ++r) {
+        const int c = r * stride + hw * gridDim.x + blockIdx.x;
+        const bool valid = c < a.n_chunks;
+        int b = 0, t0 = 0, t1 = 0;
+        if (valid) {
+            b = c / a.chunks_per_signal;
+            t0 = (c - b * a.chunks_per_signal) * a.chunk_len;
+            t1 = min(a.T, t0 + a.chunk_len);
+        }
         const int tf0 = max(0, t0 - 3);
         const float* x = a.x_in + (long long)b * a.L;
         float* xo = a.x_out + (long long)b * a.L;
 
-        float2 acc[32];
+        {
+            float2 zero[CARRY];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) acc[i] = f2(0.f, 0.f);
-
-        load_block(a, x, tf0, l, ring_row);
-        load_block(a, x, tf0 + 1, l, ring_row);
-        load_block(a, x, tf0 + 2, l, ring_row);
-        load_block(a, x, tf0 + 3, l, ring_row);
-
-        for (int t = tf0; t < t1; ++t) {
-            cp_async_wait_all();
-            float2 v[32];
-            const int slot0 = (8 * t) & 31;
-            static_for<16>([&](auto ic) {
-                constexpr int n1 = 2 * decltype(ic)::value;
-                const float4 r = *reinterpret_cast<const float4*>(ring_row + ((slot0 + n1) & 31));
-                const float4 w = *reinterpret_cast<const float4*>(s_wa + l * ROW + n1);
-                v[n1] = f2(r.x * w.x, r.y * w.y);
-                v[n1 + 1] = f2(r.z * w.z, r.w * w.w);
-            });
-            // the oldest block's slots are free now: fetch the block frame t+1 will need
-            if (t + 1 < t1) load_block(a, x, t + 4, l, ring_row);
-
-            phase1(l, v, tb, exch);
-            __syncwarp(hmask);
-
-            float2 A[16], Bv[16];
-            phase2_read(l, exch, A, Bv);
-            const long long row = (long long)b * a.T + t;
-            FrameIO io;
-            io.s0_in = a.s0_in + row * M;   io.s0_in_nyq = a.s0_in_nyq + row;
-            io.s0_out = a.s0_out + row * M; io.s0_out_nyq = a.s0_out_nyq + row;
-            if constexpr (OP == OP_ADMM) {
-                io.s1_in = a.s1_in + row * M;   io.s1_in_nyq = a.s1_in_nyq + row;
-                io.s1_out = a.s1_out + row * M; io.s1_out_nyq = a.s1_out_nyq + row;
-            }
-            io.mag = a.mag + row * M; io.mag_nyq = a.mag_nyq + row;
-            io.coef = a.coef; io.coef2 = a.coef2;
-            io.owned = t >= t0;
-            float dsum = 0.f, esum = 0.f;          // per-frame partial sums, folded into doubles below
-            phase2_compute<OP, SUMS>(l, A, Bv, tb, io, dsum, esum);
-            if constexpr (SUMS) { dacc += (double)dsum; eacc += (double)esum; }
-            __syncwarp(hmask);                    // every lane has read its classes: exch may be overwritten
-            phase2_write(l, exch, A, Bv);
-            __syncwarp(hmask);
-            phase3(l, v, tb, exch);
-            __syncwarp(hmask);                    // exch is free for the next frame's phase 1
-
-            // windowed overlap-add in registers: shift by one hop (8 pairs) and accumulate
-            static_for<16>([&](auto ic) {
-                constexpr int n1 = 2 * decltype(ic)::value;
-                const float4 w = *reinterpret_cast<const float4*>(s_ws + l * ROW + n1);
-                if constexpr (n1 < 24) {
-                    acc[n1] = f2(acc[n1 + 8].x + w.x * v[n1].x, acc[n1 + 8].y + w.y * v[n1].y);
-                    acc[n1 + 1] = f2(acc[n1 + 9].x + w.z * v[n1 + 1].x, acc[n1 + 9].y + w.w * v[n1 + 1].y);
-                } else {
-                    acc[n1] = f2(w.x * v[n1].x, w.y * v[n1].y);
-                    acc[n1 + 1] = f2(w.z * v[n1 + 1].x, w.w * v[n1 + 1].y);
-                }
-            });
-            if (t >= t0) store_block(a, xo, t, l, acc);
+            for (int i = 0; i < CARRY; ++i) zero[i] = f2(0.f, 0.f);
+            tmem_store_carry(taddr, zero);
         }
-        if (t1 == a.T) {     // tail of the signal: blocks T, T+1, T+2 are complete now
-            store_block(a, xo, a.T, l, acc + 8);
-            store_block(a, xo, a.T + 1, l, acc + 16);
-            store_block(a, xo, a.T + 2, l, acc + 24);
+
+        if (tf0 < t1) {
+            prefetch_rows<OP>(a, (long long)b * a.T + tf0, l);
+            load_block(a, x, tf0, l, ring_row);
+            load_block(a, x, tf0 + 1, l, ring_row);
+            load_block(a, x, tf0 + 2, l, ring_row);
+            load_block(a, x, tf0 + 3, l, ring_row);
+        }
+
+        // every half-warp runs the same number of iterations (3 halo + chunk_len frames) so that the
+        // group barriers stay matched; iterations outside [tf0, t1) only hit the barriers
+        for (int t = t0 - 3; t < t0 + a.chunk_len; ++t) {
+            const bool active = t >= tf0 && t < t1;
+            const long long row = (long long)b * a.T + t;
+            float2 v[32];
+            float2 A[16], Bv[16];
+            float mP[16], mQ[16];
+            if (active) {
+                cp_async_wait_all();
+                const int slot0 = (8 * t) & 31;
+                static_for<16>([&](auto ic) {
+                    constexpr int n1 = 2 * decltype(ic)::value;
+                    const float4 rr = *reinterpret_cast<const float4*>(ring_row + ((slot0 + n1) & 31));
+                    const float4 w = *reinterpret_cast<const float4*>(s_wa + l * ROW + n1);
+                    v[n1] = f2(rr.x * w.x, rr.y * w.y);
+                    v[n1 + 1] = f2(rr.z * w.z, rr.w * w.w);
+                });
+                // the oldest block's slots are free now: fetch the block frame t+1 will need
+                if (t + 1 < t1) {
+                    load_block(a, x, t + 4, l, ring_row);
+                    prefetch_rows<OP>(a, row + 1, l);
+                }
+                phase1(l, v, tb, exch);
+            }
+            group_barrier<GROUP_THREADS>(bar_id);
+            if (active) phase2_read(l, exch, A, Bv);
+            group_barrier<GROUP_THREADS>(bar_id);      // every lane has read its classes: exch is free
+            if (active) {
+                // stage this frame's state row (q_in / X_in, 4 KB) in the idle exchange buffer while the
+                // 16-point FFTs run: the point-wise stage then reads it from shared memory
+                const float2* src = a.s0_in + row * M;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) cp_async16(exch + 2 * (16 * i + l), src + 2 * (16 * i + l));
+                load_mags(l, a.mag + row * M, mP, mQ);
+                phase2_fft(A, Bv);
+                cp_async_wait_all();
+            }
+            group_barrier<GROUP_THREADS>(bar_id);      // staged row visible to all lanes
+            if (active) {
+                FrameIO io;
+                io.s0_stage = exch;             io.s0_in_nyq = a.s0_in_nyq + row;
+                io.s0_out = a.s0_out + row * M; io.s0_out_nyq = a.s0_out_nyq + row;
+                if constexpr (OP == OP_ADMM) {
+                    io.s1_in = a.s1_in + row * M;   io.s1_in_nyq = a.s1_in_nyq + row;
+                    io.s1_out = a.s1_out + row * M; io.s1_out_nyq = a.s1_out_nyq + row;
+                }
+                io.mag = a.mag + row * M; io.mag_nyq = a.mag_nyq + row;
+                io.coef = a.coef; io.coef2 = a.coef2;
+                io.owned = t >= t0;
+                float dsum = 0.f, esum = 0.f;          // per-frame partial sums, folded into doubles below
+                phase2_pointwise<OP, SUMS>(l, A, Bv, tb, io, mP, mQ, dsum, esum);
+                if constexpr (SUMS) { dacc += (double)dsum; eacc += (double)esum; }
+            }
+            group_barrier<GROUP_THREADS>(bar_id);      // staged row consumed: exch may be overwritten
+            if (active) phase2_write(l, exch, A, Bv);
+            group_barrier<GROUP_THREADS>(bar_id);
+            if (active) phase3(l, v, tb, exch);
+            float2 carry[CARRY];
+            tmem_load_carry(taddr, carry);             // warp-collective: outside the `active` branch
+            if (active) {
+                // windowed overlap-add: out = carry (3 hops from earlier frames) + ws * v; the first hop
+                // (8 pairs) of `out` is a finished block, the other 24 pairs are the new carry
+                float2 blk[8];
+                static_for<16>([&](auto ic) {
+                    constexpr int n1 = 2 * decltype(ic)::value;
+                    const float4 w = *reinterpret_cast<const float4*>(s_ws + l * ROW + n1);
+                    float2 o0 = f2(w.x * v[n1].x, w.y * v[n1].y), o1 = f2(w.z * v[n1 + 1].x, w.w * v[n1 + 1].y);
+                    if constexpr (n1 < CARRY) { o0 = o0 + carry[n1]; o1 = o1 + carry[n1 + 1]; }
+                    if constexpr (n1 < 8) { blk[n1] = o0; blk[n1 + 1] = o1; }
+                    else { carry[n1 - 8] = o0; carry[n1 - 7] = o1; }
+                });
+                if (t >= t0) store_block(a, xo, t, l, blk);
+            }
+            tmem_store_carry(taddr, carry);
+            group_barrier<GROUP_THREADS>(bar_id);      // exch is free for the next frame's phase 1
+        }
+        {
+            float2 carry[CARRY];
+            tmem_load_carry(taddr, carry);
+            if (valid && t1 == a.T) {     // tail of the signal: blocks T, T+1, T+2 are complete now
+                store_block(a, xo, a.T, l, carry);
+                store_block(a, xo, a.T + 1, l, carry + 8);
+                store_block(a, xo, a.T + 2, l, carry + 16);
+            }
         }
     }
 
@@ -183,6 +304,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) fast_iter_kernel(const FastArgs
         }
         if ((tid & 31) == 0) { atomicAdd(a.sums, d); atomicAdd(a.sums + 1, e); }
     }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (tid < 32) tmem_dealloc(s_tmem_base, TMEM_COLS);
 }
 
 static int g_sms = 0;
@@ -219,6 +343,17 @@ static int launch(const FastArgs& a0, cudaStream_t st) {
     return (int)cudaGetLastError();
 }
 
+// warps per CTA: 8 (255 registers / thread, no spills) or 12 (168 registers); SPECINV_FAST_WARPS overrides
+template <int OP>
+static int launch_cfg(const FastArgs& a, cudaStream_t st) {
+    static int warps = 0;
+    if (warps == 0) {
+        const char* e = getenv("SPECINV_FAST_WARPS");
+        warps = (e && atoi(e) == 12) ? 12 : 8;
+    }
+    return warps == 12 ? launch<OP, 12>(a, st) : launch<OP, 8>(a, st);
+}
+
 }  // namespace fast
 
 // Returns SPECINV_ERR_UNSUPPORTED when the shape is not the one this kernel is specialised for.
@@ -246,7 +381,7 @@ int fast_gl_iter(const specinv_desc* d, const void* plan, const void* x_in, void
     a.s0_out = (float2*)q_out_main; a.s0_out_nyq = (float2*)q_out_nyq;
     a.mag = (const float*)mag_main; a.mag_nyq = (const float*)mag_nyq;
     a.coef = (float)lr; a.sums = sums;
-    return fast::launch<fast::OP_GL, 12>(a, (cudaStream_t)stream);
+    return fast::launch_cfg<fast::OP_GL>(a, (cudaStream_t)stream);
 }
 
 int fast_admm_iter(const specinv_desc* d, const void* plan, const void* x_in, void* x_out,
@@ -264,7 +399,7 @@ int fast_admm_iter(const specinv_desc* d, const void* plan, const void* x_in, vo
     a.s1_out = (float2*)U_out_main; a.s1_out_nyq = (float2*)U_out_nyq;
     a.mag = (const float*)mag_main; a.mag_nyq = (const float*)mag_nyq;
     a.coef = (float)rho; a.coef2 = (float)(1.0 / (1.0 + rho)); a.sums = sums;
-    return fast::launch<fast::OP_ADMM, 12>(a, (cudaStream_t)stream);
+    return fast::launch_cfg<fast::OP_ADMM>(a, (cudaStream_t)stream);
 }
 
 }  // namespace specinv

@@ -36,7 +36,7 @@ int run() {
     for (int k = 0; k < M; ++k) { s0_in[k] = f2((float)(20 * frand()), (float)(20 * frand())); s1_in[k] = f2((float)(5 * frand()), (float)(5 * frand())); mag[k] = (float)(10 * fabs(frand())); }
     s0n_in = f2((float)(20 * frand()), (float)(20 * frand())); s1n_in = f2((float)frand(), (float)frand()); magn = 3.f;
     FrameIO io{};
-    io.s0_in = s0_in.data(); io.s0_in_nyq = &s0n_in; io.s0_out = s0_out.data(); io.s0_out_nyq = &s0n_out;
+    io.s0_stage = s0_in.data(); io.s0_in_nyq = &s0n_in; io.s0_out = s0_out.data(); io.s0_out_nyq = &s0n_out;
     io.s1_in = s1_in.data(); io.s1_in_nyq = &s1n_in; io.s1_out = s1_out.data(); io.s1_out_nyq = &s1n_out;
     io.mag = mag.data(); io.mag_nyq = &magn;
     const float coef = OP == OP_GL ? 0.3f : 0.1f;
@@ -53,7 +53,7 @@ int run() {
     }
     for (int l = 0; l < 16; ++l) phase2_read(l, exch.data(), A[l], Bv[l]);
     float ds = 0, es = 0;
-    for (int l = 0; l < 16; ++l) phase2_compute<OP, true>(l, A[l], Bv[l], tb, io, ds, es);
+    for (int l = 0; l < 16; ++l) { float mP[16], mQ[16]; load_mags(l, io.mag, mP, mQ); phase2_fft(A[l], Bv[l]); phase2_pointwise<OP, true>(l, A[l], Bv[l], tb, io, mP, mQ, ds, es); }
     for (int l = 0; l < 16; ++l) phase2_write(l, exch.data(), A[l], Bv[l]);
     for (int l = 0; l < 16; ++l) phase3(l, v[l], tb, exch.data());
 
