@@ -10,7 +10,8 @@ import os
 from typing import Optional
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "lib", "libspecinv_b200.so")
+# SPECINV_B200_LIB: load another build of the same ABI (kernel A/B experiments)
+LIB_PATH = os.environ.get("SPECINV_B200_LIB") or os.path.join(_PKG, "lib", "libspecinv_b200.so")
 
 F32, F64 = 0, 1
 PAD_MODES = {"reflect": 0, "constant": 1, "replicate": 2, "circular": 3}

@@ -47,7 +47,9 @@ struct FrameIO {
     float2* s0_out;       float2* s0_out_nyq;
     const float2* s1_in;  const float2* s1_in_nyq;    // ADMM: U_in
     float2* s1_out;       float2* s1_out_nyq;
-    const float* mag;     const float* mag_nyq;
+    const float* mag;     const float* mag_nyq;       // mag: main row (global, or staged in shared memory)
+    float2 s0_nyq_val;    // preloaded s0_in_nyq[0] (only lane 0 uses it)
+    float mag_nyq_val;    // preloaded mag_nyq[0]
     float coef;           // lr or rho
     float coef2;          // ADMM: 1/(1+rho)
     bool owned;           // write state / count sums for this frame
@@ -86,12 +88,12 @@ SPX_HD float2 bin_update_fast(const FrameIO& io, int kk, float2 s, float m, floa
         }
     }
     if constexpr (OP == OP_GL) {
-        const float2 qp = NYQ ? SPX_LDG(io.s0_in_nyq) : io.s0_stage[kk];
+        const float2 qp = NYQ ? io.s0_nyq_val : io.s0_stage[kk];
         const float2 q = f2(s.x - qp.x * io.coef, s.y - qp.y * io.coef);
         if (io.owned) *(NYQ ? io.s0_out_nyq : io.s0_out + kk) = q;
         return project_fast(q, m);
     } else {
-        const float2 X = NYQ ? SPX_LDG(io.s0_in_nyq) : io.s0_stage[kk];
+        const float2 X = NYQ ? io.s0_nyq_val : io.s0_stage[kk];
         const float2 U = SPX_LDG(NYQ ? io.s1_in_nyq : io.s1_in + kk);
         const float rho = io.coef, inv = io.coef2;
         const float2 Z = f2((rho * (X.x + U.x) + s.x) * inv, (rho * (X.y + U.y) + s.y) * inv);
@@ -107,15 +109,24 @@ SPX_HD float2 bin_update_fast(const FrameIO& io, int kk, float2 s, float m, floa
 
 // ---- phase 1: windowed samples -> FFT32 -> twiddle -> exchange ------------------------------------
 // v[n1] on entry = (x[32 n1 + 2 l], x[32 n1 + 2 l + 1]) * 0.5 * wa   (caller applies the window)
-SPX_HD void phase1(int l, float2* v, const Tables& tb, float2* exch) {
+SPX_HD void phase1_compute(int l, float2* v, const Tables& tb) {
     fft32<false>(v);
     static_for<16>([&](auto ic) {
         constexpr int k1 = 2 * decltype(ic)::value;
         const float4 t = *reinterpret_cast<const float4*>(tb.tw + l * ROW + k1);
-        const float2 a = k1 == 0 ? v[0] : cmulf(v[k1], f2(t.x, t.y));
-        const float2 b = cmulf(v[k1 + 1], f2(t.z, t.w));
-        *reinterpret_cast<float4*>(exch + l * ROW + k1) = make_float4(a.x, a.y, b.x, b.y);
+        if constexpr (k1 != 0) v[k1] = cmulf(v[k1], f2(t.x, t.y));
+        v[k1 + 1] = cmulf(v[k1 + 1], f2(t.z, t.w));
     });
+}
+SPX_HD void phase1_write(int l, const float2* v, float2* exch) {
+    static_for<16>([&](auto ic) {
+        constexpr int k1 = 2 * decltype(ic)::value;
+        *reinterpret_cast<float4*>(exch + l * ROW + k1) = make_float4(v[k1].x, v[k1].y, v[k1 + 1].x, v[k1 + 1].y);
+    });
+}
+SPX_HD void phase1(int l, float2* v, const Tables& tb, float2* exch) {
+    phase1_compute(l, v, tb);
+    phase1_write(l, v, exch);
 }
 
 SPX_HD int class_a(int p) { return p; }
@@ -162,8 +173,8 @@ SPX_HD void load_mags(int p, const float* mag_row, float* mP, float* mQ) {
     static_for<16>([&](auto jc) {
         constexpr int j = decltype(jc)::value;
         const int kP = slot_bin<j>(p);
-        mP[j] = SPX_LDG(mag_row + kP);
-        mQ[j] = SPX_LDG(mag_row + ((j == 0 && p == 0) ? 256 : M - kP));
+        mP[j] = mag_row[kP];
+        mQ[j] = mag_row[(j == 0 && p == 0) ? 256 : M - kP];
     });
 }
 
@@ -186,7 +197,7 @@ SPX_HD void phase2_pointwise(int p, float2* A, float2* B, const Tables& tb, cons
         // lane 0: A[0] = Zh[0] -> DC and Nyquist (both real), A[8] = Zh[256] -> bin 256 = conj(Z[256])
         const float2 z0 = A[0], z8 = A[8];
         const float2 h0 = bin_update_fast<OP, SUMS, false>(io, 0, f2(2.f * (z0.x + z0.y), 0.f), mP[0], dsum, esum);
-        const float2 hM = bin_update_fast<OP, SUMS, true>(io, 0, f2(2.f * (z0.x - z0.y), 0.f), SPX_LDG(io.mag_nyq), dsum, esum);
+        const float2 hM = bin_update_fast<OP, SUMS, true>(io, 0, f2(2.f * (z0.x - z0.y), 0.f), io.mag_nyq_val, dsum, esum);
         const float2 h8 = bin_update_fast<OP, SUMS, false>(io, 256, f2(2.f * z8.x, -2.f * z8.y), mQ[0], dsum, esum);
         A[0] = f2(h0.x + hM.x, h0.x - hM.x);        // C2R ignores Im(DC), Im(Nyquist)
         A[8] = f2(2.f * h8.x, -2.f * h8.y);

@@ -37,6 +37,11 @@ __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// cp.async.wait_all that the compiler cannot hoist above the computation of the given values (it would
+// otherwise place the wait right after the copies were issued and expose their whole latency)
+__device__ __forceinline__ void cp_async_wait_all_after(float& d0, float& d1, float& d2, float& d3) {
+    asm volatile("cp.async.wait_all;" : "+f"(d0), "+f"(d1), "+f"(d2), "+f"(d3)::"memory");
+}
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // Pull the state / magnitude rows of frame `row` into L2 (one 128-byte line per call and lane) so the
@@ -72,16 +77,24 @@ __device__ __forceinline__ void load_block(const FastArgs& a, const float* __res
     }
 }
 
-// Store a finished block (8 sample pairs per lane) times 1/envelope.
-__device__ __forceinline__ void store_block(const FastArgs& a, float* __restrict__ xo, int u, int l, const float2* blk) {
+// Block u of the output exists (is not trimmed away by the centre padding)?
+__device__ __forceinline__ bool block_valid(const FastArgs& a, int u) {
     const long long base = (long long)u * HOP - a.P;
-    if (base < 0 || base + HOP > a.L) return;                  // trimmed (centre padding) block
+    return base >= 0 && base + HOP <= a.L;
+}
+// Load the 1/envelope values of block u (issued early so the latency hides behind the inverse FFT).
+__device__ __forceinline__ void load_inv_env(const FastArgs& a, int u, int l, float2* ie) {
+    const long long base = (long long)u * HOP - a.P;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const long long m = base + 32 * j + 2 * l;
-        const float2 ie = __ldg(reinterpret_cast<const float2*>(a.inv_env + m));
-        *reinterpret_cast<float2*>(xo + m) = f2(blk[j].x * ie.x, blk[j].y * ie.y);
-    }
+    for (int j = 0; j < 8; ++j) ie[j] = __ldg(reinterpret_cast<const float2*>(a.inv_env + base + 32 * j + 2 * l));
+}
+// Store a finished block (8 sample pairs per lane) times 1/envelope.
+__device__ __forceinline__ void store_block(const FastArgs& a, float* __restrict__ xo, int u, int l, const float2* blk,
+                                            const float2* ie) {
+    const long long base = (long long)u * HOP - a.P;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<float2*>(xo + base + 32 * j + 2 * l) = f2(blk[j].x * ie[j].x, blk[j].y * ie[j].y);
 }
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
@@ -133,13 +146,27 @@ __device__ __forceinline__ void tmem_load_carry(unsigned taddr, float2* carry) {
 __device__ __forceinline__ void tmem_store_carry(unsigned taddr, const float2* carry) {
     const float* c = reinterpret_cast<const float*>(carry);
     tmem_st16(taddr, c); tmem_st16(taddr + 16, c + 16); tmem_st16(taddr + 32, c + 32);
-    tmem_wait_st();
+    // completion is awaited (tmem_wait_st) right before the next tmem_load_carry, one frame later
 }
+constexpr int HW_F2 = 2 * TBL + 256;   // float2 elements of shared memory per half-warp: ring, exchange, magnitude row
 constexpr int CARRY = 24;            // sample pairs carried from frame to frame (3 hops)
 constexpr int TMEM_COLS = 256;       // >= (WARPS / 4) * 2 * CARRY, power of two
 
+// Synchronisation of one half-warp exchange step.  LOCKSTEP: barrier over the whole sub-partition group
+// (keeps its warps on the same instructions); otherwise only the 16 lanes that share the frame.
+template <bool LOCKSTEP, int THREADS>
+__device__ __forceinline__ void exch_sync(int bar_id, unsigned hmask, bool active) {
+    if constexpr (LOCKSTEP) group_barrier<THREADS>(bar_id);
+    else if (active) __syncwarp(hmask);
+}
+
+#ifndef SPX_LOCKSTEP
+#define SPX_LOCKSTEP 1
+#endif
+
 template <int OP, bool SUMS, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, 1) fast_iter_kernel(const FastArgs a) {
+    constexpr bool LOCKSTEP = SPX_LOCKSTEP != 0;
     static_assert((WARPS / 4) * 2 * CARRY <= TMEM_COLS, "TMEM columns");
     static_assert(WARPS % 4 == 0, "warps are grouped by SM sub-partition");
     constexpr int GROUP_THREADS = (WARPS / 4) * 32;
@@ -172,8 +199,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) fast_iter_kernel(const FastArgs
     const int l = tid & 15;
     const int hw = tid >> 4;                                       // half-warp slot in the CTA
     const int bar_id = 1 + ((tid >> 5) & 3);                       // one named barrier per sub-partition
-    float2* ring_row = s_hw + hw * 2 * TBL + l * ROW;
-    float2* exch = s_hw + hw * 2 * TBL + TBL;
+    const unsigned hmask = 0xFFFFu << (16 * ((tid >> 4) & 1));
+    float2* ring_row = s_hw + hw * HW_F2 + l * ROW;
+    float2* exch = s_hw + hw * HW_F2 + TBL;
+    float* mstage = reinterpret_cast<float*>(s_hw + hw * HW_F2 + 2 * TBL);   // 512 magnitudes of the current frame
     const Tables tb{s_tw, s_wa, s_ws, s_twr};
 
     double dacc = 0.0, eacc = 0.0;
@@ -216,6 +245,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) fast_iter_kernel(const FastArgs
             float2 v[32];
             float2 A[16], Bv[16];
             float mP[16], mQ[16];
+            float2 s0n = f2(0.f, 0.f);
+            float mgn = 0.f;
             if (active) {
                 cp_async_wait_all();
                 const int slot0 = (8 * t) & 31;
@@ -231,22 +262,28 @@ __global__ void __launch_bounds__(WARPS * 32, 1) fast_iter_kernel(const FastArgs
                     load_block(a, x, t + 4, l, ring_row);
                     prefetch_rows<OP>(a, row + 1, l);
                 }
-                phase1(l, v, tb, exch);
+                phase1_compute(l, v, tb);
             }
-            group_barrier<GROUP_THREADS>(bar_id);
+            group_barrier<GROUP_THREADS>(bar_id);      // previous frame's phase-3 reads are done: exch is free
+            if (active) phase1_write(l, v, exch);
+            exch_sync<LOCKSTEP, GROUP_THREADS>(bar_id, hmask, active);
             if (active) phase2_read(l, exch, A, Bv);
-            group_barrier<GROUP_THREADS>(bar_id);      // every lane has read its classes: exch is free
+            exch_sync<LOCKSTEP, GROUP_THREADS>(bar_id, hmask, active);      // every lane has read its classes: exch is free
             if (active) {
                 // stage this frame's state row (q_in / X_in, 4 KB) in the idle exchange buffer while the
                 // 16-point FFTs run: the point-wise stage then reads it from shared memory
                 const float2* src = a.s0_in + row * M;
 #pragma unroll
                 for (int i = 0; i < 16; ++i) cp_async16(exch + 2 * (16 * i + l), src + 2 * (16 * i + l));
-                load_mags(l, a.mag + row * M, mP, mQ);
+                const float* msrc = a.mag + row * M;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) cp_async16(mstage + 4 * (16 * i + l), msrc + 4 * (16 * i + l));
+                s0n = (l == 0) ? __ldg(a.s0_in_nyq + row) : f2(0.f, 0.f);
+                mgn = (l == 0) ? __ldg(a.mag_nyq + row) : 0.f;
                 phase2_fft(A, Bv);
-                cp_async_wait_all();
+                cp_async_wait_all_after(A[15].x, A[7].y, Bv[15].x, Bv[11].y);
             }
-            group_barrier<GROUP_THREADS>(bar_id);      // staged row visible to all lanes
+            exch_sync<LOCKSTEP, GROUP_THREADS>(bar_id, hmask, active);      // staged row visible to all lanes
             if (active) {
                 FrameIO io;
                 io.s0_stage = exch;             io.s0_in_nyq = a.s0_in_nyq + row;
@@ -256,17 +293,23 @@ __global__ void __launch_bounds__(WARPS * 32, 1) fast_iter_kernel(const FastArgs
                     io.s1_out = a.s1_out + row * M; io.s1_out_nyq = a.s1_out_nyq + row;
                 }
                 io.mag = a.mag + row * M; io.mag_nyq = a.mag_nyq + row;
+                io.s0_nyq_val = s0n; io.mag_nyq_val = mgn;
                 io.coef = a.coef; io.coef2 = a.coef2;
                 io.owned = t >= t0;
+                load_mags(l, mstage, mP, mQ);
                 float dsum = 0.f, esum = 0.f;          // per-frame partial sums, folded into doubles below
                 phase2_pointwise<OP, SUMS>(l, A, Bv, tb, io, mP, mQ, dsum, esum);
                 if constexpr (SUMS) { dacc += (double)dsum; eacc += (double)esum; }
             }
-            group_barrier<GROUP_THREADS>(bar_id);      // staged row consumed: exch may be overwritten
+            exch_sync<LOCKSTEP, GROUP_THREADS>(bar_id, hmask, active);      // staged row consumed: exch may be overwritten
             if (active) phase2_write(l, exch, A, Bv);
-            group_barrier<GROUP_THREADS>(bar_id);
+            exch_sync<LOCKSTEP, GROUP_THREADS>(bar_id, hmask, active);
+            const bool emit = active && t >= t0 && block_valid(a, t);
+            float2 ie[8];
+            if (emit) load_inv_env(a, t, l, ie);
             if (active) phase3(l, v, tb, exch);
             float2 carry[CARRY];
+            tmem_wait_st();
             tmem_load_carry(taddr, carry);             // warp-collective: outside the `active` branch
             if (active) {
                 // windowed overlap-add: out = carry (3 hops from earlier frames) + ws * v; the first hop
@@ -280,18 +323,22 @@ __global__ void __launch_bounds__(WARPS * 32, 1) fast_iter_kernel(const FastArgs
                     if constexpr (n1 < 8) { blk[n1] = o0; blk[n1 + 1] = o1; }
                     else { carry[n1 - 8] = o0; carry[n1 - 7] = o1; }
                 });
-                if (t >= t0) store_block(a, xo, t, l, blk);
+                if (emit) store_block(a, xo, t, l, blk, ie);
             }
             tmem_store_carry(taddr, carry);
-            group_barrier<GROUP_THREADS>(bar_id);      // exch is free for the next frame's phase 1
         }
         {
             float2 carry[CARRY];
+            tmem_wait_st();
             tmem_load_carry(taddr, carry);
             if (valid && t1 == a.T) {     // tail of the signal: blocks T, T+1, T+2 are complete now
-                store_block(a, xo, a.T, l, carry);
-                store_block(a, xo, a.T + 1, l, carry + 8);
-                store_block(a, xo, a.T + 2, l, carry + 16);
+#pragma unroll
+                for (int k = 0; k < 3; ++k)
+                    if (block_valid(a, a.T + k)) {
+                        float2 ie[8];
+                        load_inv_env(a, a.T + k, l, ie);
+                        store_block(a, xo, a.T + k, l, carry + 8 * k, ie);
+                    }
             }
         }
     }
@@ -329,7 +376,7 @@ static int launch(const FastArgs& a0, cudaStream_t st) {
     a.chunk_len = (a.T + cps - 1) / cps;
     a.chunks_per_signal = (a.T + a.chunk_len - 1) / a.chunk_len;
     a.n_chunks = a.B * a.chunks_per_signal;
-    const size_t smem = (size_t)(3 * TBL + 512 + 2 * WARPS * 2 * TBL) * sizeof(float2);
+    const size_t smem = (size_t)(3 * TBL + 512 + 2 * WARPS * HW_F2) * sizeof(float2);
     cudaError_t e;
     if (a.sums) {
         e = cudaFuncSetAttribute(fast_iter_kernel<OP, true, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -38,7 +38,7 @@ int run() {
     FrameIO io{};
     io.s0_stage = s0_in.data(); io.s0_in_nyq = &s0n_in; io.s0_out = s0_out.data(); io.s0_out_nyq = &s0n_out;
     io.s1_in = s1_in.data(); io.s1_in_nyq = &s1n_in; io.s1_out = s1_out.data(); io.s1_out_nyq = &s1n_out;
-    io.mag = mag.data(); io.mag_nyq = &magn;
+    io.mag = mag.data(); io.mag_nyq = &magn; io.s0_nyq_val = s0n_in; io.mag_nyq_val = magn;
     const float coef = OP == OP_GL ? 0.3f : 0.1f;
     io.coef = coef; io.coef2 = 1.f / (1.f + coef); io.owned = true;
 
