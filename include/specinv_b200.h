@@ -91,6 +91,15 @@ int specinv_pack_real(const specinv_desc* d, const void* mag, int64_t sb, int64_
 int specinv_unpack_complex(const specinv_desc* d, const void* main_in, const void* nyq_in,
                            void* spec_out, int64_t sb, int64_t sf, int64_t st, void* stream);
 
+/* ---- one-shot setup on the split layout ---------------------------------------------------------
+ * specinv_phase_init : phase_init, methods.py:572-615 (magnitude -> complex start C = mag*exp(i*phi)),
+ *                      one fused pass instead of ~15 full-tensor ops; hop / n_fft come from the desc.
+ * specinv_spec_abs   : target magnitude |C| of a complex initial estimate, methods.py:110. */
+int specinv_phase_init(const specinv_desc* d, const void* mag_main, const void* mag_nyq, void* c_main, void* c_nyq,
+                       void* stream);
+int specinv_spec_abs(const specinv_desc* d, const void* c_main, const void* c_nyq, void* mag_main, void* mag_nyq,
+                     void* stream);
+
 /* ---- primitives ---------------------------------------------------------------------------
  * specinv_stft  : torch.stft as called at methods.py:241, :464  (x (B,L) -> spectrum)
  * specinv_istft : _istft, methods.py:135-150 (spectrum -> x (B,L)), envelope from the plan */

@@ -260,7 +260,8 @@ def phase_init(mag: np.ndarray, **stft_kwargs) -> np.ndarray:
     phase[i1, i2, i3] = omega
     phase[i1, i2 - 1, i3] = omega
     phase[i1, i2 + 1, i3] = omega
-    phase = np.cumsum(phase, axis=2, dtype=rdt)
+    # torch's CPU cumsum accumulates float32 inputs in float64 (acc_type) and rounds every output
+    phase = np.cumsum(phase.astype(np.float64), axis=2).astype(rdt)
     cdt = np.result_type(rdt, np.complex64)
     out = m * np.exp(phase.astype(cdt) * cdt.type(1j))
     return out.reshape(shape)

@@ -131,3 +131,23 @@ def metric_sums(a: Tensor, b: Tensor, out3: Tensor) -> None:
     with torch.cuda.device(a.device):
         _ok(_lib.lib().specinv_metric_sums(_DT[a.dtype], _p(a), _p(b), a.numel(), _p(out3), _stream(a)),
                    "metric_sums")
+
+
+@torch.library.custom_op("specinv_b200::phase_init", mutates_args=("c_main", "c_nyq"), device_types="cuda")
+def phase_init(mag_main: Tensor, mag_nyq: Tensor, c_main: Tensor, c_nyq: Tensor, n_fft: int, hop: int,
+               onesided: bool) -> None:
+    """split real magnitude -> split complex start (methods.py:572-615), one fused kernel."""
+    _need_cuda(mag_main, mag_nyq, c_main, c_nyq)
+    d = _desc(mag_main, n_fft, hop, mag_main.shape[1], mag_main.shape[0], False, 0, False, onesided)
+    with torch.cuda.device(mag_main.device):
+        _ok(_lib.lib().specinv_phase_init(C.byref(d), _p(mag_main), _p(mag_nyq), _p(c_main), _p(c_nyq),
+                                          _stream(mag_main)), "phase_init")
+
+
+@torch.library.custom_op("specinv_b200::spec_abs", mutates_args=("mag_main", "mag_nyq"), device_types="cuda")
+def spec_abs(c_main: Tensor, c_nyq: Tensor, mag_main: Tensor, mag_nyq: Tensor, n_fft: int, onesided: bool) -> None:
+    _need_cuda(c_main, c_nyq, mag_main, mag_nyq)
+    d = _desc(mag_main, n_fft, 1, mag_main.shape[1], mag_main.shape[0], False, 0, False, onesided)
+    with torch.cuda.device(mag_main.device):
+        _ok(_lib.lib().specinv_spec_abs(C.byref(d), _p(c_main), _p(c_nyq), _p(mag_main), _p(mag_nyq),
+                                        _stream(mag_main)), "spec_abs", 2 if onesided else 1)

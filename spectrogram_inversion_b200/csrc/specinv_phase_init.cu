@@ -1,0 +1,120 @@
+// One-shot kernels that run before the iteration loop, on the split frame-major layout:
+//   * phase_init : the reference's simplified single-pass spectrogram inversion start
+//                  (torch_specinv/methods.py:572-615), fused into ONE pass over the magnitude:
+//                  strict spectral peaks along frequency (:597-598), parabolic interpolation (:604),
+//                  instantaneous frequency (:605) assigned to the peak bin and its two neighbours with
+//                  the reference's write order (:607-609: a peak at k-1 wins over a peak at k+1),
+//                  running sum over time (:611) and C = mag * exp(i*phi) (:612-614).
+//                  The reference does this with ~15 full-tensor PyTorch ops.
+//   * spec_abs   : |C| for a complex initial estimate (methods.py:110).
+#include "specinv_common.cuh"
+
+namespace specinv {
+
+template <typename T> __device__ __forceinline__ void sincos_t(T x, T* s, T* c);
+template <> __device__ __forceinline__ void sincos_t<float>(float x, float* s, float* c) { sincosf(x, s, c); }
+template <> __device__ __forceinline__ void sincos_t<double>(double x, double* s, double* c) { sincos(x, s, c); }
+
+// magnitude of bin k (0..F-1) of frame row `fr`; out-of-range bins are never peaks
+template <typename T>
+__device__ __forceinline__ T mag_at(const T* __restrict__ main, const T* __restrict__ nyq, const Dims& dm, long long fr,
+                                    int k) {
+    if (dm.onesided && k == dm.M) return __ldg(nyq + fr);
+    return __ldg(main + fr * dm.row + k);
+}
+
+// One thread per (signal, bin); it walks over time carrying the running phase.  Consecutive threads
+// handle consecutive bins, so every load / store of a time step is coalesced in the frame-major layout.
+template <typename T>
+__global__ void __launch_bounds__(128) phase_init_kernel(Dims dm, int F, T hop, T n_fft, const T* __restrict__ mag_main,
+                                                         const T* __restrict__ mag_nyq, cx_t<T>* __restrict__ c_main,
+                                                         cx_t<T>* __restrict__ c_nyq) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    if (k >= F) return;
+    const T pi2 = (T)6.283185307179586476925286766559;
+    double phase = 0.0;          // torch's CPU cumsum accumulates float32 in float64 and rounds each output
+    // strict local maximum at bin j (1 <= j <= F-2), and its interpolated angular frequency * hop
+    auto peak_omega = [&](long long fr, int j, T& omega) -> bool {
+        if (j < 1 || j > F - 2) return false;
+        const T lo = mag_at(mag_main, mag_nyq, dm, fr, j - 1);
+        const T mid = mag_at(mag_main, mag_nyq, dm, fr, j);
+        const T hi = mag_at(mag_main, mag_nyq, dm, fr, j + 1);
+        if (!(mid > hi && mid > lo)) return false;
+        const T p = T(0.5) * (lo - hi) / (lo - T(2) * mid + hi);
+        omega = pi2 * ((T)j + p) / n_fft * hop;
+        return true;
+    };
+    for (int t = 0; t < dm.T; ++t) {
+        const long long fr = (long long)b * dm.T + t;
+        T omega = T(0), w;
+        // reference write order: own peak, then peak at k+1 (writes k), then peak at k-1 (writes k): last wins
+        if (peak_omega(fr, k, w)) omega = w;
+        if (peak_omega(fr, k + 1, w)) omega = w;
+        if (peak_omega(fr, k - 1, w)) omega = w;
+        phase += (double)omega;
+        const T ph = (T)phase;
+        T s, c;
+        sincos_t<T>(ph, &s, &c);
+        const T m = mag_at(mag_main, mag_nyq, dm, fr, k);
+        const cx_t<T> v = mk<T>(m * c, m * s);
+        if (dm.onesided && k == dm.M) c_nyq[fr] = v;
+        else c_main[fr * dm.row + k] = v;
+    }
+}
+
+template <typename T>
+__global__ void spec_abs_kernel(const cx_t<T>* __restrict__ c, T* __restrict__ m, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const cx_t<T> v = c[i];
+        m[i] = hypot(v.x, v.y);      // torch's complex abs is hypot
+    }
+}
+
+template <typename T>
+static int phase_init_t(const Dims& dm, const void* mag_main, const void* mag_nyq, void* c_main, void* c_nyq, cudaStream_t st) {
+    const int F = dm.onesided ? dm.M + 1 : dm.N;
+    dim3 grid((F + 127) / 128, dm.B);
+    if (grid.y > 65535) return SPECINV_ERR_UNSUPPORTED;
+    phase_init_kernel<T><<<grid, 128, 0, st>>>(dm, F, (T)dm.hop, (T)dm.N, (const T*)mag_main, (const T*)mag_nyq,
+                                               (cx_t<T>*)c_main, (cx_t<T>*)c_nyq);
+    return (int)cudaGetLastError();
+}
+
+template <typename T>
+static int spec_abs_t(const Dims& dm, const void* c_main, const void* c_nyq, void* m_main, void* m_nyq, cudaStream_t st) {
+    const long long n = (long long)dm.B * dm.T * dm.row;
+    long long blocks = (n + 1023) / 1024;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    spec_abs_kernel<T><<<(unsigned)blocks, 256, 0, st>>>((const cx_t<T>*)c_main, (T*)m_main, n);
+    if (dm.onesided) {
+        const long long nn = (long long)dm.B * dm.T;
+        spec_abs_kernel<T><<<(unsigned)((nn + 255) / 256 > 1184 ? 1184 : (nn + 255) / 256), 256, 0, st>>>(
+            (const cx_t<T>*)c_nyq, (T*)m_nyq, nn);
+    }
+    return (int)cudaGetLastError();
+}
+
+}  // namespace specinv
+
+using namespace specinv;
+
+extern "C" {
+
+int specinv_phase_init(const specinv_desc* d, const void* mag_main, const void* mag_nyq, void* c_main, void* c_nyq,
+                       void* stream) {
+    Dims dm; int rc = make_dims(d, &dm); if (rc) return rc;
+    if (!mag_main || !c_main || (dm.onesided && (!mag_nyq || !c_nyq))) return SPECINV_ERR_INVALID;
+    return d->dtype == SPECINV_F64 ? phase_init_t<double>(dm, mag_main, mag_nyq, c_main, c_nyq, (cudaStream_t)stream)
+                                   : phase_init_t<float>(dm, mag_main, mag_nyq, c_main, c_nyq, (cudaStream_t)stream);
+}
+
+int specinv_spec_abs(const specinv_desc* d, const void* c_main, const void* c_nyq, void* mag_main, void* mag_nyq,
+                     void* stream) {
+    Dims dm; int rc = make_dims(d, &dm); if (rc) return rc;
+    if (!mag_main || !c_main || (dm.onesided && (!mag_nyq || !c_nyq))) return SPECINV_ERR_INVALID;
+    return d->dtype == SPECINV_F64 ? spec_abs_t<double>(dm, c_main, c_nyq, mag_main, mag_nyq, (cudaStream_t)stream)
+                                   : spec_abs_t<float>(dm, c_main, c_nyq, mag_main, mag_nyq, (cudaStream_t)stream);
+}
+
+}  // extern "C"

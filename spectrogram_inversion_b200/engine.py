@@ -46,7 +46,8 @@ class SplitSpec:
 class StftPlan:
     """Twiddles, scaled windows and 1/envelope for one (stft args, T, B, dtype, device)."""
 
-    def __init__(self, args: StftArgs, n_frames: int, batch: int, dtype: torch.dtype, device: torch.device):
+    def __init__(self, args: StftArgs, n_frames: int, batch: int, dtype: torch.dtype, device: torch.device,
+                 tables: bool = True):
         require_cuda()
         if dtype not in _CDT:
             raise NotImplementedError(f"dtype {dtype} is not supported (float32 / float64 only)")
@@ -61,6 +62,10 @@ class StftPlan:
         self.length = args.signal_length(self.T)
         self.row = n // 2 if args.onesided else n
         self.n_bins = args.n_bins
+        self._k = (n, args.hop_length, args.center, self.pad_mode, args.normalized, args.onesided)
+        self.buf = None
+        if not tables:          # layout conversion / phase_init only
+            return
         d = _lib.make_desc(n, args.hop_length, self.T, self.B, args.center, self.pad_mode, args.normalized,
                            args.onesided, _ops._DT[dtype])
         nbytes = _lib.C.c_size_t(0)
@@ -69,7 +74,6 @@ class StftPlan:
         window = args.window.detach().to(device=device, dtype=dtype).contiguous()
         _ops.plan_init(self.buf, window, n, args.hop_length, self.T, self.B, args.center, self.pad_mode,
                        args.normalized, args.onesided)
-        self._k = (n, args.hop_length, args.center, self.pad_mode, args.normalized, args.onesided)
 
     # ---- buffers ---------------------------------------------------------------------------
     def empty_spec(self, real: bool = False) -> SplitSpec:
@@ -96,6 +100,20 @@ class StftPlan:
         (frame-major: strides (F*T, 1, F))."""
         out = torch.empty(self.B, self.T, self.n_bins, dtype=self.cdtype, device=self.device).transpose(1, 2)
         _ops.unpack(s.main, s.nyq, out, self.args.n_fft, self.args.onesided)
+        return out
+
+    # ---- one-shot setup --------------------------------------------------------------------
+    def phase_init(self, mag: SplitSpec) -> SplitSpec:
+        """split magnitude -> split complex start, the reference's phase_init (methods.py:572-615)."""
+        out = self.empty_spec()
+        _ops.phase_init(mag.main, mag.nyq, out.main, out.nyq, self.args.n_fft, self.args.hop_length,
+                        self.args.onesided)
+        return out
+
+    def spec_abs(self, c: SplitSpec) -> SplitSpec:
+        """|C| of a complex split spectrum (target magnitude of a complex start, methods.py:110)."""
+        out = self.empty_spec(real=True)
+        _ops.spec_abs(c.main, c.nyq, out.main, out.nyq, self.args.n_fft, self.args.onesided)
         return out
 
     # ---- primitives ------------------------------------------------------------------------

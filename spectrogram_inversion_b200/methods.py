@@ -9,7 +9,7 @@ import torch
 
 from .engine import (ADMMSolver, GriffinLimSolver, METRIC_NAMES, SplitSpec, StftPlan, compute_device,
                      training_loop)
-from .stft_args import StftArgs, args_helper
+from .stft_args import StftArgs, args_helper, real_dtype_of
 
 __all__ = ["griffin_lim", "RTISI_LA", "ADMM", "phase_init"]
 
@@ -26,26 +26,25 @@ def _pop_aliases(kw: dict, max_iter, eva_iter):
     return max_iter, eva_iter
 
 
-def _spec_formatter(spec: torch.Tensor, **stft_kwargs) -> Tuple[torch.Tensor, torch.Tensor]:
-    """methods.py:99-111: 2-D -> 3-D; real input gets a phase from phase_init, complex input is the
-    initial estimate and its modulus the target."""
+def _setup(spec: torch.Tensor, stft_kwargs: dict):
+    """Input formatting of the reference (methods.py:99-111 and :225-227) on the device, in the split
+    layout: 2-D -> 3-D; a real input is the target magnitude and gets its start from phase_init, a
+    complex input is the start and its modulus the target."""
     shape = spec.shape
     assert 4 > len(shape) > 1
-    if len(shape) == 2:
-        spec = spec.unsqueeze(0)
-    if not spec.is_complex():
-        return phase_init(spec, **stft_kwargs), spec
-    return spec, spec.abs()
-
-
-def _setup(spec: torch.Tensor, stft_kwargs: dict):
     dev = compute_device(spec)
-    work = spec.detach().to(dev)
-    cmplx, target = _spec_formatter(work, **stft_kwargs)
-    args = args_helper(target, **stft_kwargs)
-    B, _, T = target.shape
-    plan = StftPlan(args, T, B, target.dtype, dev)
-    return plan, plan.pack(cmplx), plan.pack(target)
+    work = spec.detach()
+    if len(shape) == 2:
+        work = work.unsqueeze(0)
+    work = work.to(dev, non_blocking=True)
+    args = args_helper(work, **stft_kwargs)
+    B, _, T = work.shape
+    plan = StftPlan(args, T, B, real_dtype_of(work.dtype), dev)
+    if work.is_complex():
+        C = plan.pack(work)
+        return plan, C, plan.spec_abs(C)
+    mag = plan.pack(work)
+    return plan, plan.phase_init(mag), mag
 
 
 def _finish(x: torch.Tensor, spec: torch.Tensor) -> torch.Tensor:
@@ -126,24 +125,7 @@ def phase_init(spec, **stft_kwargs):
     dev = compute_device(spec)
     m = spec.detach().to(dev)
     args = args_helper(m, **stft_kwargs)
-    # TODO(kernel): one-shot, off the per-iteration path; runs as device-side tensor ops for now
-    F_, dt = m.shape[1], m.dtype
-    peak = torch.zeros_like(m, dtype=torch.bool)
-    peak[:, 1:-1] = (m[:, 1:-1] > m[:, 2:]) & (m[:, 1:-1] > m[:, :-2])
-    lo = torch.roll(m, 1, 1)
-    hi = torch.roll(m, -1, 1)
-    k = torch.arange(F_, device=dev, dtype=dt).view(1, -1, 1)
-    p = 0.5 * (lo - hi) / (lo - 2 * m + hi)
-    omega = torch.where(peak, pi2 * (k + p) / args.n_fft * args.hop_length, torch.zeros_like(m))
-    up = torch.roll(omega, -1, 1)      # omega of a peak at k+1
-    up[:, -1] = 0
-    down = torch.roll(omega, 1, 1)     # omega of a peak at k-1 (written last in the reference, so it wins)
-    down[:, 0] = 0
-    pk_dn = torch.roll(peak, 1, 1)
-    pk_dn[:, 0] = False
-    pk_up = torch.roll(peak, -1, 1)
-    pk_up[:, -1] = False
-    phase = torch.where(pk_dn, down, torch.where(pk_up, up, omega))
-    phase = torch.cumsum(phase, 2)
-    out = m * torch.exp(phase * 1j)
-    return out.view(shape).to(spec.device)
+    B, _, T = m.shape
+    plan = StftPlan(args, T, B, m.dtype, dev, tables=False)
+    out = plan.unpack(plan.phase_init(plan.pack(m)))
+    return out.reshape(shape).to(spec.device)

@@ -1,0 +1,126 @@
+"""CPU-side checks: the C-ABI library builds/loads and exports every symbol the header declares (no
+compute calls), the host-side kwargs logic mirrors the reference, and the product package has no CPU
+fallback and never touches the oracle."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import cases
+from oracle import specinv_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from spectrogram_inversion_b200.build import build_library
+    build_library()
+    from spectrogram_inversion_b200 import _lib
+    return _lib
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "specinv_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(specinv_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(lib):
+    handle = lib.lib()
+    syms = header_symbols()
+    assert len(syms) >= 15
+    for s in syms:
+        assert hasattr(handle, s), s
+    assert sorted(lib.EXPORTS) == syms
+    assert handle.specinv_abi_version() == 1
+    assert handle.specinv_error_string(-2).decode().startswith("configuration not supported")
+
+
+def test_host_only_entry_points(lib):
+    """specinv_signal_length / specinv_plan_bytes are pure host arithmetic: callable without a GPU."""
+    import ctypes as C
+    handle = lib.lib()
+    for case in cases.ITER_CASES:
+        inp = cases.make_case_inputs(case)
+        mag = inp["mag"] if inp["mag"].ndim == 3 else inp["mag"][None]
+        a = O.args_helper(mag.shape[1], mag.dtype, **inp["kwargs"])
+        d = lib.make_desc(a.n_fft, a.hop_length, mag.shape[2], mag.shape[0], a.center,
+                          lib.PAD_MODES[a.pad_mode], a.normalized, a.onesided,
+                          lib.F32 if mag.dtype == np.float32 else lib.F64)
+        L = C.c_int64()
+        assert handle.specinv_signal_length(C.byref(d), C.byref(L)) == 0
+        assert L.value == a.signal_length(mag.shape[2])
+        nbytes = C.c_size_t()
+        assert handle.specinv_plan_bytes(C.byref(d), C.byref(nbytes)) == 0
+        assert nbytes.value > 2 * L.value * mag.dtype.itemsize
+    bad = lib.make_desc(1000, 250, 10, 1, True, 0, False, True, lib.F32)      # not a power of two
+    assert handle.specinv_signal_length(C.byref(bad), C.byref(L)) == lib.ERR_UNSUPPORTED
+    bad = lib.make_desc(1024, 0, 10, 1, True, 0, False, True, lib.F32)
+    assert handle.specinv_signal_length(C.byref(bad), C.byref(L)) == -1
+
+
+@pytest.mark.parametrize("case", cases.ITER_CASES, ids=lambda c: c["name"])
+def test_args_helper_mirrors_reference_rules(case):
+    from spectrogram_inversion_b200.stft_args import args_helper
+    inp = cases.make_case_inputs(case)
+    mag = inp["mag"] if inp["mag"].ndim == 3 else inp["mag"][None]
+    kw = {k: (torch.from_numpy(v) if isinstance(v, np.ndarray) else v) for k, v in inp["kwargs"].items()}
+    kw["not_an_stft_kwarg"] = 123            # unknown keys are ignored (methods.py:42-46)
+    got = args_helper(torch.from_numpy(mag), **kw)
+    want = O.args_helper(mag.shape[1], mag.dtype, **inp["kwargs"])
+    assert (got.n_fft, got.hop_length, got.win_length) == (want.n_fft, want.hop_length, want.win_length)
+    assert (got.center, got.pad_mode, got.normalized, got.onesided) == (want.center, want.pad_mode, want.normalized, want.onesided)
+    assert got.window.shape == (want.n_fft,) and np.array_equal(got.window.numpy(), want.window)
+    assert got.signal_length(mag.shape[2]) == want.signal_length(mag.shape[2])
+
+
+def test_assertions_fire_before_any_gpu_work():
+    import spectrogram_inversion_b200 as S
+    spec = torch.rand(65, 20)
+    with pytest.raises(AssertionError):
+        S.griffin_lim(spec, alpha=-0.1)
+    with pytest.raises(AssertionError):
+        S.griffin_lim(spec, max_iter=0)
+    with pytest.raises(AssertionError):
+        S.griffin_lim(spec, eva_iter=0)
+    with pytest.raises(AssertionError):
+        S.griffin_lim(spec, tol=-1.0)
+    with pytest.raises(AssertionError):
+        S.griffin_lim(spec, metric="xx")
+    with pytest.raises(AssertionError):
+        S.ADMM(spec, metric="xx")
+    with pytest.raises(AssertionError):
+        S.RTISI_LA(spec.to(torch.complex64))
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="only meaningful on a box without a GPU")
+def test_no_cpu_fallback():
+    import spectrogram_inversion_b200 as S
+    spec = torch.rand(65, 20)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        S.griffin_lim(spec, max_iter=2, verbose=False)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        S.sc(spec, spec)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "spectrogram_inversion_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "specinv_oracle" not in text and "import oracle" not in text and "from oracle" not in text, f
+                assert "/root/reference" not in text, f
+
+
+def test_metric_value_formulas():
+    from spectrogram_inversion_b200.engine import metric_value
+    rs = np.random.RandomState(0)
+    a, b = np.abs(rs.randn(5, 9, 7)), np.abs(rs.randn(5, 9, 7))
+    d, e, g = O.metric_sums(a, b)
+    assert abs(metric_value("SC", d, e, g) - O.sc(a, b)) < 1e-9
+    assert abs(metric_value("SNR", d, e, g) - O.snr(a, b)) < 1e-9
+    assert abs(metric_value("SER", d, e, g) - O.ser(a, b)) < 1e-9

@@ -302,3 +302,21 @@ def test_fast_and_generic_kernels_agree(monkeypatch):
     close(outs[0][0], outs[1][0].cpu().numpy(), 2e-4, "fast vs generic after 5 iterations")
     for (d0, e0), (d1, e1) in zip(outs[0][1], outs[1][1]):
         assert abs(d0 - d1) <= 1e-4 * d1 and abs(e0 - e1) <= 1e-4 * e1
+
+
+@pytest.mark.parametrize("case", cases.ITER_CASES, ids=lambda c: c["name"])
+def test_phase_init_and_magnitude_entry_match_reference(case):
+    """Real-magnitude entry: the fused phase_init kernel against the reference's phase_init, and
+    griffin_lim(mag) (phase_init inside) against the reference after 2 iterations."""
+    import spectrogram_inversion_b200 as S
+    inp = cases.make_case_inputs(case)
+    kw = {k: (torch.from_numpy(v) if isinstance(v, np.ndarray) else v) for k, v in inp["kwargs"].items()}
+    mag = torch.from_numpy(inp["mag"]).cuda()
+    f32 = case["dtype"] == "float32"
+    pi = S.phase_init(mag, **kw)
+    assert pi.shape == mag.shape and pi.is_complex() and pi.is_cuda
+    # fp32: the phase reaches O(1e3) rad, so one ulp of phase is ~1e-4 rad of angle error
+    close(pi, PRIM[f"{case['name']}/phase_init"], 5e-4 if f32 else 1e-9, "phase_init")
+    close(pi, O.phase_init(inp["mag"], **inp["kwargs"]), 5e-4 if f32 else 1e-9, "phase_init vs oracle")
+    y = S.griffin_lim(mag, max_iter=2, tol=0, alpha=0.99, verbose=False, **kw)
+    close(y, GL[f"{case['name']}/mag_in/k2"], 2e-3 if f32 else 1e-8, "griffin_lim(mag)")
