@@ -124,6 +124,15 @@ int specinv_admm_iter(const specinv_desc* d, const void* plan, const void* x_in,
                       void* X_out_main, void* X_out_nyq, void* U_out_main, void* U_out_nyq,
                       const void* mag_main, const void* mag_nyq, double rho, double* sums, void* stream);
 
+/* ---- RTISI-LA ---------------------------------------------------------------------------------
+ * The whole of RTISI_LA's loops and final overlap-add, methods.py:353-408, as one persistent kernel
+ * (one CTA per signal, all sliding state on chip).  `window` is the padded n_fft window (as for
+ * specinv_plan_init), synth_coeff = hop / (window . window) (methods.py:318), look_ahead < 0 means
+ * (n_fft-1)/hop (methods.py:322-324), `scratch` holds 2*n_fft reals (asym_window1/2, methods.py:326-336). */
+int specinv_rtisi_la(const specinv_desc* d, const void* plan, const void* window, const void* mag_main,
+                     const void* mag_nyq, void* x_out, void* scratch, int look_ahead, int asymmetric_window,
+                     int max_iter, double alpha, double synth_coeff, void* stream);
+
 /* ---- metrics (metrics.py:4-43, F.mse_loss at methods.py:182) ---------------------------------
  * out[0] += sum (a-b)^2, out[1] += sum a^2, out[2] += sum b^2 over n contiguous reals. */
 int specinv_metric_sums(int dtype, const void* a, const void* b, int64_t n, double* out3, void* stream);

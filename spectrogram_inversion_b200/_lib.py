@@ -22,7 +22,7 @@ EXPORTS = (
     "specinv_plan_bytes", "specinv_plan_init", "specinv_plan_envelope",
     "specinv_pack_complex", "specinv_pack_real", "specinv_unpack_complex",
     "specinv_stft", "specinv_istft", "specinv_gl_iter", "specinv_admm_iter",
-    "specinv_metric_sums", "specinv_phase_init", "specinv_spec_abs",
+    "specinv_metric_sums", "specinv_phase_init", "specinv_spec_abs", "specinv_rtisi_la",
 )
 
 
@@ -53,6 +53,7 @@ def _declare(lib: C.CDLL) -> None:
         "specinv_unpack_complex": [dp, vp, vp, vp, i64, i64, i64, vp],
         "specinv_phase_init": [dp, vp, vp, vp, vp, vp],
         "specinv_spec_abs": [dp, vp, vp, vp, vp, vp],
+        "specinv_rtisi_la": [dp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, dbl, dbl, vp],
         "specinv_stft": [dp, vp, vp, vp, vp, vp],
         "specinv_istft": [dp, vp, vp, vp, vp, vp],
         "specinv_gl_iter": [dp, vp, vp, vp, vp, vp, vp, vp, vp, vp, dbl, vp, vp],

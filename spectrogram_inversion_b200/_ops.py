@@ -151,3 +151,16 @@ def spec_abs(c_main: Tensor, c_nyq: Tensor, mag_main: Tensor, mag_nyq: Tensor, n
     with torch.cuda.device(mag_main.device):
         _ok(_lib.lib().specinv_spec_abs(C.byref(d), _p(c_main), _p(c_nyq), _p(mag_main), _p(mag_nyq),
                                         _stream(mag_main)), "spec_abs", 2 if onesided else 1)
+
+
+@torch.library.custom_op("specinv_b200::rtisi_la", mutates_args=("x_out", "scratch"), device_types="cuda")
+def rtisi_la(plan: Tensor, window: Tensor, mag_main: Tensor, mag_nyq: Tensor, x_out: Tensor, scratch: Tensor,
+             look_ahead: int, asymmetric: bool, max_iter: int, alpha: float, synth_coeff: float, n_fft: int, hop: int,
+             center: bool, pad_mode: int, normalized: bool, onesided: bool) -> None:
+    """RTISI_LA's loops + final overlap-add (methods.py:353-408) as one persistent kernel."""
+    _need_cuda(plan, window, mag_main, mag_nyq, x_out, scratch)
+    d = _desc(x_out, n_fft, hop, mag_main.shape[1], mag_main.shape[0], center, pad_mode, normalized, onesided)
+    with torch.cuda.device(x_out.device):
+        _ok(_lib.lib().specinv_rtisi_la(C.byref(d), _p(plan), _p(window), _p(mag_main), _p(mag_nyq), _p(x_out),
+                                        _p(scratch), int(look_ahead), int(bool(asymmetric)), int(max_iter),
+                                        float(alpha), float(synth_coeff), _stream(x_out)), "rtisi_la", 2)

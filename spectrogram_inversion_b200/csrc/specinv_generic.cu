@@ -15,6 +15,7 @@
 // Replaces, per iteration, torch.stft + ~8 point-wise kernels + fft.irfft + conv_transpose1d with
 // a dense diag(window) weight of the reference (methods.py:241-248, :464-477, :127-132).
 #include "specinv_common.cuh"
+#include "generic_fft.cuh"
 
 namespace specinv {
 
@@ -35,8 +36,6 @@ struct TileArgs {
     int tile_frames;   // owned frames per tile
     int Mp;            // padded complex elements per frame in shared memory
 };
-
-__device__ __forceinline__ int padidx(int n) { return n + (n >> 4); }
 
 template <typename T>
 struct BinIO {
@@ -139,38 +138,8 @@ __global__ void __launch_bounds__(256) tile_kernel(const TileArgs a) {
         }
         __syncthreads();
 
-        // ---- B: forward DIF passes, spans M, M/4, ... (two radix-2 stages per pass) -------
-        int S = M;
-        for (; S >= 4; S >>= 2) {
-            const int q4 = S >> 2, step = M / S;
-            for (int idx = tid; idx < nfr * (M >> 2); idx += NT) {
-                const int f = idx / (M >> 2), r = idx - f * (M >> 2);
-                const int blk = r / q4, j = r - blk * q4;
-                C* v = wb + f * Mp;
-                const int e0 = blk * S + j;
-                const int i0 = padidx(e0), i1 = padidx(e0 + q4), i2 = padidx(e0 + 2 * q4), i3 = padidx(e0 + 3 * q4);
-                const C v0 = v[i0], v1 = v[i1], v2 = v[i2], v3 = v[i3];
-                const C w1 = tw[j * step], w2 = tw[2 * j * step];
-                const C a0 = cadd(v0, v2), a2 = cmul(csub(v0, v2), w1);
-                const C a1 = cadd(v1, v3), a3 = mul_mi(cmul(csub(v1, v3), w1));
-                v[i0] = cadd(a0, a1);
-                v[i1] = cmul(csub(a0, a1), w2);
-                v[i2] = cadd(a2, a3);
-                v[i3] = cmul(csub(a2, a3), w2);
-            }
-            __syncthreads();
-        }
-        if (S == 2) {  // odd log2(M): one plain radix-2 stage of span 2 (trivial twiddle)
-            for (int idx = tid; idx < nfr * (M >> 1); idx += NT) {
-                const int f = idx / (M >> 1), r = idx - f * (M >> 1);
-                C* v = wb + f * Mp;
-                const int i0 = padidx(2 * r), i1 = padidx(2 * r + 1);
-                const C v0 = v[i0], v1 = v[i1];
-                v[i0] = cadd(v0, v1);
-                v[i1] = csub(v0, v1);
-            }
-            __syncthreads();
-        }
+        // ---- B: forward DIF passes (natural -> bit-reversed) ------------------------------------
+        fft_forward_inplace<T>(wb, nfr, M, Mp, tw);
     }
 
     // ---- C: real-FFT post-process, point-wise update, inverse pre-process (pairs k, M-k) ----
@@ -190,12 +159,7 @@ __global__ void __launch_bounds__(256) tile_kernel(const TileArgs a) {
             const C w = twr[k];
             C sA = mk<T>(T(0), T(0)), sB = sA;
             if constexpr (OP != OP_ISTFT) {
-                const C za = v[pA], zb = v[pB];
-                const T er = T(0.5) * (za.x + zb.x), ei = T(0.5) * (za.y - zb.y);
-                const T orr = T(0.5) * (za.y + zb.y), oi = T(-0.5) * (za.x - zb.x);
-                const T wor = w.x * orr - w.y * oi, woi = w.x * oi + w.y * orr;
-                sA = mk<T>(er + wor, ei + woi);
-                sB = mk<T>(er - wor, -(ei - woi));
+                rfft_post_pair<T>(v[pA], v[pB], w, sA, sB);
             }
             const BinIO<T> io(a, (long long)b * dm.T + t);
             C hA, hB;
@@ -222,11 +186,10 @@ __global__ void __launch_bounds__(256) tile_kernel(const TileArgs a) {
             }
             if constexpr (OP != OP_STFT) {
                 if (k == 0) { hA.y = T(0); hB.y = T(0); }  // C2R ignores Im(DC), Im(Nyquist)
-                const T Ar = hA.x + hB.x, Ai = hA.y - hB.y;
-                const T Dr = hA.x - hB.x, Di = hA.y + hB.y;
-                const T Gr = w.x * Dr + w.y * Di, Gi = w.x * Di - w.y * Dr;   // conj(w) * D
-                v[pA] = mk<T>(Ar - Gi, Ai + Gr);
-                if (kB != kA && k != 0) v[pB] = mk<T>(Ar + Gi, Gr - Ai);
+                C zA, zB;
+                irfft_pre_pair<T>(hA, hB, w, zA, zB);
+                v[pA] = zA;
+                if (kB != kA && k != 0) v[pB] = zB;
             }
         }
     }
@@ -252,41 +215,8 @@ __global__ void __launch_bounds__(256) tile_kernel(const TileArgs a) {
     if constexpr (OP == OP_STFT) return;
     __syncthreads();
 
-    // ---- D: inverse DIT passes, spans (2), 4*.., conj twiddles --------------------------------
-    {
-        int S = 4;
-        if (dm.logM & 1) {
-            for (int idx = tid; idx < nfr * (M >> 1); idx += NT) {
-                const int f = idx / (M >> 1), r = idx - f * (M >> 1);
-                C* v = wb + f * Mp;
-                const int i0 = padidx(2 * r), i1 = padidx(2 * r + 1);
-                const C v0 = v[i0], v1 = v[i1];
-                v[i0] = cadd(v0, v1);
-                v[i1] = csub(v0, v1);
-            }
-            __syncthreads();
-            S = 8;
-        }
-        for (; S <= M; S <<= 2) {
-            const int q4 = S >> 2, step = M / S;
-            for (int idx = tid; idx < nfr * (M >> 2); idx += NT) {
-                const int f = idx / (M >> 2), r = idx - f * (M >> 2);
-                const int blk = r / q4, j = r - blk * q4;
-                C* v = wb + f * Mp;
-                const int e0 = blk * S + j;
-                const int i0 = padidx(e0), i1 = padidx(e0 + q4), i2 = padidx(e0 + 2 * q4), i3 = padidx(e0 + 3 * q4);
-                const C w1 = tw[j * step], w2 = tw[2 * j * step];
-                const C v0 = v[i0], v1 = cmulc(v[i1], w2), v2 = v[i2], v3 = cmulc(v[i3], w2);
-                const C a0 = cadd(v0, v1), a1 = csub(v0, v1);
-                const C a2 = cmulc(cadd(v2, v3), w1), a3 = mul_pi(cmulc(csub(v2, v3), w1));
-                v[i0] = cadd(a0, a2);
-                v[i2] = csub(a0, a2);
-                v[i1] = cadd(a1, a3);
-                v[i3] = csub(a1, a3);
-            }
-            __syncthreads();
-        }
-    }
+    // ---- D: inverse DIT passes (bit-reversed -> natural), conj twiddles ------------------------
+    fft_inverse_inplace<T>(wb, nfr, M, dm.logM, Mp, tw);
 
     // ---- E: windowed overlap-add of the owned output range (gather), times 1/envelope --------
     {

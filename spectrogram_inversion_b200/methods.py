@@ -7,6 +7,7 @@ from typing import Optional, Tuple
 
 import torch
 
+from . import _ops
 from .engine import (ADMMSolver, GriffinLimSolver, METRIC_NAMES, SplitSpec, StftPlan, compute_device,
                      training_loop)
 from .stft_args import StftArgs, args_helper, real_dtype_of
@@ -110,7 +111,22 @@ def RTISI_LA(spec, look_ahead=-1, asymmetric_window=False, max_iter=25, alpha=0.
     assert alpha >= 0
     assert not spec.is_complex()
     assert 4 > len(spec.shape) > 1
-    raise NotImplementedError("RTISI_LA: the persistent sm_100a kernel is not built yet")
+    dev = compute_device(spec)
+    work = spec.detach()
+    if len(spec.shape) == 2:
+        work = work.unsqueeze(0)
+    work = work.to(dev, non_blocking=True)
+    args = args_helper(work, **stft_kwargs)
+    B, _, T = work.shape
+    plan = StftPlan(args, T, B, work.dtype, dev)
+    mag = plan.pack(work)
+    window = args.window.detach().to(device=dev, dtype=work.dtype).contiguous()
+    synth_coeff = float(args.hop_length / (window @ window))                 # methods.py:318
+    x = plan.empty_signal()
+    scratch = torch.empty(2 * args.n_fft, dtype=work.dtype, device=dev)
+    _ops.rtisi_la(plan.buf, window, mag.main, mag.nyq, x, scratch, int(look_ahead), bool(asymmetric_window),
+                  int(max_iter), float(alpha), synth_coeff, *plan._k)
+    return _finish(x, spec)
 
 
 def phase_init(spec, **stft_kwargs):

@@ -20,6 +20,7 @@ ADMM = np.load(os.path.join(G, "admm.npz"))
 PRIM = np.load(os.path.join(G, "primitives.npz"))
 LOOP = np.load(os.path.join(G, "loop.npz"))
 MISC = np.load(os.path.join(G, "misc.npz"))
+RTISI = np.load(os.path.join(G, "rtisi.npz"))
 
 
 def tol_of(dtype):
@@ -193,7 +194,9 @@ def test_public_api_shapes_and_asserts():
     with pytest.raises(AssertionError):
         S.ADMM(spec, metric="nope")
     with pytest.raises(AssertionError):
-        S.RTISI_LA(spec)
+        S.RTISI_LA(spec)                     # complex input is rejected (methods.py:297)
+    with pytest.raises(AssertionError):
+        S.RTISI_LA(spec.abs(), max_iter=0)
     # host input -> host output (staged through the GPU, never computed on the CPU)
     y = S.griffin_lim(spec.cpu(), max_iter=2, verbose=False, window=torch.hann_window(128), maxiter=3)
     assert not y.is_cuda
@@ -320,3 +323,43 @@ def test_phase_init_and_magnitude_entry_match_reference(case):
     close(pi, O.phase_init(inp["mag"], **inp["kwargs"]), 5e-4 if f32 else 1e-9, "phase_init vs oracle")
     y = S.griffin_lim(mag, max_iter=2, tol=0, alpha=0.99, verbose=False, **kw)
     close(y, GL[f"{case['name']}/mag_in/k2"], 2e-3 if f32 else 1e-8, "griffin_lim(mag)")
+
+
+@pytest.mark.parametrize("case", cases.RTISI_CASES, ids=lambda c: c["name"])
+def test_rtisi_la_matches_reference(case):
+    """Whole RTISI-LA runs (small T, few inner iterations so round-off is not yet amplified) against the
+    reference's output and the oracle's."""
+    import spectrogram_inversion_b200 as S
+    inp = cases.make_case_inputs(case)
+    kw = {k: (torch.from_numpy(v) if isinstance(v, np.ndarray) else v) for k, v in inp["kwargs"].items()}
+    mag = torch.from_numpy(inp["mag"]).cuda()
+    y = S.RTISI_LA(mag, look_ahead=case["look_ahead"], asymmetric_window=case["asym"], max_iter=case["max_iter"],
+                   alpha=case["alpha"], verbose=0, **kw)
+    f32 = case["dtype"] == "float32"
+    close(y, RTISI[case["name"]], 5e-3 if f32 else 1e-7, "vs reference")
+    yo = O.RTISI_LA(inp["mag"], look_ahead=case["look_ahead"], asymmetric_window=case["asym"],
+                    max_iter=case["max_iter"], alpha=case["alpha"], **inp["kwargs"])
+    close(y, yo, 5e-3 if f32 else 1e-7, "vs oracle")
+
+
+def test_rtisi_la_shapes_and_quality():
+    import spectrogram_inversion_b200 as S
+    for shape in [(4410,), (2, 4410), (1, 4410)]:
+        for dtype in (torch.float32, torch.float64):
+            x = torch.randn(*shape, dtype=dtype, device="cuda")
+            spec = torch.stft(x, 256, return_complex=True, window=torch.ones(256, dtype=dtype, device="cuda")).abs()
+            y = S.RTISI_LA(spec, max_iter=4, verbose=0)
+            assert y.ndim == x.ndim and y.dtype == dtype and y.is_cuda
+            if y.ndim > 1:
+                assert y.shape[0] == x.shape[0] and y.shape[1] <= x.shape[1]
+    # a longer run at the cfg3 frame shape: spectral convergence comparable with the oracle's
+    rs = np.random.RandomState(1)
+    w = cases.window_of("hann", 1024, np.float32)
+    a = O.args_helper(513, np.float32, window=w, hop_length=256)
+    mag = np.abs(O.stft(rs.randn(2, 12000).astype(np.float32), a))
+    yo = O.RTISI_LA(mag, look_ahead=3, max_iter=8, alpha=0.99, window=w, hop_length=256)
+    yg = S.RTISI_LA(torch.from_numpy(mag).cuda(), look_ahead=3, max_iter=8, alpha=0.99, verbose=0,
+                    window=torch.from_numpy(w).cuda(), hop_length=256)
+    sco = O.sc(np.abs(O.stft(yo, a)), mag)
+    scg = O.sc(np.abs(O.stft(yg.cpu().numpy(), a)), mag)
+    assert abs(scg - sco) <= 0.02 * abs(sco) + 0.2, (scg, sco)
