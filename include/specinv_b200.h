@@ -80,6 +80,12 @@ int specinv_signal_length(const specinv_desc* d, int64_t* length);
  * epsilon: a zero envelope gives inf, like the reference's division (methods.py:132). */
 int specinv_plan_bytes(const specinv_desc* d, size_t* bytes);
 int specinv_plan_init(const specinv_desc* d, const void* window, void* plan, void* stream);
+/* Frame-range sharding of one long signal: the plan describes frames [frame_offset, frame_offset + T)
+ * of a signal with total_frames frames, un-centred (d->center must be 0; the caller keeps the centre
+ * padding inside its local buffer); the envelope counts the neighbouring ranks' frames too, so
+ * partial overlap-add sums of two ranks can simply be added. */
+int specinv_plan_init_ranged(const specinv_desc* d, const void* window, void* plan, int64_t frame_offset,
+                             int64_t total_frames, void* stream);
 /* copies the length-L envelope (not its inverse) out of the plan */
 int specinv_plan_envelope(const specinv_desc* d, const void* plan, void* env_out, void* stream);
 
@@ -97,6 +103,9 @@ int specinv_unpack_complex(const specinv_desc* d, const void* main_in, const voi
  * specinv_spec_abs   : target magnitude |C| of a complex initial estimate, methods.py:110. */
 int specinv_phase_init(const specinv_desc* d, const void* mag_main, const void* mag_nyq, void* c_main, void* c_nyq,
                        void* stream);
+/* phase_in / phase_out (nullable): B*F doubles, the running phase before / after this frame range */
+int specinv_phase_init_ex(const specinv_desc* d, const void* mag_main, const void* mag_nyq, void* c_main, void* c_nyq,
+                          const double* phase_in, double* phase_out, void* stream);
 int specinv_spec_abs(const specinv_desc* d, const void* c_main, const void* c_nyq, void* mag_main, void* mag_nyq,
                      void* stream);
 
@@ -132,6 +141,17 @@ int specinv_admm_iter(const specinv_desc* d, const void* plan, const void* x_in,
 int specinv_rtisi_la(const specinv_desc* d, const void* plan, const void* window, const void* mag_main,
                      const void* mag_nyq, void* x_out, void* scratch, int look_ahead, int asymmetric_window,
                      int max_iter, double alpha, double synth_coeff, void* stream);
+
+/* ---- frame-range sharding helpers (single long signal over several GPUs) --------------------------
+ * specinv_halo_sum    : out = left + right over rows x n strided views -- the per-iteration combination of
+ *                       the two partial overlap-add sums of the (n_fft - hop)-sample region two neighbouring
+ *                       ranks share (each rank receives the other's partial by NVLink P2P / NCCL send-recv).
+ * specinv_fill_padding: re-creates the centre padding (torch.stft pad_mode) of the GLOBAL signal inside a
+ *                       rank-local padded buffer holding padded samples [padded_offset, padded_offset+local_len). */
+int specinv_halo_sum(int dtype, const void* left, int64_t ld_left, const void* right, int64_t ld_right, void* out,
+                     int64_t ld_out, int rows, int64_t n, void* stream);
+int specinv_fill_padding(int dtype, void* x, int64_t ld, int rows, int64_t padded_offset, int64_t local_len, int pad,
+                         int64_t signal_len, int pad_mode, void* stream);
 
 /* ---- metrics (metrics.py:4-43, F.mse_loss at methods.py:182) ---------------------------------
  * out[0] += sum (a-b)^2, out[1] += sum a^2, out[2] += sum b^2 over n contiguous reals. */

@@ -22,7 +22,8 @@ EXPORTS = (
     "specinv_plan_bytes", "specinv_plan_init", "specinv_plan_envelope",
     "specinv_pack_complex", "specinv_pack_real", "specinv_unpack_complex",
     "specinv_stft", "specinv_istft", "specinv_gl_iter", "specinv_admm_iter",
-    "specinv_metric_sums", "specinv_phase_init", "specinv_spec_abs", "specinv_rtisi_la",
+    "specinv_metric_sums", "specinv_phase_init", "specinv_spec_abs", "specinv_rtisi_la", "specinv_plan_init_ranged",
+    "specinv_phase_init_ex", "specinv_halo_sum", "specinv_fill_padding",
 )
 
 
@@ -48,6 +49,10 @@ def _declare(lib: C.CDLL) -> None:
         "specinv_plan_bytes": [dp, C.POINTER(C.c_size_t)],
         "specinv_plan_init": [dp, vp, vp, vp],
         "specinv_plan_envelope": [dp, vp, vp, vp],
+        "specinv_plan_init_ranged": [dp, vp, vp, i64, i64, vp],
+        "specinv_phase_init_ex": [dp, vp, vp, vp, vp, vp, vp, vp],
+        "specinv_halo_sum": [C.c_int, vp, i64, vp, i64, vp, i64, C.c_int, i64, vp],
+        "specinv_fill_padding": [C.c_int, vp, i64, C.c_int, i64, i64, C.c_int, i64, C.c_int, vp],
         "specinv_pack_complex": [dp, vp, i64, i64, i64, vp, vp, vp],
         "specinv_pack_real": [dp, vp, i64, i64, i64, vp, vp, vp],
         "specinv_unpack_complex": [dp, vp, vp, vp, i64, i64, i64, vp],

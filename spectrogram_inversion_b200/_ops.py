@@ -164,3 +164,47 @@ def rtisi_la(plan: Tensor, window: Tensor, mag_main: Tensor, mag_nyq: Tensor, x_
         _ok(_lib.lib().specinv_rtisi_la(C.byref(d), _p(plan), _p(window), _p(mag_main), _p(mag_nyq), _p(x_out),
                                         _p(scratch), int(look_ahead), int(bool(asymmetric)), int(max_iter),
                                         float(alpha), float(synth_coeff), _stream(x_out)), "rtisi_la", 2)
+
+
+@torch.library.custom_op("specinv_b200::plan_init_ranged", mutates_args=("plan",), device_types="cuda")
+def plan_init_ranged(plan: Tensor, window: Tensor, n_fft: int, hop: int, n_frames: int, batch: int, normalized: bool,
+                     onesided: bool, frame_offset: int, total_frames: int) -> None:
+    """plan for frames [frame_offset, frame_offset + n_frames) of a longer signal (frame-range sharding)."""
+    _need_cuda(plan, window)
+    d = _desc(window, n_fft, hop, n_frames, batch, False, 0, normalized, onesided)
+    with torch.cuda.device(plan.device):
+        _ok(_lib.lib().specinv_plan_init_ranged(C.byref(d), _p(window), _p(plan), int(frame_offset), int(total_frames),
+                                                _stream(plan)), "plan_init_ranged", 2)
+
+
+@torch.library.custom_op("specinv_b200::phase_init_ex", mutates_args=("c_main", "c_nyq", "phase_out"),
+                         device_types="cuda")
+def phase_init_ex(mag_main: Tensor, mag_nyq: Tensor, c_main: Tensor, c_nyq: Tensor, phase_in: Tensor,
+                  phase_out: Tensor, n_fft: int, hop: int, onesided: bool) -> None:
+    """phase_init over a frame range: phase_in / phase_out are (B, F) float64 running phases (may be empty)."""
+    _need_cuda(mag_main, mag_nyq, c_main, c_nyq, phase_in, phase_out)
+    d = _desc(mag_main, n_fft, hop, mag_main.shape[1], mag_main.shape[0], False, 0, False, onesided)
+    with torch.cuda.device(mag_main.device):
+        _ok(_lib.lib().specinv_phase_init_ex(C.byref(d), _p(mag_main), _p(mag_nyq), _p(c_main), _p(c_nyq), _p(phase_in),
+                                             _p(phase_out), _stream(mag_main)), "phase_init_ex")
+
+
+@torch.library.custom_op("specinv_b200::halo_sum", mutates_args=("out",), device_types="cuda")
+def halo_sum(left: Tensor, right: Tensor, out: Tensor) -> None:
+    """out = left + right for (rows, n) views with unit inner stride (out may alias left or right)."""
+    for t in (left, right, out):
+        if not t.is_cuda or t.dim() != 2 or t.stride(1) != 1:
+            raise RuntimeError("halo_sum needs 2-D CUDA views with unit inner stride")
+    rows, n = out.shape
+    with torch.cuda.device(out.device):
+        _ok(_lib.lib().specinv_halo_sum(_DT[out.dtype], _p(left), left.stride(0), _p(right), right.stride(0), _p(out),
+                                        out.stride(0), rows, n, _stream(out)), "halo_sum")
+
+
+@torch.library.custom_op("specinv_b200::fill_padding", mutates_args=("x",), device_types="cuda")
+def fill_padding(x: Tensor, padded_offset: int, pad: int, signal_len: int, pad_mode: int) -> None:
+    """re-create the global centre padding inside the rank-local padded buffer x (rows, local_len)."""
+    _need_cuda(x)
+    with torch.cuda.device(x.device):
+        _ok(_lib.lib().specinv_fill_padding(_DT[x.dtype], _p(x), x.stride(0), x.shape[0], int(padded_offset), x.shape[1],
+                                            int(pad), int(signal_len), int(pad_mode), _stream(x)), "fill_padding")

@@ -50,14 +50,17 @@ __global__ void plan_tables_kernel(int N, int M, int normalized, const T* __rest
 }
 
 // env[m] = sum_t w^2[m + P - t*hop]  (methods.py:129-131), inv_env = 1/env without epsilon.
+// frame_offset / total_frames: the plan describes frames [frame_offset, frame_offset + T) of a longer signal
+// with total_frames frames (frame-range sharding); the envelope then also counts the neighbours' frames.
 template <typename T>
-__global__ void plan_envelope_kernel(Dims dm, const T* __restrict__ window, T* env, T* inv_env) {
+__global__ void plan_envelope_kernel(Dims dm, long long frame_offset, long long total_frames,
+                                     const T* __restrict__ window, T* env, T* inv_env) {
     const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= dm.L) return;
-    const long long pp = m + dm.P;
+    const long long pp = m + dm.P + frame_offset * dm.hop;
     long long tlo = pp >= dm.N ? (pp - dm.N) / dm.hop + 1 : 0;
     long long thi = pp / dm.hop;
-    if (thi > dm.T - 1) thi = dm.T - 1;
+    if (thi > total_frames - 1) thi = total_frames - 1;
     T acc = T(0);
     for (long long t = tlo; t <= thi; ++t) {
         const T w = window[pp - t * dm.hop];
@@ -68,14 +71,16 @@ __global__ void plan_envelope_kernel(Dims dm, const T* __restrict__ window, T* e
 }
 
 template <typename T>
-static int plan_init_t(const Dims& dm, const specinv_desc* d, const void* window, void* plan, cudaStream_t st) {
+static int plan_init_t(const Dims& dm, const specinv_desc* d, const void* window, void* plan, long long frame_offset,
+                       long long total_frames, cudaStream_t st) {
     const PlanLayout pl = plan_layout(dm, d->dtype);
     char* p = (char*)plan;
     const int n = dm.N;
     plan_tables_kernel<T><<<(n + 255) / 256, 256, 0, st>>>(dm.N, dm.M, d->normalized, (const T*)window,
                                                            (cx_t<T>*)(p + pl.tw), (cx_t<T>*)(p + pl.twr),
                                                            (T*)(p + pl.wa), (T*)(p + pl.ws));
-    plan_envelope_kernel<T><<<(unsigned)((dm.L + 255) / 256), 256, 0, st>>>(dm, (const T*)window, (T*)(p + pl.env),
+    plan_envelope_kernel<T><<<(unsigned)((dm.L + 255) / 256), 256, 0, st>>>(dm, frame_offset, total_frames,
+                                                                            (const T*)window, (T*)(p + pl.env),
                                                                             (T*)(p + pl.inv_env));
     return (int)cudaGetLastError();
 }
@@ -155,6 +160,37 @@ __global__ void metric_sums_kernel(const T* __restrict__ a, const T* __restrict_
     }
 }
 
+// ---------------------------------------------------------------- frame-range sharding helpers
+// out[b][i] = left[b][i] + right[b][i] on a (rows x n) strided view: both neighbours add the two partial
+// overlap-add sums of the shared (n_fft - hop)-sample region in the SAME order, so they hold bit-identical values.
+template <typename T>
+__global__ void halo_sum_kernel(const T* __restrict__ left, long long ld_left, const T* __restrict__ right,
+                                long long ld_right, T* out, long long ld_out, int rows, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    if (i < n && b < rows) out[b * ld_out + i] = left[b * ld_left + i] + right[b * ld_right + i];
+}
+
+// Re-create the centre padding of the global signal inside a rank-local padded buffer (the reference
+// re-pads x at every torch.stft call, methods.py:241).  x holds padded samples [off, off + len) of every row.
+template <typename T>
+__global__ void fill_padding_kernel(T* x, long long ld, int rows, long long off, long long len, int P, long long L,
+                                    int pad_mode) {
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // 0 .. 2P-1: left pad then right pad
+    const int b = blockIdx.y;
+    if (j >= 2LL * P || b >= rows) return;
+    const long long pp = j < P ? j : P + L + (j - P);        // global padded index of a padding sample
+    if (pp < off || pp >= off + len) return;
+    const long long src = pad_index(pp, P, L, pad_mode);     // index into the unpadded global signal, or -1
+    T v = T(0);
+    if (src >= 0) {
+        const long long sl = src + P - off;                   // local position of the source sample
+        if (sl < 0 || sl >= len) return;                      // source lives on another rank (circular): caller forbids
+        v = x[b * ld + sl];
+    }
+    x[b * ld + (pp - off)] = v;
+}
+
 }  // namespace specinv
 
 using namespace specinv;
@@ -190,8 +226,18 @@ int specinv_plan_bytes(const specinv_desc* d, size_t* bytes) {
 int specinv_plan_init(const specinv_desc* d, const void* window, void* plan, void* stream) {
     Dims dm; int rc = make_dims(d, &dm); if (rc) return rc;
     if (!window || !plan) return SPECINV_ERR_INVALID;
-    return d->dtype == SPECINV_F64 ? plan_init_t<double>(dm, d, window, plan, (cudaStream_t)stream)
-                                   : plan_init_t<float>(dm, d, window, plan, (cudaStream_t)stream);
+    return d->dtype == SPECINV_F64 ? plan_init_t<double>(dm, d, window, plan, 0, dm.T, (cudaStream_t)stream)
+                                   : plan_init_t<float>(dm, d, window, plan, 0, dm.T, (cudaStream_t)stream);
+}
+
+int specinv_plan_init_ranged(const specinv_desc* d, const void* window, void* plan, int64_t frame_offset,
+                             int64_t total_frames, void* stream) {
+    Dims dm; int rc = make_dims(d, &dm); if (rc) return rc;
+    if (!window || !plan || d->center) return SPECINV_ERR_INVALID;   // a frame range is described un-centred
+    if (frame_offset < 0 || frame_offset + dm.T > total_frames) return SPECINV_ERR_INVALID;
+    return d->dtype == SPECINV_F64
+               ? plan_init_t<double>(dm, d, window, plan, frame_offset, total_frames, (cudaStream_t)stream)
+               : plan_init_t<float>(dm, d, window, plan, frame_offset, total_frames, (cudaStream_t)stream);
 }
 
 int specinv_plan_envelope(const specinv_desc* d, const void* plan, void* env_out, void* stream) {
@@ -267,6 +313,35 @@ int specinv_admm_iter(const specinv_desc* d, const void* plan, const void* x_in,
     }
     return generic_admm_iter(d, plan, x_in, x_out, X_in_main, X_in_nyq, U_in_main, U_in_nyq, X_out_main, X_out_nyq,
                              U_out_main, U_out_nyq, mag_main, mag_nyq, rho, sums, stream);
+}
+
+int specinv_halo_sum(int dtype, const void* left, int64_t ld_left, const void* right, int64_t ld_right, void* out,
+                     int64_t ld_out, int rows, int64_t n, void* stream) {
+    if (!left || !right || !out || rows < 1 || n < 1) return SPECINV_ERR_INVALID;
+    dim3 grid((unsigned)((n + 255) / 256), rows);
+    if (dtype == SPECINV_F64)
+        halo_sum_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>((const double*)left, ld_left, (const double*)right,
+                                                                         ld_right, (double*)out, ld_out, rows, n);
+    else if (dtype == SPECINV_F32)
+        halo_sum_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)left, ld_left, (const float*)right,
+                                                                        ld_right, (float*)out, ld_out, rows, n);
+    else return SPECINV_ERR_INVALID;
+    return (int)cudaGetLastError();
+}
+
+int specinv_fill_padding(int dtype, void* x, int64_t ld, int rows, int64_t padded_offset, int64_t local_len, int pad,
+                         int64_t signal_len, int pad_mode, void* stream) {
+    if (!x || rows < 1 || pad < 0 || local_len < 1 || signal_len < 1) return SPECINV_ERR_INVALID;
+    if (pad == 0) return SPECINV_OK;
+    dim3 grid((unsigned)((2LL * pad + 255) / 256), rows);
+    if (dtype == SPECINV_F64)
+        fill_padding_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>((double*)x, ld, rows, padded_offset, local_len,
+                                                                             pad, signal_len, pad_mode);
+    else if (dtype == SPECINV_F32)
+        fill_padding_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((float*)x, ld, rows, padded_offset, local_len,
+                                                                            pad, signal_len, pad_mode);
+    else return SPECINV_ERR_INVALID;
+    return (int)cudaGetLastError();
 }
 
 int specinv_metric_sums(int dtype, const void* a, const void* b, int64_t n, double* out3, void* stream) {

@@ -28,12 +28,15 @@ __device__ __forceinline__ T mag_at(const T* __restrict__ main, const T* __restr
 template <typename T>
 __global__ void __launch_bounds__(128) phase_init_kernel(Dims dm, int F, T hop, T n_fft, const T* __restrict__ mag_main,
                                                          const T* __restrict__ mag_nyq, cx_t<T>* __restrict__ c_main,
-                                                         cx_t<T>* __restrict__ c_nyq) {
+                                                         cx_t<T>* __restrict__ c_nyq, const double* __restrict__ phase_in,
+                                                         double* __restrict__ phase_out) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     const int b = blockIdx.y;
     if (k >= F) return;
     const T pi2 = (T)6.283185307179586476925286766559;
-    double phase = 0.0;          // torch's CPU cumsum accumulates float32 in float64 and rounds each output
+    // torch's CPU cumsum accumulates float32 in float64 and rounds each output; phase_in (frame-range
+    // sharding) is the phase accumulated by the frames before this range
+    double phase = phase_in ? phase_in[(long long)b * F + k] : 0.0;
     // strict local maximum at bin j (1 <= j <= F-2), and its interpolated angular frequency * hop
     auto peak_omega = [&](long long fr, int j, T& omega) -> bool {
         if (j < 1 || j > F - 2) return false;
@@ -61,6 +64,7 @@ __global__ void __launch_bounds__(128) phase_init_kernel(Dims dm, int F, T hop, 
         if (dm.onesided && k == dm.M) c_nyq[fr] = v;
         else c_main[fr * dm.row + k] = v;
     }
+    if (phase_out) phase_out[(long long)b * F + k] = phase;
 }
 
 template <typename T>
@@ -72,12 +76,13 @@ __global__ void spec_abs_kernel(const cx_t<T>* __restrict__ c, T* __restrict__ m
 }
 
 template <typename T>
-static int phase_init_t(const Dims& dm, const void* mag_main, const void* mag_nyq, void* c_main, void* c_nyq, cudaStream_t st) {
+static int phase_init_t(const Dims& dm, const void* mag_main, const void* mag_nyq, void* c_main, void* c_nyq,
+                        const double* phase_in, double* phase_out, cudaStream_t st) {
     const int F = dm.onesided ? dm.M + 1 : dm.N;
     dim3 grid((F + 127) / 128, dm.B);
     if (grid.y > 65535) return SPECINV_ERR_UNSUPPORTED;
     phase_init_kernel<T><<<grid, 128, 0, st>>>(dm, F, (T)dm.hop, (T)dm.N, (const T*)mag_main, (const T*)mag_nyq,
-                                               (cx_t<T>*)c_main, (cx_t<T>*)c_nyq);
+                                               (cx_t<T>*)c_main, (cx_t<T>*)c_nyq, phase_in, phase_out);
     return (int)cudaGetLastError();
 }
 
@@ -101,12 +106,18 @@ using namespace specinv;
 
 extern "C" {
 
-int specinv_phase_init(const specinv_desc* d, const void* mag_main, const void* mag_nyq, void* c_main, void* c_nyq,
-                       void* stream) {
+int specinv_phase_init_ex(const specinv_desc* d, const void* mag_main, const void* mag_nyq, void* c_main, void* c_nyq,
+                          const double* phase_in, double* phase_out, void* stream) {
     Dims dm; int rc = make_dims(d, &dm); if (rc) return rc;
     if (!mag_main || !c_main || (dm.onesided && (!mag_nyq || !c_nyq))) return SPECINV_ERR_INVALID;
-    return d->dtype == SPECINV_F64 ? phase_init_t<double>(dm, mag_main, mag_nyq, c_main, c_nyq, (cudaStream_t)stream)
-                                   : phase_init_t<float>(dm, mag_main, mag_nyq, c_main, c_nyq, (cudaStream_t)stream);
+    return d->dtype == SPECINV_F64
+               ? phase_init_t<double>(dm, mag_main, mag_nyq, c_main, c_nyq, phase_in, phase_out, (cudaStream_t)stream)
+               : phase_init_t<float>(dm, mag_main, mag_nyq, c_main, c_nyq, phase_in, phase_out, (cudaStream_t)stream);
+}
+
+int specinv_phase_init(const specinv_desc* d, const void* mag_main, const void* mag_nyq, void* c_main, void* c_nyq,
+                       void* stream) {
+    return specinv_phase_init_ex(d, mag_main, mag_nyq, c_main, c_nyq, nullptr, nullptr, stream);
 }
 
 int specinv_spec_abs(const specinv_desc* d, const void* c_main, const void* c_nyq, void* mag_main, void* mag_nyq,

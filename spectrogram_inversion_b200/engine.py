@@ -228,9 +228,15 @@ def metric_value(name: str, d: float, e: float, g: float) -> float:
 METRIC_NAMES = ("SC", "SNR", "SER")   # methods.py:14-18
 
 
-def training_loop(solver: _Solver, max_iter: int, tol: float, verbose, eva_iter: int, metric: str,
-                  history: Optional[List] = None) -> int:
-    """Host loop with the reference's evaluation cadence and early-stop rule (methods.py:153-190)."""
+def training_loop(solver, max_iter: int, tol: float, verbose, eva_iter: int, metric: str,
+                  history: Optional[List] = None, reduce_sums: Optional[Callable] = None) -> int:
+    """Host loop with the reference's evaluation cadence and early-stop rule (methods.py:153-190).
+
+    ``solver`` needs ``step(evaluate) -> (d, e) | None``, ``g`` and ``n_bins_total``.  ``reduce_sums``
+    (multi-GPU): maps the local ``(d, e)`` of an evaluation to the global ones (an all-reduce), so that the
+    metric, the loss and therefore the stopping decision are those of the whole batch on every rank --
+    the reference evaluates over the entire batch (methods.py:181-182); ``solver.g`` / ``n_bins_total`` must
+    then be global too."""
     assert eva_iter > 0
     assert max_iter > 0
     assert tol >= 0
@@ -244,6 +250,8 @@ def training_loop(solver: _Solver, max_iter: int, tol: float, verbose, eva_iter:
         for i in range(max_iter):
             if i % eva_iter == eva_iter - 1:
                 d, e = solver.step(evaluate=True)
+                if reduce_sums is not None:
+                    d, e = reduce_sums(d, e)
                 done = i + 1
                 bar[metric] = metric_value(metric, d, e, solver.g)
                 l2_loss = d / solver.n_bins_total
