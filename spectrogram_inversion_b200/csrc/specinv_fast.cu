@@ -1,6 +1,8 @@
-// Fast fused iteration kernel for n_fft = 1024, hop = 256 (onesided, fp32): the headline shape.
+// Fast fused iteration kernels (onesided, fp32, hop = n_fft/4):
+//   LANES = 16: n_fft = 1024, hop = 256 -- half-warp per frame  (gl_fast_core.cuh),   the headline shape
+//   LANES = 32: n_fft = 2048, hop = 512 -- one warp per frame   (gl_fast_core32.cuh)
 //
-// Every half-warp streams through a chunk of consecutive frames of ONE signal:
+// Every group of LANES lanes (a "stream") walks through a chunk of consecutive frames of ONE signal:
 //   * the new 256 input samples of each frame arrive by cp.async into a thread-private ring in
 //     shared memory (a hop is 8 of the lane's 32 sample pairs, see gl_fast_core.cuh);
 //   * forward real FFT, point-wise update + projection, inverse real FFT run in registers with one
@@ -14,6 +16,7 @@
 
 #include "specinv_common.cuh"
 #include "gl_fast_core.cuh"
+#include "gl_fast_core32.cuh"
 
 namespace specinv {
 namespace fast {
@@ -23,7 +26,7 @@ struct FastArgs {
     const float2* s0_in;  const float2* s0_in_nyq;  float2* s0_out; float2* s0_out_nyq;
     const float2* s1_in;  const float2* s1_in_nyq;  float2* s1_out; float2* s1_out_nyq;
     const float* mag;     const float* mag_nyq;
-    const float2* tw512;  const float2* twr1024;
+    const float2* tw;     const float2* twr;        // plan tables: W_M^j (M entries), W_N^k (k <= M/2)
     const float* wa; const float* ws; const float* inv_env;
     double* sums;
     float coef, coef2;
@@ -46,31 +49,34 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 
 // Pull the state / magnitude rows of frame `row` into L2 (one 128-byte line per call and lane) so the
 // point-wise stage of that frame hits L2 instead of paying a DRAM round trip in the middle of the frame.
-template <int OP>
+template <int OP, int LANES>
 __device__ __forceinline__ void prefetch_rows(const FastArgs& a, long long row, int l) {
-    const char* q = reinterpret_cast<const char*>(a.s0_in + row * M);
+    constexpr int MC = 32 * LANES;
+    const char* q = reinterpret_cast<const char*>(a.s0_in + row * MC);      // MC*8 bytes = 2*LANES lines
     prefetch_l2(q + 128 * l);
-    prefetch_l2(q + 128 * (l + 16));
-    prefetch_l2(reinterpret_cast<const char*>(a.mag + row * M) + 128 * l);
+    prefetch_l2(q + 128 * (l + LANES));
+    prefetch_l2(reinterpret_cast<const char*>(a.mag + row * MC) + 128 * l); // MC*4 bytes = LANES lines
     if constexpr (OP == OP_ADMM) {
-        const char* u = reinterpret_cast<const char*>(a.s1_in + row * M);
+        const char* u = reinterpret_cast<const char*>(a.s1_in + row * MC);
         prefetch_l2(u + 128 * l);
-        prefetch_l2(u + 128 * (l + 16));
+        prefetch_l2(u + 128 * (l + LANES));
     }
 }
 
-// Issue the load of block u (padded samples [256 u, 256 u + 256)) of signal x into the lane's ring row.
+// Issue the load of block u (padded samples [hop u, hop u + hop)) of signal x into the lane's ring row.
+template <int LANES>
 __device__ __forceinline__ void load_block(const FastArgs& a, const float* __restrict__ x, int u, int l, float2* ring_row) {
-    const long long base = (long long)u * HOP - a.P;          // unpadded index of the block's first sample
-    const bool interior = base >= 0 && base + HOP <= a.L;
+    constexpr int HOPC = 16 * LANES, SPAN = 2 * LANES;
+    const long long base = (long long)u * HOPC - a.P;         // unpadded index of the block's first sample
+    const bool interior = base >= 0 && base + HOPC <= a.L;
     if (interior) {
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-            cp_async8(ring_row + ((8 * u + j) & 31), x + base + 32 * j + 2 * l);
+            cp_async8(ring_row + ((8 * u + j) & 31), x + base + SPAN * j + 2 * l);
     } else {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const long long pp = (long long)u * HOP + 32 * j + 2 * l;
+            const long long pp = (long long)u * HOPC + SPAN * j + 2 * l;
             const long long i0 = pad_index(pp, a.P, a.L, a.pad_mode), i1 = pad_index(pp + 1, a.P, a.L, a.pad_mode);
             ring_row[(8 * u + j) & 31] = f2(i0 >= 0 ? x[i0] : 0.f, i1 >= 0 ? x[i1] : 0.f);
         }
@@ -78,23 +84,26 @@ __device__ __forceinline__ void load_block(const FastArgs& a, const float* __res
 }
 
 // Block u of the output exists (is not trimmed away by the centre padding)?
+template <int LANES>
 __device__ __forceinline__ bool block_valid(const FastArgs& a, int u) {
-    const long long base = (long long)u * HOP - a.P;
-    return base >= 0 && base + HOP <= a.L;
+    const long long base = (long long)u * (16 * LANES) - a.P;
+    return base >= 0 && base + 16 * LANES <= a.L;
 }
 // Load the 1/envelope values of block u (issued early so the latency hides behind the inverse FFT).
+template <int LANES>
 __device__ __forceinline__ void load_inv_env(const FastArgs& a, int u, int l, float2* ie) {
-    const long long base = (long long)u * HOP - a.P;
+    const long long base = (long long)u * (16 * LANES) - a.P;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) ie[j] = __ldg(reinterpret_cast<const float2*>(a.inv_env + base + 32 * j + 2 * l));
+    for (int j = 0; j < 8; ++j) ie[j] = __ldg(reinterpret_cast<const float2*>(a.inv_env + base + 2 * LANES * j + 2 * l));
 }
 // Store a finished block (8 sample pairs per lane) times 1/envelope.
+template <int LANES>
 __device__ __forceinline__ void store_block(const FastArgs& a, float* __restrict__ xo, int u, int l, const float2* blk,
                                             const float2* ie) {
-    const long long base = (long long)u * HOP - a.P;
+    const long long base = (long long)u * (16 * LANES) - a.P;
 #pragma unroll
     for (int j = 0; j < 8; ++j)
-        *reinterpret_cast<float2*>(xo + base + 32 * j + 2 * l) = f2(blk[j].x * ie[j].x, blk[j].y * ie[j].y);
+        *reinterpret_cast<float2*>(xo + base + 2 * LANES * j + 2 * l) = f2(blk[j].x * ie[j].x, blk[j].y * ie[j].y);
 }
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
@@ -104,9 +113,8 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
 // Named barrier over the warps that share one SM sub-partition (warp_id % 4): they run the frame
 // pipeline in lockstep so that the (large, fully unrolled) instruction stream is fetched once per
 // group instead of once per warp.  It also orders the half-warp exchanges through shared memory.
-template <int THREADS>
-__device__ __forceinline__ void group_barrier(int id) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(THREADS) : "memory");
+__device__ __forceinline__ void group_barrier(int id, int threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
 // ---- tensor memory as a software-managed register extension -------------------------------------------
@@ -148,15 +156,16 @@ __device__ __forceinline__ void tmem_store_carry(unsigned taddr, const float2* c
     tmem_st16(taddr, c); tmem_st16(taddr + 16, c + 16); tmem_st16(taddr + 32, c + 32);
     // completion is awaited (tmem_wait_st) right before the next tmem_load_carry, one frame later
 }
-constexpr int HW_F2 = 2 * TBL + 256;   // float2 elements of shared memory per half-warp: ring, exchange, magnitude row
+// float2 elements of shared memory per stream: ring, exchange (+ magnitude row when it is staged)
+constexpr int stream_f2(int lanes, bool stage_mag) { return 2 * lanes * ROW + (stage_mag ? 16 * lanes : 0); }
 constexpr int CARRY = 24;            // sample pairs carried from frame to frame (3 hops)
 constexpr int TMEM_COLS = 256;       // >= (WARPS / 4) * 2 * CARRY, power of two
 
 // Synchronisation of one half-warp exchange step.  LOCKSTEP: barrier over the whole sub-partition group
 // (keeps its warps on the same instructions); otherwise only the 16 lanes that share the frame.
-template <bool LOCKSTEP, int THREADS>
-__device__ __forceinline__ void exch_sync(int bar_id, unsigned hmask, bool active) {
-    if constexpr (LOCKSTEP) group_barrier<THREADS>(bar_id);
+template <bool LOCKSTEP>
+__device__ __forceinline__ void exch_sync(int bar_id, int threads, unsigned hmask, bool active) {
+    if constexpr (LOCKSTEP) group_barrier(bar_id, threads);
     else if (active) __syncwarp(hmask);
 }
 
@@ -164,30 +173,43 @@ __device__ __forceinline__ void exch_sync(int bar_id, unsigned hmask, bool activ
 #define SPX_LOCKSTEP 1
 #endif
 
-template <int OP, bool SUMS, int WARPS>
+template <int OP, bool SUMS, int WARPS, int LANES>
 __global__ void __launch_bounds__(WARPS * 32, 1) fast_iter_kernel(const FastArgs a) {
     constexpr bool LOCKSTEP = SPX_LOCKSTEP != 0;
-    static_assert((WARPS / 4) * 2 * CARRY <= TMEM_COLS, "TMEM columns");
-    static_assert(WARPS % 4 == 0, "warps are grouped by SM sub-partition");
-    constexpr int GROUP_THREADS = (WARPS / 4) * 32;
+    constexpr bool STAGE_MAG = WARPS <= 10;     // with 12 warps the shared memory is full: magnitudes come by LDG
+    constexpr int MC = 32 * LANES;              // complex FFT size = bins in a main row
+    constexpr int SPAN = 2 * LANES;             // samples between consecutive n1 of one lane
+    constexpr int TBLC = LANES * ROW;           // float2 elements of one lane-major table
+    constexpr int STREAMS = WARPS * (32 / LANES);
+    constexpr int HW_F2 = stream_f2(LANES, STAGE_MAG);
+    static_assert(((WARPS + 3) / 4) * 2 * CARRY <= TMEM_COLS, "TMEM columns");
+#ifndef SPX_GROUP_MODE
+#define SPX_GROUP_MODE 0
+#endif
+#if SPX_GROUP_MODE == 0
+    // warps w, w+4, w+8 ... share sub-partition w % 4 and form one lockstep group
+    const int group_threads = 32 * ((WARPS - 1 - (int)((threadIdx.x >> 5) & 3)) / 4 + 1);
+#else
+    const int group_threads = 64;     // adjacent warp pairs (on different sub-partitions)
+#endif
     extern __shared__ __align__(16) float2 sm[];
     float2* s_tw = sm;
-    float2* s_wa = s_tw + TBL;
-    float2* s_ws = s_wa + TBL;
-    float2* s_twr = s_ws + TBL;
-    float2* s_hw = s_twr + 512;
+    float2* s_wa = s_tw + TBLC;
+    float2* s_ws = s_wa + TBLC;
+    float2* s_twr = s_ws + TBLC;
+    float2* s_hw = s_twr + MC;
 
     __shared__ unsigned s_tmem_base;
     const int tid = threadIdx.x;
     if (tid < 32) tmem_alloc(&s_tmem_base, TMEM_COLS);
-    for (int i = tid; i < 512; i += WARPS * 32) {
+    for (int i = tid; i < MC; i += WARPS * 32) {
         const int n2 = i >> 5, k = i & 31;
-        s_tw[n2 * ROW + k] = a.tw512[(n2 * k) & 511];
-        s_wa[n2 * ROW + k] = f2(0.5f * a.wa[32 * k + 2 * n2], 0.5f * a.wa[32 * k + 2 * n2 + 1]);
-        s_ws[n2 * ROW + k] = f2(a.ws[32 * k + 2 * n2], a.ws[32 * k + 2 * n2 + 1]);
+        s_tw[n2 * ROW + k] = a.tw[(n2 * k) & (MC - 1)];
+        s_wa[n2 * ROW + k] = f2(0.5f * a.wa[SPAN * k + 2 * n2], 0.5f * a.wa[SPAN * k + 2 * n2 + 1]);
+        s_ws[n2 * ROW + k] = f2(a.ws[SPAN * k + 2 * n2], a.ws[SPAN * k + 2 * n2 + 1]);
         float2 t;
-        if (i <= 256) t = a.twr1024[i];
-        else { t = a.twr1024[512 - i]; t.x = -t.x; }              // W^k = -conj(W^(512-k))
+        if (i <= MC / 2) t = a.twr[i];
+        else { t = a.twr[MC - i]; t.x = -t.x; }                   // W_N^k = -conj(W_N^(M-k))
         s_twr[i] = t;
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -196,18 +218,22 @@ __global__ void __launch_bounds__(WARPS * 32, 1) fast_iter_kernel(const FastArgs
     // this warp's TMEM window: lanes 32 * (warp % 4) .. +31, columns 48 * (warp / 4) .. +47
     const unsigned taddr = s_tmem_base + ((unsigned)(32 * ((tid >> 5) & 3)) << 16) + (unsigned)(2 * CARRY * (tid >> 7));
 
-    const int l = tid & 15;
-    const int hw = tid >> 4;                                       // half-warp slot in the CTA
+    const int l = tid & (LANES - 1);
+    const int hw = tid / LANES;                                    // stream slot in the CTA
+#if SPX_GROUP_MODE == 0
     const int bar_id = 1 + ((tid >> 5) & 3);                       // one named barrier per sub-partition
-    const unsigned hmask = 0xFFFFu << (16 * ((tid >> 4) & 1));
+#else
+    const int bar_id = 1 + (tid >> 6);
+#endif
+    const unsigned hmask = LANES == 32 ? 0xFFFFFFFFu : 0xFFFFu << (16 * ((tid >> 4) & 1));
     float2* ring_row = s_hw + hw * HW_F2 + l * ROW;
-    float2* exch = s_hw + hw * HW_F2 + TBL;
-    float* mstage = reinterpret_cast<float*>(s_hw + hw * HW_F2 + 2 * TBL);   // 512 magnitudes of the current frame
+    float2* exch = s_hw + hw * HW_F2 + TBLC;
+    float* mstage = reinterpret_cast<float*>(s_hw + hw * HW_F2 + 2 * TBLC);  // magnitudes of the current frame
     const Tables tb{s_tw, s_wa, s_ws, s_twr};
 
     double dacc = 0.0, eacc = 0.0;
 
-    const int stride = gridDim.x * 2 * WARPS;
+    const int stride = gridDim.x * STREAMS;
     const int rounds = (a.n_chunks + stride - 1) / stride;
     for (int r = 0; r < rounds; ++r) {
         const int c = r * stride + hw * gridDim.x + blockIdx.x;
@@ -230,11 +256,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) fast_iter_kernel(const FastArgs
         }
 
         if (tf0 < t1) {
-            prefetch_rows<OP>(a, (long long)b * a.T + tf0, l);
-            load_block(a, x, tf0, l, ring_row);
-            load_block(a, x, tf0 + 1, l, ring_row);
-            load_block(a, x, tf0 + 2, l, ring_row);
-            load_block(a, x, tf0 + 3, l, ring_row);
+            prefetch_rows<OP, LANES>(a, (long long)b * a.T + tf0, l);
+            load_block<LANES>(a, x, tf0, l, ring_row);
+            load_block<LANES>(a, x, tf0 + 1, l, ring_row);
+            load_block<LANES>(a, x, tf0 + 2, l, ring_row);
+            load_block<LANES>(a, x, tf0 + 3, l, ring_row);
         }
 
         // every half-warp runs the same number of iterations (3 halo + chunk_len frames) so that the
@@ -243,8 +269,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) fast_iter_kernel(const FastArgs
             const bool active = t >= tf0 && t < t1;
             const long long row = (long long)b * a.T + t;
             float2 v[32];
-            float2 A[16], Bv[16];
-            float mP[16], mQ[16];
+            float2 A[32];                       // LANES = 16: A[0..15] / A[16..31] are the two residue classes
+            float2* const Bv = A + 16;
+            float mg[LANES == 16 ? 32 : 1];     // LANES = 16: mP = mg[0..15], mQ = mg[16..31]
             float2 s0n = f2(0.f, 0.f);
             float mgn = 0.f;
             if (active) {
@@ -259,55 +286,86 @@ __global__ void __launch_bounds__(WARPS * 32, 1) fast_iter_kernel(const FastArgs
                 });
                 // the oldest block's slots are free now: fetch the block frame t+1 will need
                 if (t + 1 < t1) {
-                    load_block(a, x, t + 4, l, ring_row);
-                    prefetch_rows<OP>(a, row + 1, l);
+                    load_block<LANES>(a, x, t + 4, l, ring_row);
+                    prefetch_rows<OP, LANES>(a, row + 1, l);
                 }
-                phase1_compute(l, v, tb);
+                if constexpr (LANES == 16) fast::phase1_compute(l, v, tb); else fast32::phase1_compute(l, v, tb);
             }
-            group_barrier<GROUP_THREADS>(bar_id);      // previous frame's phase-3 reads are done: exch is free
-            if (active) phase1_write(l, v, exch);
-            exch_sync<LOCKSTEP, GROUP_THREADS>(bar_id, hmask, active);
-            if (active) phase2_read(l, exch, A, Bv);
-            exch_sync<LOCKSTEP, GROUP_THREADS>(bar_id, hmask, active);      // every lane has read its classes: exch is free
+            group_barrier(bar_id, group_threads);      // previous frame's phase-3 reads are done: exch is free
+            if (active) { if constexpr (LANES == 16) fast::phase1_write(l, v, exch); else fast32::phase1_write(l, v, exch); }
+            exch_sync<LOCKSTEP>(bar_id, group_threads, hmask, active);
             if (active) {
-                // stage this frame's state row (q_in / X_in, 4 KB) in the idle exchange buffer while the
-                // 16-point FFTs run: the point-wise stage then reads it from shared memory
-                const float2* src = a.s0_in + row * M;
+                if constexpr (LANES == 16) fast::phase2_read(l, exch, A, Bv);
+                else static_for<32>([&](auto nc) { constexpr int n2 = decltype(nc)::value; A[n2] = exch[n2 * ROW + l]; });
+            }
+            exch_sync<LOCKSTEP>(bar_id, group_threads, hmask, active);      // every lane has read its classes: exch is free
+            float2 Zp[LANES == 32 ? 32 : 1];           // LANES = 32: the partner lane's spectrum (shuffle exchange)
+            if (active) {
+                // stage this frame's state row (q_in / X_in) in the idle exchange buffer while the second-pass
+                // FFTs run: the point-wise stage then reads it from shared memory
+                const float2* src = a.s0_in + row * MC;
 #pragma unroll
-                for (int i = 0; i < 16; ++i) cp_async16(exch + 2 * (16 * i + l), src + 2 * (16 * i + l));
-                const float* msrc = a.mag + row * M;
+                for (int i = 0; i < 16; ++i) cp_async16(exch + 2 * (LANES * i + l), src + 2 * (LANES * i + l));
+                if constexpr (STAGE_MAG) {
+                    const float* msrc = a.mag + row * MC;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) cp_async16(mstage + 4 * (16 * i + l), msrc + 4 * (16 * i + l));
+                    for (int i = 0; i < 8; ++i) cp_async16(mstage + 4 * (LANES * i + l), msrc + 4 * (LANES * i + l));
+                }
                 s0n = (l == 0) ? __ldg(a.s0_in_nyq + row) : f2(0.f, 0.f);
                 mgn = (l == 0) ? __ldg(a.mag_nyq + row) : 0.f;
-                phase2_fft(A, Bv);
-                cp_async_wait_all_after(A[15].x, A[7].y, Bv[15].x, Bv[11].y);
+                if constexpr (LANES == 16) {
+                    fast::phase2_fft(A, Bv);
+                } else {
+                    fft32<false>(A);                   // A[k2] = Zh[l + 32 k2]
+                    const int partner = (32 - l) & 31; // owner of the mirrored bins M - k
+                    static_for<32>([&](auto jc) {
+                        constexpr int j = decltype(jc)::value;
+                        Zp[j] = f2(__shfl_sync(0xffffffffu, A[j].x, partner), __shfl_sync(0xffffffffu, A[j].y, partner));
+                    });
+                }
+                cp_async_wait_all_after(A[15].x, A[7].y, A[31].x, A[27].y);
             }
-            exch_sync<LOCKSTEP, GROUP_THREADS>(bar_id, hmask, active);      // staged row visible to all lanes
+            exch_sync<LOCKSTEP>(bar_id, group_threads, hmask, active);      // staged row visible to all lanes
             if (active) {
                 FrameIO io;
-                io.s0_stage = exch;             io.s0_in_nyq = a.s0_in_nyq + row;
-                io.s0_out = a.s0_out + row * M; io.s0_out_nyq = a.s0_out_nyq + row;
+                io.s0_stage = exch;              io.s0_in_nyq = a.s0_in_nyq + row;
+                io.s0_out = a.s0_out + row * MC; io.s0_out_nyq = a.s0_out_nyq + row;
                 if constexpr (OP == OP_ADMM) {
-                    io.s1_in = a.s1_in + row * M;   io.s1_in_nyq = a.s1_in_nyq + row;
-                    io.s1_out = a.s1_out + row * M; io.s1_out_nyq = a.s1_out_nyq + row;
+                    io.s1_in = a.s1_in + row * MC;   io.s1_in_nyq = a.s1_in_nyq + row;
+                    io.s1_out = a.s1_out + row * MC; io.s1_out_nyq = a.s1_out_nyq + row;
                 }
-                io.mag = a.mag + row * M; io.mag_nyq = a.mag_nyq + row;
+                io.mag = a.mag + row * MC; io.mag_nyq = a.mag_nyq + row;
                 io.s0_nyq_val = s0n; io.mag_nyq_val = mgn;
                 io.coef = a.coef; io.coef2 = a.coef2;
                 io.owned = t >= t0;
-                load_mags(l, mstage, mP, mQ);
+                const float* mrow = STAGE_MAG ? mstage : a.mag + row * MC;
                 float dsum = 0.f, esum = 0.f;          // per-frame partial sums, folded into doubles below
-                phase2_pointwise<OP, SUMS>(l, A, Bv, tb, io, mP, mQ, dsum, esum);
+                if constexpr (LANES == 16) {
+                    fast::load_mags(l, mrow, mg, mg + 16);
+                    fast::phase2_pointwise<OP, SUMS>(l, A, Bv, tb, io, mg, mg + 16, dsum, esum);
+                } else {
+                    float h_nyq = 0.f;
+                    fast32::pointwise_own<OP, SUMS>(l, A, Zp, tb, io, mrow, h_nyq, dsum, esum);
+                    const int partner = (32 - l) & 31;
+                    static_for<32>([&](auto jc) {      // second exchange: the partner's projected bins
+                        constexpr int j = decltype(jc)::value;
+                        Zp[j] = f2(__shfl_sync(0xffffffffu, A[j].x, partner), __shfl_sync(0xffffffffu, A[j].y, partner));
+                    });
+                    fast32::pre_own(l, A, Zp, tb, h_nyq);
+                    fft32<true>(A);                    // A[n2] = Y_l[n2]
+                }
                 if constexpr (SUMS) { dacc += (double)dsum; eacc += (double)esum; }
             }
-            exch_sync<LOCKSTEP, GROUP_THREADS>(bar_id, hmask, active);      // staged row consumed: exch may be overwritten
-            if (active) phase2_write(l, exch, A, Bv);
-            exch_sync<LOCKSTEP, GROUP_THREADS>(bar_id, hmask, active);
-            const bool emit = active && t >= t0 && block_valid(a, t);
+            exch_sync<LOCKSTEP>(bar_id, group_threads, hmask, active);      // staged row consumed: exch may be overwritten
+            if (active) {
+                if constexpr (LANES == 16) fast::phase2_write(l, exch, A, Bv);
+                else static_for<32>([&](auto nc) { constexpr int n2 = decltype(nc)::value; exch[n2 * ROW + l] = A[n2]; });
+            }
+            exch_sync<LOCKSTEP>(bar_id, group_threads, hmask, active);
+            const bool emit = active && t >= t0 && block_valid<LANES>(a, t);
             float2 ie[8];
-            if (emit) load_inv_env(a, t, l, ie);
-            if (active) phase3(l, v, tb, exch);
+            if (emit) load_inv_env<LANES>(a, t, l, ie);
+            if (active) { if constexpr (LANES == 16) fast::phase3(l, v, tb, exch); else fast32::phase3(l, v, tb, exch); }
             float2 carry[CARRY];
             tmem_wait_st();
             tmem_load_carry(taddr, carry);             // warp-collective: outside the `active` branch
@@ -323,7 +381,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) fast_iter_kernel(const FastArgs
                     if constexpr (n1 < 8) { blk[n1] = o0; blk[n1 + 1] = o1; }
                     else { carry[n1 - 8] = o0; carry[n1 - 7] = o1; }
                 });
-                if (emit) store_block(a, xo, t, l, blk, ie);
+                if (emit) store_block<LANES>(a, xo, t, l, blk, ie);
             }
             tmem_store_carry(taddr, carry);
         }
@@ -334,10 +392,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) fast_iter_kernel(const FastArgs
             if (valid && t1 == a.T) {     // tail of the signal: blocks T, T+1, T+2 are complete now
 #pragma unroll
                 for (int k = 0; k < 3; ++k)
-                    if (block_valid(a, a.T + k)) {
+                    if (block_valid<LANES>(a, a.T + k)) {
                         float2 ie[8];
-                        load_inv_env(a, a.T + k, l, ie);
-                        store_block(a, xo, a.T + k, l, carry + 8 * k, ie);
+                        load_inv_env<LANES>(a, a.T + k, l, ie);
+                        store_block<LANES>(a, xo, a.T + k, l, carry + 8 * k, ie);
                     }
             }
         }
@@ -358,7 +416,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) fast_iter_kernel(const FastArgs
 
 static int g_sms = 0;
 
-template <int OP, int WARPS>
+template <int OP, int WARPS, int LANES>
 static int launch(const FastArgs& a0, cudaStream_t st) {
     FastArgs a = a0;
     if (g_sms == 0) {
@@ -367,51 +425,49 @@ static int launch(const FastArgs& a0, cudaStream_t st) {
         if (cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return SPECINV_ERR_NO_DEVICE;
     }
     const int grid = g_sms;
-    const int slots = grid * 2 * WARPS;
+    const int slots = grid * WARPS * (32 / LANES);     // streams resident at once: size chunks for one even wave
     int cps = slots / a.B;
     if (cps < 1) cps = 1;
-    const int min_len = 24;                       // keep the 3-frame halo below ~12 %
+    const int min_len = 24;                            // keep the 3-frame halo below ~12 %
     if (cps > (a.T + min_len - 1) / min_len) cps = (a.T + min_len - 1) / min_len;
     if (cps < 1) cps = 1;
     a.chunk_len = (a.T + cps - 1) / cps;
     a.chunks_per_signal = (a.T + a.chunk_len - 1) / a.chunk_len;
     a.n_chunks = a.B * a.chunks_per_signal;
-    const size_t smem = (size_t)(3 * TBL + 512 + 2 * WARPS * HW_F2) * sizeof(float2);
+    // streams that would stay idle make the generic tile kernel the better choice (tiny problems)
+    if (a.n_chunks * 4 < slots) return SPECINV_ERR_UNSUPPORTED;
+    const size_t smem = (size_t)(3 * LANES * ROW + 32 * LANES + WARPS * (32 / LANES) * stream_f2(LANES, WARPS <= 10)) * sizeof(float2);
     cudaError_t e;
     if (a.sums) {
-        e = cudaFuncSetAttribute(fast_iter_kernel<OP, true, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute(fast_iter_kernel<OP, true, WARPS, LANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
-        fast_iter_kernel<OP, true, WARPS><<<grid, WARPS * 32, smem, st>>>(a);
+        fast_iter_kernel<OP, true, WARPS, LANES><<<grid, WARPS * 32, smem, st>>>(a);
     } else {
-        e = cudaFuncSetAttribute(fast_iter_kernel<OP, false, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute(fast_iter_kernel<OP, false, WARPS, LANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
-        fast_iter_kernel<OP, false, WARPS><<<grid, WARPS * 32, smem, st>>>(a);
+        fast_iter_kernel<OP, false, WARPS, LANES><<<grid, WARPS * 32, smem, st>>>(a);
     }
     return (int)cudaGetLastError();
 }
 
-// warps per CTA: 8 (255 registers / thread, no spills) or 12 (168 registers); SPECINV_FAST_WARPS overrides
+// 8 warps per CTA = 2 per SM sub-partition: 255 registers / thread, no spills.  (12 warps = 168 registers
+// spill ~800 bytes per thread and run 1.6x slower; the register file, not shared memory, sets the occupancy.)
 template <int OP>
-static int launch_cfg(const FastArgs& a, cudaStream_t st) {
-    static int warps = 0;
-    if (warps == 0) {
-        const char* e = getenv("SPECINV_FAST_WARPS");
-        warps = (e && atoi(e) == 12) ? 12 : 8;
-    }
-    return warps == 12 ? launch<OP, 12>(a, st) : launch<OP, 8>(a, st);
+static int launch_cfg(const FastArgs& a, int n_fft, cudaStream_t st) {
+    return n_fft == 1024 ? launch<OP, 8, 16>(a, st) : launch<OP, 8, 32>(a, st);
 }
 
 }  // namespace fast
 
 // Returns SPECINV_ERR_UNSUPPORTED when the shape is not the one this kernel is specialised for.
 static bool fast_applicable(const specinv_desc* d) {
-    return d->dtype == SPECINV_F32 && d->n_fft == 1024 && d->hop == 256 && d->onesided;
+    return d->dtype == SPECINV_F32 && d->onesided && d->hop * 4 == d->n_fft && (d->n_fft == 1024 || d->n_fft == 2048);
 }
 
 static void fill_common(fast::FastArgs& a, const Dims& dm, const specinv_desc* d, const void* plan) {
     const PlanLayout pl = plan_layout(dm, d->dtype);
     const char* p = (const char*)plan;
-    a.tw512 = (const float2*)(p + pl.tw); a.twr1024 = (const float2*)(p + pl.twr);
+    a.tw = (const float2*)(p + pl.tw); a.twr = (const float2*)(p + pl.twr);
     a.wa = (const float*)(p + pl.wa); a.ws = (const float*)(p + pl.ws); a.inv_env = (const float*)(p + pl.inv_env);
     a.B = dm.B; a.T = dm.T; a.P = dm.P; a.pad_mode = dm.pad_mode; a.L = dm.L;
 }
@@ -428,7 +484,7 @@ int fast_gl_iter(const specinv_desc* d, const void* plan, const void* x_in, void
     a.s0_out = (float2*)q_out_main; a.s0_out_nyq = (float2*)q_out_nyq;
     a.mag = (const float*)mag_main; a.mag_nyq = (const float*)mag_nyq;
     a.coef = (float)lr; a.sums = sums;
-    return fast::launch_cfg<fast::OP_GL>(a, (cudaStream_t)stream);
+    return fast::launch_cfg<fast::OP_GL>(a, d->n_fft, (cudaStream_t)stream);
 }
 
 int fast_admm_iter(const specinv_desc* d, const void* plan, const void* x_in, void* x_out,
@@ -446,7 +502,7 @@ int fast_admm_iter(const specinv_desc* d, const void* plan, const void* x_in, vo
     a.s1_out = (float2*)U_out_main; a.s1_out_nyq = (float2*)U_out_nyq;
     a.mag = (const float*)mag_main; a.mag_nyq = (const float*)mag_nyq;
     a.coef = (float)rho; a.coef2 = (float)(1.0 / (1.0 + rho)); a.sums = sums;
-    return fast::launch_cfg<fast::OP_ADMM>(a, (cudaStream_t)stream);
+    return fast::launch_cfg<fast::OP_ADMM>(a, d->n_fft, (cudaStream_t)stream);
 }
 
 }  // namespace specinv

@@ -14,6 +14,8 @@
 //
 // Replaces, per iteration, torch.stft + ~8 point-wise kernels + fft.irfft + conv_transpose1d with
 // a dense diag(window) weight of the reference (methods.py:241-248, :464-477, :127-132).
+#include <cstdlib>
+
 #include "specinv_common.cuh"
 #include "generic_fft.cuh"
 
@@ -105,7 +107,7 @@ __device__ __forceinline__ cx_t<T> bin_update(const TileArgs& a, const BinIO<T>&
 }
 
 template <typename T, int OP>
-__global__ void __launch_bounds__(256) tile_kernel(const TileArgs a) {
+__global__ void __launch_bounds__(1024) tile_kernel(const TileArgs a) {
     using C = cx_t<T>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     C* wb = reinterpret_cast<C*>(smem_raw);
@@ -196,7 +198,7 @@ __global__ void __launch_bounds__(256) tile_kernel(const TileArgs a) {
 
     if constexpr (OP == OP_GL || OP == OP_ADMM) {
         if (want_sums) {   // fused metric epilogue: block reduce, one double atomic pair per CTA
-            __shared__ double red[2][8];
+            __shared__ double red[2][32];
             double d = (double)dsum, e = (double)esum;
             for (int o = 16; o > 0; o >>= 1) {
                 d += __shfl_xor_sync(0xffffffffu, d, o);
@@ -281,7 +283,12 @@ static int launch_tile(TileArgs& a, cudaStream_t st) {
     if (e != cudaSuccess) return (int)e;
     dim3 grid((dm.T + owned - 1) / owned, dm.B);
     if (grid.y > 65535) return SPECINV_ERR_UNSUPPORTED;
-    tile_kernel<T, OP><<<grid, 256, smem, st>>>(a);
+    // threads per CTA: enough to give every thread a few butterflies per pass; SPECINV_TILE_THREADS overrides
+    static int forced = -1;
+    if (forced < 0) { const char* e = getenv("SPECINV_TILE_THREADS"); forced = e ? atoi(e) : 0; }
+    const long long bf = (long long)(owned + halo) * (dm.M >> 2);     // radix-4 butterflies per pass
+    int threads = forced > 0 ? forced : (bf >= 4096 ? 1024 : bf >= 1024 ? 512 : 256);
+    tile_kernel<T, OP><<<grid, threads, smem, st>>>(a);
     return (int)cudaGetLastError();
 }
 

@@ -363,3 +363,49 @@ def test_rtisi_la_shapes_and_quality():
     sco = O.sc(np.abs(O.stft(yo, a)), mag)
     scg = O.sc(np.abs(O.stft(yg.cpu().numpy(), a)), mag)
     assert abs(scg - sco) <= 0.02 * abs(sco) + 0.2, (scg, sco)
+
+
+# ---------------------------------------------------------------------------------------------
+# fast path for n_fft = 2048, hop = 512 (one warp per frame)
+# ---------------------------------------------------------------------------------------------
+FAST2048_CASES = [
+    dict(B=40, T=130, center=True, pad_mode="reflect", normalized=False),
+    dict(B=37, T=77, center=True, pad_mode="constant", normalized=True),
+    dict(B=64, T=64, center=False, pad_mode="reflect", normalized=False),
+]
+
+
+@pytest.mark.parametrize("fc", FAST2048_CASES, ids=lambda c: f"B{c['B']}_T{c['T']}_{c['pad_mode']}_c{int(c['center'])}")
+def test_fast_path_2048_against_oracle(fc):
+    from spectrogram_inversion_b200.engine import ADMMSolver, GriffinLimSolver, StftPlan
+    from spectrogram_inversion_b200.stft_args import args_helper
+    rs = np.random.RandomState(fc["T"])
+    n_fft, hop, F = 2048, 512, 1025
+    B, T = fc["B"], fc["T"]
+    w = cases.window_of("hann" if fc["center"] else "hamming", n_fft, np.float32)
+    kw = dict(hop_length=hop, center=fc["center"], pad_mode=fc["pad_mode"], normalized=fc["normalized"], window=w)
+    oa = O.args_helper(F, np.float32, **kw)
+    mag = (np.abs(rs.randn(B, F, T) + 1j * rs.randn(B, F, T)) * 8).astype(np.float32)
+    C = (mag * np.exp(2j * np.pi * rs.rand(B, F, T))).astype(np.complex64)
+    tkw = {k: (torch.from_numpy(v).cuda() if isinstance(v, np.ndarray) else v) for k, v in kw.items()}
+    magt = torch.from_numpy(mag).cuda()
+    plan = StftPlan(args_helper(magt, **tkw), T, B, torch.float32, torch.device("cuda"))
+    solver = GriffinLimSolver(plan, plan.pack(torch.from_numpy(C)), plan.pack(magt), 0.99)
+    st = O.gl_init(C, oa)
+    for k in range(2):
+        solver.x[solver.cur].copy_(torch.from_numpy(st.x))
+        solver.q[solver.cur] = plan.pack(torch.from_numpy(st.q))
+        solver.q[solver.cur ^ 1] = solver.q[solver.cur].like()
+        out = solver.step(evaluate=(k == 1))
+        st = O.gl_step(st, mag, 0.99 / 1.99, oa)
+        close(solver.signal, st.x, 1e-5, f"fast2048 GL x step {k}")
+        close(plan.unpack(solver.q_state), st.q, 1e-4, f"fast2048 GL q step {k}")
+        if out is not None:
+            do, eo, _ = O.metric_sums(st.out_mag, mag)
+            assert abs(out[0] - do) <= 1e-4 * do and abs(out[1] - eo) <= 1e-4 * eo
+    solver = ADMMSolver(plan, plan.pack(torch.from_numpy(C)), plan.pack(magt), 0.1)
+    st = O.admm_init(C, oa)
+    solver.step(evaluate=True)
+    st = O.admm_step(st, mag, 0.1, oa)
+    close(solver.signal, st.x, 2e-5, "fast2048 ADMM x")
+    close(plan.unpack(solver.U[solver.cur]), st.U, 1e-3, "fast2048 ADMM U")
