@@ -1,0 +1,259 @@
+// Per-lane building blocks of the "warp per frame" fused iteration kernel (n_fft = 1024, hop = 256).
+//
+// A frame's real FFT of N = 1024 is a complex FFT of M = 512 = 8 x 8 x 8 points done by the 32 lanes of ONE
+// warp holding 16 complex values each, in three radix-8 passes with two exchanges through shared memory
+// per direction.  With n = 64 a + 8 b + c and k = ka + 8 kb + 64 kc:
+//   pass 1 : lane l owns z[32 i + l], i = 0..15 (i = 2 a + s; c = l & 7, b = (l >> 3) + 4 s): two FFT8 over a,
+//            times W_512^((8 b + c) ka)                                        -- exchange E1 (ka, b, c) --
+//   pass 2 : lane l owns (ka = (l >> 3) + 4 r, c = l & 7), r = 0, 1: two FFT8 over b, times W_64^(c kb)
+//                                                                              -- exchange E2 (k1, c) --
+//   pass 3 : lane l owns the residue classes k1 = ka + 8 kb in {l, 64 - l} ({0, 32} for l = 0): two FFT8
+//            over c -> Zh[k1 + 64 kc].
+// Class 64 - l is the mirror (k -> M - k) of class l, so every (Z[k], Z[M-k]) pair of the real-FFT
+// post/pre-processing lives in ONE thread (as in gl_fast_core.cuh): projection and momentum / ADMM update
+// run in registers on the FFT outputs; for a fixed kc the 32 lanes touch 32 consecutive bins (256-byte
+// coalesced rows of q / mag).  The inverse runs the passes backwards.
+// A hop of 256 samples is 4 of a lane's 16 sample pairs (i -> i + 4): overlap-add is a per-thread
+// shift-accumulate and the input ring is thread-private, as in the half-warp kernel.
+//
+// 16 complex values per lane (instead of 32) keep the kernel under 128 registers, so 16 warps per SM run
+// free (no lockstep), and the fully unrolled frame body (~26 KB) fits the 32 KB instruction cache.
+//
+// Everything is __host__ __device__: tests/host_emu runs the exact index logic on the CPU.
+#pragma once
+
+#include "gl_fast_core.cuh"
+
+namespace specinv {
+namespace wfast {
+
+using fast::cmulf;
+using fast::cmulcf;
+using fast::post_pair;
+using fast::pre_pair;
+using fast::project_fast;
+using fast::approx_sqrt;
+using fast::OP_GL;
+using fast::OP_ADMM;
+
+constexpr int N = 1024;
+constexpr int M = 512;
+constexpr int HOP = 256;
+constexpr int V = 16;            // complex values per lane
+constexpr int EXF2 = 512;        // float2 elements of one exchange buffer (4 KB, XOR-swizzled, no padding)
+
+// ---- exchange addressing (float2 units) ----------------------------------------------------------------
+// Rows of 8 float2 = four 16-byte columns; column index XOR ((row >> 1) & 3) makes both the 128-bit
+// row accesses (8 consecutive rows per quarter-warp) and the 64-bit scattered accesses conflict free.
+SPX_HD int ex_addr(int row, int col) { return 8 * row + 2 * (((col >> 1) ^ (row >> 1)) & 3) + (col & 1); }
+// 128-bit access: elements (row, 2 p) and (row, 2 p + 1)
+SPX_HD int ex_addr4(int row, int p) { return 8 * row + 2 * ((p ^ (row >> 1)) & 3); }
+
+SPX_HD int class_b(int l) { return l == 0 ? 32 : 64 - l; }
+// bin of the P element of pair slot j (the Q element is bin 512 - kP); lane 0 slot 0 is the special
+// DC / Nyquist / bin-256 slot
+template <int J>
+SPX_HD int slot_bin(int l) {
+    if (l != 0) return l + 64 * J;
+    if constexpr (J < 4) return 64 * J;
+    else return 32 + 64 * (J - 4);
+}
+SPX_HD int slot_bin_rt(int l, int j) { return l != 0 ? l + 64 * j : (j < 4 ? 64 * j : 32 + 64 * (j - 4)); }
+
+// Per-lane constant tables (the kernel keeps them in tensor memory, the host emulation in arrays)
+struct LaneTables {
+    float2 wa[V];     // 0.5 * analysis window pairs (w[64 i + 2 l], w[64 i + 2 l + 1])
+    float2 ws[V];     // synthesis window pairs (already scaled by 1/N or N^-1/2)
+    float2 tw1[V];    // [8 s + ka]  W_512^((l + 32 s) ka)
+    float2 tw2[8];    // [kb]        W_64^((l & 7) kb)
+    float2 twr[8];    // [j]         W_1024^(slot_bin<j>(l))
+};
+
+// ---- forward ---------------------------------------------------------------------------------------------
+// v[i] = windowed z[32 i + l] on entry
+SPX_HD void fwd_pass1(int l, float2* v, const float2* tw1, float2* e1) {
+    const int c = l & 7;
+    static_for<2>([&](auto sc) {
+        constexpr int s = decltype(sc)::value;
+        float2 t[8];
+        static_for<8>([&](auto ac) { constexpr int a = decltype(ac)::value; t[a] = v[2 * a + s]; });
+        fft8<false>(t);
+        const int b = (l >> 3) + 4 * s;
+        static_for<8>([&](auto kc) {
+            constexpr int ka = decltype(kc)::value;
+            const float2 y = ka == 0 ? t[0] : cmulf(t[ka], tw1[8 * s + ka]);
+            e1[ex_addr(8 * ka + c, b)] = y;
+        });
+    });
+}
+
+// u[8 r + kb] = Y2[ka_r, kb, c] (already twiddled), written to E2
+SPX_HD void fwd_pass2(int l, const float2* e1, const float2* tw2, float2* e2) {
+    const int c = l & 7;
+    static_for<2>([&](auto rc) {
+        constexpr int r = decltype(rc)::value;
+        const int ka = (l >> 3) + 4 * r;
+        float2 t[8];
+        static_for<4>([&](auto pc) {
+            constexpr int p = decltype(pc)::value;
+            const float4 q = *reinterpret_cast<const float4*>(e1 + ex_addr4(8 * ka + c, p));
+            t[2 * p] = f2(q.x, q.y); t[2 * p + 1] = f2(q.z, q.w);
+        });
+        fft8<false>(t);
+        static_for<8>([&](auto kc) {
+            constexpr int kb = decltype(kc)::value;
+            const float2 y = kb == 0 ? t[0] : cmulf(t[kb], tw2[kb]);
+            e2[ex_addr(ka + 8 * kb, c)] = y;
+        });
+    });
+}
+
+// A[kc] = Zh[l + 64 kc], B[kc] = Zh[class_b(l) + 64 kc]
+SPX_HD void fwd_pass3(int l, const float2* e2, float2* A, float2* B) {
+    const int ra = l, rb = class_b(l);
+    static_for<4>([&](auto pc) {
+        constexpr int p = decltype(pc)::value;
+        const float4 qa = *reinterpret_cast<const float4*>(e2 + ex_addr4(ra, p));
+        const float4 qb = *reinterpret_cast<const float4*>(e2 + ex_addr4(rb, p));
+        A[2 * p] = f2(qa.x, qa.y); A[2 * p + 1] = f2(qa.z, qa.w);
+        B[2 * p] = f2(qb.x, qb.y); B[2 * p + 1] = f2(qb.z, qb.w);
+    });
+    fft8<false>(A);
+    fft8<false>(B);
+}
+
+// ---- point-wise stage ------------------------------------------------------------------------------------
+// Values of the state / magnitude arrays at the lane's 16 bins (+ the Nyquist bin for lane 0), loaded by
+// the caller: index 2 j = the P bin of slot j, 2 j + 1 = the Q bin (lane 0 slot 0: bins 0 and 256).
+struct LaneState {
+    float2 s0[V];     // GL: q_in / ADMM: X_in
+    float2 s1[V];     // ADMM: U_in
+    float mag[V];
+    float2 s0_nyq, s1_nyq;
+    float mag_nyq;
+};
+struct LaneOut {
+    float2 s0[V];     // GL: q_out / ADMM: X_out
+    float2 s1[V];     // ADMM: U_out
+    float2 s0_nyq, s1_nyq;
+};
+
+// One bin: s = STFT bin of the current estimate.  Returns the value fed to the inverse transform.
+template <int OP, bool SUMS>
+SPX_HD float2 bin_update(float2 s, float2 a0, float2 a1, float m, float coef, float coef2, float2& o0, float2& o1,
+                         float& dsum, float& esum) {
+    if constexpr (SUMS) {
+        const float r = approx_sqrt(s.x * s.x + s.y * s.y);
+        dsum += (r - m) * (r - m);
+        esum += r * r;
+    }
+    if constexpr (OP == OP_GL) {
+        const float2 q = f2(s.x - a0.x * coef, s.y - a0.y * coef);
+        o0 = q;
+        return project_fast(q, m);
+    } else {
+        const float rho = coef, inv = coef2;
+        const float2 Z = f2((rho * (a0.x + a1.x) + s.x) * inv, (rho * (a0.y + a1.y) + s.y) * inv);
+        const float2 Un = f2(a1.x + a0.x - Z.x, a1.y + a0.y - Z.y);
+        const float2 Xn = project_fast(f2(Z.x - Un.x, Z.y - Un.y), m);
+        o0 = Xn; o1 = Un;
+        return f2(Xn.x + Un.x, Xn.y + Un.y);
+    }
+}
+
+// Pair processing with the point-wise update, in place: on return A / B hold the inputs of the inverse
+// pass 3.  (dsum, esum) += this lane's share of sum (|s|-mag)^2, sum |s|^2.
+template <int OP, bool SUMS>
+SPX_HD void pointwise(int l, float2* A, float2* B, const float2* twr, const LaneState& in, LaneOut& out, float coef,
+                      float coef2, float& dsum, float& esum) {
+    const bool l0 = l == 0;
+    // slot 0
+    if (l0) {
+        // lane 0: A[0] = Zh[0] -> DC and Nyquist (both real), A[4] = Zh[256] -> bin 256 = conj(Z[256])
+        const float2 z0 = A[0], z4 = A[4];
+        const float2 h0 = bin_update<OP, SUMS>(f2(2.f * (z0.x + z0.y), 0.f), in.s0[0], in.s1[0], in.mag[0], coef, coef2,
+                                               out.s0[0], out.s1[0], dsum, esum);
+        const float2 hM = bin_update<OP, SUMS>(f2(2.f * (z0.x - z0.y), 0.f), in.s0_nyq, in.s1_nyq, in.mag_nyq, coef, coef2,
+                                               out.s0_nyq, out.s1_nyq, dsum, esum);
+        const float2 h4 = bin_update<OP, SUMS>(f2(2.f * z4.x, -2.f * z4.y), in.s0[1], in.s1[1], in.mag[1], coef, coef2,
+                                               out.s0[1], out.s1[1], dsum, esum);
+        A[0] = f2(h0.x + hM.x, h0.x - hM.x);        // C2R ignores Im(DC), Im(Nyquist)
+        A[4] = f2(2.f * h4.x, -2.f * h4.y);
+    } else {
+        float2 sP, sQ, P, Q;
+        const float2 w = twr[0];
+        post_pair(A[0], B[7], w, sP, sQ);
+        const float2 hP = bin_update<OP, SUMS>(sP, in.s0[0], in.s1[0], in.mag[0], coef, coef2, out.s0[0], out.s1[0], dsum, esum);
+        const float2 hQ = bin_update<OP, SUMS>(sQ, in.s0[1], in.s1[1], in.mag[1], coef, coef2, out.s0[1], out.s1[1], dsum, esum);
+        pre_pair(hP, hQ, w, P, Q);
+        A[0] = P; B[7] = Q;
+    }
+    // slots 1..7.  general lanes: (A[j], B[7-j]); lane 0, j < 4: (A[j], A[8-j]); lane 0, j >= 4: (B[j-4], B[11-j])
+    static_for<7>([&](auto jc) {
+        constexpr int j = decltype(jc)::value + 1;
+        float2 P, Q;
+        if constexpr (j < 4) { P = A[j]; Q = l0 ? A[8 - j] : B[7 - j]; }
+        else { P = l0 ? B[j - 4] : A[j]; Q = l0 ? B[11 - j] : B[7 - j]; }
+        const float2 w = twr[j];
+        float2 sP, sQ;
+        post_pair(P, Q, w, sP, sQ);
+        const float2 hP = bin_update<OP, SUMS>(sP, in.s0[2 * j], in.s1[2 * j], in.mag[2 * j], coef, coef2, out.s0[2 * j],
+                                               out.s1[2 * j], dsum, esum);
+        const float2 hQ = bin_update<OP, SUMS>(sQ, in.s0[2 * j + 1], in.s1[2 * j + 1], in.mag[2 * j + 1], coef, coef2,
+                                               out.s0[2 * j + 1], out.s1[2 * j + 1], dsum, esum);
+        pre_pair(hP, hQ, w, P, Q);
+        if constexpr (j < 4) { A[j] = P; if (l0) A[8 - j] = Q; else B[7 - j] = Q; }
+        else { if (l0) { B[j - 4] = P; B[11 - j] = Q; } else { A[j] = P; B[7 - j] = Q; } }
+    });
+}
+
+// ---- inverse ---------------------------------------------------------------------------------------------
+SPX_HD void inv_pass3(int l, float2* A, float2* B, float2* e2) {
+    fft8<true>(A);       // A[c] = Y2'[class a, c]
+    fft8<true>(B);
+    const int ra = l, rb = class_b(l);
+    static_for<4>([&](auto pc) {
+        constexpr int p = decltype(pc)::value;
+        *reinterpret_cast<float4*>(e2 + ex_addr4(ra, p)) = make_float4(A[2 * p].x, A[2 * p].y, A[2 * p + 1].x, A[2 * p + 1].y);
+        *reinterpret_cast<float4*>(e2 + ex_addr4(rb, p)) = make_float4(B[2 * p].x, B[2 * p].y, B[2 * p + 1].x, B[2 * p + 1].y);
+    });
+}
+
+SPX_HD void inv_pass2(int l, const float2* e2, const float2* tw2, float2* e1) {
+    const int c = l & 7;
+    static_for<2>([&](auto rc) {
+        constexpr int r = decltype(rc)::value;
+        const int ka = (l >> 3) + 4 * r;
+        float2 t[8];
+        static_for<8>([&](auto kc) {
+            constexpr int kb = decltype(kc)::value;
+            const float2 y = e2[ex_addr(ka + 8 * kb, c)];
+            t[kb] = kb == 0 ? y : cmulcf(y, tw2[kb]);
+        });
+        fft8<true>(t);   // t[b] = Y1'[ka, b, c] (before the pass-1 twiddle)
+        static_for<4>([&](auto pc) {
+            constexpr int p = decltype(pc)::value;
+            *reinterpret_cast<float4*>(e1 + ex_addr4(8 * ka + c, p)) = make_float4(t[2 * p].x, t[2 * p].y, t[2 * p + 1].x, t[2 * p + 1].y);
+        });
+    });
+}
+
+// v[i] = z'[32 i + l] (unscaled)
+SPX_HD void inv_pass1(int l, const float2* e1, const float2* tw1, float2* v) {
+    const int c = l & 7;
+    static_for<2>([&](auto sc) {
+        constexpr int s = decltype(sc)::value;
+        const int b = (l >> 3) + 4 * s;
+        float2 t[8];
+        static_for<8>([&](auto kc) {
+            constexpr int ka = decltype(kc)::value;
+            const float2 y = e1[ex_addr(8 * ka + c, b)];
+            t[ka] = ka == 0 ? y : cmulcf(y, tw1[8 * s + ka]);
+        });
+        fft8<true>(t);
+        static_for<8>([&](auto ac) { constexpr int a = decltype(ac)::value; v[2 * a + s] = t[a]; });
+    });
+}
+
+}  // namespace wfast
+}  // namespace specinv

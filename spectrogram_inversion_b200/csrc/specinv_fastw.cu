@@ -1,0 +1,489 @@
+// "Warp per frame" fused iteration kernel for n_fft = 1024, hop = 256 (onesided, fp32): the headline shape.
+//
+// One launch = one whole Griffin-Lim (or ADMM) iteration.  Every warp walks through a contiguous range of
+// the B*T frames (crossing signal boundaries if need be) and for each frame does, entirely on chip:
+//   window -> real FFT (512-point complex FFT as 8 x 8 x 8, gl_warp_core.cuh) -> momentum / ADMM update and
+//   magnitude projection on the FFT outputs in registers -> inverse FFT -> windowed overlap-add.
+//   * 16 complex values per lane: < 128 registers, 16 free-running warps per SM (no lockstep barriers), and
+//     the unrolled frame body fits the instruction cache;
+//   * the lane-constant tables (windows, twiddles), the lane-private input ring and the overlap-add carry
+//     live in TENSOR MEMORY and move with tcgen05.ld / tcgen05.st (one instruction per 8..32 registers, no
+//     shared-memory bandwidth); shared memory only carries the four FFT exchanges (swizzled, conflict free);
+//   * state rows (q / X, U, mag) are read and written straight from / to global memory, 256 contiguous bytes
+//     per warp instruction, after an L2 prefetch one frame ahead; new input samples arrive by cp.async.
+// A range re-computes the 3 frames before it as a halo (state not written, output not stored), so ranges are
+// independent: no atomics, deterministic.  State arrays are ping-ponged (q_in != q_out).
+#include <cstdlib>
+
+#include "specinv_common.cuh"
+#include "gl_warp_core.cuh"
+
+namespace specinv {
+namespace wfast {
+
+struct WArgs {
+    const float* x_in; float* x_out;
+    const float2* s0_in;  const float2* s0_in_nyq;  float2* s0_out; float2* s0_out_nyq;
+    const float2* s1_in;  const float2* s1_in_nyq;  float2* s1_out; float2* s1_out_nyq;
+    const float* mag;     const float* mag_nyq;
+    const float2* tw;     const float2* twr;        // plan tables: W_M^j (M entries), W_N^k (k <= M/2)
+    const float* wa; const float* ws; const float* inv_env;
+    double* sums;
+    float coef, coef2;
+    int B, T, P, pad_mode;
+    long long L;
+    long long frames_total;     // B * T
+    int ranges;                 // number of warps that get a frame range
+};
+
+// ---- small PTX wrappers ---------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ float2 ldg_nc_f2(const float2* p) {
+    float2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float ldg_nc_f(const float* p) {
+    float r;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+    return r;
+}
+
+// ---- tensor memory as a software-managed register extension --------------------------------------------
+__device__ __forceinline__ void tmem_alloc(unsigned* smem_dst, int ncols) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(d), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(unsigned taddr, int ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// Loads complete inside the same asm statement (tcgen05.wait::ld), so the results can be used right away.
+__device__ __forceinline__ void tmem_ld8(unsigned taddr, float* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n\t"
+                 "tcgen05.wait::ld.sync.aligned;"
+                 : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(unsigned taddr, float* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n\t"
+                 "tcgen05.wait::ld.sync.aligned;"
+                 : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7]),
+                   "=f"(r[8]), "=f"(r[9]), "=f"(r[10]), "=f"(r[11]), "=f"(r[12]), "=f"(r[13]), "=f"(r[14]), "=f"(r[15])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(unsigned taddr, float* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n\t"
+                 "tcgen05.wait::ld.sync.aligned;"
+                 : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7]),
+                   "=f"(r[8]), "=f"(r[9]), "=f"(r[10]), "=f"(r[11]), "=f"(r[12]), "=f"(r[13]), "=f"(r[14]), "=f"(r[15]),
+                   "=f"(r[16]), "=f"(r[17]), "=f"(r[18]), "=f"(r[19]), "=f"(r[20]), "=f"(r[21]), "=f"(r[22]), "=f"(r[23]),
+                   "=f"(r[24]), "=f"(r[25]), "=f"(r[26]), "=f"(r[27]), "=f"(r[28]), "=f"(r[29]), "=f"(r[30]), "=f"(r[31])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_st8(unsigned taddr, const float* r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "f"(r[0]), "f"(r[1]), "f"(r[2]), "f"(r[3]), "f"(r[4]), "f"(r[5]), "f"(r[6]), "f"(r[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_st16(unsigned taddr, const float* r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+                 ::"r"(taddr), "f"(r[0]), "f"(r[1]), "f"(r[2]), "f"(r[3]), "f"(r[4]), "f"(r[5]), "f"(r[6]), "f"(r[7]),
+                   "f"(r[8]), "f"(r[9]), "f"(r[10]), "f"(r[11]), "f"(r[12]), "f"(r[13]), "f"(r[14]), "f"(r[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_st32(unsigned taddr, const float* r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+                 "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+                 ::"r"(taddr), "f"(r[0]), "f"(r[1]), "f"(r[2]), "f"(r[3]), "f"(r[4]), "f"(r[5]), "f"(r[6]), "f"(r[7]),
+                   "f"(r[8]), "f"(r[9]), "f"(r[10]), "f"(r[11]), "f"(r[12]), "f"(r[13]), "f"(r[14]), "f"(r[15]),
+                   "f"(r[16]), "f"(r[17]), "f"(r[18]), "f"(r[19]), "f"(r[20]), "f"(r[21]), "f"(r[22]), "f"(r[23]),
+                   "f"(r[24]), "f"(r[25]), "f"(r[26]), "f"(r[27]), "f"(r[28]), "f"(r[29]), "f"(r[30]), "f"(r[31]) : "memory");
+}
+
+// TMEM columns (per lane): constant tables shared by the warps of one sub-partition, then per-warp state
+constexpr int TC_WA = 0, TC_WS = 32, TC_TW1 = 64, TC_TW2 = 96, TC_TWR = 112, TC_WARP = 128;
+constexpr int TC_PER_WARP = 48;     // ring: 3 blocks x 8 words, carry: 24 words
+constexpr int TMEM_COLS = 512;
+constexpr int WARP_F2 = 2 * EXF2 + 128;   // float2 of shared memory per warp: E1, E2, staged input block
+
+// Fetch block u (padded samples [256 u, 256 u + 256)) of signal x: lane l gets the pairs at 64 j + 2 l.
+__device__ __forceinline__ void fetch_block_regs(const WArgs& a, const float* __restrict__ x, int u, int l, float2* nb) {
+    const long long base = (long long)u * HOP - a.P;
+    if (base >= 0 && base + HOP <= a.L) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) nb[j] = __ldg(reinterpret_cast<const float2*>(x + base + 64 * j + 2 * l));
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const long long pp = (long long)u * HOP + 64 * j + 2 * l;
+            const long long i0 = pad_index(pp, a.P, a.L, a.pad_mode), i1 = pad_index(pp + 1, a.P, a.L, a.pad_mode);
+            nb[j] = f2(i0 >= 0 ? x[i0] : 0.f, i1 >= 0 ? x[i1] : 0.f);
+        }
+    }
+}
+// Same, asynchronously into the lane's slots of the staging buffer xs[32 j + l].
+__device__ __forceinline__ void fetch_block_async(const WArgs& a, const float* __restrict__ x, int u, int l, float2* xs) {
+    const long long base = (long long)u * HOP - a.P;
+    if (base >= 0 && base + HOP <= a.L) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) cp_async8(xs + 32 * j + l, x + base + 64 * j + 2 * l);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const long long pp = (long long)u * HOP + 64 * j + 2 * l;
+            const long long i0 = pad_index(pp, a.P, a.L, a.pad_mode), i1 = pad_index(pp + 1, a.P, a.L, a.pad_mode);
+            xs[32 * j + l] = f2(i0 >= 0 ? x[i0] : 0.f, i1 >= 0 ? x[i1] : 0.f);
+        }
+    }
+}
+__device__ __forceinline__ bool block_valid(const WArgs& a, int u) {
+    const long long base = (long long)u * HOP - a.P;
+    return base >= 0 && base + HOP <= a.L;
+}
+__device__ __forceinline__ void store_block(const WArgs& a, float* __restrict__ xo, int u, int l, const float2* blk) {
+    const long long base = (long long)u * HOP - a.P;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float2 ie = __ldg(reinterpret_cast<const float2*>(a.inv_env + base + 64 * j + 2 * l));
+        *reinterpret_cast<float2*>(xo + base + 64 * j + 2 * l) = f2(blk[j].x * ie.x, blk[j].y * ie.y);
+    }
+}
+// Pull the state / magnitude rows of frame `row` into L2 one frame ahead.
+template <int OP>
+__device__ __forceinline__ void prefetch_rows(const WArgs& a, long long row, int l) {
+    prefetch_l2(reinterpret_cast<const char*>(a.s0_in + row * M) + 128 * l);             // 4 KB = 32 lines
+    if (l < 16) prefetch_l2(reinterpret_cast<const char*>(a.mag + row * M) + 128 * l);  // 2 KB = 16 lines
+    if constexpr (OP == OP_ADMM) prefetch_l2(reinterpret_cast<const char*>(a.s1_in + row * M) + 128 * l);
+}
+
+template <int OP, bool SUMS, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1) warp_iter_kernel(const WArgs a) {
+    static_assert(TC_WARP + ((WARPS + 3) / 4) * TC_PER_WARP <= TMEM_COLS, "TMEM columns");
+    extern __shared__ __align__(16) float2 sm[];
+    __shared__ unsigned s_tmem_base;
+    const int tid = threadIdx.x, warp = tid >> 5, l = tid & 31;
+    if (warp == 0) tmem_alloc(&s_tmem_base, TMEM_COLS);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // this warp's TMEM window: lanes 32 * (warp % 4) .. +31
+    const unsigned tlane = s_tmem_base + ((unsigned)(32 * (warp & 3)) << 16);
+    if (warp < 4) {
+        // lane-constant tables of this sub-partition
+        float t[32];
+#pragma unroll
+        for (int i = 0; i < V; ++i) { t[2 * i] = 0.5f * a.wa[64 * i + 2 * l]; t[2 * i + 1] = 0.5f * a.wa[64 * i + 2 * l + 1]; }
+        tmem_st32(tlane + TC_WA, t);
+#pragma unroll
+        for (int i = 0; i < V; ++i) { t[2 * i] = a.ws[64 * i + 2 * l]; t[2 * i + 1] = a.ws[64 * i + 2 * l + 1]; }
+        tmem_st32(tlane + TC_WS, t);
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            const float2 w = a.tw[((l + 32 * (i >> 3)) * (i & 7)) & (M - 1)];
+            t[2 * i] = w.x; t[2 * i + 1] = w.y;
+        }
+        tmem_st32(tlane + TC_TW1, t);
+#pragma unroll
+        for (int kb = 0; kb < 8; ++kb) {
+            const float2 w = a.tw[(8 * (l & 7) * kb) & (M - 1)];
+            t[2 * kb] = w.x; t[2 * kb + 1] = w.y;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int k = slot_bin_rt(l, j);
+            float2 w;
+            if (k <= M / 2) w = a.twr[k];
+            else { w = a.twr[M - k]; w.x = -w.x; }                  // W_N^k = -conj(W_N^(M-k))
+            t[16 + 2 * j] = w.x; t[16 + 2 * j + 1] = w.y;
+        }
+        tmem_st32(tlane + TC_TW2, t);                               // TW2 and TWR are adjacent
+        tmem_wait_st();
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+    const unsigned twarp = tlane + TC_WARP + TC_PER_WARP * (warp >> 2);   // ring (24 columns) then carry (24)
+    float2* e1 = sm + warp * WARP_F2;
+    float2* e2 = e1 + EXF2;
+    float2* xs = e2 + EXF2;
+
+    // bin offsets of the lane's pair slots inside a main row
+    const int hi_adj = l == 0 ? -224 : 0;        // lane 0, slots 4..7: 32 + 64 (j - 4) = 64 j - 224
+    const int kq0 = l == 0 ? 256 : M - l;
+
+    double dacc = 0.0, eacc = 0.0;
+    const int gw = blockIdx.x + gridDim.x * warp;                   // global warp index
+    long long g = 0, g1 = 0;
+    if (gw < a.ranges) {
+        g = a.frames_total * gw / a.ranges;
+        g1 = a.frames_total * (gw + 1) / a.ranges;
+    }
+    while (g < g1) {
+        const int b = (int)(g / a.T);
+        const int t0 = (int)(g - (long long)b * a.T);
+        const int t1 = (int)min((long long)a.T, t0 + (g1 - g));
+        g += t1 - t0;
+        const int tf0 = max(0, t0 - 3);
+        const float* x = a.x_in + (long long)b * a.L;
+        float* xo = a.x_out + (long long)b * a.L;
+
+        // ---- prologue: empty carry, ring = blocks tf0 .. tf0 + 2, block tf0 + 3 on its way
+        tmem_wait_st();
+        {
+            float z[24];
+#pragma unroll
+            for (int i = 0; i < 24; ++i) z[i] = 0.f;
+            tmem_st16(twarp + 24, z); tmem_st8(twarp + 40, z + 16);
+        }
+        int m = tf0 % 3;                                            // ring slot of block t
+        {
+            int mm = m;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                float2 nb[4];
+                fetch_block_regs(a, x, tf0 + i, l, nb);
+                tmem_st8(twarp + 8 * mm, reinterpret_cast<const float*>(nb));
+                mm = mm == 2 ? 0 : mm + 1;
+            }
+        }
+        fetch_block_async(a, x, tf0 + 3, l, xs);
+        prefetch_rows<OP>(a, (long long)b * a.T + tf0, l);
+
+        for (int t = tf0; t < t1; ++t) {
+            const long long row = (long long)b * a.T + t;
+            const bool owned = t >= t0;
+            float2 v[V];
+            // ---- assemble the frame: blocks t .. t+2 from the ring, block t+3 from the staging buffer
+            {
+                const int m1 = m == 2 ? 0 : m + 1, m2 = m1 == 2 ? 0 : m1 + 1;
+                tmem_wait_st();
+                tmem_ld8(twarp + 8 * m, reinterpret_cast<float*>(v));
+                tmem_ld8(twarp + 8 * m1, reinterpret_cast<float*>(v + 4));
+                tmem_ld8(twarp + 8 * m2, reinterpret_cast<float*>(v + 8));
+                cp_async_wait_all();
+#pragma unroll
+                for (int j = 0; j < 4; ++j) v[12 + j] = xs[32 * j + l];
+                tmem_st8(twarp + 8 * m, reinterpret_cast<const float*>(v + 12));   // block t+3 replaces block t
+                m = m1;
+            }
+            if (t + 1 < t1) {
+                fetch_block_async(a, x, t + 4, l, xs);
+                prefetch_rows<OP>(a, row + 1, l);
+            }
+            {
+                float2 w[V];
+                tmem_ld32(tlane + TC_WA, reinterpret_cast<float*>(w));
+#pragma unroll
+                for (int i = 0; i < V; ++i) v[i] = f2(v[i].x * w[i].x, v[i].y * w[i].y);
+            }
+            __syncwarp();                          // the previous frame's reads of E1 are done
+            {
+                float2 tw1[V];
+                tmem_ld32(tlane + TC_TW1, reinterpret_cast<float*>(tw1));
+                fwd_pass1(l, v, tw1, e1);
+            }
+            __syncwarp();
+            float2 tw2[8];
+            tmem_ld16(tlane + TC_TW2, reinterpret_cast<float*>(tw2));
+            fwd_pass2(l, e1, tw2, e2);
+            __syncwarp();
+
+            // ---- state of the lane's 16 bins (+ Nyquist for lane 0)
+            LaneState in;
+            {
+                const float2* s0 = a.s0_in + row * M;
+                const float* mg = a.mag + row * M;
+                static_for<8>([&](auto jc) {
+                    constexpr int j = decltype(jc)::value;
+                    const int kP = l + 64 * j + (j >= 4 ? hi_adj : 0);
+                    const int kQ = j == 0 ? kq0 : M - kP;
+                    in.s0[2 * j] = ldg_nc_f2(s0 + kP); in.s0[2 * j + 1] = ldg_nc_f2(s0 + kQ);
+                    in.mag[2 * j] = ldg_nc_f(mg + kP); in.mag[2 * j + 1] = ldg_nc_f(mg + kQ);
+                    if constexpr (OP == OP_ADMM) {
+                        const float2* s1 = a.s1_in + row * M;
+                        in.s1[2 * j] = ldg_nc_f2(s1 + kP); in.s1[2 * j + 1] = ldg_nc_f2(s1 + kQ);
+                    }
+                });
+                in.s0_nyq = f2(0.f, 0.f); in.s1_nyq = f2(0.f, 0.f); in.mag_nyq = 0.f;
+                if (l == 0) {
+                    in.s0_nyq = __ldg(a.s0_in_nyq + row); in.mag_nyq = __ldg(a.mag_nyq + row);
+                    if constexpr (OP == OP_ADMM) in.s1_nyq = __ldg(a.s1_in_nyq + row);
+                }
+            }
+            float2 A[8], Bv[8];
+            fwd_pass3(l, e2, A, Bv);
+            {
+                float2 twr[8];
+                tmem_ld16(tlane + TC_TWR, reinterpret_cast<float*>(twr));
+                LaneOut out;
+                float dsum = 0.f, esum = 0.f;
+                pointwise<OP, SUMS>(l, A, Bv, twr, in, out, a.coef, a.coef2, dsum, esum);
+                if (owned) {
+                    float2* o0 = a.s0_out + row * M;
+                    static_for<8>([&](auto jc) {
+                        constexpr int j = decltype(jc)::value;
+                        const int kP = l + 64 * j + (j >= 4 ? hi_adj : 0);
+                        const int kQ = j == 0 ? kq0 : M - kP;
+                        o0[kP] = out.s0[2 * j]; o0[kQ] = out.s0[2 * j + 1];
+                        if constexpr (OP == OP_ADMM) {
+                            float2* o1 = a.s1_out + row * M;
+                            o1[kP] = out.s1[2 * j]; o1[kQ] = out.s1[2 * j + 1];
+                        }
+                    });
+                    if (l == 0) {
+                        a.s0_out_nyq[row] = out.s0_nyq;
+                        if constexpr (OP == OP_ADMM) a.s1_out_nyq[row] = out.s1_nyq;
+                    }
+                    if constexpr (SUMS) { dacc += (double)dsum; eacc += (double)esum; }
+                }
+            }
+            __syncwarp();                          // every lane has read its classes from E2
+            inv_pass3(l, A, Bv, e2);
+            __syncwarp();
+            inv_pass2(l, e2, tw2, e1);
+            __syncwarp();
+            {
+                float2 tw1[V];
+                tmem_ld32(tlane + TC_TW1, reinterpret_cast<float*>(tw1));
+                inv_pass1(l, e1, tw1, v);
+            }
+            // ---- windowed overlap-add: out = carry (3 hops from earlier frames) + ws * v; the first hop
+            // (4 pairs) of `out` is a finished block, the other 12 pairs are the new carry
+            {
+                float2 w[V], carry[12];
+                tmem_ld32(tlane + TC_WS, reinterpret_cast<float*>(w));
+                tmem_ld16(twarp + 24, reinterpret_cast<float*>(carry));
+                tmem_ld8(twarp + 40, reinterpret_cast<float*>(carry + 8));
+#pragma unroll
+                for (int i = 0; i < V; ++i) {
+                    v[i] = f2(w[i].x * v[i].x, w[i].y * v[i].y);
+                    if (i < 12) v[i] = v[i] + carry[i];
+                }
+                tmem_st16(twarp + 24, reinterpret_cast<const float*>(v + 4));
+                tmem_st8(twarp + 40, reinterpret_cast<const float*>(v + 12));
+                if (owned && block_valid(a, t)) store_block(a, xo, t, l, v);
+            }
+        }
+        if (t1 == a.T) {      // tail of the signal: blocks T, T+1, T+2 are complete now
+            float2 carry[12];
+            tmem_wait_st();
+            tmem_ld16(twarp + 24, reinterpret_cast<float*>(carry));
+            tmem_ld8(twarp + 40, reinterpret_cast<float*>(carry + 8));
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+                if (block_valid(a, a.T + k)) store_block(a, xo, a.T + k, l, carry + 4 * k);
+        }
+    }
+
+    if constexpr (SUMS) {
+        double d = dacc, e = eacc;
+        for (int o = 16; o > 0; o >>= 1) {
+            d += __shfl_xor_sync(0xffffffffu, d, o);
+            e += __shfl_xor_sync(0xffffffffu, e, o);
+        }
+        if (l == 0 && (d != 0.0 || e != 0.0)) { atomicAdd(a.sums, d); atomicAdd(a.sums + 1, e); }
+    }
+    tmem_wait_st();
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(s_tmem_base, TMEM_COLS);
+}
+
+static int g_sms = 0;
+
+template <int OP, int WARPS>
+static int launch(const WArgs& a0, cudaStream_t st) {
+    WArgs a = a0;
+    if (g_sms == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return SPECINV_ERR_NO_DEVICE;
+        if (cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return SPECINV_ERR_NO_DEVICE;
+    }
+    // SPECINV_FAST_FORCE=1: send even tiny problems through this kernel (the tests do)
+    const char* env_force = getenv("SPECINV_FAST_FORCE");
+    const bool force = env_force && env_force[0] == '1';
+    a.frames_total = (long long)a.B * a.T;
+    const int slots = g_sms * WARPS;
+    // ranges of at least 24 frames keep the 3-frame halo below ~12 %
+    long long ranges = a.frames_total / 24;
+    if (ranges < 1) ranges = 1;
+    if (ranges > slots) ranges = slots;
+    // warps that would stay idle make the generic tile kernel the better choice (tiny problems)
+    if (!force && a.frames_total < 6LL * slots) return SPECINV_ERR_UNSUPPORTED;
+    a.ranges = (int)ranges;
+    const int grid = (int)min((long long)g_sms, ranges);
+    // with fewer ranges than warp slots, spread them over all CTAs of the grid: range index = blockIdx + grid * warp
+    const size_t smem = (size_t)WARPS * WARP_F2 * sizeof(float2);
+    cudaError_t e;
+    if (a.sums) {
+        e = cudaFuncSetAttribute(warp_iter_kernel<OP, true, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        warp_iter_kernel<OP, true, WARPS><<<grid, WARPS * 32, smem, st>>>(a);
+    } else {
+        e = cudaFuncSetAttribute(warp_iter_kernel<OP, false, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        warp_iter_kernel<OP, false, WARPS><<<grid, WARPS * 32, smem, st>>>(a);
+    }
+    return (int)cudaGetLastError();
+}
+
+#ifndef SPX_WFAST_WARPS
+#define SPX_WFAST_WARPS 16
+#endif
+
+}  // namespace wfast
+
+static bool fastw_applicable(const specinv_desc* d) {
+    return d->dtype == SPECINV_F32 && d->onesided && d->n_fft == 1024 && d->hop == 256;
+}
+
+static void fill_common(wfast::WArgs& a, const Dims& dm, const specinv_desc* d, const void* plan) {
+    const PlanLayout pl = plan_layout(dm, d->dtype);
+    const char* p = (const char*)plan;
+    a.tw = (const float2*)(p + pl.tw); a.twr = (const float2*)(p + pl.twr);
+    a.wa = (const float*)(p + pl.wa); a.ws = (const float*)(p + pl.ws); a.inv_env = (const float*)(p + pl.inv_env);
+    a.B = dm.B; a.T = dm.T; a.P = dm.P; a.pad_mode = dm.pad_mode; a.L = dm.L;
+}
+
+// Return SPECINV_ERR_UNSUPPORTED when the shape is not the one this kernel is specialised for.
+int fastw_gl_iter(const specinv_desc* d, const void* plan, const void* x_in, void* x_out,
+                  const void* q_in_main, const void* q_in_nyq, void* q_out_main, void* q_out_nyq,
+                  const void* mag_main, const void* mag_nyq, double lr, double* sums, void* stream) {
+    if (!fastw_applicable(d)) return SPECINV_ERR_UNSUPPORTED;
+    Dims dm; int rc = make_dims(d, &dm); if (rc) return rc;
+    wfast::WArgs a{};
+    fill_common(a, dm, d, plan);
+    a.x_in = (const float*)x_in; a.x_out = (float*)x_out;
+    a.s0_in = (const float2*)q_in_main; a.s0_in_nyq = (const float2*)q_in_nyq;
+    a.s0_out = (float2*)q_out_main; a.s0_out_nyq = (float2*)q_out_nyq;
+    a.mag = (const float*)mag_main; a.mag_nyq = (const float*)mag_nyq;
+    a.coef = (float)lr; a.sums = sums;
+    return wfast::launch<wfast::OP_GL, SPX_WFAST_WARPS>(a, (cudaStream_t)stream);
+}
+
+int fastw_admm_iter(const specinv_desc* d, const void* plan, const void* x_in, void* x_out,
+                    const void* X_in_main, const void* X_in_nyq, const void* U_in_main, const void* U_in_nyq,
+                    void* X_out_main, void* X_out_nyq, void* U_out_main, void* U_out_nyq,
+                    const void* mag_main, const void* mag_nyq, double rho, double* sums, void* stream) {
+    if (!fastw_applicable(d)) return SPECINV_ERR_UNSUPPORTED;
+    Dims dm; int rc = make_dims(d, &dm); if (rc) return rc;
+    wfast::WArgs a{};
+    fill_common(a, dm, d, plan);
+    a.x_in = (const float*)x_in; a.x_out = (float*)x_out;
+    a.s0_in = (const float2*)X_in_main; a.s0_in_nyq = (const float2*)X_in_nyq;
+    a.s0_out = (float2*)X_out_main; a.s0_out_nyq = (float2*)X_out_nyq;
+    a.s1_in = (const float2*)U_in_main; a.s1_in_nyq = (const float2*)U_in_nyq;
+    a.s1_out = (float2*)U_out_main; a.s1_out_nyq = (float2*)U_out_nyq;
+    a.mag = (const float*)mag_main; a.mag_nyq = (const float*)mag_nyq;
+    a.coef = (float)rho; a.coef2 = (float)(1.0 / (1.0 + rho)); a.sums = sums;
+    return wfast::launch<wfast::OP_ADMM, SPX_WFAST_WARPS>(a, (cudaStream_t)stream);
+}
+
+}  // namespace specinv

@@ -1,0 +1,149 @@
+// Host emulation of the warp-per-frame pipeline of gl_warp_core.cuh (n_fft = 1024, 8 x 8 x 8): 32 lanes run
+// sequentially, phase boundaries stand in for __syncwarp.  Checks the state update and the inverse-transform
+// output against a double-precision naive real DFT of one frame, and the bank-conflict freedom of the
+// exchange addressing.
+#include <cmath>
+#include <complex>
+#include <cstdio>
+#include <cstdlib>
+#include <set>
+#include <vector>
+#include "../../spectrogram_inversion_b200/csrc/gl_warp_core.cuh"
+using namespace specinv;
+using namespace specinv::wfast;
+typedef std::complex<double> cd;
+static double frand() { return (double)rand() / RAND_MAX - 0.5; }
+
+static float2 cis(double num, double den) { const double a = -2 * M_PI * num / den; return f2((float)cos(a), (float)sin(a)); }
+
+template <int J> static void fill_twr(int l, LaneTables& t) { t.twr[J] = cis(slot_bin<J>(l), N); }
+
+static void make_tables(int l, const std::vector<float>& wa, const std::vector<float>& ws, LaneTables& t) {
+    for (int i = 0; i < V; ++i) {
+        t.wa[i] = f2(0.5f * wa[64 * i + 2 * l], 0.5f * wa[64 * i + 2 * l + 1]);
+        t.ws[i] = f2(ws[64 * i + 2 * l], ws[64 * i + 2 * l + 1]);
+    }
+    for (int s = 0; s < 2; ++s) for (int ka = 0; ka < 8; ++ka) t.tw1[8 * s + ka] = cis(((l + 32 * s) * ka) % 512, 512);
+    for (int kb = 0; kb < 8; ++kb) t.tw2[kb] = cis((l & 7) * kb, 64);
+    fill_twr<0>(l, t); fill_twr<1>(l, t); fill_twr<2>(l, t); fill_twr<3>(l, t);
+    fill_twr<4>(l, t); fill_twr<5>(l, t); fill_twr<6>(l, t); fill_twr<7>(l, t);
+}
+
+// wavefronts of one warp-wide shared-memory access (word addresses of the first word, width in words)
+static int wavefronts(const int* addr_f2, int words) {
+    const int group = words == 4 ? 8 : 16;        // lanes served together: 128-bit -> quarter warps, 64-bit -> half warps
+    int total = 0;
+    for (int g = 0; g < 32; g += group) {
+        std::set<int> banks[32];
+        int worst = 1;
+        for (int l = g; l < g + group; ++l)
+            for (int w = 0; w < words; ++w) {
+                const int word = addr_f2[l] * 2 + w;
+                banks[word & 31].insert(word);
+            }
+        for (auto& b : banks) worst = std::max(worst, (int)b.size());
+        total += worst;
+    }
+    return total;
+}
+
+static int check_conflicts() {
+    int bad = 0, addr[32];
+    for (int s = 0; s < 2; ++s) for (int ka = 0; ka < 8; ++ka) {        // E1 scattered 64-bit (pass 1 side)
+        for (int l = 0; l < 32; ++l) addr[l] = ex_addr(8 * ka + (l & 7), (l >> 3) + 4 * s);
+        bad += wavefronts(addr, 2) != 2;
+    }
+    for (int r = 0; r < 2; ++r) for (int p = 0; p < 4; ++p) {           // E1 rows 128-bit (pass 2 side)
+        for (int l = 0; l < 32; ++l) addr[l] = ex_addr4(8 * ((l >> 3) + 4 * r) + (l & 7), p);
+        bad += wavefronts(addr, 4) != 4;
+    }
+    for (int r = 0; r < 2; ++r) for (int kb = 0; kb < 8; ++kb) {        // E2 scattered 64-bit (pass 2 side)
+        for (int l = 0; l < 32; ++l) addr[l] = ex_addr((l >> 3) + 4 * r + 8 * kb, l & 7);
+        bad += wavefronts(addr, 2) != 2;
+    }
+    for (int cls = 0; cls < 2; ++cls) for (int p = 0; p < 4; ++p) {     // E2 rows 128-bit (pass 3 side)
+        for (int l = 0; l < 32; ++l) addr[l] = ex_addr4(cls ? class_b(l) : l, p);
+        bad += wavefronts(addr, 4) != 4;
+    }
+    printf("exchange accesses with bank conflicts: %d\n", bad);
+    return bad;
+}
+
+template <int OP>
+int run() {
+    std::vector<float> x(N), wa(N), ws(N);
+    for (int i = 0; i < N; ++i) { x[i] = (float)(4 * frand()); wa[i] = (float)(0.5 - 0.5 * cos(2 * M_PI * i / N)); ws[i] = wa[i] / N; }
+    std::vector<LaneTables> tb(32);
+    for (int l = 0; l < 32; ++l) make_tables(l, wa, ws, tb[l]);
+    std::vector<float2> s0_in(M + 1), s1_in(M + 1), s0_out(M + 1), s1_out(M + 1);
+    std::vector<float> mag(M + 1);
+    for (int k = 0; k <= M; ++k) {
+        s0_in[k] = f2((float)(20 * frand()), (float)(20 * frand())); s1_in[k] = f2((float)(5 * frand()), (float)(5 * frand()));
+        mag[k] = (float)(10 * fabs(frand()));
+    }
+    const float coef = OP == OP_GL ? 0.3f : 0.1f, coef2 = 1.f / (1.f + coef);
+
+    std::vector<float2> e1(EXF2), e2(EXF2);
+    static float2 v[32][V], A[32][8], Bv[32][8];
+    for (int l = 0; l < 32; ++l) {
+        for (int i = 0; i < V; ++i) v[l][i] = f2(x[64 * i + 2 * l] * tb[l].wa[i].x, x[64 * i + 2 * l + 1] * tb[l].wa[i].y);
+        fwd_pass1(l, v[l], tb[l].tw1, e1.data());
+    }
+    for (int l = 0; l < 32; ++l) fwd_pass2(l, e1.data(), tb[l].tw2, e2.data());
+    float ds = 0, es = 0;
+    for (int l = 0; l < 32; ++l) {
+        fwd_pass3(l, e2.data(), A[l], Bv[l]);
+        LaneState in; LaneOut out;
+        for (int j = 0; j < 8; ++j) {
+            int kP = slot_bin_rt(l, j), kQ = (l == 0 && j == 0) ? 256 : M - kP;
+            in.s0[2 * j] = s0_in[kP]; in.s0[2 * j + 1] = s0_in[kQ];
+            in.s1[2 * j] = s1_in[kP]; in.s1[2 * j + 1] = s1_in[kQ];
+            in.mag[2 * j] = mag[kP]; in.mag[2 * j + 1] = mag[kQ];
+        }
+        in.s0_nyq = s0_in[M]; in.s1_nyq = s1_in[M]; in.mag_nyq = mag[M];
+        pointwise<OP, true>(l, A[l], Bv[l], tb[l].twr, in, out, coef, coef2, ds, es);
+        for (int j = 0; j < 8; ++j) {
+            int kP = slot_bin_rt(l, j), kQ = (l == 0 && j == 0) ? 256 : M - kP;
+            s0_out[kP] = out.s0[2 * j]; s0_out[kQ] = out.s0[2 * j + 1];
+            s1_out[kP] = out.s1[2 * j]; s1_out[kQ] = out.s1[2 * j + 1];
+        }
+        if (l == 0) { s0_out[M] = out.s0_nyq; s1_out[M] = out.s1_nyq; }
+    }
+    for (int l = 0; l < 32; ++l) inv_pass3(l, A[l], Bv[l], e2.data());
+    for (int l = 0; l < 32; ++l) inv_pass2(l, e2.data(), tb[l].tw2, e1.data());
+    for (int l = 0; l < 32; ++l) inv_pass1(l, e1.data(), tb[l].tw1, v[l]);
+
+    std::vector<cd> s(M + 1), h(M + 1);
+    double dref = 0, eref = 0, err_state = 0, err_x = 0;
+    for (int k = 0; k <= M; ++k) {
+        cd acc = 0;
+        for (int n = 0; n < N; ++n) acc += (double)x[n] * (double)wa[n] * std::polar(1.0, -2 * M_PI * k * n / N);
+        s[k] = acc;
+        cd a0(s0_in[k].x, s0_in[k].y), a1(s1_in[k].x, s1_in[k].y), o0(s0_out[k].x, s0_out[k].y), o1(s1_out[k].x, s1_out[k].y);
+        double m = mag[k];
+        dref += (std::abs(s[k]) - m) * (std::abs(s[k]) - m); eref += std::norm(s[k]);
+        if (OP == OP_GL) {
+            cd q = s[k] - (double)coef * a0;
+            err_state = fmax(err_state, std::abs(q - o0));
+            h[k] = q * m / (std::abs(q) + 1e-16);
+        } else {
+            cd Z = ((double)coef * (a0 + a1) + s[k]) / (1.0 + coef);
+            cd Un = a1 + a0 - Z;
+            cd Xn = (Z - Un) * m / (std::abs(Z - Un) + 1e-16);
+            err_state = fmax(err_state, fmax(std::abs(Xn - o0), std::abs(Un - o1)));
+            h[k] = Xn + Un;
+        }
+    }
+    for (int n = 0; n < N; ++n) {
+        double acc = h[0].real() + h[M].real() * ((n & 1) ? -1 : 1);
+        for (int k = 1; k < M; ++k) acc += 2 * (h[k] * std::polar(1.0, 2 * M_PI * k * n / N)).real();
+        const int l = (n >> 1) & 31, i = n >> 6;
+        const double ours = ((n & 1) ? v[l][i].y : v[l][i].x) / N;
+        err_x = fmax(err_x, fabs(ours - acc / N));
+    }
+    printf("OP %d: state err %.3e  frame err %.3e  sums rel err %.3e %.3e\n", OP, err_state, err_x, fabs(ds - dref) / dref,
+           fabs(es - eref) / eref);
+    return (err_state < 2e-4 && err_x < 2e-5 && fabs(ds - dref) / dref < 1e-4 && fabs(es - eref) / eref < 1e-4) ? 0 : 1;
+}
+
+int main() { return check_conflicts() | run<OP_GL>() | run<OP_ADMM>(); }

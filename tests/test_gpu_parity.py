@@ -235,8 +235,11 @@ FAST_CASES = [
 ]
 
 
+@pytest.mark.parametrize("impl", ["warp", "half"])
 @pytest.mark.parametrize("fc", FAST_CASES, ids=lambda c: f"B{c['B']}_T{c['T']}_{c['pad_mode']}_c{int(c['center'])}")
-def test_fast_path_1024_against_oracle(fc):
+def test_fast_path_1024_against_oracle(fc, monkeypatch, impl):
+    monkeypatch.setenv("SPECINV_FAST_FORCE", "1")       # small problems would otherwise go to the generic kernel
+    monkeypatch.setenv("SPECINV_FAST_IMPL", impl)
     from spectrogram_inversion_b200.engine import ADMMSolver, GriffinLimSolver, StftPlan
     from spectrogram_inversion_b200.stft_args import args_helper
     rs = np.random.RandomState(fc["T"])
@@ -297,6 +300,7 @@ def test_fast_and_generic_kernels_agree(monkeypatch):
     magt = torch.from_numpy(mag).cuda()
     plan = StftPlan(args_helper(magt, window=w, hop_length=256), T, B, torch.float32, torch.device("cuda"))
     outs = []
+    monkeypatch.setenv("SPECINV_FAST_FORCE", "1")
     for force in ("0", "1"):
         monkeypatch.setenv("SPECINV_FORCE_GENERIC", force)
         s = GriffinLimSolver(plan, plan.pack(torch.from_numpy(C)), plan.pack(magt), 0.99)
@@ -376,7 +380,8 @@ FAST2048_CASES = [
 
 
 @pytest.mark.parametrize("fc", FAST2048_CASES, ids=lambda c: f"B{c['B']}_T{c['T']}_{c['pad_mode']}_c{int(c['center'])}")
-def test_fast_path_2048_against_oracle(fc):
+def test_fast_path_2048_against_oracle(fc, monkeypatch):
+    monkeypatch.setenv("SPECINV_FAST_FORCE", "1")
     from spectrogram_inversion_b200.engine import ADMMSolver, GriffinLimSolver, StftPlan
     from spectrogram_inversion_b200.stft_args import args_helper
     rs = np.random.RandomState(fc["T"])
