@@ -123,21 +123,6 @@ SPX_HD void fwd_pass3(int l, const float2* e2, float2* A, float2* B) {
 }
 
 // ---- point-wise stage ------------------------------------------------------------------------------------
-// Values of the state / magnitude arrays at the lane's 16 bins (+ the Nyquist bin for lane 0), loaded by
-// the caller: index 2 j = the P bin of slot j, 2 j + 1 = the Q bin (lane 0 slot 0: bins 0 and 256).
-struct LaneState {
-    float2 s0[V];     // GL: q_in / ADMM: X_in
-    float2 s1[V];     // ADMM: U_in
-    float mag[V];
-    float2 s0_nyq, s1_nyq;
-    float mag_nyq;
-};
-struct LaneOut {
-    float2 s0[V];     // GL: q_out / ADMM: X_out
-    float2 s1[V];     // ADMM: U_out
-    float2 s0_nyq, s1_nyq;
-};
-
 // One bin: s = STFT bin of the current estimate.  Returns the value fed to the inverse transform.
 template <int OP, bool SUMS>
 SPX_HD float2 bin_update(float2 s, float2 a0, float2 a1, float m, float coef, float coef2, float2& o0, float2& o1,
@@ -163,28 +148,37 @@ SPX_HD float2 bin_update(float2 s, float2 a0, float2 a1, float m, float coef, fl
 
 // Pair processing with the point-wise update, in place: on return A / B hold the inputs of the inverse
 // pass 3.  (dsum, esum) += this lane's share of sum (|s|-mag)^2, sum |s|^2.
-template <int OP, bool SUMS>
-SPX_HD void pointwise(int l, float2* A, float2* B, const float2* twr, const LaneState& in, LaneOut& out, float coef,
-                      float coef2, float& dsum, float& esum) {
+// `io` gives access to the state of the lane's bins, element e = 2 j (the P bin of slot j) or 2 j + 1 (the Q
+// bin; lane 0 slot 0: bins 0 and 256), e = -1: the Nyquist bin (lane 0 only):
+//     float2 io.s0(e), io.s1(e); float io.mag(e); void io.put(e, o0, o1)
+// so that values are fetched right where they are used (no block of 48 live registers).
+template <int OP, bool SUMS, typename IO>
+SPX_HD void pointwise(int l, float2* A, float2* B, const float2* twr, IO& io, float coef, float coef2, float& dsum,
+                      float& esum) {
     const bool l0 = l == 0;
+    auto upd = [&](auto ec, float2 sv) {
+        constexpr int e = decltype(ec)::value;
+        float2 o0 = f2(0.f, 0.f), o1 = f2(0.f, 0.f);
+        const float2 h = bin_update<OP, SUMS>(sv, io.s0(e), OP == OP_ADMM ? io.s1(e) : f2(0.f, 0.f), io.mag(e), coef, coef2,
+                                              o0, o1, dsum, esum);
+        io.put(e, o0, o1);
+        return h;
+    };
     // slot 0
     if (l0) {
         // lane 0: A[0] = Zh[0] -> DC and Nyquist (both real), A[4] = Zh[256] -> bin 256 = conj(Z[256])
         const float2 z0 = A[0], z4 = A[4];
-        const float2 h0 = bin_update<OP, SUMS>(f2(2.f * (z0.x + z0.y), 0.f), in.s0[0], in.s1[0], in.mag[0], coef, coef2,
-                                               out.s0[0], out.s1[0], dsum, esum);
-        const float2 hM = bin_update<OP, SUMS>(f2(2.f * (z0.x - z0.y), 0.f), in.s0_nyq, in.s1_nyq, in.mag_nyq, coef, coef2,
-                                               out.s0_nyq, out.s1_nyq, dsum, esum);
-        const float2 h4 = bin_update<OP, SUMS>(f2(2.f * z4.x, -2.f * z4.y), in.s0[1], in.s1[1], in.mag[1], coef, coef2,
-                                               out.s0[1], out.s1[1], dsum, esum);
+        const float2 h0 = upd(std::integral_constant<int, 0>{}, f2(2.f * (z0.x + z0.y), 0.f));
+        const float2 hM = upd(std::integral_constant<int, -1>{}, f2(2.f * (z0.x - z0.y), 0.f));
+        const float2 h4 = upd(std::integral_constant<int, 1>{}, f2(2.f * z4.x, -2.f * z4.y));
         A[0] = f2(h0.x + hM.x, h0.x - hM.x);        // C2R ignores Im(DC), Im(Nyquist)
         A[4] = f2(2.f * h4.x, -2.f * h4.y);
     } else {
         float2 sP, sQ, P, Q;
         const float2 w = twr[0];
         post_pair(A[0], B[7], w, sP, sQ);
-        const float2 hP = bin_update<OP, SUMS>(sP, in.s0[0], in.s1[0], in.mag[0], coef, coef2, out.s0[0], out.s1[0], dsum, esum);
-        const float2 hQ = bin_update<OP, SUMS>(sQ, in.s0[1], in.s1[1], in.mag[1], coef, coef2, out.s0[1], out.s1[1], dsum, esum);
+        const float2 hP = upd(std::integral_constant<int, 0>{}, sP);
+        const float2 hQ = upd(std::integral_constant<int, 1>{}, sQ);
         pre_pair(hP, hQ, w, P, Q);
         A[0] = P; B[7] = Q;
     }
@@ -197,10 +191,8 @@ SPX_HD void pointwise(int l, float2* A, float2* B, const float2* twr, const Lane
         const float2 w = twr[j];
         float2 sP, sQ;
         post_pair(P, Q, w, sP, sQ);
-        const float2 hP = bin_update<OP, SUMS>(sP, in.s0[2 * j], in.s1[2 * j], in.mag[2 * j], coef, coef2, out.s0[2 * j],
-                                               out.s1[2 * j], dsum, esum);
-        const float2 hQ = bin_update<OP, SUMS>(sQ, in.s0[2 * j + 1], in.s1[2 * j + 1], in.mag[2 * j + 1], coef, coef2,
-                                               out.s0[2 * j + 1], out.s1[2 * j + 1], dsum, esum);
+        const float2 hP = upd(std::integral_constant<int, 2 * j>{}, sP);
+        const float2 hQ = upd(std::integral_constant<int, 2 * j + 1>{}, sQ);
         pre_pair(hP, hQ, w, P, Q);
         if constexpr (j < 4) { A[j] = P; if (l0) A[8 - j] = Q; else B[7 - j] = Q; }
         else { if (l0) { B[j - 4] = P; B[11 - j] = Q; } else { A[j] = P; B[7 - j] = Q; } }

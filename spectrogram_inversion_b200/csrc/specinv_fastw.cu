@@ -41,6 +41,10 @@ __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
 }
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ float2 ldg_nc_f2(const float2* p) {
@@ -110,7 +114,7 @@ __device__ __forceinline__ void tmem_st32(unsigned taddr, const float* r) {
 constexpr int TC_WA = 0, TC_WS = 32, TC_TW1 = 64, TC_TW2 = 96, TC_TWR = 112, TC_WARP = 128;
 constexpr int TC_PER_WARP = 48;     // ring: 3 blocks x 8 words, carry: 24 words
 constexpr int TMEM_COLS = 512;
-constexpr int WARP_F2 = 2 * EXF2 + 128;   // float2 of shared memory per warp: E1, E2, staged input block
+constexpr int WARP_F2 = 2 * EXF2 + 128 + 256;   // float2 of shared memory per warp: E1, E2, staged input block, magnitude row
 
 // Fetch block u (padded samples [256 u, 256 u + 256)) of signal x: lane l gets the pairs at 64 j + 2 l.
 __device__ __forceinline__ void fetch_block_regs(const WArgs& a, const float* __restrict__ x, int u, int l, float2* nb) {
@@ -160,6 +164,13 @@ __device__ __forceinline__ void prefetch_rows(const WArgs& a, long long row, int
     prefetch_l2(reinterpret_cast<const char*>(a.s0_in + row * M) + 128 * l);             // 4 KB = 32 lines
     if (l < 16) prefetch_l2(reinterpret_cast<const char*>(a.mag + row * M) + 128 * l);  // 2 KB = 16 lines
     if constexpr (OP == OP_ADMM) prefetch_l2(reinterpret_cast<const char*>(a.s1_in + row * M) + 128 * l);
+}
+
+// Stage the magnitude row of frame `row` (2 KB) in shared memory: 4 x 16 bytes per lane.
+__device__ __forceinline__ void stage_mag(const WArgs& a, long long row, int l, float* mstage) {
+    const float* src = a.mag + row * M;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) cp_async16(mstage + 4 * (32 * i + l), src + 4 * (32 * i + l));
 }
 
 template <int OP, bool SUMS, int WARPS>
@@ -213,6 +224,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) warp_iter_kernel(const WArgs a)
     float2* e1 = sm + warp * WARP_F2;
     float2* e2 = e1 + EXF2;
     float2* xs = e2 + EXF2;
+    float* mstage = reinterpret_cast<float*>(xs + 128);             // magnitudes of the current frame (512 floats)
 
     // bin offsets of the lane's pair slots inside a main row
     const int hi_adj = l == 0 ? -224 : 0;        // lane 0, slots 4..7: 32 + 64 (j - 4) = 64 j - 224
@@ -255,6 +267,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) warp_iter_kernel(const WArgs a)
         }
         fetch_block_async(a, x, tf0 + 3, l, xs);
         prefetch_rows<OP>(a, (long long)b * a.T + tf0, l);
+        __syncwarp();                              // nobody still reads the magnitude row of an earlier range
+        stage_mag(a, (long long)b * a.T + tf0, l, mstage);
 
         for (int t = tf0; t < t1; ++t) {
             const long long row = (long long)b * a.T + t;
@@ -295,56 +309,55 @@ __global__ void __launch_bounds__(WARPS * 32, 1) warp_iter_kernel(const WArgs a)
             fwd_pass2(l, e1, tw2, e2);
             __syncwarp();
 
-            // ---- state of the lane's 16 bins (+ Nyquist for lane 0)
-            LaneState in;
+            // ---- the frame's q / X row (4 KB) goes to the idle exchange buffer E1 while pass 3 runs
             {
-                const float2* s0 = a.s0_in + row * M;
-                const float* mg = a.mag + row * M;
-                static_for<8>([&](auto jc) {
-                    constexpr int j = decltype(jc)::value;
-                    const int kP = l + 64 * j + (j >= 4 ? hi_adj : 0);
-                    const int kQ = j == 0 ? kq0 : M - kP;
-                    in.s0[2 * j] = ldg_nc_f2(s0 + kP); in.s0[2 * j + 1] = ldg_nc_f2(s0 + kQ);
-                    in.mag[2 * j] = ldg_nc_f(mg + kP); in.mag[2 * j + 1] = ldg_nc_f(mg + kQ);
-                    if constexpr (OP == OP_ADMM) {
-                        const float2* s1 = a.s1_in + row * M;
-                        in.s1[2 * j] = ldg_nc_f2(s1 + kP); in.s1[2 * j + 1] = ldg_nc_f2(s1 + kQ);
-                    }
-                });
-                in.s0_nyq = f2(0.f, 0.f); in.s1_nyq = f2(0.f, 0.f); in.mag_nyq = 0.f;
-                if (l == 0) {
-                    in.s0_nyq = __ldg(a.s0_in_nyq + row); in.mag_nyq = __ldg(a.mag_nyq + row);
-                    if constexpr (OP == OP_ADMM) in.s1_nyq = __ldg(a.s1_in_nyq + row);
-                }
+                const float2* src = a.s0_in + row * M;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) cp_async16(e1 + 2 * (32 * i + l), src + 2 * (32 * i + l));
+            }
+            float2 s0n = f2(0.f, 0.f), s1n = f2(0.f, 0.f);
+            float mgn = 0.f;
+            if (l == 0) {
+                s0n = __ldg(a.s0_in_nyq + row); mgn = __ldg(a.mag_nyq + row);
+                if constexpr (OP == OP_ADMM) s1n = __ldg(a.s1_in_nyq + row);
             }
             float2 A[8], Bv[8];
             fwd_pass3(l, e2, A, Bv);
+            cp_async_wait_all();
+            __syncwarp();                          // staged rows visible to all lanes
             {
+                // ---- point-wise stage on the lane's 16 bins (+ Nyquist for lane 0), state fetched where it is used
+                struct IO {
+                    const WArgs& a; const float2* q; const float* mg; long long row; int l, hi_adj, kq0; bool owned;
+                    float2 s0n, s1n; float mgn;
+                    __device__ __forceinline__ int bin(int e) const {
+                        const int j = e >> 1, kP = l + 64 * j + (j >= 4 ? hi_adj : 0);
+                        return (e & 1) ? (j == 0 ? kq0 : M - kP) : kP;
+                    }
+                    __device__ __forceinline__ float2 s0(int e) const { return e < 0 ? s0n : q[bin(e)]; }
+                    __device__ __forceinline__ float2 s1(int e) const {
+                        return e < 0 ? s1n : ldg_nc_f2(a.s1_in + row * M + bin(e));
+                    }
+                    __device__ __forceinline__ float mag(int e) const { return e < 0 ? mgn : mg[bin(e)]; }
+                    __device__ __forceinline__ void put(int e, float2 o0, float2 o1) const {
+                        if (!owned) return;
+                        if (e < 0) {
+                            a.s0_out_nyq[row] = o0;
+                            if constexpr (OP == OP_ADMM) a.s1_out_nyq[row] = o1;
+                        } else {
+                            a.s0_out[row * M + bin(e)] = o0;
+                            if constexpr (OP == OP_ADMM) a.s1_out[row * M + bin(e)] = o1;
+                        }
+                    }
+                } io{a, e1, mstage, row, l, hi_adj, kq0, owned, s0n, s1n, mgn};
                 float2 twr[8];
                 tmem_ld16(tlane + TC_TWR, reinterpret_cast<float*>(twr));
-                LaneOut out;
                 float dsum = 0.f, esum = 0.f;
-                pointwise<OP, SUMS>(l, A, Bv, twr, in, out, a.coef, a.coef2, dsum, esum);
-                if (owned) {
-                    float2* o0 = a.s0_out + row * M;
-                    static_for<8>([&](auto jc) {
-                        constexpr int j = decltype(jc)::value;
-                        const int kP = l + 64 * j + (j >= 4 ? hi_adj : 0);
-                        const int kQ = j == 0 ? kq0 : M - kP;
-                        o0[kP] = out.s0[2 * j]; o0[kQ] = out.s0[2 * j + 1];
-                        if constexpr (OP == OP_ADMM) {
-                            float2* o1 = a.s1_out + row * M;
-                            o1[kP] = out.s1[2 * j]; o1[kQ] = out.s1[2 * j + 1];
-                        }
-                    });
-                    if (l == 0) {
-                        a.s0_out_nyq[row] = out.s0_nyq;
-                        if constexpr (OP == OP_ADMM) a.s1_out_nyq[row] = out.s1_nyq;
-                    }
-                    if constexpr (SUMS) { dacc += (double)dsum; eacc += (double)esum; }
-                }
+                pointwise<OP, SUMS>(l, A, Bv, twr, io, a.coef, a.coef2, dsum, esum);
+                if constexpr (SUMS) { if (owned) { dacc += (double)dsum; eacc += (double)esum; } }
             }
-            __syncwarp();                          // every lane has read its classes from E2
+            __syncwarp();                          // every lane has read its classes from E2 and its staged state
+            if (t + 1 < t1) stage_mag(a, row + 1, l, mstage);
             inv_pass3(l, A, Bv, e2);
             __syncwarp();
             inv_pass2(l, e2, tw2, e1);
@@ -434,9 +447,12 @@ static int launch(const WArgs& a0, cudaStream_t st) {
     return (int)cudaGetLastError();
 }
 
-#ifndef SPX_WFAST_WARPS
-#define SPX_WFAST_WARPS 16
-#endif
+// 12 warps per CTA with 168 registers each (no spills) beat 16 x 128 (a few spills): GL 1.18 vs 1.21 ms, ADMM 1.98
+// vs 2.67 ms per iteration at B = 512, T = 938.  SPECINV_FASTW_WARPS=16 selects the latter (A-B timing).
+static int warps_choice() {
+    const char* e = getenv("SPECINV_FASTW_WARPS");
+    return e && atoi(e) == 16 ? 16 : 12;
+}
 
 }  // namespace wfast
 
@@ -465,7 +481,8 @@ int fastw_gl_iter(const specinv_desc* d, const void* plan, const void* x_in, voi
     a.s0_out = (float2*)q_out_main; a.s0_out_nyq = (float2*)q_out_nyq;
     a.mag = (const float*)mag_main; a.mag_nyq = (const float*)mag_nyq;
     a.coef = (float)lr; a.sums = sums;
-    return wfast::launch<wfast::OP_GL, SPX_WFAST_WARPS>(a, (cudaStream_t)stream);
+    return wfast::warps_choice() == 12 ? wfast::launch<wfast::OP_GL, 12>(a, (cudaStream_t)stream)
+                                       : wfast::launch<wfast::OP_GL, 16>(a, (cudaStream_t)stream);
 }
 
 int fastw_admm_iter(const specinv_desc* d, const void* plan, const void* x_in, void* x_out,
@@ -483,7 +500,8 @@ int fastw_admm_iter(const specinv_desc* d, const void* plan, const void* x_in, v
     a.s1_out = (float2*)U_out_main; a.s1_out_nyq = (float2*)U_out_nyq;
     a.mag = (const float*)mag_main; a.mag_nyq = (const float*)mag_nyq;
     a.coef = (float)rho; a.coef2 = (float)(1.0 / (1.0 + rho)); a.sums = sums;
-    return wfast::launch<wfast::OP_ADMM, SPX_WFAST_WARPS>(a, (cudaStream_t)stream);
+    return wfast::warps_choice() == 12 ? wfast::launch<wfast::OP_ADMM, 12>(a, (cudaStream_t)stream)
+                                       : wfast::launch<wfast::OP_ADMM, 16>(a, (cudaStream_t)stream);
 }
 
 }  // namespace specinv

@@ -93,21 +93,15 @@ int run() {
     float ds = 0, es = 0;
     for (int l = 0; l < 32; ++l) {
         fwd_pass3(l, e2.data(), A[l], Bv[l]);
-        LaneState in; LaneOut out;
-        for (int j = 0; j < 8; ++j) {
-            int kP = slot_bin_rt(l, j), kQ = (l == 0 && j == 0) ? 256 : M - kP;
-            in.s0[2 * j] = s0_in[kP]; in.s0[2 * j + 1] = s0_in[kQ];
-            in.s1[2 * j] = s1_in[kP]; in.s1[2 * j + 1] = s1_in[kQ];
-            in.mag[2 * j] = mag[kP]; in.mag[2 * j + 1] = mag[kQ];
-        }
-        in.s0_nyq = s0_in[M]; in.s1_nyq = s1_in[M]; in.mag_nyq = mag[M];
-        pointwise<OP, true>(l, A[l], Bv[l], tb[l].twr, in, out, coef, coef2, ds, es);
-        for (int j = 0; j < 8; ++j) {
-            int kP = slot_bin_rt(l, j), kQ = (l == 0 && j == 0) ? 256 : M - kP;
-            s0_out[kP] = out.s0[2 * j]; s0_out[kQ] = out.s0[2 * j + 1];
-            s1_out[kP] = out.s1[2 * j]; s1_out[kQ] = out.s1[2 * j + 1];
-        }
-        if (l == 0) { s0_out[M] = out.s0_nyq; s1_out[M] = out.s1_nyq; }
+        struct IO {
+            int l; const float2* s0i; const float2* s1i; const float* mg; float2* s0o; float2* s1o;
+            SPX_HD int bin(int e) const { if (e < 0) return M; const int kP = slot_bin_rt(l, e >> 1); return (e & 1) ? ((l == 0 && e == 1) ? 256 : M - kP) : kP; }
+            SPX_HD float2 s0(int e) const { return s0i[bin(e)]; }
+            SPX_HD float2 s1(int e) const { return s1i[bin(e)]; }
+            SPX_HD float mag(int e) const { return mg[bin(e)]; }
+            SPX_HD void put(int e, float2 o0, float2 o1) { s0o[bin(e)] = o0; s1o[bin(e)] = o1; }
+        } io{l, s0_in.data(), s1_in.data(), mag.data(), s0_out.data(), s1_out.data()};
+        pointwise<OP, true>(l, A[l], Bv[l], tb[l].twr, io, coef, coef2, ds, es);
     }
     for (int l = 0; l < 32; ++l) inv_pass3(l, A[l], Bv[l], e2.data());
     for (int l = 0; l < 32; ++l) inv_pass2(l, e2.data(), tb[l].tw2, e1.data());
