@@ -9,8 +9,10 @@
 //   * the lane-constant tables (windows, twiddles), the lane-private input ring and the overlap-add carry
 //     live in TENSOR MEMORY and move with tcgen05.ld / tcgen05.st (one instruction per 8..32 registers, no
 //     shared-memory bandwidth); shared memory only carries the four FFT exchanges (swizzled, conflict free);
-//   * state rows (q / X, U, mag) are read and written straight from / to global memory, 256 contiguous bytes
-//     per warp instruction, after an L2 prefetch one frame ahead; new input samples arrive by cp.async.
+//   * the q / X and magnitude rows of the NEXT frame and the next 256 input samples are fetched by the TMA
+//     (cp.async.bulk, one elected lane, mbarrier completion) into per-warp staging rows one frame ahead, so
+//     the compute never waits on DRAM; the new state is written straight from registers, 256 contiguous
+//     bytes per warp instruction.
 // A range re-computes the 3 frames before it as a halo (state not written, output not stored), so ranges are
 // independent: no atomics, deterministic.  State arrays are ping-ponged (q_in != q_out).
 #include <cstdlib>
@@ -37,15 +39,31 @@ struct WArgs {
 };
 
 // ---- small PTX wrappers ---------------------------------------------------------------------------------
-__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+// ---- TMA bulk copies (global -> shared) completing on an mbarrier ---------------------------------------
+// All shared-memory operands are 32-bit shared-window addresses computed once per warp.
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void bulk_g2s(unsigned smem_dst, const void* gsrc, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_dst), "l"(gsrc), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+// one elected lane of the (converged) warp
+__device__ __forceinline__ bool elect_one() {
+    unsigned pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ float2 ldg_nc_f2(const float2* p) {
     float2 r;
@@ -114,7 +132,8 @@ __device__ __forceinline__ void tmem_st32(unsigned taddr, const float* r) {
 constexpr int TC_WA = 0, TC_WS = 32, TC_TW1 = 64, TC_TW2 = 96, TC_TWR = 112, TC_WARP = 128;
 constexpr int TC_PER_WARP = 48;     // ring: 3 blocks x 8 words, carry: 24 words
 constexpr int TMEM_COLS = 512;
-constexpr int WARP_F2 = 2 * EXF2 + 128 + 256;   // float2 of shared memory per warp: E1, E2, staged input block, magnitude row
+// float2 of shared memory per warp: E1, E2, staged input block (1 KB), magnitude row (2 KB), q / X row (4 KB)
+constexpr int WARP_F2 = 2 * EXF2 + 128 + 256 + 512;
 
 // Fetch block u (padded samples [256 u, 256 u + 256)) of signal x: lane l gets the pairs at 64 j + 2 l.
 __device__ __forceinline__ void fetch_block_regs(const WArgs& a, const float* __restrict__ x, int u, int l, float2* nb) {
@@ -131,20 +150,22 @@ __device__ __forceinline__ void fetch_block_regs(const WArgs& a, const float* __
         }
     }
 }
-// Same, asynchronously into the lane's slots of the staging buffer xs[32 j + l].
-__device__ __forceinline__ void fetch_block_async(const WArgs& a, const float* __restrict__ x, int u, int l, float2* xs) {
+// Same into the staging buffer xs[32 j + l] (= the block's 1 KB in memory order): interior blocks by one TMA
+// bulk copy (returns true: the data arrives on `bar`), padded edge blocks element by element.
+__device__ __forceinline__ bool fetch_block_staged(const WArgs& a, const float* __restrict__ x, int u, int l, float2* xs,
+                                                   unsigned xs_s, unsigned bar) {
     const long long base = (long long)u * HOP - a.P;
     if (base >= 0 && base + HOP <= a.L) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) cp_async8(xs + 32 * j + l, x + base + 64 * j + 2 * l);
-    } else {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const long long pp = (long long)u * HOP + 64 * j + 2 * l;
-            const long long i0 = pad_index(pp, a.P, a.L, a.pad_mode), i1 = pad_index(pp + 1, a.P, a.L, a.pad_mode);
-            xs[32 * j + l] = f2(i0 >= 0 ? x[i0] : 0.f, i1 >= 0 ? x[i1] : 0.f);
-        }
+        if (elect_one()) { mbar_expect_tx(bar, HOP * 4); bulk_g2s(xs_s, x + base, HOP * 4, bar); }
+        return true;
     }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const long long pp = (long long)u * HOP + 64 * j + 2 * l;
+        const long long i0 = pad_index(pp, a.P, a.L, a.pad_mode), i1 = pad_index(pp + 1, a.P, a.L, a.pad_mode);
+        xs[32 * j + l] = f2(i0 >= 0 ? x[i0] : 0.f, i1 >= 0 ? x[i1] : 0.f);
+    }
+    return false;
 }
 __device__ __forceinline__ bool block_valid(const WArgs& a, int u) {
     const long long base = (long long)u * HOP - a.P;
@@ -158,19 +179,25 @@ __device__ __forceinline__ void store_block(const WArgs& a, float* __restrict__ 
         *reinterpret_cast<float2*>(xo + base + 64 * j + 2 * l) = f2(blk[j].x * ie.x, blk[j].y * ie.y);
     }
 }
-// Pull the state / magnitude rows of frame `row` into L2 one frame ahead.
-template <int OP>
-__device__ __forceinline__ void prefetch_rows(const WArgs& a, long long row, int l) {
-    prefetch_l2(reinterpret_cast<const char*>(a.s0_in + row * M) + 128 * l);             // 4 KB = 32 lines
-    if (l < 16) prefetch_l2(reinterpret_cast<const char*>(a.mag + row * M) + 128 * l);  // 2 KB = 16 lines
-    if constexpr (OP == OP_ADMM) prefetch_l2(reinterpret_cast<const char*>(a.s1_in + row * M) + 128 * l);
-}
-
-// Stage the magnitude row of frame `row` (2 KB) in shared memory: 4 x 16 bytes per lane.
-__device__ __forceinline__ void stage_mag(const WArgs& a, long long row, int l, float* mstage) {
-    const float* src = a.mag + row * M;
+__device__ __forceinline__ void load_inv_env(const WArgs& a, int u, int l, float2* ie) {
+    const long long base = (long long)u * HOP - a.P;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) cp_async16(mstage + 4 * (32 * i + l), src + 4 * (32 * i + l));
+    for (int j = 0; j < 4; ++j) ie[j] = __ldg(reinterpret_cast<const float2*>(a.inv_env + base + 64 * j + 2 * l));
+}
+__device__ __forceinline__ void store_block_ie(const WArgs& a, float* __restrict__ xo, int u, int l, const float2* blk,
+                                               const float2* ie) {
+    const long long base = (long long)u * HOP - a.P;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        *reinterpret_cast<float2*>(xo + base + 64 * j + 2 * l) = f2(blk[j].x * ie[j].x, blk[j].y * ie[j].y);
+}
+// Fetch the q / X row and the magnitude row of frame `row` into the staging rows (one elected lane, TMA).
+__device__ __forceinline__ void stage_rows(const WArgs& a, long long row, unsigned qstage_s, unsigned mstage_s, unsigned bar) {
+    if (elect_one()) {
+        mbar_expect_tx(bar, M * 8 + M * 4);
+        bulk_g2s(qstage_s, a.s0_in + row * M, M * 8, bar);
+        bulk_g2s(mstage_s, a.mag + row * M, M * 4, bar);
+    }
 }
 
 template <int OP, bool SUMS, int WARPS>
@@ -178,8 +205,12 @@ __global__ void __launch_bounds__(WARPS * 32, 1) warp_iter_kernel(const WArgs a)
     static_assert(TC_WARP + ((WARPS + 3) / 4) * TC_PER_WARP <= TMEM_COLS, "TMEM columns");
     extern __shared__ __align__(16) float2 sm[];
     __shared__ unsigned s_tmem_base;
+    __shared__ __align__(8) unsigned long long s_bar[WARPS][2];    // per warp: input block, state rows
     const int tid = threadIdx.x, warp = tid >> 5, l = tid & 31;
     if (warp == 0) tmem_alloc(&s_tmem_base, TMEM_COLS);
+    const unsigned xbar = (unsigned)__cvta_generic_to_shared(&s_bar[warp][0]), sbar = xbar + 8;
+    if (l == 0) { mbar_init(xbar, 1); mbar_init(sbar, 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -224,7 +255,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) warp_iter_kernel(const WArgs a)
     float2* e1 = sm + warp * WARP_F2;
     float2* e2 = e1 + EXF2;
     float2* xs = e2 + EXF2;
-    float* mstage = reinterpret_cast<float*>(xs + 128);             // magnitudes of the current frame (512 floats)
+    float* mstage = reinterpret_cast<float*>(xs + 128);             // magnitudes of the coming frame (512 floats)
+    float2* qstage = xs + 128 + 256;                                // q / X row of the coming frame
+    const unsigned warp_s = (unsigned)__cvta_generic_to_shared(sm) + warp * (WARP_F2 * 8);   // shared-window addresses
+    const unsigned xs_s = warp_s + 2 * EXF2 * 8, mstage_s = xs_s + 128 * 8, qstage_s = mstage_s + 256 * 8;
+    unsigned xpar = 0, spar = 0;                                    // mbarrier phase parities
 
     // bin offsets of the lane's pair slots inside a main row
     const int hi_adj = l == 0 ? -224 : 0;        // lane 0, slots 4..7: 32 + 64 (j - 4) = 64 j - 224
@@ -265,10 +300,18 @@ __global__ void __launch_bounds__(WARPS * 32, 1) warp_iter_kernel(const WArgs a)
                 mm = mm == 2 ? 0 : mm + 1;
             }
         }
-        fetch_block_async(a, x, tf0 + 3, l, xs);
-        prefetch_rows<OP>(a, (long long)b * a.T + tf0, l);
-        __syncwarp();                              // nobody still reads the magnitude row of an earlier range
-        stage_mag(a, (long long)b * a.T + tf0, l, mstage);
+        __syncwarp();                              // nobody still reads the staging rows of an earlier range
+        bool x_async = fetch_block_staged(a, x, tf0 + 3, l, xs, xs_s, xbar);
+        stage_rows(a, (long long)b * a.T + tf0, qstage_s, mstage_s, sbar);
+        // Nyquist scalars of the coming frame (lane 0), fetched one frame ahead like the rows
+        float2 s0n_next = f2(0.f, 0.f), s1n_next = f2(0.f, 0.f);
+        float mgn_next = 0.f;
+        if (l == 0) {
+            const long long r0 = (long long)b * a.T + tf0;
+            s0n_next = __ldg(a.s0_in_nyq + r0); mgn_next = __ldg(a.mag_nyq + r0);
+            if constexpr (OP == OP_ADMM) s1n_next = __ldg(a.s1_in_nyq + r0);
+        }
+        if constexpr (OP == OP_ADMM) prefetch_l2(reinterpret_cast<const char*>(a.s1_in + ((long long)b * a.T + tf0) * M) + 128 * l);
 
         for (int t = tf0; t < t1; ++t) {
             const long long row = (long long)b * a.T + t;
@@ -281,15 +324,16 @@ __global__ void __launch_bounds__(WARPS * 32, 1) warp_iter_kernel(const WArgs a)
                 tmem_ld8(twarp + 8 * m, reinterpret_cast<float*>(v));
                 tmem_ld8(twarp + 8 * m1, reinterpret_cast<float*>(v + 4));
                 tmem_ld8(twarp + 8 * m2, reinterpret_cast<float*>(v + 8));
-                cp_async_wait_all();
+                if (x_async) { mbar_wait(xbar, xpar); xpar ^= 1; }
 #pragma unroll
                 for (int j = 0; j < 4; ++j) v[12 + j] = xs[32 * j + l];
                 tmem_st8(twarp + 8 * m, reinterpret_cast<const float*>(v + 12));   // block t+3 replaces block t
                 m = m1;
             }
+            __syncwarp();                          // xs consumed by every lane; the previous frame's reads of E1 are done
             if (t + 1 < t1) {
-                fetch_block_async(a, x, t + 4, l, xs);
-                prefetch_rows<OP>(a, row + 1, l);
+                x_async = fetch_block_staged(a, x, t + 4, l, xs, xs_s, xbar);
+                if constexpr (OP == OP_ADMM) prefetch_l2(reinterpret_cast<const char*>(a.s1_in + (row + 1) * M) + 128 * l);
             }
             {
                 float2 w[V];
@@ -297,7 +341,6 @@ __global__ void __launch_bounds__(WARPS * 32, 1) warp_iter_kernel(const WArgs a)
 #pragma unroll
                 for (int i = 0; i < V; ++i) v[i] = f2(v[i].x * w[i].x, v[i].y * w[i].y);
             }
-            __syncwarp();                          // the previous frame's reads of E1 are done
             {
                 float2 tw1[V];
                 tmem_ld32(tlane + TC_TW1, reinterpret_cast<float*>(tw1));
@@ -309,47 +352,42 @@ __global__ void __launch_bounds__(WARPS * 32, 1) warp_iter_kernel(const WArgs a)
             fwd_pass2(l, e1, tw2, e2);
             __syncwarp();
 
-            // ---- the frame's q / X row (4 KB) goes to the idle exchange buffer E1 while pass 3 runs
-            {
-                const float2* src = a.s0_in + row * M;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) cp_async16(e1 + 2 * (32 * i + l), src + 2 * (32 * i + l));
-            }
-            float2 s0n = f2(0.f, 0.f), s1n = f2(0.f, 0.f);
-            float mgn = 0.f;
-            if (l == 0) {
-                s0n = __ldg(a.s0_in_nyq + row); mgn = __ldg(a.mag_nyq + row);
-                if constexpr (OP == OP_ADMM) s1n = __ldg(a.s1_in_nyq + row);
-            }
+            const float2 s0n = s0n_next, s1n = s1n_next;
+            const float mgn = mgn_next;
             float2 A[8], Bv[8];
             fwd_pass3(l, e2, A, Bv);
-            cp_async_wait_all();
-            __syncwarp();                          // staged rows visible to all lanes
+            mbar_wait(sbar, spar); spar ^= 1;      // this frame's staged rows have landed
             {
                 // ---- point-wise stage on the lane's 16 bins (+ Nyquist for lane 0), state fetched where it is used
+                // Element e = 2 j / 2 j + 1 is the P / Q bin of slot j: bins l + 64 j and 512 - l - 64 j, except for
+                // lane 0 (slots 4..7: 64 j - 224 and its mirror; slot 0: bins 0 and 256).  Four per-lane base offsets
+                // turn every access into base + compile-time offset.
                 struct IO {
-                    const WArgs& a; const float2* q; const float* mg; long long row; int l, hi_adj, kq0; bool owned;
+                    const float2* q; const float* mg; const float2* u; float2* o0; float2* o1;
+                    float2* o0n; float2* o1n;
+                    int pl, ph, ql, qh, q0; bool owned;
                     float2 s0n, s1n; float mgn;
                     __device__ __forceinline__ int bin(int e) const {
-                        const int j = e >> 1, kP = l + 64 * j + (j >= 4 ? hi_adj : 0);
-                        return (e & 1) ? (j == 0 ? kq0 : M - kP) : kP;
+                        const int j = e >> 1;
+                        return (e & 1) ? (j == 0 ? q0 : (j >= 4 ? qh : ql) - 64 * j) : (j >= 4 ? ph : pl) + 64 * j;
                     }
                     __device__ __forceinline__ float2 s0(int e) const { return e < 0 ? s0n : q[bin(e)]; }
-                    __device__ __forceinline__ float2 s1(int e) const {
-                        return e < 0 ? s1n : ldg_nc_f2(a.s1_in + row * M + bin(e));
-                    }
+                    __device__ __forceinline__ float2 s1(int e) const { return e < 0 ? s1n : ldg_nc_f2(u + bin(e)); }
                     __device__ __forceinline__ float mag(int e) const { return e < 0 ? mgn : mg[bin(e)]; }
-                    __device__ __forceinline__ void put(int e, float2 o0, float2 o1) const {
+                    __device__ __forceinline__ void put(int e, float2 v0, float2 v1) const {
                         if (!owned) return;
                         if (e < 0) {
-                            a.s0_out_nyq[row] = o0;
-                            if constexpr (OP == OP_ADMM) a.s1_out_nyq[row] = o1;
+                            *o0n = v0;
+                            if constexpr (OP == OP_ADMM) *o1n = v1;
                         } else {
-                            a.s0_out[row * M + bin(e)] = o0;
-                            if constexpr (OP == OP_ADMM) a.s1_out[row * M + bin(e)] = o1;
+                            o0[bin(e)] = v0;
+                            if constexpr (OP == OP_ADMM) o1[bin(e)] = v1;
                         }
                     }
-                } io{a, e1, mstage, row, l, hi_adj, kq0, owned, s0n, s1n, mgn};
+                } io{qstage, mstage, OP == OP_ADMM ? a.s1_in + row * M : nullptr, a.s0_out + row * M,
+                     OP == OP_ADMM ? a.s1_out + row * M : nullptr, a.s0_out_nyq + row,
+                     OP == OP_ADMM ? a.s1_out_nyq + row : nullptr, l, l + hi_adj, M - l, M - l - hi_adj, kq0, owned,
+                     s0n, s1n, mgn};
                 float2 twr[8];
                 tmem_ld16(tlane + TC_TWR, reinterpret_cast<float*>(twr));
                 float dsum = 0.f, esum = 0.f;
@@ -357,9 +395,18 @@ __global__ void __launch_bounds__(WARPS * 32, 1) warp_iter_kernel(const WArgs a)
                 if constexpr (SUMS) { if (owned) { dacc += (double)dsum; eacc += (double)esum; } }
             }
             __syncwarp();                          // every lane has read its classes from E2 and its staged state
-            if (t + 1 < t1) stage_mag(a, row + 1, l, mstage);
+            if (t + 1 < t1) {
+                stage_rows(a, row + 1, qstage_s, mstage_s, sbar);
+                if (l == 0) {
+                    s0n_next = __ldg(a.s0_in_nyq + row + 1); mgn_next = __ldg(a.mag_nyq + row + 1);
+                    if constexpr (OP == OP_ADMM) s1n_next = __ldg(a.s1_in_nyq + row + 1);
+                }
+            }
             inv_pass3(l, A, Bv, e2);
             __syncwarp();
+            const bool emit = owned && block_valid(a, t);
+            float2 ie[4];
+            if (emit) load_inv_env(a, t, l, ie);    // early: the latency hides behind the last two passes
             inv_pass2(l, e2, tw2, e1);
             __syncwarp();
             {
@@ -381,7 +428,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) warp_iter_kernel(const WArgs a)
                 }
                 tmem_st16(twarp + 24, reinterpret_cast<const float*>(v + 4));
                 tmem_st8(twarp + 40, reinterpret_cast<const float*>(v + 12));
-                if (owned && block_valid(a, t)) store_block(a, xo, t, l, v);
+                if (emit) store_block_ie(a, xo, t, l, v, ie);
             }
         }
         if (t1 == a.T) {      // tail of the signal: blocks T, T+1, T+2 are complete now
@@ -422,6 +469,8 @@ static int launch(const WArgs& a0, cudaStream_t st) {
     // SPECINV_FAST_FORCE=1: send even tiny problems through this kernel (the tests do)
     const char* env_force = getenv("SPECINV_FAST_FORCE");
     const bool force = env_force && env_force[0] == '1';
+    // the TMA bulk copies need 16-byte aligned rows
+    if ((((uintptr_t)a.x_in | (uintptr_t)a.s0_in | (uintptr_t)a.mag) & 15) != 0) return SPECINV_ERR_UNSUPPORTED;
     a.frames_total = (long long)a.B * a.T;
     const int slots = g_sms * WARPS;
     // ranges of at least 24 frames keep the 3-frame halo below ~12 %
@@ -448,11 +497,8 @@ static int launch(const WArgs& a0, cudaStream_t st) {
 }
 
 // 12 warps per CTA with 168 registers each (no spills) beat 16 x 128 (a few spills): GL 1.18 vs 1.21 ms, ADMM 1.98
-// vs 2.67 ms per iteration at B = 512, T = 938.  SPECINV_FASTW_WARPS=16 selects the latter (A-B timing).
-static int warps_choice() {
-    const char* e = getenv("SPECINV_FASTW_WARPS");
-    return e && atoi(e) == 16 ? 16 : 12;
-}
+// vs 2.67 ms per iteration at B = 512, T = 938; 12 x 15 KB of staging also is what fits the shared memory.
+constexpr int WARPS = 12;
 
 }  // namespace wfast
 
@@ -481,8 +527,7 @@ int fastw_gl_iter(const specinv_desc* d, const void* plan, const void* x_in, voi
     a.s0_out = (float2*)q_out_main; a.s0_out_nyq = (float2*)q_out_nyq;
     a.mag = (const float*)mag_main; a.mag_nyq = (const float*)mag_nyq;
     a.coef = (float)lr; a.sums = sums;
-    return wfast::warps_choice() == 12 ? wfast::launch<wfast::OP_GL, 12>(a, (cudaStream_t)stream)
-                                       : wfast::launch<wfast::OP_GL, 16>(a, (cudaStream_t)stream);
+    return wfast::launch<wfast::OP_GL, wfast::WARPS>(a, (cudaStream_t)stream);
 }
 
 int fastw_admm_iter(const specinv_desc* d, const void* plan, const void* x_in, void* x_out,
@@ -500,8 +545,7 @@ int fastw_admm_iter(const specinv_desc* d, const void* plan, const void* x_in, v
     a.s1_out = (float2*)U_out_main; a.s1_out_nyq = (float2*)U_out_nyq;
     a.mag = (const float*)mag_main; a.mag_nyq = (const float*)mag_nyq;
     a.coef = (float)rho; a.coef2 = (float)(1.0 / (1.0 + rho)); a.sums = sums;
-    return wfast::warps_choice() == 12 ? wfast::launch<wfast::OP_ADMM, 12>(a, (cudaStream_t)stream)
-                                       : wfast::launch<wfast::OP_ADMM, 16>(a, (cudaStream_t)stream);
+    return wfast::launch<wfast::OP_ADMM, wfast::WARPS>(a, (cudaStream_t)stream);
 }
 
 }  // namespace specinv
