@@ -123,6 +123,18 @@ SPX_HD void fwd_pass3(int l, const float2* e2, float2* A, float2* B) {
 }
 
 // ---- point-wise stage ------------------------------------------------------------------------------------
+// q * mag / (|q| + 1e-16) (methods.py:246-247) with ONE special-function op: mag * rsqrt(|q|^2 + 1e-32).  The two
+// agree to rounding unless |q| ~ 1e-16 (where both give q * mag * ~1e16), and |q| = 0 gives 0, not NaN.
+#ifdef __CUDA_ARCH__
+__device__ __forceinline__ float approx_rsqrt(float v) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
+#else
+inline float approx_rsqrt(float v) { return 1.0f / sqrtf(v); }
+#endif
+SPX_HD float2 project_rsq(float2 q, float mag) {
+    const float s = mag * approx_rsqrt(q.x * q.x + (q.y * q.y + 1e-32f));
+    return f2(q.x * s, q.y * s);
+}
+
 // One bin: s = STFT bin of the current estimate.  Returns the value fed to the inverse transform.
 template <int OP, bool SUMS>
 SPX_HD float2 bin_update(float2 s, float2 a0, float2 a1, float m, float coef, float coef2, float2& o0, float2& o1,
@@ -135,12 +147,12 @@ SPX_HD float2 bin_update(float2 s, float2 a0, float2 a1, float m, float coef, fl
     if constexpr (OP == OP_GL) {
         const float2 q = f2(s.x - a0.x * coef, s.y - a0.y * coef);
         o0 = q;
-        return project_fast(q, m);
+        return project_rsq(q, m);
     } else {
         const float rho = coef, inv = coef2;
         const float2 Z = f2((rho * (a0.x + a1.x) + s.x) * inv, (rho * (a0.y + a1.y) + s.y) * inv);
         const float2 Un = f2(a1.x + a0.x - Z.x, a1.y + a0.y - Z.y);
-        const float2 Xn = project_fast(f2(Z.x - Un.x, Z.y - Un.y), m);
+        const float2 Xn = project_rsq(f2(Z.x - Un.x, Z.y - Un.y), m);
         o0 = Xn; o1 = Un;
         return f2(Xn.x + Un.x, Xn.y + Un.y);
     }

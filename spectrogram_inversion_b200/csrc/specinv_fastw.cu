@@ -182,7 +182,11 @@ __device__ __forceinline__ void store_block(const WArgs& a, float* __restrict__ 
 __device__ __forceinline__ void load_inv_env(const WArgs& a, int u, int l, float2* ie) {
     const long long base = (long long)u * HOP - a.P;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) ie[j] = __ldg(reinterpret_cast<const float2*>(a.inv_env + base + 64 * j + 2 * l));
+    for (int j = 0; j < 4; ++j) {
+        // volatile + "memory": the compiler must not sink these loads down to their use
+        asm volatile("ld.global.nc.v2.f32 {%0, %1}, [%2];" : "=f"(ie[j].x), "=f"(ie[j].y)
+                     : "l"(a.inv_env + base + 64 * j + 2 * l) : "memory");
+    }
 }
 __device__ __forceinline__ void store_block_ie(const WArgs& a, float* __restrict__ xo, int u, int l, const float2* blk,
                                                const float2* ie) {
