@@ -1,23 +1,26 @@
-// Per-lane building blocks of the "warp per frame" fused iteration kernel (n_fft = 1024, hop = 256).
+// Per-lane building blocks of the "16 values per lane" fused iteration kernels (onesided, fp32, hop = n_fft/4):
+//   LANES =  32: n_fft = 1024, hop =  256 -- one warp per frame        (M = 512  = 8 x 8 x 8)
+//   LANES =  64: n_fft = 2048, hop =  512 -- two warps per frame       (M = 1024 = 8 x 16 x 8)
+//   LANES = 128: n_fft = 4096, hop = 1024 -- four warps per frame      (M = 2048 = 16 x 16 x 8)
 //
-// A frame's real FFT of N = 1024 is a complex FFT of M = 512 = 8 x 8 x 8 points done by the 32 lanes of ONE
-// warp holding 16 complex values each, in three radix-8 passes with two exchanges through shared memory
-// per direction.  With n = 64 a + 8 b + c and k = ka + 8 kb + 64 kc:
-//   pass 1 : lane l owns z[32 i + l], i = 0..15 (i = 2 a + s; c = l & 7, b = (l >> 3) + 4 s): two FFT8 over a,
-//            times W_512^((8 b + c) ka)                                        -- exchange E1 (ka, b, c) --
-//   pass 2 : lane l owns (ka = (l >> 3) + 4 r, c = l & 7), r = 0, 1: two FFT8 over b, times W_64^(c kb)
-//                                                                              -- exchange E2 (k1, c) --
-//   pass 3 : lane l owns the residue classes k1 = ka + 8 kb in {l, 64 - l} ({0, 32} for l = 0): two FFT8
-//            over c -> Zh[k1 + 64 kc].
-// Class 64 - l is the mirror (k -> M - k) of class l, so every (Z[k], Z[M-k]) pair of the real-FFT
-// post/pre-processing lives in ONE thread (as in gl_fast_core.cuh): projection and momentum / ADMM update
-// run in registers on the FFT outputs; for a fixed kc the 32 lanes touch 32 consecutive bins (256-byte
-// coalesced rows of q / mag).  The inverse runs the passes backwards.
-// A hop of 256 samples is 4 of a lane's 16 sample pairs (i -> i + 4): overlap-add is a per-thread
-// shift-accumulate and the input ring is thread-private, as in the half-warp kernel.
+// A frame's real FFT of N points is a complex FFT of M = N/2 = R1 x R2 x 8 points done by LANES lanes holding
+// 16 complex values each, in three passes with two exchanges through shared memory per direction.  With
+// n = 8 R2 a + 8 b + c and k = ka + R1 kb + R1 R2 kc:
+//   pass 1 : lane l owns z[LANES i + l], i = 0..15: 16/R1 FFTs of R1 points over a, times W_M^((8 b + c) ka)
+//                                                                              -- exchange E1 (ka, b, c) --
+//   pass 2 : lane l owns (ka = (l >> 3) + (LANES / 8) r, c = l & 7), r < 16/R2: FFTs of R2 points over b,
+//            times W_(8 R2)^(c kb)                                             -- exchange E2 (k1, c) --
+//   pass 3 : lane l owns the residue classes k1 = ka + R1 kb in {l, 2 LANES - l} ({0, LANES} for l = 0): two
+//            FFT8 over c -> Zh[k1 + 2 LANES kc].
+// Class 2 LANES - l is the mirror (k -> M - k) of class l, so every (Z[k], Z[M-k]) pair of the real-FFT
+// post/pre-processing lives in ONE thread: projection and momentum / ADMM update run in registers on the FFT
+// outputs; for a fixed kc consecutive lanes touch consecutive bins (coalesced rows of q / mag).  The inverse
+// runs the passes backwards.
+// A hop is 4 of a lane's 16 sample pairs (i -> i + 4): overlap-add is a per-thread shift-accumulate and the
+// input ring is thread-private.
 //
-// 16 complex values per lane (instead of 32) keep the kernel under 128 registers, so 16 warps per SM run
-// free (no lockstep), and the fully unrolled frame body (~26 KB) fits the 32 KB instruction cache.
+// 16 complex values per lane keep the kernels under 168 registers (12 free-running warps per SM, no lockstep)
+// and the fully unrolled frame body (~28 KB) inside the instruction cache.
 //
 // Everything is __host__ __device__: tests/host_emu runs the exact index logic on the CPU.
 #pragma once
@@ -31,90 +34,106 @@ using fast::cmulf;
 using fast::cmulcf;
 using fast::post_pair;
 using fast::pre_pair;
-using fast::project_fast;
 using fast::approx_sqrt;
 using fast::OP_GL;
 using fast::OP_ADMM;
 
-constexpr int N = 1024;
-constexpr int M = 512;
-constexpr int HOP = 256;
 constexpr int V = 16;            // complex values per lane
-constexpr int EXF2 = 512;        // float2 elements of one exchange buffer (4 KB, XOR-swizzled, no padding)
 
-// ---- exchange addressing (float2 units) ----------------------------------------------------------------
-// Rows of 8 float2 = four 16-byte columns; column index XOR ((row >> 1) & 3) makes both the 128-bit
-// row accesses (8 consecutive rows per quarter-warp) and the 64-bit scattered accesses conflict free.
-SPX_HD int ex_addr(int row, int col) { return 8 * row + 2 * (((col >> 1) ^ (row >> 1)) & 3) + (col & 1); }
-// 128-bit access: elements (row, 2 p) and (row, 2 p + 1)
-SPX_HD int ex_addr4(int row, int p) { return 8 * row + 2 * ((p ^ (row >> 1)) & 3); }
+template <int LANES>
+struct Cfg {
+    static_assert(LANES == 32 || LANES == 64 || LANES == 128, "LANES");
+    static constexpr int M = 16 * LANES;          // complex FFT size = bins in a main row
+    static constexpr int N = 2 * M;               // n_fft
+    static constexpr int HOP = N / 4;             // samples
+    static constexpr int R1 = LANES == 128 ? 16 : 8;
+    static constexpr int R2 = 2 * LANES / R1;     // 8, 16, 16
+    static constexpr int S1 = V / R1;             // pass-1 transforms per lane
+    static constexpr int S2 = V / R2;             // pass-2 transforms per lane
+    static constexpr int CLS = 2 * LANES;         // residue classes k1 = ka + R1 kb
+};
 
-SPX_HD int class_b(int l) { return l == 0 ? 32 : 64 - l; }
-// bin of the P element of pair slot j (the Q element is bin 512 - kP); lane 0 slot 0 is the special
-// DC / Nyquist / bin-256 slot
-template <int J>
-SPX_HD int slot_bin(int l) {
-    if (l != 0) return l + 64 * J;
-    if constexpr (J < 4) return 64 * J;
-    else return 32 + 64 * (J - 4);
+template <int R, bool INV> SPX_HD void fft_small(float2* t) {
+    if constexpr (R == 8) fft8<INV>(t); else fft16<INV>(t);
 }
-SPX_HD int slot_bin_rt(int l, int j) { return l != 0 ? l + 64 * j : (j < 4 ? 64 * j : 32 + 64 * (j - 4)); }
+
+// ---- exchange addressing (float2 units), XOR-swizzled 16-byte columns, no padding --------------------------
+// E1: rows (ka, c) -> 8 ka + c of R2 float2; E2: rows k1 of 8 float2.  The swizzle makes both the 128-bit row
+// accesses (8 consecutive rows per quarter-warp) and the 64-bit scattered accesses conflict free.
+template <int RLEN> SPX_HD int ex_swz(int row) { return RLEN == 8 ? ((row >> 1) & 3) : (row & 7); }
+template <int RLEN> SPX_HD int ex_addr(int row, int col) {
+    return RLEN * row + 2 * (((col >> 1) ^ ex_swz<RLEN>(row)) & (RLEN / 2 - 1)) + (col & 1);
+}
+// 128-bit access: elements (row, 2 p) and (row, 2 p + 1)
+template <int RLEN> SPX_HD int ex_addr4(int row, int p) { return RLEN * row + 2 * ((p ^ ex_swz<RLEN>(row)) & (RLEN / 2 - 1)); }
+
+template <int LANES> SPX_HD int class_b(int l) { return l == 0 ? LANES : 2 * LANES - l; }
+// bin of the P element of pair slot j (the Q element is bin M - kP); lane 0 slot 0 is the special
+// DC / Nyquist / bin-M/2 slot
+template <int LANES> SPX_HD int slot_bin_rt(int l, int j) {
+    return l != 0 ? l + 2 * LANES * j : (j < 4 ? 2 * LANES * j : LANES + 2 * LANES * (j - 4));
+}
 
 // Per-lane constant tables (the kernel keeps them in tensor memory, the host emulation in arrays)
+template <int LANES>
 struct LaneTables {
-    float2 wa[V];     // 0.5 * analysis window pairs (w[64 i + 2 l], w[64 i + 2 l + 1])
-    float2 ws[V];     // synthesis window pairs (already scaled by 1/N or N^-1/2)
-    float2 tw1[V];    // [8 s + ka]  W_512^((l + 32 s) ka)
-    float2 tw2[8];    // [kb]        W_64^((l & 7) kb)
-    float2 twr[8];    // [j]         W_1024^(slot_bin<j>(l))
+    float2 wa[V];                     // 0.5 * analysis window pairs (w[2 LANES i + 2 l], w[2 LANES i + 2 l + 1])
+    float2 ws[V];                     // synthesis window pairs (already scaled by 1/N or N^-1/2)
+    float2 tw1[V];                    // [R1 s + ka]  W_M^((l + LANES s) ka)
+    float2 tw2[Cfg<LANES>::R2];       // [kb]         W_(8 R2)^((l & 7) kb)
+    float2 twr[8];                    // [j]          W_N^(slot_bin(l, j))
 };
 
 // ---- forward ---------------------------------------------------------------------------------------------
-// v[i] = windowed z[32 i + l] on entry
+// v[i] = windowed z[LANES i + l] on entry
+template <int LANES>
 SPX_HD void fwd_pass1(int l, float2* v, const float2* tw1, float2* e1) {
+    using C = Cfg<LANES>;
     const int c = l & 7;
-    static_for<2>([&](auto sc) {
+    static_for<C::S1>([&](auto sc) {
         constexpr int s = decltype(sc)::value;
-        float2 t[8];
-        static_for<8>([&](auto ac) { constexpr int a = decltype(ac)::value; t[a] = v[2 * a + s]; });
-        fft8<false>(t);
-        const int b = (l >> 3) + 4 * s;
-        static_for<8>([&](auto kc) {
+        float2 t[C::R1];
+        static_for<C::R1>([&](auto ac) { constexpr int a = decltype(ac)::value; t[a] = v[C::S1 * a + s]; });
+        fft_small<C::R1, false>(t);
+        const int b = (l + LANES * s) >> 3;
+        static_for<C::R1>([&](auto kc) {
             constexpr int ka = decltype(kc)::value;
-            const float2 y = ka == 0 ? t[0] : cmulf(t[ka], tw1[8 * s + ka]);
-            e1[ex_addr(8 * ka + c, b)] = y;
+            const float2 y = ka == 0 ? t[0] : cmulf(t[ka], tw1[C::R1 * s + ka]);
+            e1[ex_addr<C::R2>(8 * ka + c, b)] = y;
         });
     });
 }
 
-// u[8 r + kb] = Y2[ka_r, kb, c] (already twiddled), written to E2
+template <int LANES>
 SPX_HD void fwd_pass2(int l, const float2* e1, const float2* tw2, float2* e2) {
+    using C = Cfg<LANES>;
     const int c = l & 7;
-    static_for<2>([&](auto rc) {
+    static_for<C::S2>([&](auto rc) {
         constexpr int r = decltype(rc)::value;
-        const int ka = (l >> 3) + 4 * r;
-        float2 t[8];
-        static_for<4>([&](auto pc) {
+        const int ka = (l >> 3) + (LANES / 8) * r;
+        float2 t[C::R2];
+        static_for<C::R2 / 2>([&](auto pc) {
             constexpr int p = decltype(pc)::value;
-            const float4 q = *reinterpret_cast<const float4*>(e1 + ex_addr4(8 * ka + c, p));
+            const float4 q = *reinterpret_cast<const float4*>(e1 + ex_addr4<C::R2>(8 * ka + c, p));
             t[2 * p] = f2(q.x, q.y); t[2 * p + 1] = f2(q.z, q.w);
         });
-        fft8<false>(t);
-        static_for<8>([&](auto kc) {
+        fft_small<C::R2, false>(t);
+        static_for<C::R2>([&](auto kc) {
             constexpr int kb = decltype(kc)::value;
             const float2 y = kb == 0 ? t[0] : cmulf(t[kb], tw2[kb]);
-            e2[ex_addr(ka + 8 * kb, c)] = y;
+            e2[ex_addr<8>(ka + C::R1 * kb, c)] = y;
         });
     });
 }
 
-// A[kc] = Zh[l + 64 kc], B[kc] = Zh[class_b(l) + 64 kc]
+// A[kc] = Zh[l + 2 LANES kc], B[kc] = Zh[class_b(l) + 2 LANES kc]
+template <int LANES>
 SPX_HD void fwd_pass3(int l, const float2* e2, float2* A, float2* B) {
-    const int ra = l, rb = class_b(l);
+    const int ra = l, rb = class_b<LANES>(l);
     static_for<4>([&](auto pc) {
         constexpr int p = decltype(pc)::value;
-        const float4 qa = *reinterpret_cast<const float4*>(e2 + ex_addr4(ra, p));
-        const float4 qb = *reinterpret_cast<const float4*>(e2 + ex_addr4(rb, p));
+        const float4 qa = *reinterpret_cast<const float4*>(e2 + ex_addr4<8>(ra, p));
+        const float4 qb = *reinterpret_cast<const float4*>(e2 + ex_addr4<8>(rb, p));
         A[2 * p] = f2(qa.x, qa.y); A[2 * p + 1] = f2(qa.z, qa.w);
         B[2 * p] = f2(qb.x, qb.y); B[2 * p + 1] = f2(qb.z, qb.w);
     });
@@ -161,7 +180,7 @@ SPX_HD float2 bin_update(float2 s, float2 a0, float2 a1, float m, float coef, fl
 // Pair processing with the point-wise update, in place: on return A / B hold the inputs of the inverse
 // pass 3.  (dsum, esum) += this lane's share of sum (|s|-mag)^2, sum |s|^2.
 // `io` gives access to the state of the lane's bins, element e = 2 j (the P bin of slot j) or 2 j + 1 (the Q
-// bin; lane 0 slot 0: bins 0 and 256), e = -1: the Nyquist bin (lane 0 only):
+// bin; lane 0 slot 0: bins 0 and M/2), e = -1: the Nyquist bin (lane 0 only):
 //     float2 io.s0(e), io.s1(e); float io.mag(e); void io.put(e, o0, o1)
 // so that values are fetched right where they are used (no block of 48 live registers).
 template <int OP, bool SUMS, typename IO>
@@ -178,7 +197,7 @@ SPX_HD void pointwise(int l, float2* A, float2* B, const float2* twr, IO& io, fl
     };
     // slot 0
     if (l0) {
-        // lane 0: A[0] = Zh[0] -> DC and Nyquist (both real), A[4] = Zh[256] -> bin 256 = conj(Z[256])
+        // lane 0: A[0] = Zh[0] -> DC and Nyquist (both real), A[4] = Zh[M/2] -> bin M/2 = conj(Z[M/2])
         const float2 z0 = A[0], z4 = A[4];
         const float2 h0 = upd(std::integral_constant<int, 0>{}, f2(2.f * (z0.x + z0.y), 0.f));
         const float2 hM = upd(std::integral_constant<int, -1>{}, f2(2.f * (z0.x - z0.y), 0.f));
@@ -212,50 +231,56 @@ SPX_HD void pointwise(int l, float2* A, float2* B, const float2* twr, IO& io, fl
 }
 
 // ---- inverse ---------------------------------------------------------------------------------------------
+template <int LANES>
 SPX_HD void inv_pass3(int l, float2* A, float2* B, float2* e2) {
     fft8<true>(A);       // A[c] = Y2'[class a, c]
     fft8<true>(B);
-    const int ra = l, rb = class_b(l);
+    const int ra = l, rb = class_b<LANES>(l);
     static_for<4>([&](auto pc) {
         constexpr int p = decltype(pc)::value;
-        *reinterpret_cast<float4*>(e2 + ex_addr4(ra, p)) = make_float4(A[2 * p].x, A[2 * p].y, A[2 * p + 1].x, A[2 * p + 1].y);
-        *reinterpret_cast<float4*>(e2 + ex_addr4(rb, p)) = make_float4(B[2 * p].x, B[2 * p].y, B[2 * p + 1].x, B[2 * p + 1].y);
+        *reinterpret_cast<float4*>(e2 + ex_addr4<8>(ra, p)) = make_float4(A[2 * p].x, A[2 * p].y, A[2 * p + 1].x, A[2 * p + 1].y);
+        *reinterpret_cast<float4*>(e2 + ex_addr4<8>(rb, p)) = make_float4(B[2 * p].x, B[2 * p].y, B[2 * p + 1].x, B[2 * p + 1].y);
     });
 }
 
+template <int LANES>
 SPX_HD void inv_pass2(int l, const float2* e2, const float2* tw2, float2* e1) {
+    using C = Cfg<LANES>;
     const int c = l & 7;
-    static_for<2>([&](auto rc) {
+    static_for<C::S2>([&](auto rc) {
         constexpr int r = decltype(rc)::value;
-        const int ka = (l >> 3) + 4 * r;
-        float2 t[8];
-        static_for<8>([&](auto kc) {
+        const int ka = (l >> 3) + (LANES / 8) * r;
+        float2 t[C::R2];
+        static_for<C::R2>([&](auto kc) {
             constexpr int kb = decltype(kc)::value;
-            const float2 y = e2[ex_addr(ka + 8 * kb, c)];
+            const float2 y = e2[ex_addr<8>(ka + C::R1 * kb, c)];
             t[kb] = kb == 0 ? y : cmulcf(y, tw2[kb]);
         });
-        fft8<true>(t);   // t[b] = Y1'[ka, b, c] (before the pass-1 twiddle)
-        static_for<4>([&](auto pc) {
+        fft_small<C::R2, true>(t);   // t[b] = Y1'[ka, b, c] (before the pass-1 twiddle)
+        static_for<C::R2 / 2>([&](auto pc) {
             constexpr int p = decltype(pc)::value;
-            *reinterpret_cast<float4*>(e1 + ex_addr4(8 * ka + c, p)) = make_float4(t[2 * p].x, t[2 * p].y, t[2 * p + 1].x, t[2 * p + 1].y);
+            *reinterpret_cast<float4*>(e1 + ex_addr4<C::R2>(8 * ka + c, p)) =
+                make_float4(t[2 * p].x, t[2 * p].y, t[2 * p + 1].x, t[2 * p + 1].y);
         });
     });
 }
 
-// v[i] = z'[32 i + l] (unscaled)
+// v[i] = z'[LANES i + l] (unscaled)
+template <int LANES>
 SPX_HD void inv_pass1(int l, const float2* e1, const float2* tw1, float2* v) {
+    using C = Cfg<LANES>;
     const int c = l & 7;
-    static_for<2>([&](auto sc) {
+    static_for<C::S1>([&](auto sc) {
         constexpr int s = decltype(sc)::value;
-        const int b = (l >> 3) + 4 * s;
-        float2 t[8];
-        static_for<8>([&](auto kc) {
+        const int b = (l + LANES * s) >> 3;
+        float2 t[C::R1];
+        static_for<C::R1>([&](auto kc) {
             constexpr int ka = decltype(kc)::value;
-            const float2 y = e1[ex_addr(8 * ka + c, b)];
-            t[ka] = ka == 0 ? y : cmulcf(y, tw1[8 * s + ka]);
+            const float2 y = e1[ex_addr<C::R2>(8 * ka + c, b)];
+            t[ka] = ka == 0 ? y : cmulcf(y, tw1[C::R1 * s + ka]);
         });
-        fft8<true>(t);
-        static_for<8>([&](auto ac) { constexpr int a = decltype(ac)::value; v[2 * a + s] = t[a]; });
+        fft_small<C::R1, true>(t);
+        static_for<C::R1>([&](auto ac) { constexpr int a = decltype(ac)::value; v[C::S1 * a + s] = t[a]; });
     });
 }
 

@@ -1,16 +1,21 @@
-// "Warp per frame" fused iteration kernel for n_fft = 1024, hop = 256 (onesided, fp32): the headline shape.
+// Fused iteration kernels for hop = n_fft/4, onesided, fp32 with 16 complex values per lane (gl_warp_core.cuh):
+//   n_fft = 1024 / hop = 256  : one warp per frame    (LANES = 32)   -- the headline shape (cfg2)
+//   n_fft = 2048 / hop = 512  : two warps per frame   (LANES = 64)   -- cfg1, cfg4
+//   n_fft = 4096 / hop = 1024 : four warps per frame  (LANES = 128)  -- cfg5
 //
-// One launch = one whole Griffin-Lim (or ADMM) iteration.  Every warp walks through a contiguous range of
-// the B*T frames (crossing signal boundaries if need be) and for each frame does, entirely on chip:
-//   window -> real FFT (512-point complex FFT as 8 x 8 x 8, gl_warp_core.cuh) -> momentum / ADMM update and
+// One launch = one whole Griffin-Lim (or ADMM) iteration.  Every group of LANES/32 warps walks through a
+// contiguous range of the B*T frames (crossing signal boundaries if need be) and for each frame does,
+// entirely on chip:
+//   window -> real FFT (M-point complex FFT in three passes, gl_warp_core.cuh) -> momentum / ADMM update and
 //   magnitude projection on the FFT outputs in registers -> inverse FFT -> windowed overlap-add.
-//   * 16 complex values per lane: < 128 registers, 16 free-running warps per SM (no lockstep barriers), and
-//     the unrolled frame body fits the instruction cache;
+//   * 16 complex values per lane: <= 168 registers, 12 free-running warps per SM (no CTA-wide barriers; the
+//     warps of a frame group meet at a named barrier per exchange), and the unrolled frame body fits the
+//     instruction cache;
 //   * the lane-constant tables (windows, twiddles), the lane-private input ring and the overlap-add carry
 //     live in TENSOR MEMORY and move with tcgen05.ld / tcgen05.st (one instruction per 8..32 registers, no
 //     shared-memory bandwidth); shared memory only carries the four FFT exchanges (swizzled, conflict free);
-//   * the q / X and magnitude rows of the NEXT frame and the next 256 input samples are fetched by the TMA
-//     (cp.async.bulk, one elected lane, mbarrier completion) into per-warp staging rows one frame ahead, so
+//   * the q / X and magnitude rows of the NEXT frame and the next hop of input samples are fetched by the TMA
+//     (cp.async.bulk, one elected lane, mbarrier completion) into per-group staging rows one frame ahead, so
 //     the compute never waits on DRAM; the new state is written straight from registers, 256 contiguous
 //     bytes per warp instruction.
 // A range re-computes the 3 frames before it as a halo (state not written, output not stored), so ranges are
@@ -35,7 +40,7 @@ struct WArgs {
     int B, T, P, pad_mode;
     long long L;
     long long frames_total;     // B * T
-    int ranges;                 // number of warps that get a frame range
+    int ranges;                 // number of warp groups that get a frame range
 };
 
 // ---- small PTX wrappers ---------------------------------------------------------------------------------
@@ -129,126 +134,148 @@ __device__ __forceinline__ void tmem_st32(unsigned taddr, const float* r) {
 }
 
 // TMEM columns (per lane): constant tables shared by the warps of one sub-partition, then per-warp state
-constexpr int TC_WA = 0, TC_WS = 32, TC_TW1 = 64, TC_TW2 = 96, TC_TWR = 112, TC_WARP = 128;
+constexpr int TC_WA = 0, TC_WS = 32, TC_TW1 = 64, TC_TW2 = 96, TC_TWR = 128, TC_WARP = 144;
 constexpr int TC_PER_WARP = 48;     // ring: 3 blocks x 8 words, carry: 24 words
 constexpr int TMEM_COLS = 512;
-// float2 of shared memory per warp: E1, E2, staged input block (1 KB), magnitude row (2 KB), q / X row (4 KB)
-constexpr int WARP_F2 = 2 * EXF2 + 128 + 256 + 512;
+constexpr int WARPS = 12;           // 12 warps x 168 registers (no spills); 12 x 15 KB of staging fills the shared memory
+// float2 of shared memory per WARP (a frame group owns LANES/32 times as much): E1, E2 (M float2 each per group),
+// staged input block (HOP floats), magnitude row (M floats), q / X row (M float2)
+constexpr int WARP_F2 = 2 * 512 + 128 + 256 + 512;
 
-// Fetch block u (padded samples [256 u, 256 u + 256)) of signal x: lane l gets the pairs at 64 j + 2 l.
+// Synchronise the warps that share a frame (named barrier per group) or just the warp.
+template <int LANES>
+__device__ __forceinline__ void group_sync(int bar_id) {
+    if constexpr (LANES == 32) __syncwarp();
+    else asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(LANES) : "memory");
+}
+
+// Fetch block u (padded samples [HOP u, HOP u + HOP)) of signal x: lane l gets the pairs at 2 LANES j + 2 l.
+template <int LANES>
 __device__ __forceinline__ void fetch_block_regs(const WArgs& a, const float* __restrict__ x, int u, int l, float2* nb) {
+    constexpr int HOP = Cfg<LANES>::HOP;
     const long long base = (long long)u * HOP - a.P;
     if (base >= 0 && base + HOP <= a.L) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) nb[j] = __ldg(reinterpret_cast<const float2*>(x + base + 64 * j + 2 * l));
+        for (int j = 0; j < 4; ++j) nb[j] = __ldg(reinterpret_cast<const float2*>(x + base + 2 * LANES * j + 2 * l));
     } else {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const long long pp = (long long)u * HOP + 64 * j + 2 * l;
+            const long long pp = (long long)u * HOP + 2 * LANES * j + 2 * l;
             const long long i0 = pad_index(pp, a.P, a.L, a.pad_mode), i1 = pad_index(pp + 1, a.P, a.L, a.pad_mode);
             nb[j] = f2(i0 >= 0 ? x[i0] : 0.f, i1 >= 0 ? x[i1] : 0.f);
         }
     }
 }
-// Same into the staging buffer xs[32 j + l] (= the block's 1 KB in memory order): interior blocks by one TMA
-// bulk copy (returns true: the data arrives on `bar`), padded edge blocks element by element.
+// Same into the staging buffer xs[LANES j + l] (= the block's bytes in memory order): interior blocks by one TMA
+// bulk copy issued by the group's first warp (returns true: the data arrives on `bar`), padded edge blocks
+// element by element.
+template <int LANES>
 __device__ __forceinline__ bool fetch_block_staged(const WArgs& a, const float* __restrict__ x, int u, int l, float2* xs,
                                                    unsigned xs_s, unsigned bar) {
+    constexpr int HOP = Cfg<LANES>::HOP;
     const long long base = (long long)u * HOP - a.P;
     if (base >= 0 && base + HOP <= a.L) {
-        if (elect_one()) { mbar_expect_tx(bar, HOP * 4); bulk_g2s(xs_s, x + base, HOP * 4, bar); }
+        if (l < 32) { if (elect_one()) { mbar_expect_tx(bar, HOP * 4); bulk_g2s(xs_s, x + base, HOP * 4, bar); } }
         return true;
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        const long long pp = (long long)u * HOP + 64 * j + 2 * l;
+        const long long pp = (long long)u * HOP + 2 * LANES * j + 2 * l;
         const long long i0 = pad_index(pp, a.P, a.L, a.pad_mode), i1 = pad_index(pp + 1, a.P, a.L, a.pad_mode);
-        xs[32 * j + l] = f2(i0 >= 0 ? x[i0] : 0.f, i1 >= 0 ? x[i1] : 0.f);
+        xs[LANES * j + l] = f2(i0 >= 0 ? x[i0] : 0.f, i1 >= 0 ? x[i1] : 0.f);
     }
     return false;
 }
+template <int LANES>
 __device__ __forceinline__ bool block_valid(const WArgs& a, int u) {
-    const long long base = (long long)u * HOP - a.P;
-    return base >= 0 && base + HOP <= a.L;
+    const long long base = (long long)u * Cfg<LANES>::HOP - a.P;
+    return base >= 0 && base + Cfg<LANES>::HOP <= a.L;
 }
-__device__ __forceinline__ void store_block(const WArgs& a, float* __restrict__ xo, int u, int l, const float2* blk) {
-    const long long base = (long long)u * HOP - a.P;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const float2 ie = __ldg(reinterpret_cast<const float2*>(a.inv_env + base + 64 * j + 2 * l));
-        *reinterpret_cast<float2*>(xo + base + 64 * j + 2 * l) = f2(blk[j].x * ie.x, blk[j].y * ie.y);
-    }
-}
+template <int LANES>
 __device__ __forceinline__ void load_inv_env(const WArgs& a, int u, int l, float2* ie) {
-    const long long base = (long long)u * HOP - a.P;
+    const long long base = (long long)u * Cfg<LANES>::HOP - a.P;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         // volatile + "memory": the compiler must not sink these loads down to their use
         asm volatile("ld.global.nc.v2.f32 {%0, %1}, [%2];" : "=f"(ie[j].x), "=f"(ie[j].y)
-                     : "l"(a.inv_env + base + 64 * j + 2 * l) : "memory");
+                     : "l"(a.inv_env + base + 2 * LANES * j + 2 * l) : "memory");
     }
 }
+template <int LANES>
 __device__ __forceinline__ void store_block_ie(const WArgs& a, float* __restrict__ xo, int u, int l, const float2* blk,
                                                const float2* ie) {
-    const long long base = (long long)u * HOP - a.P;
+    const long long base = (long long)u * Cfg<LANES>::HOP - a.P;
 #pragma unroll
     for (int j = 0; j < 4; ++j)
-        *reinterpret_cast<float2*>(xo + base + 64 * j + 2 * l) = f2(blk[j].x * ie[j].x, blk[j].y * ie[j].y);
+        *reinterpret_cast<float2*>(xo + base + 2 * LANES * j + 2 * l) = f2(blk[j].x * ie[j].x, blk[j].y * ie[j].y);
 }
 // Fetch the q / X row and the magnitude row of frame `row` into the staging rows (one elected lane, TMA).
-__device__ __forceinline__ void stage_rows(const WArgs& a, long long row, unsigned qstage_s, unsigned mstage_s, unsigned bar) {
-    if (elect_one()) {
-        mbar_expect_tx(bar, M * 8 + M * 4);
-        bulk_g2s(qstage_s, a.s0_in + row * M, M * 8, bar);
-        bulk_g2s(mstage_s, a.mag + row * M, M * 4, bar);
+template <int LANES>
+__device__ __forceinline__ void stage_rows(const WArgs& a, long long row, int l, unsigned qstage_s, unsigned mstage_s, unsigned bar) {
+    constexpr int M = Cfg<LANES>::M;
+    if (l < 32) {
+        if (elect_one()) {
+            mbar_expect_tx(bar, M * 8 + M * 4);
+            bulk_g2s(qstage_s, a.s0_in + row * M, M * 8, bar);
+            bulk_g2s(mstage_s, a.mag + row * M, M * 4, bar);
+        }
     }
 }
 
-template <int OP, bool SUMS, int WARPS>
+template <int OP, bool SUMS, int LANES>
 __global__ void __launch_bounds__(WARPS * 32, 1) warp_iter_kernel(const WArgs a) {
+    using C = Cfg<LANES>;
+    constexpr int M = C::M;
+    constexpr int G = LANES / 32;                 // warps per frame group
+    constexpr int GROUPS = WARPS / G;
     static_assert(TC_WARP + ((WARPS + 3) / 4) * TC_PER_WARP <= TMEM_COLS, "TMEM columns");
     extern __shared__ __align__(16) float2 sm[];
     __shared__ unsigned s_tmem_base;
-    __shared__ __align__(8) unsigned long long s_bar[WARPS][2];    // per warp: input block, state rows
-    const int tid = threadIdx.x, warp = tid >> 5, l = tid & 31;
+    __shared__ __align__(8) unsigned long long s_bar[GROUPS][2];   // per group: input block, state rows
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int grp = warp / G;                     // frame group inside the CTA
+    const int l = tid - grp * LANES;              // lane inside the group, 0 .. LANES-1
+    const int bar_id = 1 + grp;
     if (warp == 0) tmem_alloc(&s_tmem_base, TMEM_COLS);
-    const unsigned xbar = (unsigned)__cvta_generic_to_shared(&s_bar[warp][0]), sbar = xbar + 8;
+    const unsigned xbar = (unsigned)__cvta_generic_to_shared(&s_bar[grp][0]), sbar = xbar + 8;
     if (l == 0) { mbar_init(xbar, 1); mbar_init(sbar, 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    // this warp's TMEM window: lanes 32 * (warp % 4) .. +31
+    // this warp's TMEM window: lanes 32 * (warp % 4) .. +31.  A group's warps sit on consecutive sub-partitions
+    // (G divides 4), so the position inside the group, hence the lane-constant tables, depend on warp % 4 only.
     const unsigned tlane = s_tmem_base + ((unsigned)(32 * (warp & 3)) << 16);
     if (warp < 4) {
-        // lane-constant tables of this sub-partition
+        const int tl = 32 * (warp % G) + (tid & 31);       // group lane served by this sub-partition
         float t[32];
 #pragma unroll
-        for (int i = 0; i < V; ++i) { t[2 * i] = 0.5f * a.wa[64 * i + 2 * l]; t[2 * i + 1] = 0.5f * a.wa[64 * i + 2 * l + 1]; }
+        for (int i = 0; i < V; ++i) { t[2 * i] = 0.5f * a.wa[2 * LANES * i + 2 * tl]; t[2 * i + 1] = 0.5f * a.wa[2 * LANES * i + 2 * tl + 1]; }
         tmem_st32(tlane + TC_WA, t);
 #pragma unroll
-        for (int i = 0; i < V; ++i) { t[2 * i] = a.ws[64 * i + 2 * l]; t[2 * i + 1] = a.ws[64 * i + 2 * l + 1]; }
+        for (int i = 0; i < V; ++i) { t[2 * i] = a.ws[2 * LANES * i + 2 * tl]; t[2 * i + 1] = a.ws[2 * LANES * i + 2 * tl + 1]; }
         tmem_st32(tlane + TC_WS, t);
 #pragma unroll
-        for (int i = 0; i < V; ++i) {
-            const float2 w = a.tw[((l + 32 * (i >> 3)) * (i & 7)) & (M - 1)];
+        for (int i = 0; i < V; ++i) {       // [R1 s + ka]: W_M^((tl + LANES s) ka)
+            const float2 w = a.tw[((tl + LANES * (i / C::R1)) * (i % C::R1)) & (M - 1)];
             t[2 * i] = w.x; t[2 * i + 1] = w.y;
         }
         tmem_st32(tlane + TC_TW1, t);
 #pragma unroll
-        for (int kb = 0; kb < 8; ++kb) {
-            const float2 w = a.tw[(8 * (l & 7) * kb) & (M - 1)];
+        for (int kb = 0; kb < 16; ++kb) {   // W_(8 R2)^((tl & 7) kb) = W_M^(R1 (tl & 7) kb)
+            const float2 w = a.tw[(C::R1 * (tl & 7) * (kb % C::R2)) & (M - 1)];
             t[2 * kb] = w.x; t[2 * kb + 1] = w.y;
         }
+        tmem_st32(tlane + TC_TW2, t);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const int k = slot_bin_rt(l, j);
+            const int k = slot_bin_rt<LANES>(tl, j);
             float2 w;
             if (k <= M / 2) w = a.twr[k];
             else { w = a.twr[M - k]; w.x = -w.x; }                  // W_N^k = -conj(W_N^(M-k))
-            t[16 + 2 * j] = w.x; t[16 + 2 * j + 1] = w.y;
+            t[2 * j] = w.x; t[2 * j + 1] = w.y;
         }
-        tmem_st32(tlane + TC_TW2, t);                               // TW2 and TWR are adjacent
+        tmem_st16(tlane + TC_TWR, t);
         tmem_wait_st();
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -256,25 +283,25 @@ __global__ void __launch_bounds__(WARPS * 32, 1) warp_iter_kernel(const WArgs a)
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
     const unsigned twarp = tlane + TC_WARP + TC_PER_WARP * (warp >> 2);   // ring (24 columns) then carry (24)
-    float2* e1 = sm + warp * WARP_F2;
-    float2* e2 = e1 + EXF2;
-    float2* xs = e2 + EXF2;
-    float* mstage = reinterpret_cast<float*>(xs + 128);             // magnitudes of the coming frame (512 floats)
-    float2* qstage = xs + 128 + 256;                                // q / X row of the coming frame
-    const unsigned warp_s = (unsigned)__cvta_generic_to_shared(sm) + warp * (WARP_F2 * 8);   // shared-window addresses
-    const unsigned xs_s = warp_s + 2 * EXF2 * 8, mstage_s = xs_s + 128 * 8, qstage_s = mstage_s + 256 * 8;
+    float2* e1 = sm + grp * (G * WARP_F2);
+    float2* e2 = e1 + M;
+    float2* xs = e2 + M;                                            // HOP floats = M / 4 float2
+    float* mstage = reinterpret_cast<float*>(xs + M / 4);           // magnitudes of the coming frame (M floats)
+    float2* qstage = xs + M / 4 + M / 2;                            // q / X row of the coming frame
+    const unsigned grp_s = (unsigned)__cvta_generic_to_shared(sm) + grp * (G * WARP_F2 * 8);   // shared-window addresses
+    const unsigned xs_s = grp_s + 2 * M * 8, mstage_s = xs_s + (M / 4) * 8, qstage_s = mstage_s + (M / 2) * 8;
     unsigned xpar = 0, spar = 0;                                    // mbarrier phase parities
 
     // bin offsets of the lane's pair slots inside a main row
-    const int hi_adj = l == 0 ? -224 : 0;        // lane 0, slots 4..7: 32 + 64 (j - 4) = 64 j - 224
-    const int kq0 = l == 0 ? 256 : M - l;
+    const int hi_adj = l == 0 ? -7 * LANES : 0;  // lane 0, slots 4..7: LANES + 2 LANES (j - 4) = 2 LANES j - 7 LANES
+    const int kq0 = l == 0 ? M / 2 : M - l;
 
     double dacc = 0.0, eacc = 0.0;
-    const int gw = blockIdx.x + gridDim.x * warp;                   // global warp index
+    const int gg = blockIdx.x + gridDim.x * grp;                    // global group index
     long long g = 0, g1 = 0;
-    if (gw < a.ranges) {
-        g = a.frames_total * gw / a.ranges;
-        g1 = a.frames_total * (gw + 1) / a.ranges;
+    if (gg < a.ranges) {
+        g = a.frames_total * gg / a.ranges;
+        g1 = a.frames_total * (gg + 1) / a.ranges;
     }
     while (g < g1) {
         const int b = (int)(g / a.T);
@@ -285,7 +312,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) warp_iter_kernel(const WArgs a)
         const float* x = a.x_in + (long long)b * a.L;
         float* xo = a.x_out + (long long)b * a.L;
 
-        // ---- prologue: empty carry, ring = blocks tf0 .. tf0 + 2, block tf0 + 3 on its way
+        // ---- prologue: empty carry, ring = blocks tf0 .. tf0 + 2, block tf0 + 3 and the first rows on their way
         tmem_wait_st();
         {
             float z[24];
@@ -299,14 +326,14 @@ __global__ void __launch_bounds__(WARPS * 32, 1) warp_iter_kernel(const WArgs a)
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
                 float2 nb[4];
-                fetch_block_regs(a, x, tf0 + i, l, nb);
+                fetch_block_regs<LANES>(a, x, tf0 + i, l, nb);
                 tmem_st8(twarp + 8 * mm, reinterpret_cast<const float*>(nb));
                 mm = mm == 2 ? 0 : mm + 1;
             }
         }
-        __syncwarp();                              // nobody still reads the staging rows of an earlier range
-        bool x_async = fetch_block_staged(a, x, tf0 + 3, l, xs, xs_s, xbar);
-        stage_rows(a, (long long)b * a.T + tf0, qstage_s, mstage_s, sbar);
+        group_sync<LANES>(bar_id);                 // nobody still reads the staging rows of an earlier range
+        bool x_async = fetch_block_staged<LANES>(a, x, tf0 + 3, l, xs, xs_s, xbar);
+        stage_rows<LANES>(a, (long long)b * a.T + tf0, l, qstage_s, mstage_s, sbar);
         // Nyquist scalars of the coming frame (lane 0), fetched one frame ahead like the rows
         float2 s0n_next = f2(0.f, 0.f), s1n_next = f2(0.f, 0.f);
         float mgn_next = 0.f;
@@ -315,7 +342,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) warp_iter_kernel(const WArgs a)
             s0n_next = __ldg(a.s0_in_nyq + r0); mgn_next = __ldg(a.mag_nyq + r0);
             if constexpr (OP == OP_ADMM) s1n_next = __ldg(a.s1_in_nyq + r0);
         }
-        if constexpr (OP == OP_ADMM) prefetch_l2(reinterpret_cast<const char*>(a.s1_in + ((long long)b * a.T + tf0) * M) + 128 * l);
+        if constexpr (OP == OP_ADMM) {             // U rows are read straight from global memory: pull them into L2
+            const char* u0 = reinterpret_cast<const char*>(a.s1_in + ((long long)b * a.T + tf0) * M);
+            if (128 * l < M * 8) prefetch_l2(u0 + 128 * l);
+        }
 
         for (int t = tf0; t < t1; ++t) {
             const long long row = (long long)b * a.T + t;
@@ -330,14 +360,17 @@ __global__ void __launch_bounds__(WARPS * 32, 1) warp_iter_kernel(const WArgs a)
                 tmem_ld8(twarp + 8 * m2, reinterpret_cast<float*>(v + 8));
                 if (x_async) { mbar_wait(xbar, xpar); xpar ^= 1; }
 #pragma unroll
-                for (int j = 0; j < 4; ++j) v[12 + j] = xs[32 * j + l];
+                for (int j = 0; j < 4; ++j) v[12 + j] = xs[LANES * j + l];
                 tmem_st8(twarp + 8 * m, reinterpret_cast<const float*>(v + 12));   // block t+3 replaces block t
                 m = m1;
             }
-            __syncwarp();                          // xs consumed by every lane; the previous frame's reads of E1 are done
+            group_sync<LANES>(bar_id);             // xs consumed by every lane; the previous frame's reads of E1 are done
             if (t + 1 < t1) {
-                x_async = fetch_block_staged(a, x, t + 4, l, xs, xs_s, xbar);
-                if constexpr (OP == OP_ADMM) prefetch_l2(reinterpret_cast<const char*>(a.s1_in + (row + 1) * M) + 128 * l);
+                x_async = fetch_block_staged<LANES>(a, x, t + 4, l, xs, xs_s, xbar);
+                if constexpr (OP == OP_ADMM) {
+                    const char* u1 = reinterpret_cast<const char*>(a.s1_in + (row + 1) * M);
+                    if (128 * l < M * 8) prefetch_l2(u1 + 128 * l);
+                }
             }
             {
                 float2 w[V];
@@ -348,24 +381,25 @@ __global__ void __launch_bounds__(WARPS * 32, 1) warp_iter_kernel(const WArgs a)
             {
                 float2 tw1[V];
                 tmem_ld32(tlane + TC_TW1, reinterpret_cast<float*>(tw1));
-                fwd_pass1(l, v, tw1, e1);
+                fwd_pass1<LANES>(l, v, tw1, e1);
             }
-            __syncwarp();
-            float2 tw2[8];
-            tmem_ld16(tlane + TC_TW2, reinterpret_cast<float*>(tw2));
-            fwd_pass2(l, e1, tw2, e2);
-            __syncwarp();
+            group_sync<LANES>(bar_id);
+            float2 tw2[C::R2];
+            if constexpr (C::R2 == 8) tmem_ld16(tlane + TC_TW2, reinterpret_cast<float*>(tw2));
+            else tmem_ld32(tlane + TC_TW2, reinterpret_cast<float*>(tw2));
+            fwd_pass2<LANES>(l, e1, tw2, e2);
+            group_sync<LANES>(bar_id);
 
             const float2 s0n = s0n_next, s1n = s1n_next;
             const float mgn = mgn_next;
             float2 A[8], Bv[8];
-            fwd_pass3(l, e2, A, Bv);
+            fwd_pass3<LANES>(l, e2, A, Bv);
             mbar_wait(sbar, spar); spar ^= 1;      // this frame's staged rows have landed
             {
-                // ---- point-wise stage on the lane's 16 bins (+ Nyquist for lane 0), state fetched where it is used
-                // Element e = 2 j / 2 j + 1 is the P / Q bin of slot j: bins l + 64 j and 512 - l - 64 j, except for
-                // lane 0 (slots 4..7: 64 j - 224 and its mirror; slot 0: bins 0 and 256).  Four per-lane base offsets
-                // turn every access into base + compile-time offset.
+                // ---- point-wise stage on the lane's 16 bins (+ Nyquist for lane 0), state fetched where it is used.
+                // Element e = 2 j / 2 j + 1 is the P / Q bin of slot j: bins l + 2 LANES j and M - l - 2 LANES j, except
+                // for lane 0 (slots 4..7: 2 LANES j - 7 LANES and its mirror; slot 0: bins 0 and M/2).  Four per-lane
+                // base offsets turn every access into base + compile-time offset.
                 struct IO {
                     const float2* q; const float* mg; const float2* u; float2* o0; float2* o1;
                     float2* o0n; float2* o1n;
@@ -373,7 +407,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) warp_iter_kernel(const WArgs a)
                     float2 s0n, s1n; float mgn;
                     __device__ __forceinline__ int bin(int e) const {
                         const int j = e >> 1;
-                        return (e & 1) ? (j == 0 ? q0 : (j >= 4 ? qh : ql) - 64 * j) : (j >= 4 ? ph : pl) + 64 * j;
+                        return (e & 1) ? (j == 0 ? q0 : (j >= 4 ? qh : ql) - 2 * LANES * j) : (j >= 4 ? ph : pl) + 2 * LANES * j;
                     }
                     __device__ __forceinline__ float2 s0(int e) const { return e < 0 ? s0n : q[bin(e)]; }
                     __device__ __forceinline__ float2 s1(int e) const { return e < 0 ? s1n : ldg_nc_f2(u + bin(e)); }
@@ -398,25 +432,25 @@ __global__ void __launch_bounds__(WARPS * 32, 1) warp_iter_kernel(const WArgs a)
                 pointwise<OP, SUMS>(l, A, Bv, twr, io, a.coef, a.coef2, dsum, esum);
                 if constexpr (SUMS) { if (owned) { dacc += (double)dsum; eacc += (double)esum; } }
             }
-            __syncwarp();                          // every lane has read its classes from E2 and its staged state
+            group_sync<LANES>(bar_id);             // every lane has read its classes from E2 and its staged state
             if (t + 1 < t1) {
-                stage_rows(a, row + 1, qstage_s, mstage_s, sbar);
+                stage_rows<LANES>(a, row + 1, l, qstage_s, mstage_s, sbar);
                 if (l == 0) {
                     s0n_next = __ldg(a.s0_in_nyq + row + 1); mgn_next = __ldg(a.mag_nyq + row + 1);
                     if constexpr (OP == OP_ADMM) s1n_next = __ldg(a.s1_in_nyq + row + 1);
                 }
             }
-            inv_pass3(l, A, Bv, e2);
-            __syncwarp();
-            const bool emit = owned && block_valid(a, t);
+            inv_pass3<LANES>(l, A, Bv, e2);
+            group_sync<LANES>(bar_id);
+            const bool emit = owned && block_valid<LANES>(a, t);
             float2 ie[4];
-            if (emit) load_inv_env(a, t, l, ie);    // early: the latency hides behind the last two passes
-            inv_pass2(l, e2, tw2, e1);
-            __syncwarp();
+            if (emit) load_inv_env<LANES>(a, t, l, ie);    // early: the latency hides behind the last two passes
+            inv_pass2<LANES>(l, e2, tw2, e1);
+            group_sync<LANES>(bar_id);
             {
                 float2 tw1[V];
                 tmem_ld32(tlane + TC_TW1, reinterpret_cast<float*>(tw1));
-                inv_pass1(l, e1, tw1, v);
+                inv_pass1<LANES>(l, e1, tw1, v);
             }
             // ---- windowed overlap-add: out = carry (3 hops from earlier frames) + ws * v; the first hop
             // (4 pairs) of `out` is a finished block, the other 12 pairs are the new carry
@@ -432,7 +466,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) warp_iter_kernel(const WArgs a)
                 }
                 tmem_st16(twarp + 24, reinterpret_cast<const float*>(v + 4));
                 tmem_st8(twarp + 40, reinterpret_cast<const float*>(v + 12));
-                if (emit) store_block_ie(a, xo, t, l, v, ie);
+                if (emit) store_block_ie<LANES>(a, xo, t, l, v, ie);
             }
         }
         if (t1 == a.T) {      // tail of the signal: blocks T, T+1, T+2 are complete now
@@ -442,7 +476,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) warp_iter_kernel(const WArgs a)
             tmem_ld8(twarp + 40, reinterpret_cast<float*>(carry + 8));
 #pragma unroll
             for (int k = 0; k < 3; ++k)
-                if (block_valid(a, a.T + k)) store_block(a, xo, a.T + k, l, carry + 4 * k);
+                if (block_valid<LANES>(a, a.T + k)) {
+                    float2 ie[4];
+                    load_inv_env<LANES>(a, a.T + k, l, ie);
+                    store_block_ie<LANES>(a, xo, a.T + k, l, carry + 4 * k, ie);
+                }
         }
     }
 
@@ -452,7 +490,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) warp_iter_kernel(const WArgs a)
             d += __shfl_xor_sync(0xffffffffu, d, o);
             e += __shfl_xor_sync(0xffffffffu, e, o);
         }
-        if (l == 0 && (d != 0.0 || e != 0.0)) { atomicAdd(a.sums, d); atomicAdd(a.sums + 1, e); }
+        if ((tid & 31) == 0 && (d != 0.0 || e != 0.0)) { atomicAdd(a.sums, d); atomicAdd(a.sums + 1, e); }
     }
     tmem_wait_st();
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -462,7 +500,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) warp_iter_kernel(const WArgs a)
 
 static int g_sms = 0;
 
-template <int OP, int WARPS>
+template <int OP, int LANES>
 static int launch(const WArgs& a0, cudaStream_t st) {
     WArgs a = a0;
     if (g_sms == 0) {
@@ -470,44 +508,46 @@ static int launch(const WArgs& a0, cudaStream_t st) {
         if (cudaGetDevice(&dev) != cudaSuccess) return SPECINV_ERR_NO_DEVICE;
         if (cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return SPECINV_ERR_NO_DEVICE;
     }
-    // SPECINV_FAST_FORCE=1: send even tiny problems through this kernel (the tests do)
-    const char* env_force = getenv("SPECINV_FAST_FORCE");
-    const bool force = env_force && env_force[0] == '1';
     // the TMA bulk copies need 16-byte aligned rows
     if ((((uintptr_t)a.x_in | (uintptr_t)a.s0_in | (uintptr_t)a.mag) & 15) != 0) return SPECINV_ERR_UNSUPPORTED;
     a.frames_total = (long long)a.B * a.T;
-    const int slots = g_sms * WARPS;
-    // ranges of at least 24 frames keep the 3-frame halo below ~12 %
-    long long ranges = a.frames_total / 24;
-    if (ranges < 1) ranges = 1;
-    if (ranges > slots) ranges = slots;
-    // warps that would stay idle make the generic tile kernel the better choice (tiny problems)
-    if (!force && a.frames_total < 6LL * slots) return SPECINV_ERR_UNSUPPORTED;
+    constexpr int GROUPS = WARPS / (LANES / 32);
+    const int slots = g_sms * GROUPS;
+    // One frame range per group slot.  A range re-computes 3 halo frames, which costs ~1.5 % when the ranges are
+    // long (the batched configs) and buys parallelism when the problem is small (one short signal).
+    long long ranges = a.frames_total < slots ? a.frames_total : slots;
     a.ranges = (int)ranges;
     const int grid = (int)min((long long)g_sms, ranges);
-    // with fewer ranges than warp slots, spread them over all CTAs of the grid: range index = blockIdx + grid * warp
+    // with fewer ranges than group slots, spread them over all CTAs of the grid: range index = blockIdx + grid * group
     const size_t smem = (size_t)WARPS * WARP_F2 * sizeof(float2);
     cudaError_t e;
     if (a.sums) {
-        e = cudaFuncSetAttribute(warp_iter_kernel<OP, true, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute(warp_iter_kernel<OP, true, LANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
-        warp_iter_kernel<OP, true, WARPS><<<grid, WARPS * 32, smem, st>>>(a);
+        warp_iter_kernel<OP, true, LANES><<<grid, WARPS * 32, smem, st>>>(a);
     } else {
-        e = cudaFuncSetAttribute(warp_iter_kernel<OP, false, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute(warp_iter_kernel<OP, false, LANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
-        warp_iter_kernel<OP, false, WARPS><<<grid, WARPS * 32, smem, st>>>(a);
+        warp_iter_kernel<OP, false, LANES><<<grid, WARPS * 32, smem, st>>>(a);
     }
     return (int)cudaGetLastError();
 }
 
-// 12 warps per CTA with 168 registers each (no spills) beat 16 x 128 (a few spills): GL 1.18 vs 1.21 ms, ADMM 1.98
-// vs 2.67 ms per iteration at B = 512, T = 938; 12 x 15 KB of staging also is what fits the shared memory.
-constexpr int WARPS = 12;
+template <int OP>
+static int launch_any(const WArgs& a, int n_fft, cudaStream_t st) {
+    switch (n_fft) {
+        case 1024: return launch<OP, 32>(a, st);
+        case 2048: return launch<OP, 64>(a, st);
+        case 4096: return launch<OP, 128>(a, st);
+        default: return SPECINV_ERR_UNSUPPORTED;
+    }
+}
 
 }  // namespace wfast
 
 static bool fastw_applicable(const specinv_desc* d) {
-    return d->dtype == SPECINV_F32 && d->onesided && d->n_fft == 1024 && d->hop == 256;
+    return d->dtype == SPECINV_F32 && d->onesided && d->hop * 4 == d->n_fft &&
+           (d->n_fft == 1024 || d->n_fft == 2048 || d->n_fft == 4096);
 }
 
 static void fill_common(wfast::WArgs& a, const Dims& dm, const specinv_desc* d, const void* plan) {
@@ -518,7 +558,7 @@ static void fill_common(wfast::WArgs& a, const Dims& dm, const specinv_desc* d, 
     a.B = dm.B; a.T = dm.T; a.P = dm.P; a.pad_mode = dm.pad_mode; a.L = dm.L;
 }
 
-// Return SPECINV_ERR_UNSUPPORTED when the shape is not the one this kernel is specialised for.
+// Return SPECINV_ERR_UNSUPPORTED when the shape is not one these kernels are specialised for.
 int fastw_gl_iter(const specinv_desc* d, const void* plan, const void* x_in, void* x_out,
                   const void* q_in_main, const void* q_in_nyq, void* q_out_main, void* q_out_nyq,
                   const void* mag_main, const void* mag_nyq, double lr, double* sums, void* stream) {
@@ -531,7 +571,7 @@ int fastw_gl_iter(const specinv_desc* d, const void* plan, const void* x_in, voi
     a.s0_out = (float2*)q_out_main; a.s0_out_nyq = (float2*)q_out_nyq;
     a.mag = (const float*)mag_main; a.mag_nyq = (const float*)mag_nyq;
     a.coef = (float)lr; a.sums = sums;
-    return wfast::launch<wfast::OP_GL, wfast::WARPS>(a, (cudaStream_t)stream);
+    return wfast::launch_any<wfast::OP_GL>(a, d->n_fft, (cudaStream_t)stream);
 }
 
 int fastw_admm_iter(const specinv_desc* d, const void* plan, const void* x_in, void* x_out,
@@ -549,7 +589,7 @@ int fastw_admm_iter(const specinv_desc* d, const void* plan, const void* x_in, v
     a.s1_out = (float2*)U_out_main; a.s1_out_nyq = (float2*)U_out_nyq;
     a.mag = (const float*)mag_main; a.mag_nyq = (const float*)mag_nyq;
     a.coef = (float)rho; a.coef2 = (float)(1.0 / (1.0 + rho)); a.sums = sums;
-    return wfast::launch<wfast::OP_ADMM, wfast::WARPS>(a, (cudaStream_t)stream);
+    return wfast::launch_any<wfast::OP_ADMM>(a, d->n_fft, (cudaStream_t)stream);
 }
 
 }  // namespace specinv

@@ -370,22 +370,31 @@ def test_rtisi_la_shapes_and_quality():
 
 
 # ---------------------------------------------------------------------------------------------
-# fast path for n_fft = 2048, hop = 512 (one warp per frame)
+# fast paths for n_fft = 2048, hop = 512 (two warps per frame; "half": the older one-warp kernel) and
+# n_fft = 4096, hop = 1024 (four warps per frame)
 # ---------------------------------------------------------------------------------------------
 FAST2048_CASES = [
     dict(B=40, T=130, center=True, pad_mode="reflect", normalized=False),
     dict(B=37, T=77, center=True, pad_mode="constant", normalized=True),
     dict(B=64, T=64, center=False, pad_mode="reflect", normalized=False),
+    dict(B=1, T=9, center=True, pad_mode="reflect", normalized=False),
+    dict(B=3, T=41, center=True, pad_mode="circular", normalized=False, impl="half"),
+    dict(B=9, T=50, center=True, pad_mode="replicate", normalized=False, n_fft=4096),
+    dict(B=2, T=33, center=False, pad_mode="reflect", normalized=True, n_fft=4096),
+    dict(B=1, T=301, center=True, pad_mode="reflect", normalized=False, n_fft=4096),
 ]
 
 
-@pytest.mark.parametrize("fc", FAST2048_CASES, ids=lambda c: f"B{c['B']}_T{c['T']}_{c['pad_mode']}_c{int(c['center'])}")
+@pytest.mark.parametrize("fc", FAST2048_CASES,
+                         ids=lambda c: f"n{c.get('n_fft', 2048)}_B{c['B']}_T{c['T']}_{c['pad_mode']}_c{int(c['center'])}")
 def test_fast_path_2048_against_oracle(fc, monkeypatch):
     monkeypatch.setenv("SPECINV_FAST_FORCE", "1")
+    monkeypatch.setenv("SPECINV_FAST_IMPL", fc.get("impl", "warp"))
     from spectrogram_inversion_b200.engine import ADMMSolver, GriffinLimSolver, StftPlan
     from spectrogram_inversion_b200.stft_args import args_helper
     rs = np.random.RandomState(fc["T"])
-    n_fft, hop, F = 2048, 512, 1025
+    n_fft = fc.get("n_fft", 2048)
+    hop, F = n_fft // 4, n_fft // 2 + 1
     B, T = fc["B"], fc["T"]
     w = cases.window_of("hann" if fc["center"] else "hamming", n_fft, np.float32)
     kw = dict(hop_length=hop, center=fc["center"], pad_mode=fc["pad_mode"], normalized=fc["normalized"], window=w)
