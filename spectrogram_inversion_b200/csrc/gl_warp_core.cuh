@@ -37,6 +37,7 @@ using fast::pre_pair;
 using fast::approx_sqrt;
 using fast::OP_GL;
 using fast::OP_ADMM;
+constexpr int OP_ISTFT = 2;      // stand-alone inverse transform + overlap-add (x_0 = ISTFT(C), methods.py:233)
 
 constexpr int V = 16;            // complex values per lane
 
@@ -225,6 +226,27 @@ SPX_HD void pointwise(int l, float2* A, float2* B, const float2* twr, IO& io, fl
         const float2 hP = upd(std::integral_constant<int, 2 * j>{}, sP);
         const float2 hQ = upd(std::integral_constant<int, 2 * j + 1>{}, sQ);
         pre_pair(hP, hQ, w, P, Q);
+        if constexpr (j < 4) { A[j] = P; if (l0) A[8 - j] = Q; else B[7 - j] = Q; }
+        else { if (l0) { B[j - 4] = P; B[11 - j] = Q; } else { A[j] = P; B[7 - j] = Q; } }
+    });
+}
+
+// Stand-alone inverse transform (ISTFT): the given spectrum h replaces the point-wise stage; on return A / B hold
+// the inputs of the inverse pass 3.  `io.s0(e)` as above (e = -1: the Nyquist bin).
+template <typename IO>
+SPX_HD void spectrum_pairs(int l, float2* A, float2* B, const float2* twr, IO& io) {
+    const bool l0 = l == 0;
+    if (l0) {
+        const float2 h0 = io.s0(0), hM = io.s0(-1), h4 = io.s0(1);
+        A[0] = f2(h0.x + hM.x, h0.x - hM.x);        // C2R ignores Im(DC), Im(Nyquist)
+        A[4] = f2(2.f * h4.x, -2.f * h4.y);
+    } else {
+        pre_pair(io.s0(0), io.s0(1), twr[0], A[0], B[7]);
+    }
+    static_for<7>([&](auto jc) {
+        constexpr int j = decltype(jc)::value + 1;
+        float2 P, Q;
+        pre_pair(io.s0(2 * j), io.s0(2 * j + 1), twr[j], P, Q);
         if constexpr (j < 4) { A[j] = P; if (l0) A[8 - j] = Q; else B[7 - j] = Q; }
         else { if (l0) { B[j - 4] = P; B[11 - j] = Q; } else { A[j] = P; B[7 - j] = Q; } }
     });

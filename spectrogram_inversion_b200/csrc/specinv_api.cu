@@ -23,6 +23,7 @@ int fastw_gl_iter(const specinv_desc*, const void*, const void*, void*, const vo
                   const void*, const void*, double, double*, void*);
 int fastw_admm_iter(const specinv_desc*, const void*, const void*, void*, const void*, const void*, const void*,
                     const void*, void*, void*, void*, void*, const void*, const void*, double, double*, void*);
+int fastw_istft(const specinv_desc*, const void*, const void*, const void*, void*, void*);
 
 // SPECINV_FAST_IMPL=half keeps n_fft = 1024 on the older half-warp-per-frame kernel (A-B timing)
 static bool use_warp_kernel() {
@@ -293,6 +294,10 @@ int specinv_stft(const specinv_desc* d, const void* plan, const void* x, void* m
 
 int specinv_istft(const specinv_desc* d, const void* plan, const void* main_in, const void* nyq_in, void* x_out,
                   void* stream) {
+    if (d && plan && main_in && x_out && !force_generic() && use_warp_kernel()) {
+        const int rw = fastw_istft(d, plan, main_in, nyq_in, x_out, stream);
+        if (rw != SPECINV_ERR_UNSUPPORTED) return rw;
+    }
     return generic_istft(d, plan, main_in, nyq_in, x_out, stream);
 }
 

@@ -210,14 +210,14 @@ __device__ __forceinline__ void store_block_ie(const WArgs& a, float* __restrict
         *reinterpret_cast<float2*>(xo + base + 2 * LANES * j + 2 * l) = f2(blk[j].x * ie[j].x, blk[j].y * ie[j].y);
 }
 // Fetch the q / X row and the magnitude row of frame `row` into the staging rows (one elected lane, TMA).
-template <int LANES>
+template <int OP, int LANES>
 __device__ __forceinline__ void stage_rows(const WArgs& a, long long row, int l, unsigned qstage_s, unsigned mstage_s, unsigned bar) {
     constexpr int M = Cfg<LANES>::M;
     if (l < 32) {
         if (elect_one()) {
-            mbar_expect_tx(bar, M * 8 + M * 4);
+            mbar_expect_tx(bar, OP == OP_ISTFT ? M * 8 : M * 8 + M * 4);
             bulk_g2s(qstage_s, a.s0_in + row * M, M * 8, bar);
-            bulk_g2s(mstage_s, a.mag + row * M, M * 4, bar);
+            if constexpr (OP != OP_ISTFT) bulk_g2s(mstage_s, a.mag + row * M, M * 4, bar);
         }
     }
 }
@@ -321,7 +321,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) warp_iter_kernel(const WArgs a)
             tmem_st16(twarp + 24, z); tmem_st8(twarp + 40, z + 16);
         }
         int m = tf0 % 3;                                            // ring slot of block t
-        {
+        if constexpr (OP != OP_ISTFT) {
             int mm = m;
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
@@ -332,14 +332,16 @@ __global__ void __launch_bounds__(WARPS * 32, 1) warp_iter_kernel(const WArgs a)
             }
         }
         group_sync<LANES>(bar_id);                 // nobody still reads the staging rows of an earlier range
-        bool x_async = fetch_block_staged<LANES>(a, x, tf0 + 3, l, xs, xs_s, xbar);
-        stage_rows<LANES>(a, (long long)b * a.T + tf0, l, qstage_s, mstage_s, sbar);
+        bool x_async = false;
+        if constexpr (OP != OP_ISTFT) x_async = fetch_block_staged<LANES>(a, x, tf0 + 3, l, xs, xs_s, xbar);
+        stage_rows<OP, LANES>(a, (long long)b * a.T + tf0, l, qstage_s, mstage_s, sbar);
         // Nyquist scalars of the coming frame (lane 0), fetched one frame ahead like the rows
         float2 s0n_next = f2(0.f, 0.f), s1n_next = f2(0.f, 0.f);
         float mgn_next = 0.f;
         if (l == 0) {
             const long long r0 = (long long)b * a.T + tf0;
-            s0n_next = __ldg(a.s0_in_nyq + r0); mgn_next = __ldg(a.mag_nyq + r0);
+            s0n_next = __ldg(a.s0_in_nyq + r0);
+            if constexpr (OP != OP_ISTFT) mgn_next = __ldg(a.mag_nyq + r0);
             if constexpr (OP == OP_ADMM) s1n_next = __ldg(a.s1_in_nyq + r0);
         }
         if constexpr (OP == OP_ADMM) {             // U rows are read straight from global memory: pull them into L2
@@ -351,6 +353,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) warp_iter_kernel(const WArgs a)
             const long long row = (long long)b * a.T + t;
             const bool owned = t >= t0;
             float2 v[V];
+            float2 tw2[C::R2];
+            if constexpr (C::R2 == 8) tmem_ld16(tlane + TC_TW2, reinterpret_cast<float*>(tw2));
+            else tmem_ld32(tlane + TC_TW2, reinterpret_cast<float*>(tw2));
+            float2 A[8], Bv[8];
+            if constexpr (OP != OP_ISTFT) {
             // ---- assemble the frame: blocks t .. t+2 from the ring, block t+3 from the staging buffer
             {
                 const int m1 = m == 2 ? 0 : m + 1, m2 = m1 == 2 ? 0 : m1 + 1;
@@ -384,16 +391,12 @@ __global__ void __launch_bounds__(WARPS * 32, 1) warp_iter_kernel(const WArgs a)
                 fwd_pass1<LANES>(l, v, tw1, e1);
             }
             group_sync<LANES>(bar_id);
-            float2 tw2[C::R2];
-            if constexpr (C::R2 == 8) tmem_ld16(tlane + TC_TW2, reinterpret_cast<float*>(tw2));
-            else tmem_ld32(tlane + TC_TW2, reinterpret_cast<float*>(tw2));
             fwd_pass2<LANES>(l, e1, tw2, e2);
             group_sync<LANES>(bar_id);
-
+            fwd_pass3<LANES>(l, e2, A, Bv);
+            }  // OP != OP_ISTFT
             const float2 s0n = s0n_next, s1n = s1n_next;
             const float mgn = mgn_next;
-            float2 A[8], Bv[8];
-            fwd_pass3<LANES>(l, e2, A, Bv);
             mbar_wait(sbar, spar); spar ^= 1;      // this frame's staged rows have landed
             {
                 // ---- point-wise stage on the lane's 16 bins (+ Nyquist for lane 0), state fetched where it is used.
@@ -428,15 +431,20 @@ __global__ void __launch_bounds__(WARPS * 32, 1) warp_iter_kernel(const WArgs a)
                      s0n, s1n, mgn};
                 float2 twr[8];
                 tmem_ld16(tlane + TC_TWR, reinterpret_cast<float*>(twr));
-                float dsum = 0.f, esum = 0.f;
-                pointwise<OP, SUMS>(l, A, Bv, twr, io, a.coef, a.coef2, dsum, esum);
-                if constexpr (SUMS) { if (owned) { dacc += (double)dsum; eacc += (double)esum; } }
+                if constexpr (OP == OP_ISTFT) {
+                    spectrum_pairs(l, A, Bv, twr, io);
+                } else {
+                    float dsum = 0.f, esum = 0.f;
+                    pointwise<OP, SUMS>(l, A, Bv, twr, io, a.coef, a.coef2, dsum, esum);
+                    if constexpr (SUMS) { if (owned) { dacc += (double)dsum; eacc += (double)esum; } }
+                }
             }
             group_sync<LANES>(bar_id);             // every lane has read its classes from E2 and its staged state
             if (t + 1 < t1) {
-                stage_rows<LANES>(a, row + 1, l, qstage_s, mstage_s, sbar);
+                stage_rows<OP, LANES>(a, row + 1, l, qstage_s, mstage_s, sbar);
                 if (l == 0) {
-                    s0n_next = __ldg(a.s0_in_nyq + row + 1); mgn_next = __ldg(a.mag_nyq + row + 1);
+                    s0n_next = __ldg(a.s0_in_nyq + row + 1);
+                    if constexpr (OP != OP_ISTFT) mgn_next = __ldg(a.mag_nyq + row + 1);
                     if constexpr (OP == OP_ADMM) s1n_next = __ldg(a.s1_in_nyq + row + 1);
                 }
             }
@@ -510,6 +518,7 @@ static int launch(const WArgs& a0, cudaStream_t st) {
     }
     // the TMA bulk copies need 16-byte aligned rows
     if ((((uintptr_t)a.x_in | (uintptr_t)a.s0_in | (uintptr_t)a.mag) & 15) != 0) return SPECINV_ERR_UNSUPPORTED;
+    if (OP == OP_ISTFT && a.sums) return SPECINV_ERR_INVALID;
     a.frames_total = (long long)a.B * a.T;
     constexpr int GROUPS = WARPS / (LANES / 32);
     const int slots = g_sms * GROUPS;
@@ -572,6 +581,18 @@ int fastw_gl_iter(const specinv_desc* d, const void* plan, const void* x_in, voi
     a.mag = (const float*)mag_main; a.mag_nyq = (const float*)mag_nyq;
     a.coef = (float)lr; a.sums = sums;
     return wfast::launch_any<wfast::OP_GL>(a, d->n_fft, (cudaStream_t)stream);
+}
+
+// x_out = ISTFT(spectrum) (methods.py:135-150) with the same kernel: inverse half of the frame pipeline only.
+int fastw_istft(const specinv_desc* d, const void* plan, const void* main_in, const void* nyq_in, void* x_out,
+                void* stream) {
+    if (!fastw_applicable(d) || !nyq_in) return SPECINV_ERR_UNSUPPORTED;
+    Dims dm; int rc = make_dims(d, &dm); if (rc) return rc;
+    wfast::WArgs a{};
+    fill_common(a, dm, d, plan);
+    a.x_out = (float*)x_out;
+    a.s0_in = (const float2*)main_in; a.s0_in_nyq = (const float2*)nyq_in;
+    return wfast::launch_any<wfast::OP_ISTFT>(a, d->n_fft, (cudaStream_t)stream);
 }
 
 int fastw_admm_iter(const specinv_desc* d, const void* plan, const void* x_in, void* x_out,

@@ -23,48 +23,73 @@ __device__ __forceinline__ T mag_at(const T* __restrict__ main, const T* __restr
     return __ldg(main + fr * dm.row + k);
 }
 
-// One thread per (signal, bin); it walks over time carrying the running phase.  Consecutive threads
-// handle consecutive bins, so every load / store of a time step is coalesced in the frame-major layout.
+// One thread per (signal, bin); it walks over time carrying the running phase.  A warp covers 30 consecutive
+// bins plus one halo bin on each side: every lane tests ITS bin for a peak and interpolates its frequency once
+// (one IEEE division), the two neighbours' results arrive by warp shuffle.  Consecutive lanes handle consecutive
+// bins, so the loads / stores of a time step are coalesced in the frame-major layout.  (signal, 30-bin segment)
+// pairs are numbered linearly over the warps so that the batched shapes fit one wave of resident blocks.
+constexpr int PI_SEG = 30;
+
 template <typename T>
-__global__ void __launch_bounds__(128) phase_init_kernel(Dims dm, int F, T hop, T n_fft, const T* __restrict__ mag_main,
-                                                         const T* __restrict__ mag_nyq, cx_t<T>* __restrict__ c_main,
-                                                         cx_t<T>* __restrict__ c_nyq, const double* __restrict__ phase_in,
-                                                         double* __restrict__ phase_out) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    const int b = blockIdx.y;
-    if (k >= F) return;
+__global__ void __launch_bounds__(128) phase_init_kernel(Dims dm, int F, int segs, T hop, T inv_n_fft,
+                                                         const T* __restrict__ mag_main, const T* __restrict__ mag_nyq,
+                                                         cx_t<T>* __restrict__ c_main, cx_t<T>* __restrict__ c_nyq,
+                                                         const double* __restrict__ phase_in, double* __restrict__ phase_out) {
+    const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;      // global warp
+    const int lane = threadIdx.x & 31;
+    if (w >= (long long)dm.B * segs) return;                                           // whole warp
+    const int b = (int)(w / segs);
+    const int k = (int)(w - (long long)b * segs) * PI_SEG - 1 + lane;                  // lanes 0 and 31: halo bins
+    const bool in_spec = k >= 0 && k < F;
+    const bool owner = in_spec && lane >= 1 && lane <= PI_SEG;
+    const bool can_peak = k >= 1 && k <= F - 2;       // strict local maxima exist for 1 <= k <= F-2 only (:597-598)
     const T pi2 = (T)6.283185307179586476925286766559;
     // torch's CPU cumsum accumulates float32 in float64 and rounds each output; phase_in (frame-range
     // sharding) is the phase accumulated by the frames before this range
-    double phase = phase_in ? phase_in[(long long)b * F + k] : 0.0;
-    // strict local maximum at bin j (1 <= j <= F-2), and its interpolated angular frequency * hop
-    auto peak_omega = [&](long long fr, int j, T& omega) -> bool {
-        if (j < 1 || j > F - 2) return false;
-        const T lo = mag_at(mag_main, mag_nyq, dm, fr, j - 1);
-        const T mid = mag_at(mag_main, mag_nyq, dm, fr, j);
-        const T hi = mag_at(mag_main, mag_nyq, dm, fr, j + 1);
-        if (!(mid > hi && mid > lo)) return false;
-        const T p = T(0.5) * (lo - hi) / (lo - T(2) * mid + hi);
-        omega = pi2 * ((T)j + p) / n_fft * hop;
-        return true;
-    };
-    for (int t = 0; t < dm.T; ++t) {
-        const long long fr = (long long)b * dm.T + t;
-        T omega = T(0), w;
-        // reference write order: own peak, then peak at k+1 (writes k), then peak at k-1 (writes k): last wins
-        if (peak_omega(fr, k, w)) omega = w;
-        if (peak_omega(fr, k + 1, w)) omega = w;
-        if (peak_omega(fr, k - 1, w)) omega = w;
-        phase += (double)omega;
-        const T ph = (T)phase;
-        T s, c;
-        sincos_t<T>(ph, &s, &c);
-        const T m = mag_at(mag_main, mag_nyq, dm, fr, k);
-        const cx_t<T> v = mk<T>(m * c, m * s);
-        if (dm.onesided && k == dm.M) c_nyq[fr] = v;
-        else c_main[fr * dm.row + k] = v;
+    double phase = (owner && phase_in) ? phase_in[(long long)b * F + k] : 0.0;
+    // The running phase is the only loop-carried value: the loads of U consecutive frames are issued together.
+    constexpr int U = 4;
+    for (int t0 = 0; t0 < dm.T; t0 += U) {
+        T m[U][3];                      // mag[k-1 .. k+1] of frames t0 .. t0+U-1
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long fr = (long long)b * dm.T + min(t0 + u, dm.T - 1);
+            m[u][1] = in_spec ? mag_at(mag_main, mag_nyq, dm, fr, k) : T(0);
+            m[u][0] = can_peak ? mag_at(mag_main, mag_nyq, dm, fr, k - 1) : T(0);
+            m[u][2] = can_peak ? mag_at(mag_main, mag_nyq, dm, fr, k + 1) : T(0);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (t0 + u < dm.T) {        // warp-uniform
+                const long long fr = (long long)b * dm.T + t0 + u;
+                const T lo = m[u][0], mid = m[u][1], hi = m[u][2];
+                // own peak: interpolated angular frequency * hop (:604-605), or -1 (omega is never negative).
+                // x / n_fft == x * (1 / n_fft) exactly: n_fft is a power of two.
+                T own = T(-1);
+                if (can_peak && mid > hi && mid > lo) {
+                    const T p = T(0.5) * (lo - hi) / (lo - T(2) * mid + hi);
+                    own = pi2 * ((T)k + p) * inv_n_fft * hop;
+                }
+                const T up = __shfl_down_sync(0xffffffffu, own, 1);      // bin k + 1
+                const T dn = __shfl_up_sync(0xffffffffu, own, 1);        // bin k - 1
+                // reference write order: own peak, then peak at k+1 (writes k), then peak at k-1 (writes k): last wins
+                T omega = T(0);
+                if (own >= T(0)) omega = own;
+                if (up >= T(0)) omega = up;
+                if (dn >= T(0)) omega = dn;
+                if (owner) {
+                    phase += (double)omega;
+                    const T ph = (T)phase;
+                    T sn, cs;
+                    sincos_t<T>(ph, &sn, &cs);
+                    const cx_t<T> v = mk<T>(mid * cs, mid * sn);
+                    if (dm.onesided && k == dm.M) c_nyq[fr] = v;
+                    else c_main[fr * dm.row + k] = v;
+                }
+            }
+        }
     }
-    if (phase_out) phase_out[(long long)b * F + k] = phase;
+    if (owner && phase_out) phase_out[(long long)b * F + k] = phase;
 }
 
 template <typename T>
@@ -79,10 +104,12 @@ template <typename T>
 static int phase_init_t(const Dims& dm, const void* mag_main, const void* mag_nyq, void* c_main, void* c_nyq,
                         const double* phase_in, double* phase_out, cudaStream_t st) {
     const int F = dm.onesided ? dm.M + 1 : dm.N;
-    dim3 grid((F + 127) / 128, dm.B);
-    if (grid.y > 65535) return SPECINV_ERR_UNSUPPORTED;
-    phase_init_kernel<T><<<grid, 128, 0, st>>>(dm, F, (T)dm.hop, (T)dm.N, (const T*)mag_main, (const T*)mag_nyq,
-                                               (cx_t<T>*)c_main, (cx_t<T>*)c_nyq, phase_in, phase_out);
+    const int segs = (F + PI_SEG - 1) / PI_SEG;
+    const long long blocks = ((long long)dm.B * segs + 3) / 4;          // 4 warps per block
+    if (blocks > 0x7fffffffLL) return SPECINV_ERR_UNSUPPORTED;
+    phase_init_kernel<T><<<(unsigned)blocks, 128, 0, st>>>(dm, F, segs, (T)dm.hop, (T)(1.0 / dm.N), (const T*)mag_main,
+                                                           (const T*)mag_nyq, (cx_t<T>*)c_main, (cx_t<T>*)c_nyq, phase_in,
+                                                           phase_out);
     return (int)cudaGetLastError();
 }
 
