@@ -25,19 +25,41 @@
 // Everything is __host__ __device__: tests/host_emu runs the exact index logic on the CPU.
 #pragma once
 
-#include "gl_fast_core.cuh"
+#include "fft_regs.cuh"
 
 namespace specinv {
 namespace wfast {
 
-using fast::cmulf;
-using fast::cmulcf;
-using fast::post_pair;
-using fast::pre_pair;
-using fast::approx_sqrt;
-using fast::OP_GL;
-using fast::OP_ADMM;
-constexpr int OP_ISTFT = 2;      // stand-alone inverse transform + overlap-add (x_0 = ISTFT(C), methods.py:233)
+enum { OP_GL = 0, OP_ADMM = 1, OP_ISTFT = 2 };   // OP_ISTFT: stand-alone inverse transform + overlap-add (methods.py:233)
+
+SPX_HD float2 cmulf(float2 a, float2 b) { return f2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+SPX_HD float2 cmulcf(float2 a, float2 b) { return f2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); }   // a*conj(b)
+
+#ifdef __CUDA_ARCH__
+__device__ __forceinline__ float approx_sqrt(float v) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
+__device__ __forceinline__ float approx_rsqrt(float v) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
+#else
+inline float approx_sqrt(float v) { return sqrtf(v); }
+inline float approx_rsqrt(float v) { return 1.0f / sqrtf(v); }
+#endif
+
+// real-FFT post-process of one (P = Zh[k], Q = Zh[M-k]) pair, Zh = Z/2 (the 1/2 is folded into the analysis
+// window):  s[k], s[M-k] of the N-point real transform; w = W_N^k
+SPX_HD void post_pair(float2 P, float2 Q, float2 w, float2& sP, float2& sQ) {
+    const float er = P.x + Q.x, ei = P.y - Q.y;
+    const float orr = P.y + Q.y, oi = Q.x - P.x;
+    const float wor = w.x * orr - w.y * oi, woi = w.x * oi + w.y * orr;
+    sP = f2(er + wor, ei + woi);
+    sQ = f2(er - wor, woi - ei);
+}
+// inverse pre-process: (h[k], h[M-k]) -> (Z'[k], Z'[M-k]), the inputs of the M-point inverse complex FFT
+SPX_HD void pre_pair(float2 hP, float2 hQ, float2 w, float2& P, float2& Q) {
+    const float Ar = hP.x + hQ.x, Ai = hP.y - hQ.y;
+    const float Dr = hP.x - hQ.x, Di = hP.y + hQ.y;
+    const float Gr = w.x * Dr + w.y * Di, Gi = w.x * Di - w.y * Dr;
+    P = f2(Ar - Gi, Ai + Gr);
+    Q = f2(Ar + Gi, Gr - Ai);
+}
 
 constexpr int V = 16;            // complex values per lane
 
@@ -145,11 +167,6 @@ SPX_HD void fwd_pass3(int l, const float2* e2, float2* A, float2* B) {
 // ---- point-wise stage ------------------------------------------------------------------------------------
 // q * mag / (|q| + 1e-16) (methods.py:246-247) with ONE special-function op: mag * rsqrt(|q|^2 + 1e-32).  The two
 // agree to rounding unless |q| ~ 1e-16 (where both give q * mag * ~1e16), and |q| = 0 gives 0, not NaN.
-#ifdef __CUDA_ARCH__
-__device__ __forceinline__ float approx_rsqrt(float v) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
-#else
-inline float approx_rsqrt(float v) { return 1.0f / sqrtf(v); }
-#endif
 SPX_HD float2 project_rsq(float2 q, float mag) {
     const float s = mag * approx_rsqrt(q.x * q.x + (q.y * q.y + 1e-32f));
     return f2(q.x * s, q.y * s);

@@ -13,23 +13,13 @@ int generic_gl_iter(const specinv_desc*, const void*, const void*, void*, const 
                     const void*, const void*, double, double*, void*);
 int generic_admm_iter(const specinv_desc*, const void*, const void*, void*, const void*, const void*, const void*,
                       const void*, void*, void*, void*, void*, const void*, const void*, double, double*, void*);
-// implemented in specinv_fast.cu / specinv_fastw.cu (fast paths); return SPECINV_ERR_UNSUPPORTED when not applicable
-int fast_gl_iter(const specinv_desc*, const void*, const void*, void*, const void*, const void*, void*, void*,
-                 const void*, const void*, double, double*, void*);
-int fast_admm_iter(const specinv_desc*, const void*, const void*, void*, const void*, const void*, const void*,
-                   const void*, void*, void*, void*, void*, const void*, const void*, double, double*, void*);
+// implemented in specinv_fastw.cu (the specialised kernels); return SPECINV_ERR_UNSUPPORTED when not applicable
 
 int fastw_gl_iter(const specinv_desc*, const void*, const void*, void*, const void*, const void*, void*, void*,
                   const void*, const void*, double, double*, void*);
 int fastw_admm_iter(const specinv_desc*, const void*, const void*, void*, const void*, const void*, const void*,
                     const void*, void*, void*, void*, void*, const void*, const void*, double, double*, void*);
 int fastw_istft(const specinv_desc*, const void*, const void*, const void*, void*, void*);
-
-// SPECINV_FAST_IMPL=half keeps n_fft = 1024 on the older half-warp-per-frame kernel (A-B timing)
-static bool use_warp_kernel() {
-    const char* e = getenv("SPECINV_FAST_IMPL");
-    return !(e && e[0] == 'h');
-}
 
 // SPECINV_FORCE_GENERIC=1 routes everything through the generic tile kernels (testing / A-B timing)
 static bool force_generic() {
@@ -294,7 +284,7 @@ int specinv_stft(const specinv_desc* d, const void* plan, const void* x, void* m
 
 int specinv_istft(const specinv_desc* d, const void* plan, const void* main_in, const void* nyq_in, void* x_out,
                   void* stream) {
-    if (d && plan && main_in && x_out && !force_generic() && use_warp_kernel()) {
+    if (d && plan && main_in && x_out && !force_generic()) {
         const int rw = fastw_istft(d, plan, main_in, nyq_in, x_out, stream);
         if (rw != SPECINV_ERR_UNSUPPORTED) return rw;
     }
@@ -307,13 +297,8 @@ int specinv_gl_iter(const specinv_desc* d, const void* plan, const void* x_in, v
     if (!d || !plan || !x_in || !x_out || !q_in_main || !q_out_main || !mag_main) return SPECINV_ERR_INVALID;
     if (x_in == x_out || q_in_main == q_out_main) return SPECINV_ERR_INVALID;
     if (!force_generic() && d->onesided && q_in_nyq && q_out_nyq && mag_nyq) {
-        if (use_warp_kernel()) {
-            const int rw = fastw_gl_iter(d, plan, x_in, x_out, q_in_main, q_in_nyq, q_out_main, q_out_nyq, mag_main,
-                                         mag_nyq, lr, sums, stream);
-            if (rw != SPECINV_ERR_UNSUPPORTED) return rw;
-        }
-        const int rc = fast_gl_iter(d, plan, x_in, x_out, q_in_main, q_in_nyq, q_out_main, q_out_nyq, mag_main, mag_nyq,
-                                    lr, sums, stream);
+        const int rc = fastw_gl_iter(d, plan, x_in, x_out, q_in_main, q_in_nyq, q_out_main, q_out_nyq, mag_main, mag_nyq,
+                                     lr, sums, stream);
         if (rc != SPECINV_ERR_UNSUPPORTED) return rc;
     }
     return generic_gl_iter(d, plan, x_in, x_out, q_in_main, q_in_nyq, q_out_main, q_out_nyq, mag_main, mag_nyq, lr,
@@ -328,13 +313,8 @@ int specinv_admm_iter(const specinv_desc* d, const void* plan, const void* x_in,
         return SPECINV_ERR_INVALID;
     if (x_in == x_out || X_in_main == X_out_main || U_in_main == U_out_main) return SPECINV_ERR_INVALID;
     if (!force_generic() && d->onesided && X_in_nyq && U_in_nyq && X_out_nyq && U_out_nyq && mag_nyq) {
-        if (use_warp_kernel()) {
-            const int rw = fastw_admm_iter(d, plan, x_in, x_out, X_in_main, X_in_nyq, U_in_main, U_in_nyq, X_out_main,
-                                           X_out_nyq, U_out_main, U_out_nyq, mag_main, mag_nyq, rho, sums, stream);
-            if (rw != SPECINV_ERR_UNSUPPORTED) return rw;
-        }
-        const int rc = fast_admm_iter(d, plan, x_in, x_out, X_in_main, X_in_nyq, U_in_main, U_in_nyq, X_out_main,
-                                      X_out_nyq, U_out_main, U_out_nyq, mag_main, mag_nyq, rho, sums, stream);
+        const int rc = fastw_admm_iter(d, plan, x_in, x_out, X_in_main, X_in_nyq, U_in_main, U_in_nyq, X_out_main,
+                                       X_out_nyq, U_out_main, U_out_nyq, mag_main, mag_nyq, rho, sums, stream);
         if (rc != SPECINV_ERR_UNSUPPORTED) return rc;
     }
     return generic_admm_iter(d, plan, x_in, x_out, X_in_main, X_in_nyq, U_in_main, U_in_nyq, X_out_main, X_out_nyq,

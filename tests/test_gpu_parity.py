@@ -235,11 +235,8 @@ FAST_CASES = [
 ]
 
 
-@pytest.mark.parametrize("impl", ["warp", "half"])
 @pytest.mark.parametrize("fc", FAST_CASES, ids=lambda c: f"B{c['B']}_T{c['T']}_{c['pad_mode']}_c{int(c['center'])}")
-def test_fast_path_1024_against_oracle(fc, monkeypatch, impl):
-    monkeypatch.setenv("SPECINV_FAST_FORCE", "1")       # small problems would otherwise go to the generic kernel
-    monkeypatch.setenv("SPECINV_FAST_IMPL", impl)
+def test_fast_path_1024_against_oracle(fc):
     from spectrogram_inversion_b200.engine import ADMMSolver, GriffinLimSolver, StftPlan
     from spectrogram_inversion_b200.stft_args import args_helper
     rs = np.random.RandomState(fc["T"])
@@ -301,7 +298,6 @@ def test_fast_and_generic_kernels_agree(monkeypatch):
     magt = torch.from_numpy(mag).cuda()
     plan = StftPlan(args_helper(magt, window=w, hop_length=256), T, B, torch.float32, torch.device("cuda"))
     outs = []
-    monkeypatch.setenv("SPECINV_FAST_FORCE", "1")
     for force in ("0", "1"):
         monkeypatch.setenv("SPECINV_FORCE_GENERIC", force)
         s = GriffinLimSolver(plan, plan.pack(torch.from_numpy(C)), plan.pack(magt), 0.99)
@@ -371,7 +367,7 @@ def test_rtisi_la_shapes_and_quality():
 
 
 # ---------------------------------------------------------------------------------------------
-# fast paths for n_fft = 2048, hop = 512 (two warps per frame; "half": the older one-warp kernel) and
+# fast paths for n_fft = 2048, hop = 512 (two warps per frame) and
 # n_fft = 4096, hop = 1024 (four warps per frame)
 # ---------------------------------------------------------------------------------------------
 FAST2048_CASES = [
@@ -379,7 +375,7 @@ FAST2048_CASES = [
     dict(B=37, T=77, center=True, pad_mode="constant", normalized=True),
     dict(B=64, T=64, center=False, pad_mode="reflect", normalized=False),
     dict(B=1, T=9, center=True, pad_mode="reflect", normalized=False),
-    dict(B=3, T=41, center=True, pad_mode="circular", normalized=False, impl="half"),
+    dict(B=3, T=41, center=True, pad_mode="circular", normalized=False),
     dict(B=9, T=50, center=True, pad_mode="replicate", normalized=False, n_fft=4096),
     dict(B=2, T=33, center=False, pad_mode="reflect", normalized=True, n_fft=4096),
     dict(B=1, T=301, center=True, pad_mode="reflect", normalized=False, n_fft=4096),
@@ -388,9 +384,7 @@ FAST2048_CASES = [
 
 @pytest.mark.parametrize("fc", FAST2048_CASES,
                          ids=lambda c: f"n{c.get('n_fft', 2048)}_B{c['B']}_T{c['T']}_{c['pad_mode']}_c{int(c['center'])}")
-def test_fast_path_2048_against_oracle(fc, monkeypatch):
-    monkeypatch.setenv("SPECINV_FAST_FORCE", "1")
-    monkeypatch.setenv("SPECINV_FAST_IMPL", fc.get("impl", "warp"))
+def test_fast_path_2048_against_oracle(fc):
     from spectrogram_inversion_b200.engine import ADMMSolver, GriffinLimSolver, StftPlan
     from spectrogram_inversion_b200.stft_args import args_helper
     rs = np.random.RandomState(fc["T"])
