@@ -231,14 +231,14 @@ __global__ void __launch_bounds__(WARPS * 32, 1) warp_iter_kernel(const WArgs a)
     static_assert(TC_WARP + ((WARPS + 3) / 4) * TC_PER_WARP <= TMEM_COLS, "TMEM columns");
     extern __shared__ __align__(16) float2 sm[];
     __shared__ unsigned s_tmem_base;
-    __shared__ __align__(8) unsigned long long s_bar[GROUPS][2];   // per group: input block, state rows
+    __shared__ __align__(8) unsigned long long s_bar[GROUPS][3];   // per group: input block, state rows, ADMM U row
     const int tid = threadIdx.x, warp = tid >> 5;
     const int grp = warp / G;                     // frame group inside the CTA
     const int l = tid - grp * LANES;              // lane inside the group, 0 .. LANES-1
     const int bar_id = 1 + grp;
     if (warp == 0) tmem_alloc(&s_tmem_base, TMEM_COLS);
-    const unsigned xbar = (unsigned)__cvta_generic_to_shared(&s_bar[grp][0]), sbar = xbar + 8;
-    if (l == 0) { mbar_init(xbar, 1); mbar_init(sbar, 1); }
+    const unsigned xbar = (unsigned)__cvta_generic_to_shared(&s_bar[grp][0]), sbar = xbar + 8, ubar = xbar + 16;
+    if (l == 0) { mbar_init(xbar, 1); mbar_init(sbar, 1); mbar_init(ubar, 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) warp_iter_kernel(const WArgs a)
     float2* qstage = xs + M / 4 + M / 2;                            // q / X row of the coming frame
     const unsigned grp_s = (unsigned)__cvta_generic_to_shared(sm) + grp * (G * WARP_F2 * 8);   // shared-window addresses
     const unsigned xs_s = grp_s + 2 * M * 8, mstage_s = xs_s + (M / 4) * 8, qstage_s = mstage_s + (M / 2) * 8;
-    unsigned xpar = 0, spar = 0;                                    // mbarrier phase parities
+    unsigned xpar = 0, spar = 0, upar = 0;                          // mbarrier phase parities
 
     // bin offsets of the lane's pair slots inside a main row
     const int hi_adj = l == 0 ? -7 * LANES : 0;  // lane 0, slots 4..7: LANES + 2 LANES (j - 4) = 2 LANES j - 7 LANES
@@ -353,9 +353,6 @@ __global__ void __launch_bounds__(WARPS * 32, 1) warp_iter_kernel(const WArgs a)
             const long long row = (long long)b * a.T + t;
             const bool owned = t >= t0;
             float2 v[V];
-            float2 tw2[C::R2];
-            if constexpr (C::R2 == 8) tmem_ld16(tlane + TC_TW2, reinterpret_cast<float*>(tw2));
-            else tmem_ld32(tlane + TC_TW2, reinterpret_cast<float*>(tw2));
             float2 A[8], Bv[8];
             if constexpr (OP != OP_ISTFT) {
             // ---- assemble the frame: blocks t .. t+2 from the ring, block t+3 from the staging buffer
@@ -391,13 +388,23 @@ __global__ void __launch_bounds__(WARPS * 32, 1) warp_iter_kernel(const WArgs a)
                 fwd_pass1<LANES>(l, v, tw1, e1);
             }
             group_sync<LANES>(bar_id);
-            fwd_pass2<LANES>(l, e1, tw2, e2);
+            {
+                float2 tw2[C::R2];
+                if constexpr (C::R2 == 8) tmem_ld16(tlane + TC_TW2, reinterpret_cast<float*>(tw2));
+                else tmem_ld32(tlane + TC_TW2, reinterpret_cast<float*>(tw2));
+                fwd_pass2<LANES>(l, e1, tw2, e2);
+            }
             group_sync<LANES>(bar_id);
+            if constexpr (OP == OP_ADMM) {
+                // E1 is idle until the inverse pass 2: stage this frame's U row (L2-prefetched a frame ago) in it
+                if (l < 32) { if (elect_one()) { mbar_expect_tx(ubar, M * 8); bulk_g2s(grp_s, a.s1_in + row * M, M * 8, ubar); } }
+            }
             fwd_pass3<LANES>(l, e2, A, Bv);
             }  // OP != OP_ISTFT
             const float2 s0n = s0n_next, s1n = s1n_next;
             const float mgn = mgn_next;
             mbar_wait(sbar, spar); spar ^= 1;      // this frame's staged rows have landed
+            if constexpr (OP == OP_ADMM) { mbar_wait(ubar, upar); upar ^= 1; }
             {
                 // ---- point-wise stage on the lane's 16 bins (+ Nyquist for lane 0), state fetched where it is used.
                 // Element e = 2 j / 2 j + 1 is the P / Q bin of slot j: bins l + 2 LANES j and M - l - 2 LANES j, except
@@ -413,7 +420,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) warp_iter_kernel(const WArgs a)
                         return (e & 1) ? (j == 0 ? q0 : (j >= 4 ? qh : ql) - 2 * LANES * j) : (j >= 4 ? ph : pl) + 2 * LANES * j;
                     }
                     __device__ __forceinline__ float2 s0(int e) const { return e < 0 ? s0n : q[bin(e)]; }
-                    __device__ __forceinline__ float2 s1(int e) const { return e < 0 ? s1n : ldg_nc_f2(u + bin(e)); }
+                    __device__ __forceinline__ float2 s1(int e) const { return e < 0 ? s1n : u[bin(e)]; }
                     __device__ __forceinline__ float mag(int e) const { return e < 0 ? mgn : mg[bin(e)]; }
                     __device__ __forceinline__ void put(int e, float2 v0, float2 v1) const {
                         if (!owned) return;
@@ -425,7 +432,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) warp_iter_kernel(const WArgs a)
                             if constexpr (OP == OP_ADMM) o1[bin(e)] = v1;
                         }
                     }
-                } io{qstage, mstage, OP == OP_ADMM ? a.s1_in + row * M : nullptr, a.s0_out + row * M,
+                } io{qstage, mstage, e1, a.s0_out + row * M,
                      OP == OP_ADMM ? a.s1_out + row * M : nullptr, a.s0_out_nyq + row,
                      OP == OP_ADMM ? a.s1_out_nyq + row : nullptr, l, l + hi_adj, M - l, M - l - hi_adj, kq0, owned,
                      s0n, s1n, mgn};
@@ -453,7 +460,12 @@ __global__ void __launch_bounds__(WARPS * 32, 1) warp_iter_kernel(const WArgs a)
             const bool emit = owned && block_valid<LANES>(a, t);
             float2 ie[4];
             if (emit) load_inv_env<LANES>(a, t, l, ie);    // early: the latency hides behind the last two passes
-            inv_pass2<LANES>(l, e2, tw2, e1);
+            {
+                float2 tw2[C::R2];
+                if constexpr (C::R2 == 8) tmem_ld16(tlane + TC_TW2, reinterpret_cast<float*>(tw2));
+                else tmem_ld32(tlane + TC_TW2, reinterpret_cast<float*>(tw2));
+                inv_pass2<LANES>(l, e2, tw2, e1);
+            }
             group_sync<LANES>(bar_id);
             {
                 float2 tw1[V];
