@@ -14,10 +14,17 @@
 // is overlap-added (window w, 1/envelope, centre trimming) into the output (:406-408, fused here).
 // Frame / spectrum slots rotate by index ((a + i) mod (LA+1)), so "pre[a] <- pre[a+1]" and the slide of
 // the active frames cost nothing.
+#include <cstdlib>
+
 #include "specinv_common.cuh"
 #include "generic_fft.cuh"
 
 namespace specinv {
+
+// implemented in specinv_rtisi_fast.cu; returns SPECINV_ERR_UNSUPPORTED when the shape is not its own
+int rtisi_fast(const specinv_desc* d, const Dims& dm, const void* plan, const void* mag_main, const void* mag_nyq,
+               void* x_out, const void* asym1, const void* asym2, int look_ahead, int asymmetric, int max_iter,
+               double alpha, double synth_coeff, cudaStream_t st);
 
 struct RtisiArgs {
     const void* mag_main; const void* mag_nyq;
@@ -260,6 +267,15 @@ static int rtisi_t(const specinv_desc* d, const Dims& dm, const void* plan, cons
     const double fscale = d->normalized ? 1.0 / sqrt((double)dm.N) : 1.0;
     rtisi_windows_kernel<T><<<(dm.N + 255) / 256, 256, 0, st>>>(dm.N, dm.hop, dm.K, (const T*)window, synth_coeff, fscale,
                                                                 asym, asym + dm.N);
+    if (sizeof(T) == 4) {
+        // the register-FFT kernel of specinv_rtisi_fast.cu covers n_fft = 1024 / hop = 256 / look_ahead <= 3
+        const char* fg = getenv("SPECINV_FORCE_GENERIC");
+        if (!(fg && fg[0] == '1')) {
+            const int rf = rtisi_fast(d, dm, plan, mag_main, mag_nyq, x_out, asym, asym + dm.N, look_ahead, asymmetric,
+                                      max_iter, alpha, synth_coeff, st);
+            if (rf != SPECINV_ERR_UNSUPPORTED) return rf;
+        }
+    }
     const int NA = a.LA + 1, F = dm.onesided ? dm.M + 1 : dm.N, ylen = a.LA * dm.hop + dm.N;
     const size_t smem = ((size_t)NA * a.Mp + (size_t)NA * F) * 2 * sizeof(T) +
                         ((size_t)dm.K * dm.N + 2 * (size_t)ylen + dm.N) * sizeof(T);

@@ -366,6 +366,55 @@ def test_rtisi_la_shapes_and_quality():
     assert abs(scg - sco) <= 0.02 * abs(sco) + 0.2, (scg, sco)
 
 
+RTISI_FAST_CASES = [
+    dict(B=3, T=6, look_ahead=3, asym=False, max_iter=1, alpha=0.99, center=True, normalized=False, window="hann"),
+    dict(B=3, T=8, look_ahead=3, asym=False, max_iter=2, alpha=0.99, center=True, normalized=False, window="hann"),
+    dict(B=2, T=7, look_ahead=-1, asym=True, max_iter=2, alpha=0.99, center=True, normalized=False, window="hann"),
+    dict(B=1, T=7, look_ahead=1, asym=True, max_iter=2, alpha=0.5, center=False, normalized=True, window="hamming"),
+    dict(B=5, T=8, look_ahead=0, asym=False, max_iter=2, alpha=0.0, center=True, normalized=False, window="hann"),
+    dict(B=2, T=8, look_ahead=2, asym=False, max_iter=2, alpha=0.99, center=True, normalized=False, window=None, win_length=700),
+    dict(B=3, T=14, look_ahead=3, asym=False, max_iter=3, alpha=0.99, center=True, normalized=False, window="hann"),
+]
+
+
+@pytest.mark.parametrize("rc", RTISI_FAST_CASES, ids=lambda c: f"B{c['B']}_T{c['T']}_la{c['look_ahead']}_asym{int(c['asym'])}_it{c['max_iter']}")
+def test_rtisi_fast_kernel_1024_against_oracle(rc, monkeypatch):
+    """The register-FFT RTISI-LA kernel (n_fft = 1024, hop = 256) against the oracle in float64.  fp32 trajectories of
+    RTISI-LA drift apart quickly (the projection divides by |S|; SURVEY.md section 7: fp32 vs fp64 of the REFERENCE
+    decorrelate over a full run), so the yardstick is the drift of two other fp32 implementations from the same fp64
+    run -- the oracle in float32 and the generic shared-memory kernel: an indexing mistake gives O(1) errors."""
+    import spectrogram_inversion_b200 as S
+    rs = np.random.RandomState(rc["T"])
+    n_fft, hop = 1024, 256
+    kw = dict(hop_length=hop, center=rc["center"], normalized=rc["normalized"])
+    wl = rc.get("win_length", n_fft)
+    if rc["window"] is not None:
+        kw["window"] = cases.window_of(rc["window"], wl, np.float32)
+    if wl != n_fft:
+        kw["win_length"] = wl
+    oa = O.args_helper(513, np.float32, **kw)
+    n_samples = (rc["T"] - 1) * hop + (0 if rc["center"] else n_fft)
+    mag = np.abs(O.stft(rs.randn(rc["B"], n_samples).astype(np.float32), oa)).astype(np.float32)
+    assert mag.shape == (rc["B"], 513, rc["T"])
+    run = dict(look_ahead=rc["look_ahead"], asymmetric_window=rc["asym"], max_iter=rc["max_iter"], alpha=rc["alpha"])
+    y32 = O.RTISI_LA(mag, **run, **kw)
+    kw64 = {k: (v.astype(np.float64) if isinstance(v, np.ndarray) else v) for k, v in kw.items()}
+    y64 = O.RTISI_LA(mag.astype(np.float64), **run, **kw64)
+    tkw = {k: (torch.from_numpy(v).cuda() if isinstance(v, np.ndarray) else v) for k, v in kw.items()}
+    outs = {}
+    for force in ("0", "1"):
+        monkeypatch.setenv("SPECINV_FORCE_GENERIC", force)
+        outs[force] = S.RTISI_LA(torch.from_numpy(mag).cuda(), verbose=0, **run, **tkw).cpu().numpy()
+
+    def rel_l2(a, b):
+        return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+    assert outs["0"].shape == y64.shape and np.isfinite(outs["0"]).all()
+    drift = max(rel_l2(y32, y64), rel_l2(outs["1"], y64))
+    assert drift < 0.1, drift                              # the horizon is short enough for the comparison to mean something
+    assert rel_l2(outs["0"], y64) <= 4 * drift + 1e-5, (rel_l2(outs["0"], y64), drift)
+    assert rel_l2(outs["0"], outs["1"]) <= 4 * drift + 1e-5
+
+
 # ---------------------------------------------------------------------------------------------
 # fast paths for n_fft = 2048, hop = 512 (two warps per frame) and
 # n_fft = 4096, hop = 1024 (four warps per frame)
