@@ -88,6 +88,9 @@ int specinv_plan_init_ranged(const specinv_desc* d, const void* window, void* pl
                              int64_t total_frames, void* stream);
 /* copies the length-L envelope (not its inverse) out of the plan */
 int specinv_plan_envelope(const specinv_desc* d, const void* plan, void* env_out, void* stream);
+/* replaces the plan's envelope by 1: specinv_istft then returns the plain windowed overlap-add (no
+ * normalisation), which is what the adjoint of torch.stft needs (autograd of methods.py:241). */
+int specinv_plan_unit_envelope(const specinv_desc* d, void* plan, void* stream);
 
 /* ---- layout conversion (strides in ELEMENTS of the (batch, freq, time) tensor) ---------- */
 int specinv_pack_complex(const specinv_desc* d, const void* spec, int64_t sb, int64_t sf, int64_t st,

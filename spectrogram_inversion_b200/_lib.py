@@ -23,7 +23,7 @@ EXPORTS = (
     "specinv_pack_complex", "specinv_pack_real", "specinv_unpack_complex",
     "specinv_stft", "specinv_istft", "specinv_gl_iter", "specinv_admm_iter",
     "specinv_metric_sums", "specinv_phase_init", "specinv_spec_abs", "specinv_rtisi_la", "specinv_plan_init_ranged",
-    "specinv_phase_init_ex", "specinv_halo_sum", "specinv_fill_padding",
+    "specinv_phase_init_ex", "specinv_halo_sum", "specinv_fill_padding", "specinv_plan_unit_envelope",
 )
 
 
@@ -48,6 +48,7 @@ def _declare(lib: C.CDLL) -> None:
         "specinv_signal_length": [dp, C.POINTER(i64)],
         "specinv_plan_bytes": [dp, C.POINTER(C.c_size_t)],
         "specinv_plan_init": [dp, vp, vp, vp],
+        "specinv_plan_unit_envelope": [dp, vp, vp],
         "specinv_plan_envelope": [dp, vp, vp, vp],
         "specinv_plan_init_ranged": [dp, vp, vp, i64, i64, vp],
         "specinv_phase_init_ex": [dp, vp, vp, vp, vp, vp, vp, vp],

@@ -195,6 +195,15 @@ __global__ void fill_padding_kernel(T* x, long long ld, int rows, long long off,
 
 }  // namespace specinv
 
+namespace specinv {
+template <typename T>
+__global__ void fill_ones_kernel(T* a, T* b, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { a[i] = T(1); b[i] = T(1); }
+}
+
+}  // namespace specinv
+
 using namespace specinv;
 
 extern "C" {
@@ -249,6 +258,19 @@ int specinv_plan_envelope(const specinv_desc* d, const void* plan, void* env_out
     const size_t es = d->dtype == SPECINV_F64 ? 8 : 4;
     return (int)cudaMemcpyAsync(env_out, (const char*)plan + pl.env, (size_t)dm.L * es, cudaMemcpyDeviceToDevice,
                                 (cudaStream_t)stream);
+}
+
+int specinv_plan_unit_envelope(const specinv_desc* d, void* plan, void* stream) {
+    Dims dm; int rc = make_dims(d, &dm); if (rc) return rc;
+    if (!plan) return SPECINV_ERR_INVALID;
+    const PlanLayout pl = plan_layout(dm, d->dtype);
+    char* p = (char*)plan;
+    const unsigned blocks = (unsigned)((dm.L + 255) / 256);
+    if (d->dtype == SPECINV_F64)
+        fill_ones_kernel<double><<<blocks, 256, 0, (cudaStream_t)stream>>>((double*)(p + pl.env), (double*)(p + pl.inv_env), dm.L);
+    else
+        fill_ones_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>((float*)(p + pl.env), (float*)(p + pl.inv_env), dm.L);
+    return (int)cudaGetLastError();
 }
 
 int specinv_pack_complex(const specinv_desc* d, const void* spec, int64_t sb, int64_t sf, int64_t st,

@@ -7,12 +7,12 @@ from typing import Optional, Tuple
 
 import torch
 
-from . import _ops
+from . import _ops, autograd
 from .engine import (ADMMSolver, GriffinLimSolver, METRIC_NAMES, SplitSpec, StftPlan, compute_device,
                      training_loop)
 from .stft_args import StftArgs, args_helper, real_dtype_of
 
-__all__ = ["griffin_lim", "RTISI_LA", "ADMM", "phase_init"]
+__all__ = ["griffin_lim", "RTISI_LA", "ADMM", "L_BFGS", "phase_init"]
 
 pi2 = 2 * math.pi
 
@@ -46,6 +46,23 @@ def _setup(spec: torch.Tensor, stft_kwargs: dict):
         return plan, C, plan.spec_abs(C)
     mag = plan.pack(work)
     return plan, plan.phase_init(mag), mag
+
+
+def _diff_setup(spec: torch.Tensor, stft_kwargs: dict):
+    """Input handling of the differentiable path: everything stays attached to ``spec``'s graph."""
+    assert 4 > len(spec.shape) > 1
+    dev = compute_device(spec)
+    work = spec.unsqueeze(0) if len(spec.shape) == 2 else spec
+    work = work.to(dev)
+    args = args_helper(work, **stft_kwargs)
+    args.window = args.window.detach().to(device=dev, dtype=real_dtype_of(work.dtype))
+    return work, args
+
+
+def _diff_finish(x: torch.Tensor, spec: torch.Tensor) -> torch.Tensor:
+    if not (spec.shape[0] == 1 and len(spec.shape) == 3):
+        x = x.squeeze(0)
+    return x.to(spec.device)
 
 
 def _finish(x: torch.Tensor, spec: torch.Tensor) -> torch.Tensor:
@@ -85,6 +102,9 @@ def griffin_lim(spec, max_iter=200, tol=1e-6, alpha=0.99, verbose=True, eva_iter
     assert max_iter > 0
     assert tol >= 0
     assert metric.upper() in METRIC_NAMES
+    if autograd.wants_grad(spec):     # the reference's output is differentiable w.r.t. spec (test_griffin.py:54,65-66)
+        work, args = _diff_setup(spec, stft_kwargs)
+        return _diff_finish(autograd.griffin_lim_diff(work, args, max_iter, tol, alpha, verbose, eva_iter, metric), spec)
     plan, C, mag = _setup(spec, stft_kwargs)
     solver = GriffinLimSolver(plan, C, mag, alpha)
     training_loop(solver, max_iter, tol, verbose, eva_iter, metric)
@@ -98,6 +118,9 @@ def ADMM(spec, max_iter=1000, tol=1e-6, rho=0.1, verbose=1, eva_iter=10, metric=
     assert max_iter > 0
     assert tol >= 0
     assert metric.upper() in METRIC_NAMES
+    if autograd.wants_grad(spec):
+        work, args = _diff_setup(spec, stft_kwargs)
+        return _diff_finish(autograd.admm_diff(work, args, max_iter, tol, rho, verbose, eva_iter, metric), spec)
     plan, C, mag = _setup(spec, stft_kwargs)
     solver = ADMMSolver(plan, C, mag, rho)
     training_loop(solver, max_iter, tol, verbose, eva_iter, metric)
@@ -111,6 +134,9 @@ def RTISI_LA(spec, look_ahead=-1, asymmetric_window=False, max_iter=25, alpha=0.
     assert alpha >= 0
     assert not spec.is_complex()
     assert 4 > len(spec.shape) > 1
+    if autograd.wants_grad(spec):
+        work, args = _diff_setup(spec, stft_kwargs)
+        return _diff_finish(autograd.rtisi_diff(work, args, look_ahead, asymmetric_window, max_iter, alpha, verbose), spec)
     dev = compute_device(spec)
     work = spec.detach()
     if len(spec.shape) == 2:
@@ -145,3 +171,32 @@ def phase_init(spec, **stft_kwargs):
     plan = StftPlan(args, T, B, m.dtype, dev, tables=False)
     out = plan.unpack(plan.phase_init(plan.pack(m)))
     return out.reshape(shape).to(spec.device)
+
+
+def L_BFGS(spec, transform_fn, samples=None, init_x0=None, outer_max_iter=1000, tol=1e-6, verbose=1, eva_iter=10,
+           metric="sc", **kwargs):
+    r"""Inversion of an arbitrary differentiable representation with ``torch.optim.LBFGS`` (same signature and
+    loop as ``torch_specinv.L_BFGS``, methods.py:509-569).
+
+    This function is generic autograd on a USER transform -- nothing of it is STFT specific and none of the
+    sm_100a kernels apply (out of scope); it is provided so that the package exports the same
+    five names as the reference.  It runs wherever ``spec`` lives, on plain PyTorch.
+    """
+    if init_x0 is None:
+        init_x0 = spec.new_empty(*samples).normal_(std=1e-6)
+    x = torch.nn.Parameter(init_x0)
+    optimizer = torch.optim.LBFGS([x], **kwargs)
+
+    def inner():
+        optimizer.zero_grad()
+        loss = torch.nn.functional.mse_loss(transform_fn(x), spec)
+        loss.backward()
+        return loss
+
+    def outer():
+        optimizer.step(inner)
+        with torch.no_grad():
+            return transform_fn(x)
+
+    autograd._loop(outer, spec.detach(), outer_max_iter, tol, verbose, eva_iter, metric)
+    return x.detach()

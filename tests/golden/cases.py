@@ -116,3 +116,18 @@ LOOP_CASES = [
     dict(_c("loop_tol1e-2", window="hann", hop_length=32, T=33), tol=1e-2, eva_iter=5, max_iter=80, metric="snr"),
     dict(_c("loop_tol0", window="hann", hop_length=32, T=33), tol=0.0, eva_iter=4, max_iter=10, metric="ser"),
 ]
+
+
+# differentiable path: gradients of the reference w.r.t. spec, float64 ------------
+GRAD_CASES = [
+    _c("grad_hann64", n_fft=64, window="hann", hop_length=16, T=7, B=2),
+    _c("grad_norm_const", n_fft=64, window="hann", hop_length=16, T=6, B=1, normalized=True, pad_mode="constant"),
+    dict(_c("grad_nocenter", n_fft=64, window="hamming", hop_length=16, T=7, B=2, center=False), look_ahead=2, asym=True),
+    dict(_c("grad_twosided", n_fft=32, window="hann", hop_length=8, T=6, B=1, onesided=False), look_ahead=1),
+    dict(_c("grad_rect_default", n_fft=32, T=6, B=2), asym=True),
+]
+
+
+def probe_like(shape, seed):
+    """Fixed weights of the scalar loss sum(y * probe)."""
+    return np.random.RandomState(1000 + seed).randn(*shape)

@@ -124,3 +124,17 @@ def test_metric_value_formulas():
     assert abs(metric_value("SC", d, e, g) - O.sc(a, b)) < 1e-9
     assert abs(metric_value("SNR", d, e, g) - O.snr(a, b)) < 1e-9
     assert abs(metric_value("SER", d, e, g) - O.ser(a, b)) < 1e-9
+
+
+def test_package_exports_the_reference_names_and_lbfgs_runs():
+    """torch_specinv/__init__.py:6 re-exports griffin_lim, RTISI_LA, ADMM, L_BFGS, phase_init; L_BFGS is generic
+    autograd on a user transform (out of scope for the kernels) and runs on plain PyTorch."""
+    import spectrogram_inversion_b200 as S
+    for name in ("griffin_lim", "RTISI_LA", "ADMM", "L_BFGS", "phase_init", "sc", "snr", "ser", "spectral_convergence"):
+        assert callable(getattr(S, name)), name
+    assert S.methods.griffin_lim is S.griffin_lim and S.metrics.sc is S.sc
+    x = torch.randn(400)
+    f = lambda v: torch.stft(v, 64, return_complex=True, window=torch.hann_window(64)).abs()
+    spec = f(x)
+    y = S.L_BFGS(spec, f, samples=(400,), outer_max_iter=2, verbose=0, eva_iter=1, max_iter=5)
+    assert y.shape == (400,) and not y.requires_grad
