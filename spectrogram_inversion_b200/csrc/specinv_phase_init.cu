@@ -12,7 +12,16 @@
 namespace specinv {
 
 template <typename T> __device__ __forceinline__ void sincos_t(T x, T* s, T* c);
-template <> __device__ __forceinline__ void sincos_t<float>(float x, float* s, float* c) { sincosf(x, s, c); }
+// The running phase reaches 1e5..1e6 rad (omega = pi/2 * k per frame at hop = n_fft/4), far into the slow
+// (Payne-Hanek) range of sincosf.  The float phase is exactly representable in double, so reduce it modulo 2 pi
+// there (two-term 2 pi, error < 1e-10 rad) and take the fast path on the remainder.
+template <> __device__ __forceinline__ void sincos_t<float>(float x, float* s, float* c) {
+    const double xd = (double)x;
+    const double n = rint(xd * 0.15915494309189533576888);
+    double r = fma(-n, 6.283185307179586231996, xd);
+    r = fma(-n, 2.449293598294706353906e-16, r);
+    sincosf((float)r, s, c);
+}
 template <> __device__ __forceinline__ void sincos_t<double>(double x, double* s, double* c) { sincos(x, s, c); }
 
 // magnitude of bin k (0..F-1) of frame row `fr`; out-of-range bins are never peaks
