@@ -49,8 +49,46 @@ constexpr double cx_sin2pi(int k, int n) {
 }
 
 SPX_HD float2 f2(float x, float y) { float2 r; r.x = x; r.y = y; return r; }
-SPX_HD float2 operator+(float2 a, float2 b) { return f2(a.x + b.x, a.y + b.y); }
-SPX_HD float2 operator-(float2 a, float2 b) { return f2(a.x - b.x, a.y - b.y); }
+
+// ---- packed FP32x2 arithmetic ------------------------------------------------------------------------------
+// sm_100 executes add / sub / mul / fma on a PAIR of floats held in a 64-bit register pair as ONE instruction
+// (FADD2 / FMUL2 / FFMA2: two pipe cycles, one issue slot); the SASS operands take per-half negation, half swap
+// and scalar broadcast modifiers, so complex add is 1 instruction and complex multiply 2 (instead of 2 and 4).
+// The fused kernels are instruction-issue limited, so every complex value stays a float2 = one register pair and
+// all arithmetic goes through these helpers.  On the host (tests/host_emu) they are plain float code.
+#ifdef __CUDA_ARCH__
+__device__ __forceinline__ unsigned long long pk2(float lo, float hi) {
+    unsigned long long d; asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi)); return d;
+}
+__device__ __forceinline__ float2 upk2(unsigned long long v) {
+    float2 r; asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v)); return r;
+}
+__device__ __forceinline__ float2 padd(float2 a, float2 b) {
+    unsigned long long d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pk2(a.x, a.y)), "l"(pk2(b.x, b.y))); return upk2(d);
+}
+__device__ __forceinline__ float2 psub(float2 a, float2 b) {
+    unsigned long long d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pk2(a.x, a.y)), "l"(pk2(b.x, b.y))); return upk2(d);
+}
+__device__ __forceinline__ float2 pmul(float2 a, float2 b) {
+    unsigned long long d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pk2(a.x, a.y)), "l"(pk2(b.x, b.y))); return upk2(d);
+}
+__device__ __forceinline__ float2 pfma(float2 a, float2 b, float2 c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(pk2(a.x, a.y)), "l"(pk2(b.x, b.y)), "l"(pk2(c.x, c.y)));
+    return upk2(d);
+}
+#else
+inline float2 padd(float2 a, float2 b) { return f2(a.x + b.x, a.y + b.y); }
+inline float2 psub(float2 a, float2 b) { return f2(a.x - b.x, a.y - b.y); }
+inline float2 pmul(float2 a, float2 b) { return f2(a.x * b.x, a.y * b.y); }
+inline float2 pfma(float2 a, float2 b, float2 c) { return f2(a.x * b.x + c.x, a.y * b.y + c.y); }
+#endif
+SPX_HD float2 operator+(float2 a, float2 b) { return padd(a, b); }
+SPX_HD float2 operator-(float2 a, float2 b) { return psub(a, b); }
+// a * w and a * conj(w): (a.x, a.x) * w' + (a.y, a.y) * w'' with w', w'' = w with a half swapped / negated
+SPX_HD float2 cmul2(float2 a, float2 w) { return pfma(f2(a.x, a.x), w, pmul(f2(a.y, a.y), f2(-w.y, w.x))); }
+SPX_HD float2 cmulc2(float2 a, float2 w) { return pfma(f2(a.x, a.x), f2(w.x, -w.y), pmul(f2(a.y, a.y), f2(w.y, w.x))); }
+SPX_HD float2 smul2(float2 a, float s) { return pmul(a, f2(s, s)); }
 
 // v * exp(-+ 2 pi i K / N)   (forward: minus sign; INV: plus sign), K, N compile time
 template <int K, int N, bool INV>
@@ -63,8 +101,7 @@ SPX_HD float2 twiddle_mul(float2 v) {
     else {
         constexpr float c = (float)cx_cos2pi(k, N);
         constexpr float s = (float)(INV ? cx_sin2pi(k, N) : -cx_sin2pi(k, N));
-        // (v.x + i v.y)(c + i s)
-        return f2(v.x * c - v.y * s, v.x * s + v.y * c);
+        return cmul2(v, f2(c, s));                                                    // (v.x + i v.y)(c + i s)
     }
 }
 
@@ -84,10 +121,10 @@ SPX_HD void fft8(float2* a) {
     fft4<INV>(e0, e1, e2, e3);
     fft4<INV>(o0, o1, o2, o3);
     constexpr float h = 0.70710678118654752440f;
-    // W8^1 = (1 -+ i)/sqrt2, W8^2 = -+ i, W8^3 = (-1 -+ i)/sqrt2
-    const float2 t1 = INV ? f2((o1.x - o1.y) * h, (o1.x + o1.y) * h) : f2((o1.x + o1.y) * h, (o1.y - o1.x) * h);
+    // W8^1 = (1 -+ i)/sqrt2, W8^2 = -+ i, W8^3 = (-1 -+ i)/sqrt2:  o * (1 -+ i) = o + (-+ i) o
+    const float2 t1 = smul2(INV ? o1 + f2(-o1.y, o1.x) : o1 + f2(o1.y, -o1.x), h);
     const float2 t2 = INV ? f2(-o2.y, o2.x) : f2(o2.y, -o2.x);
-    const float2 t3 = INV ? f2(-(o3.x + o3.y) * h, (o3.x - o3.y) * h) : f2((o3.y - o3.x) * h, -(o3.x + o3.y) * h);
+    const float2 t3 = smul2(INV ? f2(-o3.y, o3.x) - o3 : f2(o3.y, -o3.x) - o3, h);
     a[0] = e0 + o0; a[4] = e0 - o0;
     a[1] = e1 + t1; a[5] = e1 - t1;
     a[2] = e2 + t2; a[6] = e2 - t2;

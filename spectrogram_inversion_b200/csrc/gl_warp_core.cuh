@@ -32,8 +32,9 @@ namespace wfast {
 
 enum { OP_GL = 0, OP_ADMM = 1, OP_ISTFT = 2 };   // OP_ISTFT: stand-alone inverse transform + overlap-add (methods.py:233)
 
-SPX_HD float2 cmulf(float2 a, float2 b) { return f2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
-SPX_HD float2 cmulcf(float2 a, float2 b) { return f2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); }   // a*conj(b)
+// complex products on the packed FP32x2 pipe (fft_regs.cuh): 2 instructions each
+SPX_HD float2 cmulf(float2 a, float2 b) { return cmul2(a, b); }
+SPX_HD float2 cmulcf(float2 a, float2 b) { return cmulc2(a, b); }     // a*conj(b)
 
 #ifdef __CUDA_ARCH__
 __device__ __forceinline__ float approx_sqrt(float v) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
@@ -46,19 +47,21 @@ inline float approx_rsqrt(float v) { return 1.0f / sqrtf(v); }
 // real-FFT post-process of one (P = Zh[k], Q = Zh[M-k]) pair, Zh = Z/2 (the 1/2 is folded into the analysis
 // window):  s[k], s[M-k] of the N-point real transform; w = W_N^k
 SPX_HD void post_pair(float2 P, float2 Q, float2 w, float2& sP, float2& sQ) {
-    const float er = P.x + Q.x, ei = P.y - Q.y;
-    const float orr = P.y + Q.y, oi = Q.x - P.x;
-    const float wor = w.x * orr - w.y * oi, woi = w.x * oi + w.y * orr;
-    sP = f2(er + wor, ei + woi);
-    sQ = f2(er - wor, woi - ei);
+    const float2 E = P + f2(Q.x, -Q.y);                 // (er, ei)   = P + conj(Q)
+    const float2 O = f2(P.y, -P.x) + f2(Q.y, Q.x);      // (orr, oi)  = -i (P - conj(Q))
+    const float2 WO = cmul2(O, w);                      // (wor, woi)
+    sP = E + WO;
+    const float2 D = E - WO;
+    sQ = f2(D.x, -D.y);                                 // (er - wor, woi - ei)
 }
 // inverse pre-process: (h[k], h[M-k]) -> (Z'[k], Z'[M-k]), the inputs of the M-point inverse complex FFT
 SPX_HD void pre_pair(float2 hP, float2 hQ, float2 w, float2& P, float2& Q) {
-    const float Ar = hP.x + hQ.x, Ai = hP.y - hQ.y;
-    const float Dr = hP.x - hQ.x, Di = hP.y + hQ.y;
-    const float Gr = w.x * Dr + w.y * Di, Gi = w.x * Di - w.y * Dr;
-    P = f2(Ar - Gi, Ai + Gr);
-    Q = f2(Ar + Gi, Gr - Ai);
+    const float2 A = hP + f2(hQ.x, -hQ.y);              // (Ar, Ai) = hP + conj(hQ)
+    const float2 D = hP - f2(hQ.x, -hQ.y);              // (Dr, Di) = hP - conj(hQ)
+    const float2 G = cmulc2(D, w);                      // (Gr, Gi) = D * conj(w)
+    P = A + f2(-G.y, G.x);                              // (Ar - Gi, Ai + Gr) = A + i G
+    const float2 R = A - f2(-G.y, G.x);                 // (Ar + Gi, Ai - Gr)
+    Q = f2(R.x, -R.y);                                  // (Ar + Gi, Gr - Ai)
 }
 
 constexpr int V = 16;            // complex values per lane
@@ -169,7 +172,7 @@ SPX_HD void fwd_pass3(int l, const float2* e2, float2* A, float2* B) {
 // agree to rounding unless |q| ~ 1e-16 (where both give q * mag * ~1e16), and |q| = 0 gives 0, not NaN.
 SPX_HD float2 project_rsq(float2 q, float mag) {
     const float s = mag * approx_rsqrt(q.x * q.x + (q.y * q.y + 1e-32f));
-    return f2(q.x * s, q.y * s);
+    return smul2(q, s);
 }
 
 // One bin: s = STFT bin of the current estimate.  Returns the value fed to the inverse transform.
@@ -182,16 +185,17 @@ SPX_HD float2 bin_update(float2 s, float2 a0, float2 a1, float m, float coef, fl
         esum += r * r;
     }
     if constexpr (OP == OP_GL) {
-        const float2 q = f2(s.x - a0.x * coef, s.y - a0.y * coef);
+        const float2 q = pfma(f2(-coef, -coef), a0, s);             // s - lr * q_prev
         o0 = q;
         return project_rsq(q, m);
     } else {
         const float rho = coef, inv = coef2;
-        const float2 Z = f2((rho * (a0.x + a1.x) + s.x) * inv, (rho * (a0.y + a1.y) + s.y) * inv);
-        const float2 Un = f2(a1.x + a0.x - Z.x, a1.y + a0.y - Z.y);
-        const float2 Xn = project_rsq(f2(Z.x - Un.x, Z.y - Un.y), m);
+        const float2 XU = a0 + a1;
+        const float2 Z = smul2(pfma(f2(rho, rho), XU, s), inv);      // (rho (X + U) + s) / (1 + rho)
+        const float2 Un = XU - Z;
+        const float2 Xn = project_rsq(Z - Un, m);
         o0 = Xn; o1 = Un;
-        return f2(Xn.x + Un.x, Xn.y + Un.y);
+        return Xn + Un;
     }
 }
 

@@ -207,7 +207,7 @@ __device__ __forceinline__ void store_block_ie(const WArgs& a, float* __restrict
     const long long base = (long long)u * Cfg<LANES>::HOP - a.P;
 #pragma unroll
     for (int j = 0; j < 4; ++j)
-        *reinterpret_cast<float2*>(xo + base + 2 * LANES * j + 2 * l) = f2(blk[j].x * ie[j].x, blk[j].y * ie[j].y);
+        *reinterpret_cast<float2*>(xo + base + 2 * LANES * j + 2 * l) = pmul(blk[j], ie[j]);
 }
 // Fetch the q / X row and the magnitude row of frame `row` into the staging rows (one elected lane, TMA).
 template <int OP, int LANES>
@@ -380,7 +380,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) warp_iter_kernel(const WArgs a)
                 float2 w[V];
                 tmem_ld32(tlane + TC_WA, reinterpret_cast<float*>(w));
 #pragma unroll
-                for (int i = 0; i < V; ++i) v[i] = f2(v[i].x * w[i].x, v[i].y * w[i].y);
+                for (int i = 0; i < V; ++i) v[i] = pmul(v[i], w[i]);
             }
             {
                 float2 tw1[V];
@@ -480,10 +480,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) warp_iter_kernel(const WArgs a)
                 tmem_ld16(twarp + 24, reinterpret_cast<float*>(carry));
                 tmem_ld8(twarp + 40, reinterpret_cast<float*>(carry + 8));
 #pragma unroll
-                for (int i = 0; i < V; ++i) {
-                    v[i] = f2(w[i].x * v[i].x, w[i].y * v[i].y);
-                    if (i < 12) v[i] = v[i] + carry[i];
-                }
+                for (int i = 0; i < V; ++i) v[i] = i < 12 ? pfma(w[i], v[i], carry[i]) : pmul(w[i], v[i]);
                 tmem_st16(twarp + 24, reinterpret_cast<const float*>(v + 4));
                 tmem_st8(twarp + 40, reinterpret_cast<const float*>(v + 12));
                 if (emit) store_block_ie<LANES>(a, xo, t, l, v, ie);

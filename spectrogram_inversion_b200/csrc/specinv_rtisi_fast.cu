@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) rtisi_fast_kernel(const RArgs a
                     tmem_ld32(tlane + TC_WSC, reinterpret_cast<float*>(w));
 #pragma unroll
                     for (int r = 0; r < V; ++r) {
-                        y[r] = f2(v[r].x * w[r].x, v[r].y * w[r].y);
+                        y[r] = pmul(v[r], w[r]);
                         Ub[p * ROWS + r * LANES + l] = y[r];
                     }
                 }
@@ -287,7 +287,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) rtisi_fast_kernel(const RArgs a
                     const unsigned wcol = (a.asymmetric && newest) ? (j ? TC_AS2 : TC_AS1) : TC_WA;
                     tmem_ld32(tlane + wcol, reinterpret_cast<float*>(w));
 #pragma unroll
-                    for (int r = 0; r < V; ++r) y[r] = f2(y[r].x * w[r].x, y[r].y * w[r].y);
+                    for (int r = 0; r < V; ++r) y[r] = pmul(y[r], w[r]);
                 }
                 {
                     float2 tw1[V];
@@ -350,7 +350,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) rtisi_fast_kernel(const RArgs a
 #pragma unroll
                     for (int r = 0; r < V; ++r) {
                         const float2 w = s_ws[r * LANES + l];
-                        c[r] = carry[r * LANES + l] + f2(v[r].x * w.x, v[r].y * w.y);
+                        c[r] = pfma(v[r], w, carry[r * LANES + l]);
                     }
                     const bool last = t == a.T - 1;                 // the last frame flushes the whole carry
 #pragma unroll
@@ -362,7 +362,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) rtisi_fast_kernel(const RArgs a
                                 for (int r = 0; r < 4; ++r) {
                                     const float2 ie = __ldg(reinterpret_cast<const float2*>(a.inv_env + m0 + 64 * r + 2 * l));
                                     const float2 val = c[4 * k + r];
-                                    *reinterpret_cast<float2*>(xo + m0 + 64 * r + 2 * l) = f2(val.x * ie.x, val.y * ie.y);
+                                    *reinterpret_cast<float2*>(xo + m0 + 64 * r + 2 * l) = pmul(val, ie);
                                 }
                             }
                         }
@@ -376,7 +376,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) rtisi_fast_kernel(const RArgs a
                     tmem_ld32(tlane + TC_WSC, reinterpret_cast<float*>(w));
                     float2* dst = Uk + kslot * ROWS + l;
 #pragma unroll
-                    for (int r = 0; r < V; ++r) dst[r * LANES] = f2(v[r].x * w[r].x, v[r].y * w[r].y);
+                    for (int r = 0; r < V; ++r) dst[r * LANES] = pmul(v[r], w[r]);
                 }
                 // this warp's frame slot becomes the newest (all-zero) active frame of the next step
 #pragma unroll
