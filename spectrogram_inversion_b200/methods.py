@@ -78,6 +78,57 @@ def _finish(x: torch.Tensor, spec: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def _pipeline_chunks(spec: torch.Tensor, tol: float, verbose) -> int:
+    """Host (non-CUDA) batches are processed in batch chunks so that the host->device copy of the next chunk and
+    the device->host copy of the previous result overlap the iterations of the current one.  The signals of a
+    batch only interact through the batch-global early-stop test (methods.py:186-190), which can never fire with
+    ``tol == 0`` ((prev - cur) / init < 0 and prev > cur contradict each other), and through the progress bar; so
+    with ``tol == 0`` and no progress bar the chunked run returns exactly what the whole-batch run returns."""
+    if spec.is_cuda or len(spec.shape) != 3 or tol != 0 or verbose:
+        return 1
+    B, _, T = spec.shape
+    return int(max(1, min(4, B, (B * T) // 60000)))
+
+
+def _run_host_pipelined(spec, n_chunks, make_solver, max_iter, eva_iter, metric, stft_kwargs):
+    dev = compute_device(spec)
+    cur = torch.cuda.current_stream(dev)
+    s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    B = spec.shape[0]
+    bounds = [(B * k) // n_chunks for k in range(n_chunks + 1)]
+
+    def stage(k):
+        with torch.cuda.stream(s_in):
+            t = spec[bounds[k]:bounds[k + 1]].detach().to(dev, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(s_in)
+        return t, ev
+
+    out, keep = None, []
+    nxt = stage(0)
+    for k in range(n_chunks):
+        work, ev = nxt
+        if k + 1 < n_chunks:
+            nxt = stage(k + 1)
+        cur.wait_event(ev)
+        work.record_stream(cur)
+        plan, C, mag = _setup(work, stft_kwargs)
+        solver = make_solver(plan, C, mag)
+        training_loop(solver, max_iter, 0.0, False, eva_iter, metric)
+        x = solver.signal
+        if out is None:
+            out = torch.empty((B, x.shape[1]), dtype=x.dtype, pin_memory=spec.is_pinned())
+        done = torch.cuda.Event()
+        done.record(cur)
+        with torch.cuda.stream(s_out):
+            s_out.wait_event(done)
+            out[bounds[k]:bounds[k + 1]].copy_(x, non_blocking=True)
+        keep.append(x)                       # alive until the copy stream has drained
+        del plan, C, mag, solver, work
+    s_out.synchronize()
+    return out
+
+
 def griffin_lim(spec, max_iter=200, tol=1e-6, alpha=0.99, verbose=True, eva_iter=10, metric="sc",
                 **stft_kwargs):
     r"""Griffin-Lim / fast Griffin-Lim phase reconstruction (drop-in for
@@ -105,6 +156,10 @@ def griffin_lim(spec, max_iter=200, tol=1e-6, alpha=0.99, verbose=True, eva_iter
     if autograd.wants_grad(spec):     # the reference's output is differentiable w.r.t. spec (test_griffin.py:54,65-66)
         work, args = _diff_setup(spec, stft_kwargs)
         return _diff_finish(autograd.griffin_lim_diff(work, args, max_iter, tol, alpha, verbose, eva_iter, metric), spec)
+    n_chunks = _pipeline_chunks(spec, tol, verbose)
+    if n_chunks > 1:
+        return _run_host_pipelined(spec, n_chunks, lambda p, c, m: GriffinLimSolver(p, c, m, alpha), max_iter, eva_iter,
+                                   metric, stft_kwargs)
     plan, C, mag = _setup(spec, stft_kwargs)
     solver = GriffinLimSolver(plan, C, mag, alpha)
     training_loop(solver, max_iter, tol, verbose, eva_iter, metric)
@@ -121,6 +176,10 @@ def ADMM(spec, max_iter=1000, tol=1e-6, rho=0.1, verbose=1, eva_iter=10, metric=
     if autograd.wants_grad(spec):
         work, args = _diff_setup(spec, stft_kwargs)
         return _diff_finish(autograd.admm_diff(work, args, max_iter, tol, rho, verbose, eva_iter, metric), spec)
+    n_chunks = _pipeline_chunks(spec, tol, verbose)
+    if n_chunks > 1:
+        return _run_host_pipelined(spec, n_chunks, lambda p, c, m: ADMMSolver(p, c, m, rho), max_iter, eva_iter, metric,
+                                   stft_kwargs)
     plan, C, mag = _setup(spec, stft_kwargs)
     solver = ADMMSolver(plan, C, mag, rho)
     training_loop(solver, max_iter, tol, verbose, eva_iter, metric)

@@ -468,3 +468,21 @@ def test_fast_path_2048_against_oracle(fc):
     st = O.admm_step(st, mag, 0.1, oa)
     close(solver.signal, st.x, 2e-5, "fast2048 ADMM x")
     close(plan.unpack(solver.U[solver.cur]), st.U, 1e-3, "fast2048 ADMM U")
+
+
+def test_host_batches_are_pipelined_in_chunks_with_identical_results():
+    """tol == 0, no progress bar, host input: the batch is processed in chunks (copies overlap compute); the signals
+    of a batch are independent then, so the result must equal the whole-batch (CUDA input) run bit for bit."""
+    import spectrogram_inversion_b200 as S
+    from spectrogram_inversion_b200 import methods
+    rs = np.random.RandomState(3)
+    B, T = 6, 22000                      # enough frames for the chunked path (>= 2 chunks of 60000 frames)
+    mag = torch.from_numpy((np.abs(rs.randn(B, 129, T)) * 3).astype(np.float32))
+    assert methods._pipeline_chunks(mag, 0.0, False) == 2
+    assert methods._pipeline_chunks(mag, 1e-6, False) == 1 and methods._pipeline_chunks(mag.cuda(), 0.0, False) == 1
+    w = torch.hann_window(256)
+    for fn, kw in ((S.griffin_lim, dict(alpha=0.99)), (S.ADMM, dict(rho=0.1))):
+        y_host = fn(mag.pin_memory(), max_iter=3, tol=0, verbose=False, eva_iter=2, window=w, hop_length=64, **kw)
+        y_dev = fn(mag.cuda(), max_iter=3, tol=0, verbose=False, eva_iter=2, window=w.cuda(), hop_length=64, **kw)
+        assert not y_host.is_cuda and y_host.shape == y_dev.shape
+        assert torch.equal(y_host, y_dev.cpu())
