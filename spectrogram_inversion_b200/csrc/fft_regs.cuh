@@ -1,4 +1,4 @@
-// Register-resident small FFTs (4, 8, 16, 32 points) with compile-time twiddles.
+// Register-resident small FFTs (4, 8, 16 points) with compile-time twiddles, on packed FP32x2 arithmetic.
 // Everything is fully unrolled over compile-time indices so the arrays live in registers and the
 // twiddles become immediates.  __host__ __device__ so that tests/host_emu can check them on the CPU.
 #pragma once
@@ -151,28 +151,6 @@ SPX_HD void fft16(float2* a) {
         float2 b0 = t[4 * k1], b1 = t[4 * k1 + 1], b2 = t[4 * k1 + 2], b3 = t[4 * k1 + 3];
         fft4<INV>(b0, b1, b2, b3);
         a[k1] = b0; a[k1 + 4] = b1; a[k1 + 8] = b2; a[k1 + 12] = b3;
-    });
-}
-
-// 32-point DFT in place (natural order in and out): 8 (over n1) x 4 (over n2), n = 4 n1 + n2.
-template <bool INV>
-SPX_HD void fft32(float2* a) {
-    float2 t[32];
-    static_for<4>([&](auto n2c) {
-        constexpr int n2 = decltype(n2c)::value;
-        float2 b[8];
-        static_for<8>([&](auto n1c) { constexpr int n1 = decltype(n1c)::value; b[n1] = a[4 * n1 + n2]; });
-        fft8<INV>(b);
-        static_for<8>([&](auto k1c) {
-            constexpr int k1 = decltype(k1c)::value;
-            t[4 * k1 + n2] = twiddle_mul<n2 * k1, 32, INV>(b[k1]);
-        });
-    });
-    static_for<8>([&](auto k1c) {
-        constexpr int k1 = decltype(k1c)::value;
-        float2 b0 = t[4 * k1], b1 = t[4 * k1 + 1], b2 = t[4 * k1 + 2], b3 = t[4 * k1 + 3];
-        fft4<INV>(b0, b1, b2, b3);
-        a[k1] = b0; a[k1 + 8] = b1; a[k1 + 16] = b2; a[k1 + 24] = b3;
     });
 }
 

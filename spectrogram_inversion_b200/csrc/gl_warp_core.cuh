@@ -76,7 +76,6 @@ struct Cfg {
     static constexpr int R2 = 2 * LANES / R1;     // 8, 16, 16
     static constexpr int S1 = V / R1;             // pass-1 transforms per lane
     static constexpr int S2 = V / R2;             // pass-2 transforms per lane
-    static constexpr int CLS = 2 * LANES;         // residue classes k1 = ka + R1 kb
 };
 
 template <int R, bool INV> SPX_HD void fft_small(float2* t) {
