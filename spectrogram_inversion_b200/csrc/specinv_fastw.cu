@@ -124,7 +124,7 @@ __device__ __forceinline__ void tmem_st32(unsigned taddr, const float* r) {
 }
 
 // TMEM columns (per lane): constant tables shared by the warps of one sub-partition, then per-warp state
-constexpr int TC_WA = 0, TC_WS = 32, TC_TW1 = 64, TC_TW2 = 96, TC_TWR = 128, TC_WARP = 144;
+constexpr int TC_WA = 0, TC_WS = 32, TC_TW1 = 64, TC_TW2 = 96, TC_TWR = 128, TC_IE = 144, TC_WARP = 152;
 constexpr int TC_PER_WARP = 48;     // ring: 3 blocks x 8 words, carry: 24 words
 constexpr int TMEM_COLS = 512;
 constexpr int WARPS = 12;           // 12 warps x 168 registers (no spills); 12 x 15 KB of staging fills the shared memory
@@ -266,6 +266,16 @@ __global__ void __launch_bounds__(WARPS * 32, 1) warp_iter_kernel(const WArgs a)
             t[2 * j] = w.x; t[2 * j + 1] = w.y;
         }
         tmem_st16(tlane + TC_TWR, t);
+        // 1/envelope of an INTERIOR hop (4 overlapping frames): the envelope is periodic with the hop there, so
+        // blocks 3 .. T-1 take it from here instead of streaming it from memory (block 3 is the first such block)
+        if (a.T >= 4) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 e = *reinterpret_cast<const float2*>(a.inv_env + (3LL * C::HOP - a.P) + 2 * LANES * j + 2 * tl);
+                t[2 * j] = e.x; t[2 * j + 1] = e.y;
+            }
+            tmem_st8(tlane + TC_IE, t);
+        }
         tmem_wait_st();
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -449,7 +459,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) warp_iter_kernel(const WArgs a)
             group_sync<LANES>(bar_id);
             const bool emit = owned && block_valid<LANES>(a, t);
             float2 ie[4];
-            if (emit) load_inv_env<LANES>(a, t, l, ie);    // early: the latency hides behind the last two passes
+            if (emit && t < 3) load_inv_env<LANES>(a, t, l, ie);    // edge blocks; early: hidden behind the last two passes
             {
                 float2 tw2[C::R2];
                 if constexpr (C::R2 == 8) tmem_ld16(tlane + TC_TW2, reinterpret_cast<float*>(tw2));
@@ -473,7 +483,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) warp_iter_kernel(const WArgs a)
                 for (int i = 0; i < V; ++i) v[i] = i < 12 ? pfma(w[i], v[i], carry[i]) : pmul(w[i], v[i]);
                 tmem_st16(twarp + 24, reinterpret_cast<const float*>(v + 4));
                 tmem_st8(twarp + 40, reinterpret_cast<const float*>(v + 12));
-                if (emit) store_block_ie<LANES>(a, xo, t, l, v, ie);
+                if (emit) {
+                    if (t >= 3) tmem_ld8(tlane + TC_IE, reinterpret_cast<float*>(ie));   // interior: periodic envelope
+                    store_block_ie<LANES>(a, xo, t, l, v, ie);
+                }
             }
         }
         if (t1 == a.T) {      // tail of the signal: blocks T, T+1, T+2 are complete now
