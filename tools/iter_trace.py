@@ -9,23 +9,26 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from spectrogram_inversion_b200.engine import GriffinLimSolver, StftPlan  # noqa: E402
+from spectrogram_inversion_b200.engine import ADMMSolver, GriffinLimSolver, StftPlan  # noqa: E402
 from spectrogram_inversion_b200.stft_args import StftArgs  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--iters", type=int, default=300)
 ap.add_argument("--eva", type=int, default=0, help="evaluate (sums + host sync) every n-th iteration")
 ap.add_argument("--batch", type=int, default=512)
+ap.add_argument("--n_fft", type=int, default=1024)
+ap.add_argument("--frames", type=int, default=938)
+ap.add_argument("--algo", default="gl")
 a = ap.parse_args()
 dev = torch.device("cuda")
-n_fft, hop, T = 1024, 256, 938
+n_fft, hop, T = a.n_fft, a.n_fft // 4, a.frames
 args = StftArgs(n_fft, hop, n_fft, torch.hann_window(n_fft, device=dev), True, "reflect", False, True)
 plan = StftPlan(args, T, a.batch, torch.float32, dev)
 torch.manual_seed(0)
 x = torch.randn(a.batch, plan.length, device=dev)
 S = plan.stft(x)
 mag = plan.spec_abs(S)
-solver = GriffinLimSolver(plan, S, mag, 0.99)
+solver = GriffinLimSolver(plan, S, mag, 0.99) if a.algo == "gl" else ADMMSolver(plan, S, mag, 0.1)
 for _ in range(3):
     solver.step()
 evs = [torch.cuda.Event(enable_timing=True) for _ in range(a.iters + 1)]
