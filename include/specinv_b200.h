@@ -156,6 +156,20 @@ int specinv_halo_sum(int dtype, const void* left, int64_t ld_left, const void* r
 int specinv_fill_padding(int dtype, void* x, int64_t ld, int rows, int64_t padded_offset, int64_t local_len, int pad,
                          int64_t signal_len, int pad_mode, void* stream);
 
+/* The same exchange as ONE kernel over NVLink peer memory (no NCCL call, no host synchronisation): every rank owns
+ * a receive area of specinv_halo_area_bytes() allocated by specinv_ipc_alloc (cudaMalloc + cudaIpcGetMemHandle, 64-byte
+ * handle to hand to the neighbours through any channel) and maps its neighbours' areas with specinv_ipc_open.
+ * specinv_halo_exchange pushes this rank's partial sums of the first / last `ov` samples of every row of x into the
+ * left / right neighbour's area (NULL: no neighbour), raises their flags to `seq` (1, 2, 3, ... per exchange), waits
+ * for its own flags and adds left partial + right partial in place. */
+size_t specinv_halo_area_bytes(int dtype, int rows, int64_t ov);
+int specinv_ipc_alloc(size_t bytes, void** dptr, void* handle64);
+int specinv_ipc_open(const void* handle64, void** dptr);
+int specinv_ipc_close(void* dptr);
+int specinv_ipc_free(void* dptr);
+int specinv_halo_exchange(int dtype, void* x, int64_t ld, int rows, int64_t local_len, int64_t ov, void* recv_self,
+                          void* recv_left_peer, void* recv_right_peer, uint32_t seq, void* stream);
+
 /* ---- metrics (metrics.py:4-43, F.mse_loss at methods.py:182) ---------------------------------
  * out[0] += sum (a-b)^2, out[1] += sum a^2, out[2] += sum b^2 over n contiguous reals. */
 int specinv_metric_sums(int dtype, const void* a, const void* b, int64_t n, double* out3, void* stream);

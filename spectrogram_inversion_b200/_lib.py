@@ -24,6 +24,8 @@ EXPORTS = (
     "specinv_stft", "specinv_istft", "specinv_gl_iter", "specinv_admm_iter",
     "specinv_metric_sums", "specinv_phase_init", "specinv_spec_abs", "specinv_rtisi_la", "specinv_plan_init_ranged",
     "specinv_phase_init_ex", "specinv_halo_sum", "specinv_fill_padding", "specinv_plan_unit_envelope",
+    "specinv_halo_area_bytes", "specinv_ipc_alloc", "specinv_ipc_open", "specinv_ipc_close", "specinv_ipc_free",
+    "specinv_halo_exchange",
 )
 
 
@@ -49,6 +51,11 @@ def _declare(lib: C.CDLL) -> None:
         "specinv_plan_bytes": [dp, C.POINTER(C.c_size_t)],
         "specinv_plan_init": [dp, vp, vp, vp],
         "specinv_plan_unit_envelope": [dp, vp, vp],
+        "specinv_ipc_alloc": [C.c_size_t, C.POINTER(vp), vp],
+        "specinv_ipc_open": [vp, C.POINTER(vp)],
+        "specinv_ipc_close": [vp],
+        "specinv_ipc_free": [vp],
+        "specinv_halo_exchange": [C.c_int, vp, i64, C.c_int, i64, i64, vp, vp, vp, C.c_uint32, vp],
         "specinv_plan_envelope": [dp, vp, vp, vp],
         "specinv_plan_init_ranged": [dp, vp, vp, i64, i64, vp],
         "specinv_phase_init_ex": [dp, vp, vp, vp, vp, vp, vp, vp],
@@ -70,6 +77,8 @@ def _declare(lib: C.CDLL) -> None:
         fn = getattr(lib, name)
         fn.restype = C.c_int
         fn.argtypes = args
+    lib.specinv_halo_area_bytes.restype = C.c_size_t
+    lib.specinv_halo_area_bytes.argtypes = [C.c_int, C.c_int, i64]
 
 
 def lib() -> C.CDLL:

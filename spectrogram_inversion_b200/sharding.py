@@ -9,6 +9,7 @@
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional, Tuple
 
 import torch
@@ -164,6 +165,59 @@ class CudaRangeEngine:
         self._ops.fill_padding(x, self.padded_offset, self.pad, self.signal_len, self.pad_mode)
 
 
+class PeerHalo:
+    """NVLink peer-memory plumbing of the one-kernel halo exchange (csrc/specinv_p2p.cu): this rank's receive area
+    (cudaMalloc + CUDA IPC handle), the mapped areas of its two neighbours, and the exchange counter.  The 64-byte
+    handles travel through ``dist.all_gather_object``; nothing else uses the process group afterwards."""
+
+    def __init__(self, rows: int, ov: int, dtype, device, group, rank: int, world: int):
+        import ctypes as C
+        from . import _lib, _ops
+        self._lib, self._C = _lib, C
+        self.dt = _ops._DT[dtype]
+        self.rows, self.ov, self.device, self.seq = rows, ov, device, 0
+        L = _lib.lib()
+        with torch.cuda.device(device):
+            nbytes = L.specinv_halo_area_bytes(self.dt, rows, ov)
+            self.area = C.c_void_p()
+            handle = C.create_string_buffer(64)
+            _lib.check(L.specinv_ipc_alloc(nbytes, C.byref(self.area), handle), "ipc_alloc")
+            handles = [None] * world
+            dist.all_gather_object(handles, bytes(handle.raw), group=group)
+            self.peers = [C.c_void_p(), C.c_void_p()]
+            for side, r in ((0, rank - 1), (1, rank + 1)):
+                if 0 <= r < world:
+                    _lib.check(L.specinv_ipc_open(C.create_string_buffer(handles[r], 64), C.byref(self.peers[side])),
+                               "ipc_open")
+        dist.barrier(group=group)
+
+    def exchange(self, x: torch.Tensor) -> None:
+        C, L = self._C, self._lib.lib()
+        self.seq += 1
+        stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        with torch.cuda.device(self.device):
+            self._lib.check(L.specinv_halo_exchange(self.dt, C.c_void_p(x.data_ptr()), x.stride(0), self.rows, x.shape[1],
+                                                    self.ov, self.area, self.peers[0], self.peers[1], self.seq, stream),
+                            "halo_exchange")
+
+    def close(self) -> None:
+        if getattr(self, "area", None) is None:
+            return
+        L = self._lib.lib()
+        torch.cuda.synchronize(self.device)
+        for p in self.peers:
+            if p:
+                L.specinv_ipc_close(p)
+        L.specinv_ipc_free(self.area)
+        self.area = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class FrameShardedGriffinLim:
     """Griffin-Lim on a signal whose FRAMES are sharded over the ranks of ``group`` (rank order = time order).
 
@@ -192,6 +246,13 @@ class FrameShardedGriffinLim:
         if self.world > 1:
             red = _all_reduce_floats([self.g, float(self.n_bins_total)], group, self._comm_device())
             self.g, self.n_bins_total = red[0], int(round(red[1]))
+        # NCCL ranks on their own GPUs: the exchange is ONE kernel over NVLink peer memory (SPECINV_P2P=0 keeps the
+        # NCCL send/recv path); gloo groups / ranks sharing a GPU use the host-staged path below
+        self.peer = None
+        if (self.world > 1 and self.x[0].is_cuda and dist.get_backend(group) == "nccl"
+                and os.environ.get("SPECINV_P2P", "1") != "0"):
+            self.peer = PeerHalo(self.x[0].shape[0], self.ov, self.x[0].dtype, self.x[0].device, group, self.rank,
+                                 self.world)
         engine.istft_partial(C_local, self.x[0])                  # x_0 = ISTFT(C)  (methods.py:233)
         self._exchange(self.x[0])
         self.iterations = 0
@@ -203,6 +264,10 @@ class FrameShardedGriffinLim:
 
     def _exchange(self, x):
         """combine the partial sums of the regions shared with the left / right neighbour, restore padding"""
+        if self.peer is not None:
+            self.peer.exchange(x)
+            self.e.fill_padding(x)
+            return
         ov, Lg = self.ov, x.shape[1]
         left = self.rank - 1 if self.rank > 0 else None
         right = self.rank + 1 if self.rank < self.world - 1 else None
