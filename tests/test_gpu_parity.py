@@ -486,3 +486,25 @@ def test_host_batches_are_pipelined_in_chunks_with_identical_results():
         y_dev = fn(mag.cuda(), max_iter=3, tol=0, verbose=False, eva_iter=2, window=w.cuda(), hop_length=64, **kw)
         assert not y_host.is_cuda and y_host.shape == y_dev.shape
         assert torch.equal(y_host, y_dev.cpu())
+
+
+def test_cuda_graph_replay_of_plain_iterations_is_identical():
+    """Small problems replay the iterations between evaluations from a CUDA graph (engine._Solver.run_plain): same
+    kernels on the same buffers, so the result must equal the step-by-step run bit for bit, for odd and even runs."""
+    import spectrogram_inversion_b200 as S
+    from spectrogram_inversion_b200.engine import ADMMSolver, GriffinLimSolver, StftPlan, training_loop
+    from spectrogram_inversion_b200.stft_args import args_helper
+    rs = np.random.RandomState(9)
+    mag = torch.from_numpy((np.abs(rs.randn(2, 513, 40)) * 3).astype(np.float32)).cuda()
+    w = torch.hann_window(1024, device="cuda")
+    plan = StftPlan(args_helper(mag, window=w, hop_length=256), 40, 2, torch.float32, mag.device)
+    pm = plan.pack(mag)
+    for make in (lambda: GriffinLimSolver(plan, plan.phase_init(pm), pm, 0.99), lambda: ADMMSolver(plan, plan.phase_init(pm), pm, 0.1)):
+        a, b = make(), make()
+        assert a.use_graphs
+        b.use_graphs = False
+        ha, hb = [], []
+        na = training_loop(a, 23, 0.0, False, 4, "sc", history=ha)       # runs of 3 plain iterations, tail of 3
+        nb = training_loop(b, 23, 0.0, False, 4, "sc", history=hb)
+        assert na == nb == 23 and a.iterations == b.iterations == 23 and ha == hb
+        assert len(a._graphs) >= 1 and torch.equal(a.signal, b.signal)

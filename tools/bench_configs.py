@@ -54,10 +54,10 @@ for name in names:
     for _ in range(3):
         solver.step()
     n = min(c["iters"], 20)
+    solver.run_plain(n)          # what training_loop does between evaluations (CUDA graph replay for small problems)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize(); e0.record()
-    for _ in range(n):
-        solver.step()
+    solver.run_plain(n)
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / n
     per_bin = 20 if c["algo"] == "gl" else 36
