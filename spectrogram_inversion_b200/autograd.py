@@ -18,8 +18,6 @@ from __future__ import annotations
 import ctypes as C
 import dataclasses
 import math
-from typing import Optional
-
 import torch
 import torch.nn.functional as F
 from tqdm import tqdm

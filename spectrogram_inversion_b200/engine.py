@@ -13,7 +13,7 @@ import torch
 from tqdm import tqdm
 
 from . import _lib, _ops
-from .stft_args import StftArgs, real_dtype_of
+from .stft_args import StftArgs
 
 _CDT = {torch.float32: torch.complex64, torch.float64: torch.complex128}
 

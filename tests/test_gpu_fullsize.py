@@ -9,9 +9,6 @@ the oracle is too slow to run: every warp group of every SM is busy, ranges cros
     2.5e8) whose |q| is tiny: two fp32 evaluations of the same q legitimately disagree there
   * the specialised and the generic kernel agree on one iteration
 """
-import os
-
-import numpy as np
 import pytest
 import torch
 

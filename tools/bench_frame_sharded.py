@@ -5,13 +5,11 @@
 import argparse
 import os
 import sys
-import time
 
 import torch
 import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from spectrogram_inversion_b200.engine import compute_device  # noqa: E402
 from spectrogram_inversion_b200.sharding import CudaRangeEngine, FrameShardedGriffinLim, shard_bounds  # noqa: E402
 from spectrogram_inversion_b200.stft_args import StftArgs  # noqa: E402
 
