@@ -64,106 +64,123 @@ SPX_HD void pre_pair(float2 hP, float2 hQ, float2 w, float2& P, float2& Q) {
     Q = f2(R.x, -R.y);                                  // (Ar + Gi, Gr - Ai)
 }
 
-constexpr int V = 16;            // complex values per lane
+constexpr int V = 16;            // complex values per lane (8 for the n_fft = 512 variant: template parameter VV)
 
-template <int LANES>
+template <int LANES, int VV = V>
 struct Cfg {
     static_assert(LANES == 32 || LANES == 64 || LANES == 128, "LANES");
-    static constexpr int M = 16 * LANES;          // complex FFT size = bins in a main row
+    static_assert(VV == 16 || (VV == 8 && LANES == 32), "values per lane");
+    static constexpr int M = VV * LANES;          // complex FFT size = bins in a main row
     static constexpr int N = 2 * M;               // n_fft
     static constexpr int HOP = N / 4;             // samples
+    static constexpr int RC = VV / 2;             // radix of pass 3 = values per residue class (8; 4 when VV = 8)
+    static constexpr int LOGRC = RC == 8 ? 3 : 2;
     static constexpr int R1 = LANES == 128 ? 16 : 8;
-    static constexpr int R2 = 2 * LANES / R1;     // 8, 16, 16
-    static constexpr int S1 = V / R1;             // pass-1 transforms per lane
-    static constexpr int S2 = V / R2;             // pass-2 transforms per lane
+    static constexpr int R2 = M / (R1 * RC);      // 8, 16, 16 (VV = 16); 8 (VV = 8)
+    static constexpr int S1 = VV / R1;            // pass-1 transforms per lane
+    static constexpr int S2 = VV / R2;            // pass-2 transforms per lane
 };
 
 template <int R, bool INV> SPX_HD void fft_small(float2* t) {
-    if constexpr (R == 8) fft8<INV>(t); else fft16<INV>(t);
+    if constexpr (R == 4) fft4<INV>(t[0], t[1], t[2], t[3]);
+    else if constexpr (R == 8) fft8<INV>(t);
+    else fft16<INV>(t);
 }
 
 // ---- exchange addressing (float2 units), XOR-swizzled 16-byte columns, no padding --------------------------
-// E1: rows (ka, c) -> 8 ka + c of R2 float2; E2: rows k1 of 8 float2.  The swizzle makes both the 128-bit row
-// accesses (8 consecutive rows per quarter-warp) and the 64-bit scattered accesses conflict free.
-template <int RLEN> SPX_HD int ex_swz(int row) { return RLEN == 8 ? ((row >> 1) & 3) : (row & 7); }
-template <int RLEN> SPX_HD int ex_addr(int row, int col) {
-    return RLEN * row + 2 * (((col >> 1) ^ ex_swz<RLEN>(row)) & (RLEN / 2 - 1)) + (col & 1);
+// E1: rows (ka, c) -> RC ka + c of R2 float2; E2: rows k1 of RC float2.  The swizzle makes both the 128-bit row
+// accesses (8 consecutive rows per quarter-warp) and the 64-bit scattered accesses conflict free
+// (tests/host_emu/test_warp_core.cu counts the wavefronts of every access).
+// GRP = 4: E1 of the 8-values-per-lane variant, whose rows come in groups of RC = 4 (the scattered side varies c in
+// the low two row bits), needs the two swizzle bits the other way round.
+template <int RLEN, int GRP = 8> SPX_HD int ex_swz(int row) {
+    if constexpr (RLEN == 4) return (row >> 2) & 1;
+    else if constexpr (RLEN == 8 && GRP == 4) return (((row >> 1) & 1) << 1) | ((row >> 2) & 1);
+    else if constexpr (RLEN == 8) return (row >> 1) & 3;
+    else return row & 7;
+}
+template <int RLEN, int GRP = 8> SPX_HD int ex_addr(int row, int col) {
+    return RLEN * row + 2 * (((col >> 1) ^ ex_swz<RLEN, GRP>(row)) & (RLEN / 2 - 1)) + (col & 1);
 }
 // 128-bit access: elements (row, 2 p) and (row, 2 p + 1)
-template <int RLEN> SPX_HD int ex_addr4(int row, int p) { return RLEN * row + 2 * ((p ^ ex_swz<RLEN>(row)) & (RLEN / 2 - 1)); }
+template <int RLEN, int GRP = 8> SPX_HD int ex_addr4(int row, int p) {
+    return RLEN * row + 2 * ((p ^ ex_swz<RLEN, GRP>(row)) & (RLEN / 2 - 1));
+}
 
 template <int LANES> SPX_HD int class_b(int l) { return l == 0 ? LANES : 2 * LANES - l; }
 // bin of the P element of pair slot j (the Q element is bin M - kP); lane 0 slot 0 is the special
 // DC / Nyquist / bin-M/2 slot
-template <int LANES> SPX_HD int slot_bin_rt(int l, int j) {
-    return l != 0 ? l + 2 * LANES * j : (j < 4 ? 2 * LANES * j : LANES + 2 * LANES * (j - 4));
+template <int LANES, int VV = V> SPX_HD int slot_bin_rt(int l, int j) {
+    constexpr int H = VV / 4;
+    return l != 0 ? l + 2 * LANES * j : (j < H ? 2 * LANES * j : LANES + 2 * LANES * (j - H));
 }
 
 // Per-lane constant tables (the kernel keeps them in tensor memory, the host emulation in arrays)
-template <int LANES>
+template <int LANES, int VV = V>
 struct LaneTables {
-    float2 wa[V];                     // 0.5 * analysis window pairs (w[2 LANES i + 2 l], w[2 LANES i + 2 l + 1])
-    float2 ws[V];                     // synthesis window pairs (already scaled by 1/N or N^-1/2)
-    float2 tw1[V];                    // [R1 s + ka]  W_M^((l + LANES s) ka)
-    float2 tw2[Cfg<LANES>::R2];       // [kb]         W_(8 R2)^((l & 7) kb)
-    float2 twr[8];                    // [j]          W_N^(slot_bin(l, j))
+    float2 wa[VV];                    // 0.5 * analysis window pairs (w[2 LANES i + 2 l], w[2 LANES i + 2 l + 1])
+    float2 ws[VV];                    // synthesis window pairs (already scaled by 1/N or N^-1/2)
+    float2 tw1[VV];                   // [R1 s + ka]  W_M^((l + LANES s) ka)
+    float2 tw2[Cfg<LANES, VV>::R2];   // [kb]         W_(RC R2)^((l & (RC-1)) kb)
+    float2 twr[VV / 2];               // [j]          W_N^(slot_bin(l, j))
 };
 
 // ---- forward ---------------------------------------------------------------------------------------------
 // v[i] = windowed z[LANES i + l] on entry
-template <int LANES>
+template <int LANES, int VV = V>
 SPX_HD void fwd_pass1(int l, float2* v, const float2* tw1, float2* e1) {
-    using C = Cfg<LANES>;
-    const int c = l & 7;
+    using C = Cfg<LANES, VV>;
+    const int c = l & (C::RC - 1);
     static_for<C::S1>([&](auto sc) {
         constexpr int s = decltype(sc)::value;
         float2 t[C::R1];
         static_for<C::R1>([&](auto ac) { constexpr int a = decltype(ac)::value; t[a] = v[C::S1 * a + s]; });
         fft_small<C::R1, false>(t);
-        const int b = (l + LANES * s) >> 3;
+        const int b = (l + LANES * s) >> C::LOGRC;
         static_for<C::R1>([&](auto kc) {
             constexpr int ka = decltype(kc)::value;
             const float2 y = ka == 0 ? t[0] : cmulf(t[ka], tw1[C::R1 * s + ka]);
-            e1[ex_addr<C::R2>(8 * ka + c, b)] = y;
+            e1[ex_addr<C::R2, C::RC>(C::RC * ka + c, b)] = y;
         });
     });
 }
 
-template <int LANES>
+template <int LANES, int VV = V>
 SPX_HD void fwd_pass2(int l, const float2* e1, const float2* tw2, float2* e2) {
-    using C = Cfg<LANES>;
-    const int c = l & 7;
+    using C = Cfg<LANES, VV>;
+    const int c = l & (C::RC - 1);
     static_for<C::S2>([&](auto rc) {
         constexpr int r = decltype(rc)::value;
-        const int ka = (l >> 3) + (LANES / 8) * r;
+        const int ka = (l >> C::LOGRC) + (LANES / C::RC) * r;
         float2 t[C::R2];
         static_for<C::R2 / 2>([&](auto pc) {
             constexpr int p = decltype(pc)::value;
-            const float4 q = *reinterpret_cast<const float4*>(e1 + ex_addr4<C::R2>(8 * ka + c, p));
+            const float4 q = *reinterpret_cast<const float4*>(e1 + ex_addr4<C::R2, C::RC>(C::RC * ka + c, p));
             t[2 * p] = f2(q.x, q.y); t[2 * p + 1] = f2(q.z, q.w);
         });
         fft_small<C::R2, false>(t);
         static_for<C::R2>([&](auto kc) {
             constexpr int kb = decltype(kc)::value;
             const float2 y = kb == 0 ? t[0] : cmulf(t[kb], tw2[kb]);
-            e2[ex_addr<8>(ka + C::R1 * kb, c)] = y;
+            e2[ex_addr<C::RC>(ka + C::R1 * kb, c)] = y;
         });
     });
 }
 
 // A[kc] = Zh[l + 2 LANES kc], B[kc] = Zh[class_b(l) + 2 LANES kc]
-template <int LANES>
+template <int LANES, int VV = V>
 SPX_HD void fwd_pass3(int l, const float2* e2, float2* A, float2* B) {
+    constexpr int RC = VV / 2;
     const int ra = l, rb = class_b<LANES>(l);
-    static_for<4>([&](auto pc) {
+    static_for<RC / 2>([&](auto pc) {
         constexpr int p = decltype(pc)::value;
-        const float4 qa = *reinterpret_cast<const float4*>(e2 + ex_addr4<8>(ra, p));
-        const float4 qb = *reinterpret_cast<const float4*>(e2 + ex_addr4<8>(rb, p));
+        const float4 qa = *reinterpret_cast<const float4*>(e2 + ex_addr4<RC>(ra, p));
+        const float4 qb = *reinterpret_cast<const float4*>(e2 + ex_addr4<RC>(rb, p));
         A[2 * p] = f2(qa.x, qa.y); A[2 * p + 1] = f2(qa.z, qa.w);
         B[2 * p] = f2(qb.x, qb.y); B[2 * p + 1] = f2(qb.z, qb.w);
     });
-    fft8<false>(A);
-    fft8<false>(B);
+    fft_small<RC, false>(A);
+    fft_small<RC, false>(B);
 }
 
 // ---- point-wise stage ------------------------------------------------------------------------------------
@@ -204,9 +221,10 @@ SPX_HD float2 bin_update(float2 s, float2 a0, float2 a1, float m, float coef, fl
 // bin; lane 0 slot 0: bins 0 and M/2), e = -1: the Nyquist bin (lane 0 only):
 //     float2 io.s0(e), io.s1(e); float io.mag(e); void io.put(e, o0, o1)
 // so that values are fetched right where they are used (no block of 48 live registers).
-template <int OP, bool SUMS, typename IO>
+template <int OP, bool SUMS, int VV = V, typename IO>
 SPX_HD void pointwise(int l, float2* A, float2* B, const float2* twr, IO& io, float coef, float coef2, float& dsum,
                       float& esum) {
+    constexpr int RC = VV / 2, H = RC / 2;      // pair slots per lane; lane 0 pairs inside its two classes
     const bool l0 = l == 0;
     auto upd = [&](auto ec, float2 sv) {
         constexpr int e = decltype(ec)::value;
@@ -218,107 +236,110 @@ SPX_HD void pointwise(int l, float2* A, float2* B, const float2* twr, IO& io, fl
     };
     // slot 0
     if (l0) {
-        // lane 0: A[0] = Zh[0] -> DC and Nyquist (both real), A[4] = Zh[M/2] -> bin M/2 = conj(Z[M/2])
-        const float2 z0 = A[0], z4 = A[4];
+        // lane 0: A[0] = Zh[0] -> DC and Nyquist (both real), A[H] = Zh[M/2] -> bin M/2 = conj(Z[M/2])
+        const float2 z0 = A[0], z4 = A[H];
         const float2 h0 = upd(std::integral_constant<int, 0>{}, f2(2.f * (z0.x + z0.y), 0.f));
         const float2 hM = upd(std::integral_constant<int, -1>{}, f2(2.f * (z0.x - z0.y), 0.f));
         const float2 h4 = upd(std::integral_constant<int, 1>{}, f2(2.f * z4.x, -2.f * z4.y));
         A[0] = f2(h0.x + hM.x, h0.x - hM.x);        // C2R ignores Im(DC), Im(Nyquist)
-        A[4] = f2(2.f * h4.x, -2.f * h4.y);
+        A[H] = f2(2.f * h4.x, -2.f * h4.y);
     } else {
         float2 sP, sQ, P, Q;
         const float2 w = twr[0];
-        post_pair(A[0], B[7], w, sP, sQ);
+        post_pair(A[0], B[RC - 1], w, sP, sQ);
         const float2 hP = upd(std::integral_constant<int, 0>{}, sP);
         const float2 hQ = upd(std::integral_constant<int, 1>{}, sQ);
         pre_pair(hP, hQ, w, P, Q);
-        A[0] = P; B[7] = Q;
+        A[0] = P; B[RC - 1] = Q;
     }
-    // slots 1..7.  general lanes: (A[j], B[7-j]); lane 0, j < 4: (A[j], A[8-j]); lane 0, j >= 4: (B[j-4], B[11-j])
-    static_for<7>([&](auto jc) {
+    // slots 1..RC-1.  general lanes: (A[j], B[RC-1-j]); lane 0, j < H: (A[j], A[RC-j]); lane 0, j >= H:
+    // (B[j-H], B[RC-1-(j-H)])
+    static_for<RC - 1>([&](auto jc) {
         constexpr int j = decltype(jc)::value + 1;
         float2 P, Q;
-        if constexpr (j < 4) { P = A[j]; Q = l0 ? A[8 - j] : B[7 - j]; }
-        else { P = l0 ? B[j - 4] : A[j]; Q = l0 ? B[11 - j] : B[7 - j]; }
+        if constexpr (j < H) { P = A[j]; Q = l0 ? A[RC - j] : B[RC - 1 - j]; }
+        else { P = l0 ? B[j - H] : A[j]; Q = l0 ? B[RC - 1 - (j - H)] : B[RC - 1 - j]; }
         const float2 w = twr[j];
         float2 sP, sQ;
         post_pair(P, Q, w, sP, sQ);
         const float2 hP = upd(std::integral_constant<int, 2 * j>{}, sP);
         const float2 hQ = upd(std::integral_constant<int, 2 * j + 1>{}, sQ);
         pre_pair(hP, hQ, w, P, Q);
-        if constexpr (j < 4) { A[j] = P; if (l0) A[8 - j] = Q; else B[7 - j] = Q; }
-        else { if (l0) { B[j - 4] = P; B[11 - j] = Q; } else { A[j] = P; B[7 - j] = Q; } }
+        if constexpr (j < H) { A[j] = P; if (l0) A[RC - j] = Q; else B[RC - 1 - j] = Q; }
+        else { if (l0) { B[j - H] = P; B[RC - 1 - (j - H)] = Q; } else { A[j] = P; B[RC - 1 - j] = Q; } }
     });
 }
 
 // Stand-alone inverse transform (ISTFT): the given spectrum h replaces the point-wise stage; on return A / B hold
 // the inputs of the inverse pass 3.  `io.s0(e)` as above (e = -1: the Nyquist bin).
-template <typename IO>
+template <int VV = V, typename IO>
 SPX_HD void spectrum_pairs(int l, float2* A, float2* B, const float2* twr, IO& io) {
+    constexpr int RC = VV / 2, H = RC / 2;
     const bool l0 = l == 0;
     if (l0) {
         const float2 h0 = io.s0(0), hM = io.s0(-1), h4 = io.s0(1);
         A[0] = f2(h0.x + hM.x, h0.x - hM.x);        // C2R ignores Im(DC), Im(Nyquist)
-        A[4] = f2(2.f * h4.x, -2.f * h4.y);
+        A[H] = f2(2.f * h4.x, -2.f * h4.y);
     } else {
-        pre_pair(io.s0(0), io.s0(1), twr[0], A[0], B[7]);
+        pre_pair(io.s0(0), io.s0(1), twr[0], A[0], B[RC - 1]);
     }
-    static_for<7>([&](auto jc) {
+    static_for<RC - 1>([&](auto jc) {
         constexpr int j = decltype(jc)::value + 1;
         float2 P, Q;
         pre_pair(io.s0(2 * j), io.s0(2 * j + 1), twr[j], P, Q);
-        if constexpr (j < 4) { A[j] = P; if (l0) A[8 - j] = Q; else B[7 - j] = Q; }
-        else { if (l0) { B[j - 4] = P; B[11 - j] = Q; } else { A[j] = P; B[7 - j] = Q; } }
+        if constexpr (j < H) { A[j] = P; if (l0) A[RC - j] = Q; else B[RC - 1 - j] = Q; }
+        else { if (l0) { B[j - H] = P; B[RC - 1 - (j - H)] = Q; } else { A[j] = P; B[RC - 1 - j] = Q; } }
     });
 }
 
 // ---- inverse ---------------------------------------------------------------------------------------------
-template <int LANES>
+template <int LANES, int VV = V>
 SPX_HD void inv_pass3(int l, float2* A, float2* B, float2* e2) {
-    fft8<true>(A);       // A[c] = Y2'[class a, c]
-    fft8<true>(B);
+    constexpr int RC = VV / 2;
+    fft_small<RC, true>(A);       // A[c] = Y2'[class a, c]
+    fft_small<RC, true>(B);
     const int ra = l, rb = class_b<LANES>(l);
-    static_for<4>([&](auto pc) {
+    static_for<RC / 2>([&](auto pc) {
         constexpr int p = decltype(pc)::value;
-        *reinterpret_cast<float4*>(e2 + ex_addr4<8>(ra, p)) = make_float4(A[2 * p].x, A[2 * p].y, A[2 * p + 1].x, A[2 * p + 1].y);
-        *reinterpret_cast<float4*>(e2 + ex_addr4<8>(rb, p)) = make_float4(B[2 * p].x, B[2 * p].y, B[2 * p + 1].x, B[2 * p + 1].y);
+        *reinterpret_cast<float4*>(e2 + ex_addr4<RC>(ra, p)) = make_float4(A[2 * p].x, A[2 * p].y, A[2 * p + 1].x, A[2 * p + 1].y);
+        *reinterpret_cast<float4*>(e2 + ex_addr4<RC>(rb, p)) = make_float4(B[2 * p].x, B[2 * p].y, B[2 * p + 1].x, B[2 * p + 1].y);
     });
 }
 
-template <int LANES>
+template <int LANES, int VV = V>
 SPX_HD void inv_pass2(int l, const float2* e2, const float2* tw2, float2* e1) {
-    using C = Cfg<LANES>;
-    const int c = l & 7;
+    using C = Cfg<LANES, VV>;
+    const int c = l & (C::RC - 1);
     static_for<C::S2>([&](auto rc) {
         constexpr int r = decltype(rc)::value;
-        const int ka = (l >> 3) + (LANES / 8) * r;
+        const int ka = (l >> C::LOGRC) + (LANES / C::RC) * r;
         float2 t[C::R2];
         static_for<C::R2>([&](auto kc) {
             constexpr int kb = decltype(kc)::value;
-            const float2 y = e2[ex_addr<8>(ka + C::R1 * kb, c)];
+            const float2 y = e2[ex_addr<C::RC>(ka + C::R1 * kb, c)];
             t[kb] = kb == 0 ? y : cmulcf(y, tw2[kb]);
         });
         fft_small<C::R2, true>(t);   // t[b] = Y1'[ka, b, c] (before the pass-1 twiddle)
         static_for<C::R2 / 2>([&](auto pc) {
             constexpr int p = decltype(pc)::value;
-            *reinterpret_cast<float4*>(e1 + ex_addr4<C::R2>(8 * ka + c, p)) =
+            *reinterpret_cast<float4*>(e1 + ex_addr4<C::R2, C::RC>(C::RC * ka + c, p)) =
                 make_float4(t[2 * p].x, t[2 * p].y, t[2 * p + 1].x, t[2 * p + 1].y);
         });
     });
 }
 
 // v[i] = z'[LANES i + l] (unscaled)
-template <int LANES>
+template <int LANES, int VV = V>
 SPX_HD void inv_pass1(int l, const float2* e1, const float2* tw1, float2* v) {
-    using C = Cfg<LANES>;
-    const int c = l & 7;
+    using C = Cfg<LANES, VV>;
+    const int c = l & (C::RC - 1);
     static_for<C::S1>([&](auto sc) {
         constexpr int s = decltype(sc)::value;
-        const int b = (l + LANES * s) >> 3;
+        const int b = (l + LANES * s) >> C::LOGRC;
         float2 t[C::R1];
         static_for<C::R1>([&](auto kc) {
             constexpr int ka = decltype(kc)::value;
-            const float2 y = e1[ex_addr<C::R2>(8 * ka + c, b)];
+            const float2 y = e1[ex_addr<C::R2, C::RC>(C::RC * ka + c, b)];
             t[ka] = ka == 0 ? y : cmulcf(y, tw1[C::R1 * s + ka]);
         });
         fft_small<C::R1, true>(t);
