@@ -1,4 +1,5 @@
 // Fused iteration kernels for hop = n_fft/4, onesided, fp32 with 16 complex values per lane (gl_warp_core.cuh):
+//   n_fft =  512 / hop = 128  : one warp per frame, 8 values per lane (LANES = 32, VV = 8)
 //   n_fft = 1024 / hop = 256  : one warp per frame    (LANES = 32)   -- the headline shape (cfg2)
 //   n_fft = 2048 / hop = 512  : two warps per frame   (LANES = 64)   -- cfg1, cfg4
 //   n_fft = 4096 / hop = 1024 : four warps per frame  (LANES = 128)  -- cfg5
@@ -123,14 +124,33 @@ __device__ __forceinline__ void tmem_st32(unsigned taddr, const float* r) {
                    "f"(r[24]), "f"(r[25]), "f"(r[26]), "f"(r[27]), "f"(r[28]), "f"(r[29]), "f"(r[30]), "f"(r[31]) : "memory");
 }
 
+__device__ __forceinline__ void tmem_ld4(unsigned taddr, float* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];\n\t"
+                 "tcgen05.wait::ld.sync.aligned;"
+                 : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_st4(unsigned taddr, const float* r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
+                 ::"r"(taddr), "f"(r[0]), "f"(r[1]), "f"(r[2]), "f"(r[3]) : "memory");
+}
+// W words per lane (4, 8, 16 or 32)
+template <int W> __device__ __forceinline__ void tmem_ldw(unsigned taddr, float* r) {
+    if constexpr (W == 4) tmem_ld4(taddr, r); else if constexpr (W == 8) tmem_ld8(taddr, r);
+    else if constexpr (W == 16) tmem_ld16(taddr, r); else tmem_ld32(taddr, r);
+}
+template <int W> __device__ __forceinline__ void tmem_stw(unsigned taddr, const float* r) {
+    if constexpr (W == 4) tmem_st4(taddr, r); else if constexpr (W == 8) tmem_st8(taddr, r);
+    else if constexpr (W == 16) tmem_st16(taddr, r); else tmem_st32(taddr, r);
+}
+
 // TMEM columns (per lane): constant tables shared by the warps of one sub-partition, then per-warp state
 constexpr int TC_WA = 0, TC_WS = 32, TC_TW1 = 64, TC_TW2 = 96, TC_TWR = 128, TC_IE = 144, TC_WARP = 152;
 constexpr int TC_PER_WARP = 48;     // ring: 3 blocks x 8 words, carry: 24 words
 constexpr int TMEM_COLS = 512;
 constexpr int WARPS = 12;           // 12 warps x 168 registers (no spills); 12 x 15 KB of staging fills the shared memory
-// float2 of shared memory per WARP (a frame group owns LANES/32 times as much): E1, E2 (M float2 each per group),
-// staged input block (HOP floats), magnitude row (M floats), q / X row (M float2)
-constexpr int WARP_F2 = 2 * 512 + 128 + 256 + 512;
+// float2 of shared memory per frame group: E1, E2 (M float2 each), staged input block (HOP floats = M/4 float2),
+// magnitude row (M floats = M/2 float2), q / X row (M float2)
+constexpr int group_f2(int m) { return 2 * m + m / 4 + m / 2 + m; }
 
 // Synchronise the warps that share a frame (named barrier per group) or just the warp.
 template <int LANES>
@@ -140,16 +160,16 @@ __device__ __forceinline__ void group_sync(int bar_id) {
 }
 
 // Fetch block u (padded samples [HOP u, HOP u + HOP)) of signal x: lane l gets the pairs at 2 LANES j + 2 l.
-template <int LANES>
+template <int LANES, int VV>
 __device__ __forceinline__ void fetch_block_regs(const WArgs& a, const float* __restrict__ x, int u, int l, float2* nb) {
-    constexpr int HOP = Cfg<LANES>::HOP;
+    constexpr int HOP = Cfg<LANES, VV>::HOP, HP = VV / 4;
     const long long base = (long long)u * HOP - a.P;
     if (base >= 0 && base + HOP <= a.L) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) nb[j] = __ldg(reinterpret_cast<const float2*>(x + base + 2 * LANES * j + 2 * l));
+        for (int j = 0; j < HP; ++j) nb[j] = __ldg(reinterpret_cast<const float2*>(x + base + 2 * LANES * j + 2 * l));
     } else {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < HP; ++j) {
             const long long pp = (long long)u * HOP + 2 * LANES * j + 2 * l;
             const long long i0 = pad_index(pp, a.P, a.L, a.pad_mode), i1 = pad_index(pp + 1, a.P, a.L, a.pad_mode);
             nb[j] = f2(i0 >= 0 ? x[i0] : 0.f, i1 >= 0 ? x[i1] : 0.f);
@@ -159,50 +179,50 @@ __device__ __forceinline__ void fetch_block_regs(const WArgs& a, const float* __
 // Same into the staging buffer xs[LANES j + l] (= the block's bytes in memory order): interior blocks by one TMA
 // bulk copy issued by the group's first warp (returns true: the data arrives on `bar`), padded edge blocks
 // element by element.
-template <int LANES>
+template <int LANES, int VV>
 __device__ __forceinline__ bool fetch_block_staged(const WArgs& a, const float* __restrict__ x, int u, int l, float2* xs,
                                                    unsigned xs_s, unsigned bar) {
-    constexpr int HOP = Cfg<LANES>::HOP;
+    constexpr int HOP = Cfg<LANES, VV>::HOP, HP = VV / 4;
     const long long base = (long long)u * HOP - a.P;
     if (base >= 0 && base + HOP <= a.L) {
         if (l < 32) { if (elect_one()) { mbar_expect_tx(bar, HOP * 4); bulk_g2s(xs_s, x + base, HOP * 4, bar); } }
         return true;
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < HP; ++j) {
         const long long pp = (long long)u * HOP + 2 * LANES * j + 2 * l;
         const long long i0 = pad_index(pp, a.P, a.L, a.pad_mode), i1 = pad_index(pp + 1, a.P, a.L, a.pad_mode);
         xs[LANES * j + l] = f2(i0 >= 0 ? x[i0] : 0.f, i1 >= 0 ? x[i1] : 0.f);
     }
     return false;
 }
-template <int LANES>
+template <int LANES, int VV>
 __device__ __forceinline__ bool block_valid(const WArgs& a, int u) {
-    const long long base = (long long)u * Cfg<LANES>::HOP - a.P;
-    return base >= 0 && base + Cfg<LANES>::HOP <= a.L;
+    const long long base = (long long)u * Cfg<LANES, VV>::HOP - a.P;
+    return base >= 0 && base + Cfg<LANES, VV>::HOP <= a.L;
 }
-template <int LANES>
+template <int LANES, int VV>
 __device__ __forceinline__ void load_inv_env(const WArgs& a, int u, int l, float2* ie) {
-    const long long base = (long long)u * Cfg<LANES>::HOP - a.P;
+    const long long base = (long long)u * Cfg<LANES, VV>::HOP - a.P;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < VV / 4; ++j) {
         // volatile + "memory": the compiler must not sink these loads down to their use
         asm volatile("ld.global.nc.v2.f32 {%0, %1}, [%2];" : "=f"(ie[j].x), "=f"(ie[j].y)
                      : "l"(a.inv_env + base + 2 * LANES * j + 2 * l) : "memory");
     }
 }
-template <int LANES>
+template <int LANES, int VV>
 __device__ __forceinline__ void store_block_ie(const WArgs& a, float* __restrict__ xo, int u, int l, const float2* blk,
                                                const float2* ie) {
-    const long long base = (long long)u * Cfg<LANES>::HOP - a.P;
+    const long long base = (long long)u * Cfg<LANES, VV>::HOP - a.P;
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
+    for (int j = 0; j < VV / 4; ++j)
         *reinterpret_cast<float2*>(xo + base + 2 * LANES * j + 2 * l) = pmul(blk[j], ie[j]);
 }
 // Fetch the q / X row and the magnitude row of frame `row` into the staging rows (one elected lane, TMA).
-template <int OP, int LANES>
+template <int OP, int LANES, int VV>
 __device__ __forceinline__ void stage_rows(const WArgs& a, long long row, int l, unsigned qstage_s, unsigned mstage_s, unsigned bar) {
-    constexpr int M = Cfg<LANES>::M;
+    constexpr int M = Cfg<LANES, VV>::M;
     if (l < 32) {
         if (elect_one()) {
             mbar_expect_tx(bar, OP == OP_ISTFT ? M * 8 : M * 8 + M * 4);
@@ -212,10 +232,14 @@ __device__ __forceinline__ void stage_rows(const WArgs& a, long long row, int l,
     }
 }
 
-template <int OP, bool SUMS, int LANES>
+template <int OP, bool SUMS, int LANES, int VV>
 __global__ void __launch_bounds__(WARPS * 32, 1) warp_iter_kernel(const WArgs a) {
-    using C = Cfg<LANES>;
+    using C = Cfg<LANES, VV>;
     constexpr int M = C::M;
+    constexpr int V = VV;                         // complex values per lane (shadows wfast::V)
+    constexpr int HP = VV / 4;                    // sample pairs per hop and lane
+    constexpr int RC = C::RC;                     // pair slots per lane
+    constexpr int GROUP_F2 = group_f2(M);
     constexpr int G = LANES / 32;                 // warps per frame group
     constexpr int GROUPS = WARPS / G;
     static_assert(TC_WARP + ((WARPS + 3) / 4) * TC_PER_WARP <= TMEM_COLS, "TMEM columns");
@@ -241,40 +265,40 @@ __global__ void __launch_bounds__(WARPS * 32, 1) warp_iter_kernel(const WArgs a)
         float t[32];
 #pragma unroll
         for (int i = 0; i < V; ++i) { t[2 * i] = 0.5f * a.wa[2 * LANES * i + 2 * tl]; t[2 * i + 1] = 0.5f * a.wa[2 * LANES * i + 2 * tl + 1]; }
-        tmem_st32(tlane + TC_WA, t);
+        tmem_stw<2 * V>(tlane + TC_WA, t);
 #pragma unroll
         for (int i = 0; i < V; ++i) { t[2 * i] = a.ws[2 * LANES * i + 2 * tl]; t[2 * i + 1] = a.ws[2 * LANES * i + 2 * tl + 1]; }
-        tmem_st32(tlane + TC_WS, t);
+        tmem_stw<2 * V>(tlane + TC_WS, t);
 #pragma unroll
         for (int i = 0; i < V; ++i) {       // [R1 s + ka]: W_M^((tl + LANES s) ka)
             const float2 w = a.tw[((tl + LANES * (i / C::R1)) * (i % C::R1)) & (M - 1)];
             t[2 * i] = w.x; t[2 * i + 1] = w.y;
         }
-        tmem_st32(tlane + TC_TW1, t);
+        tmem_stw<2 * V>(tlane + TC_TW1, t);
 #pragma unroll
-        for (int kb = 0; kb < 16; ++kb) {   // W_(8 R2)^((tl & 7) kb) = W_M^(R1 (tl & 7) kb)
-            const float2 w = a.tw[(C::R1 * (tl & 7) * (kb % C::R2)) & (M - 1)];
+        for (int kb = 0; kb < 16; ++kb) {   // W_(RC R2)^(c kb) = W_M^(R1 c kb), c = tl & (RC - 1)
+            const float2 w = a.tw[(C::R1 * (tl & (RC - 1)) * (kb % C::R2)) & (M - 1)];
             t[2 * kb] = w.x; t[2 * kb + 1] = w.y;
         }
         tmem_st32(tlane + TC_TW2, t);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int k = slot_bin_rt<LANES>(tl, j);
+        for (int j = 0; j < RC; ++j) {
+            const int k = slot_bin_rt<LANES, VV>(tl, j);
             float2 w;
             if (k <= M / 2) w = a.twr[k];
             else { w = a.twr[M - k]; w.x = -w.x; }                  // W_N^k = -conj(W_N^(M-k))
             t[2 * j] = w.x; t[2 * j + 1] = w.y;
         }
-        tmem_st16(tlane + TC_TWR, t);
+        tmem_stw<2 * RC>(tlane + TC_TWR, t);
         // 1/envelope of an INTERIOR hop (4 overlapping frames): the envelope is periodic with the hop there, so
         // blocks 3 .. T-1 take it from here instead of streaming it from memory (block 3 is the first such block)
         if (a.T >= 4) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < HP; ++j) {
                 const float2 e = *reinterpret_cast<const float2*>(a.inv_env + (3LL * C::HOP - a.P) + 2 * LANES * j + 2 * tl);
                 t[2 * j] = e.x; t[2 * j + 1] = e.y;
             }
-            tmem_st8(tlane + TC_IE, t);
+            tmem_stw<2 * HP>(tlane + TC_IE, t);
         }
         tmem_wait_st();
     }
@@ -283,17 +307,17 @@ __global__ void __launch_bounds__(WARPS * 32, 1) warp_iter_kernel(const WArgs a)
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
     const unsigned twarp = tlane + TC_WARP + TC_PER_WARP * (warp >> 2);   // ring (24 columns) then carry (24)
-    float2* e1 = sm + grp * (G * WARP_F2);
+    float2* e1 = sm + grp * GROUP_F2;
     float2* e2 = e1 + M;
     float2* xs = e2 + M;                                            // HOP floats = M / 4 float2
     float* mstage = reinterpret_cast<float*>(xs + M / 4);           // magnitudes of the coming frame (M floats)
     float2* qstage = xs + M / 4 + M / 2;                            // q / X row of the coming frame
-    const unsigned grp_s = (unsigned)__cvta_generic_to_shared(sm) + grp * (G * WARP_F2 * 8);   // shared-window addresses
+    const unsigned grp_s = (unsigned)__cvta_generic_to_shared(sm) + grp * (GROUP_F2 * 8);   // shared-window addresses
     const unsigned xs_s = grp_s + 2 * M * 8, mstage_s = xs_s + (M / 4) * 8, qstage_s = mstage_s + (M / 2) * 8;
     unsigned xpar = 0, spar = 0, upar = 0;                          // mbarrier phase parities
 
     // bin offsets of the lane's pair slots inside a main row
-    const int hi_adj = l == 0 ? -7 * LANES : 0;  // lane 0, slots 4..7: LANES + 2 LANES (j - 4) = 2 LANES j - 7 LANES
+    const int hi_adj = l == 0 ? -(RC - 1) * LANES : 0;  // lane 0, slots j >= RC/2: LANES + 2 LANES (j - RC/2)
     const int kq0 = l == 0 ? M / 2 : M - l;
 
     double dacc = 0.0, eacc = 0.0;
@@ -315,26 +339,26 @@ __global__ void __launch_bounds__(WARPS * 32, 1) warp_iter_kernel(const WArgs a)
         // ---- prologue: empty carry, ring = blocks tf0 .. tf0 + 2, block tf0 + 3 and the first rows on their way
         tmem_wait_st();
         {
-            float z[24];
+            float z[6 * HP];
 #pragma unroll
-            for (int i = 0; i < 24; ++i) z[i] = 0.f;
-            tmem_st16(twarp + 24, z); tmem_st8(twarp + 40, z + 16);
+            for (int i = 0; i < 6 * HP; ++i) z[i] = 0.f;
+            tmem_stw<4 * HP>(twarp + 24, z); tmem_stw<2 * HP>(twarp + 24 + 4 * HP, z + 4 * HP);
         }
         int m = tf0 % 3;                                            // ring slot of block t
         if constexpr (OP != OP_ISTFT) {
             int mm = m;
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
-                float2 nb[4];
-                fetch_block_regs<LANES>(a, x, tf0 + i, l, nb);
-                tmem_st8(twarp + 8 * mm, reinterpret_cast<const float*>(nb));
+                float2 nb[HP];
+                fetch_block_regs<LANES, VV>(a, x, tf0 + i, l, nb);
+                tmem_stw<2 * HP>(twarp + 2 * HP * mm, reinterpret_cast<const float*>(nb));
                 mm = mm == 2 ? 0 : mm + 1;
             }
         }
         group_sync<LANES>(bar_id);                 // nobody still reads the staging rows of an earlier range
         bool x_async = false;
-        if constexpr (OP != OP_ISTFT) x_async = fetch_block_staged<LANES>(a, x, tf0 + 3, l, xs, xs_s, xbar);
-        stage_rows<OP, LANES>(a, (long long)b * a.T + tf0, l, qstage_s, mstage_s, sbar);
+        if constexpr (OP != OP_ISTFT) x_async = fetch_block_staged<LANES, VV>(a, x, tf0 + 3, l, xs, xs_s, xbar);
+        stage_rows<OP, LANES, VV>(a, (long long)b * a.T + tf0, l, qstage_s, mstage_s, sbar);
         // Nyquist scalars of the coming frame (lane 0), fetched one frame ahead like the rows
         float2 s0n_next = f2(0.f, 0.f), s1n_next = f2(0.f, 0.f);
         float mgn_next = 0.f;
@@ -353,24 +377,24 @@ __global__ void __launch_bounds__(WARPS * 32, 1) warp_iter_kernel(const WArgs a)
             const long long row = (long long)b * a.T + t;
             const bool owned = t >= t0;
             float2 v[V];
-            float2 A[8], Bv[8];
+            float2 A[RC], Bv[RC];
             if constexpr (OP != OP_ISTFT) {
             // ---- assemble the frame: blocks t .. t+2 from the ring, block t+3 from the staging buffer
             {
                 const int m1 = m == 2 ? 0 : m + 1, m2 = m1 == 2 ? 0 : m1 + 1;
                 tmem_wait_st();
-                tmem_ld8(twarp + 8 * m, reinterpret_cast<float*>(v));
-                tmem_ld8(twarp + 8 * m1, reinterpret_cast<float*>(v + 4));
-                tmem_ld8(twarp + 8 * m2, reinterpret_cast<float*>(v + 8));
+                tmem_ldw<2 * HP>(twarp + 2 * HP * m, reinterpret_cast<float*>(v));
+                tmem_ldw<2 * HP>(twarp + 2 * HP * m1, reinterpret_cast<float*>(v + HP));
+                tmem_ldw<2 * HP>(twarp + 2 * HP * m2, reinterpret_cast<float*>(v + 2 * HP));
                 if (x_async) { mbar_wait(xbar, xpar); xpar ^= 1; }
 #pragma unroll
-                for (int j = 0; j < 4; ++j) v[12 + j] = xs[LANES * j + l];
-                tmem_st8(twarp + 8 * m, reinterpret_cast<const float*>(v + 12));   // block t+3 replaces block t
+                for (int j = 0; j < HP; ++j) v[3 * HP + j] = xs[LANES * j + l];
+                tmem_stw<2 * HP>(twarp + 2 * HP * m, reinterpret_cast<const float*>(v + 3 * HP));   // block t+3 replaces block t
                 m = m1;
             }
             group_sync<LANES>(bar_id);             // xs consumed by every lane; the previous frame's reads of E1 are done
             if (t + 1 < t1) {
-                x_async = fetch_block_staged<LANES>(a, x, t + 4, l, xs, xs_s, xbar);
+                x_async = fetch_block_staged<LANES, VV>(a, x, t + 4, l, xs, xs_s, xbar);
                 if constexpr (OP == OP_ADMM) {
                     const char* u1 = reinterpret_cast<const char*>(a.s1_in + (row + 1) * M);
                     if (128 * l < M * 8) prefetch_l2(u1 + 128 * l);
@@ -378,28 +402,28 @@ __global__ void __launch_bounds__(WARPS * 32, 1) warp_iter_kernel(const WArgs a)
             }
             {
                 float2 w[V];
-                tmem_ld32(tlane + TC_WA, reinterpret_cast<float*>(w));
+                tmem_ldw<2 * V>(tlane + TC_WA, reinterpret_cast<float*>(w));
 #pragma unroll
                 for (int i = 0; i < V; ++i) v[i] = pmul(v[i], w[i]);
             }
             {
                 float2 tw1[V];
-                tmem_ld32(tlane + TC_TW1, reinterpret_cast<float*>(tw1));
-                fwd_pass1<LANES>(l, v, tw1, e1);
+                tmem_ldw<2 * V>(tlane + TC_TW1, reinterpret_cast<float*>(tw1));
+                fwd_pass1<LANES, VV>(l, v, tw1, e1);
             }
             group_sync<LANES>(bar_id);
             {
                 float2 tw2[C::R2];
                 if constexpr (C::R2 == 8) tmem_ld16(tlane + TC_TW2, reinterpret_cast<float*>(tw2));
                 else tmem_ld32(tlane + TC_TW2, reinterpret_cast<float*>(tw2));
-                fwd_pass2<LANES>(l, e1, tw2, e2);
+                fwd_pass2<LANES, VV>(l, e1, tw2, e2);
             }
             group_sync<LANES>(bar_id);
             if constexpr (OP == OP_ADMM) {
                 // E1 is idle until the inverse pass 2: stage this frame's U row (L2-prefetched a frame ago) in it
                 if (l < 32) { if (elect_one()) { mbar_expect_tx(ubar, M * 8); bulk_g2s(grp_s, a.s1_in + row * M, M * 8, ubar); } }
             }
-            fwd_pass3<LANES>(l, e2, A, Bv);
+            fwd_pass3<LANES, VV>(l, e2, A, Bv);
             }  // OP != OP_ISTFT
             const float2 s0n = s0n_next, s1n = s1n_next;
             const float mgn = mgn_next;
@@ -417,7 +441,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) warp_iter_kernel(const WArgs a)
                     float2 s0n, s1n; float mgn;
                     __device__ __forceinline__ int bin(int e) const {
                         const int j = e >> 1;
-                        return (e & 1) ? (j == 0 ? q0 : (j >= 4 ? qh : ql) - 2 * LANES * j) : (j >= 4 ? ph : pl) + 2 * LANES * j;
+                        return (e & 1) ? (j == 0 ? q0 : (j >= RC / 2 ? qh : ql) - 2 * LANES * j)
+                                       : (j >= RC / 2 ? ph : pl) + 2 * LANES * j;
                     }
                     __device__ __forceinline__ float2 s0(int e) const { return e < 0 ? s0n : q[bin(e)]; }
                     __device__ __forceinline__ float2 s1(int e) const { return e < 0 ? s1n : u[bin(e)]; }
@@ -436,70 +461,70 @@ __global__ void __launch_bounds__(WARPS * 32, 1) warp_iter_kernel(const WArgs a)
                      OP == OP_ADMM ? a.s1_out + row * M : nullptr, a.s0_out_nyq + row,
                      OP == OP_ADMM ? a.s1_out_nyq + row : nullptr, l, l + hi_adj, M - l, M - l - hi_adj, kq0, owned,
                      s0n, s1n, mgn};
-                float2 twr[8];
-                tmem_ld16(tlane + TC_TWR, reinterpret_cast<float*>(twr));
+                float2 twr[RC];
+                tmem_ldw<2 * RC>(tlane + TC_TWR, reinterpret_cast<float*>(twr));
                 if constexpr (OP == OP_ISTFT) {
-                    spectrum_pairs(l, A, Bv, twr, io);
+                    spectrum_pairs<VV>(l, A, Bv, twr, io);
                 } else {
                     float dsum = 0.f, esum = 0.f;
-                    pointwise<OP, SUMS>(l, A, Bv, twr, io, a.coef, a.coef2, dsum, esum);
+                    pointwise<OP, SUMS, VV>(l, A, Bv, twr, io, a.coef, a.coef2, dsum, esum);
                     if constexpr (SUMS) { if (owned) { dacc += (double)dsum; eacc += (double)esum; } }
                 }
             }
             group_sync<LANES>(bar_id);             // every lane has read its classes from E2 and its staged state
             if (t + 1 < t1) {
-                stage_rows<OP, LANES>(a, row + 1, l, qstage_s, mstage_s, sbar);
+                stage_rows<OP, LANES, VV>(a, row + 1, l, qstage_s, mstage_s, sbar);
                 if (l == 0) {
                     s0n_next = __ldg(a.s0_in_nyq + row + 1);
                     if constexpr (OP != OP_ISTFT) mgn_next = __ldg(a.mag_nyq + row + 1);
                     if constexpr (OP == OP_ADMM) s1n_next = __ldg(a.s1_in_nyq + row + 1);
                 }
             }
-            inv_pass3<LANES>(l, A, Bv, e2);
+            inv_pass3<LANES, VV>(l, A, Bv, e2);
             group_sync<LANES>(bar_id);
-            const bool emit = owned && block_valid<LANES>(a, t);
-            float2 ie[4];
-            if (emit && t < 3) load_inv_env<LANES>(a, t, l, ie);    // edge blocks; early: hidden behind the last two passes
+            const bool emit = owned && block_valid<LANES, VV>(a, t);
+            float2 ie[HP];
+            if (emit && t < 3) load_inv_env<LANES, VV>(a, t, l, ie);    // edge blocks; early: hidden behind the last two passes
             {
                 float2 tw2[C::R2];
                 if constexpr (C::R2 == 8) tmem_ld16(tlane + TC_TW2, reinterpret_cast<float*>(tw2));
                 else tmem_ld32(tlane + TC_TW2, reinterpret_cast<float*>(tw2));
-                inv_pass2<LANES>(l, e2, tw2, e1);
+                inv_pass2<LANES, VV>(l, e2, tw2, e1);
             }
             group_sync<LANES>(bar_id);
             {
                 float2 tw1[V];
-                tmem_ld32(tlane + TC_TW1, reinterpret_cast<float*>(tw1));
-                inv_pass1<LANES>(l, e1, tw1, v);
+                tmem_ldw<2 * V>(tlane + TC_TW1, reinterpret_cast<float*>(tw1));
+                inv_pass1<LANES, VV>(l, e1, tw1, v);
             }
             // ---- windowed overlap-add: out = carry (3 hops from earlier frames) + ws * v; the first hop
             // (4 pairs) of `out` is a finished block, the other 12 pairs are the new carry
             {
-                float2 w[V], carry[12];
-                tmem_ld32(tlane + TC_WS, reinterpret_cast<float*>(w));
-                tmem_ld16(twarp + 24, reinterpret_cast<float*>(carry));
-                tmem_ld8(twarp + 40, reinterpret_cast<float*>(carry + 8));
+                float2 w[V], carry[3 * HP];
+                tmem_ldw<2 * V>(tlane + TC_WS, reinterpret_cast<float*>(w));
+                tmem_ldw<4 * HP>(twarp + 24, reinterpret_cast<float*>(carry));
+                tmem_ldw<2 * HP>(twarp + 24 + 4 * HP, reinterpret_cast<float*>(carry + 2 * HP));
 #pragma unroll
-                for (int i = 0; i < V; ++i) v[i] = i < 12 ? pfma(w[i], v[i], carry[i]) : pmul(w[i], v[i]);
-                tmem_st16(twarp + 24, reinterpret_cast<const float*>(v + 4));
-                tmem_st8(twarp + 40, reinterpret_cast<const float*>(v + 12));
+                for (int i = 0; i < V; ++i) v[i] = i < 3 * HP ? pfma(w[i], v[i], carry[i]) : pmul(w[i], v[i]);
+                tmem_stw<4 * HP>(twarp + 24, reinterpret_cast<const float*>(v + HP));
+                tmem_stw<2 * HP>(twarp + 24 + 4 * HP, reinterpret_cast<const float*>(v + 3 * HP));
                 if (emit) {
-                    if (t >= 3) tmem_ld8(tlane + TC_IE, reinterpret_cast<float*>(ie));   // interior: periodic envelope
-                    store_block_ie<LANES>(a, xo, t, l, v, ie);
+                    if (t >= 3) tmem_ldw<2 * HP>(tlane + TC_IE, reinterpret_cast<float*>(ie));   // interior: periodic envelope
+                    store_block_ie<LANES, VV>(a, xo, t, l, v, ie);
                 }
             }
         }
         if (t1 == a.T) {      // tail of the signal: blocks T, T+1, T+2 are complete now
-            float2 carry[12];
+            float2 carry[3 * HP];
             tmem_wait_st();
-            tmem_ld16(twarp + 24, reinterpret_cast<float*>(carry));
-            tmem_ld8(twarp + 40, reinterpret_cast<float*>(carry + 8));
+            tmem_ldw<4 * HP>(twarp + 24, reinterpret_cast<float*>(carry));
+            tmem_ldw<2 * HP>(twarp + 24 + 4 * HP, reinterpret_cast<float*>(carry + 2 * HP));
 #pragma unroll
             for (int k = 0; k < 3; ++k)
-                if (block_valid<LANES>(a, a.T + k)) {
-                    float2 ie[4];
-                    load_inv_env<LANES>(a, a.T + k, l, ie);
-                    store_block_ie<LANES>(a, xo, a.T + k, l, carry + 4 * k, ie);
+                if (block_valid<LANES, VV>(a, a.T + k)) {
+                    float2 ie[HP];
+                    load_inv_env<LANES, VV>(a, a.T + k, l, ie);
+                    store_block_ie<LANES, VV>(a, xo, a.T + k, l, carry + HP * k, ie);
                 }
         }
     }
@@ -520,7 +545,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) warp_iter_kernel(const WArgs a)
 
 static int g_sms = 0;
 
-template <int OP, int LANES>
+template <int OP, int LANES, int VV = V>
 static int launch(const WArgs& a0, cudaStream_t st) {
     WArgs a = a0;
     if (g_sms == 0) {
@@ -540,16 +565,16 @@ static int launch(const WArgs& a0, cudaStream_t st) {
     a.ranges = (int)ranges;
     const int grid = (int)min((long long)g_sms, ranges);
     // with fewer ranges than group slots, spread them over all CTAs of the grid: range index = blockIdx + grid * group
-    const size_t smem = (size_t)WARPS * WARP_F2 * sizeof(float2);
+    const size_t smem = (size_t)GROUPS * group_f2(Cfg<LANES, VV>::M) * sizeof(float2);
     cudaError_t e;
     if (a.sums) {
-        e = cudaFuncSetAttribute(warp_iter_kernel<OP, true, LANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute(warp_iter_kernel<OP, true, LANES, VV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
-        warp_iter_kernel<OP, true, LANES><<<grid, WARPS * 32, smem, st>>>(a);
+        warp_iter_kernel<OP, true, LANES, VV><<<grid, WARPS * 32, smem, st>>>(a);
     } else {
-        e = cudaFuncSetAttribute(warp_iter_kernel<OP, false, LANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute(warp_iter_kernel<OP, false, LANES, VV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
-        warp_iter_kernel<OP, false, LANES><<<grid, WARPS * 32, smem, st>>>(a);
+        warp_iter_kernel<OP, false, LANES, VV><<<grid, WARPS * 32, smem, st>>>(a);
     }
     return (int)cudaGetLastError();
 }
@@ -557,6 +582,7 @@ static int launch(const WArgs& a0, cudaStream_t st) {
 template <int OP>
 static int launch_any(const WArgs& a, int n_fft, cudaStream_t st) {
     switch (n_fft) {
+        case 512: return launch<OP, 32, 8>(a, st);
         case 1024: return launch<OP, 32>(a, st);
         case 2048: return launch<OP, 64>(a, st);
         case 4096: return launch<OP, 128>(a, st);
@@ -568,7 +594,7 @@ static int launch_any(const WArgs& a, int n_fft, cudaStream_t st) {
 
 static bool fastw_applicable(const specinv_desc* d) {
     return d->dtype == SPECINV_F32 && d->onesided && d->hop * 4 == d->n_fft &&
-           (d->n_fft == 1024 || d->n_fft == 2048 || d->n_fft == 4096);
+           (d->n_fft == 512 || d->n_fft == 1024 || d->n_fft == 2048 || d->n_fft == 4096);
 }
 
 static void fill_common(wfast::WArgs& a, const Dims& dm, const specinv_desc* d, const void* plan) {

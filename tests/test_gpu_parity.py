@@ -416,8 +416,8 @@ def test_rtisi_fast_kernel_1024_against_oracle(rc, monkeypatch):
 
 
 # ---------------------------------------------------------------------------------------------
-# fast paths for n_fft = 2048, hop = 512 (two warps per frame) and
-# n_fft = 4096, hop = 1024 (four warps per frame)
+# fast paths for n_fft = 2048, hop = 512 (two warps per frame), n_fft = 4096, hop = 1024 (four warps per frame)
+# and n_fft = 512, hop = 128 (one warp per frame, 8 values per lane)
 # ---------------------------------------------------------------------------------------------
 FAST2048_CASES = [
     dict(B=40, T=130, center=True, pad_mode="reflect", normalized=False),
@@ -425,6 +425,10 @@ FAST2048_CASES = [
     dict(B=64, T=64, center=False, pad_mode="reflect", normalized=False),
     dict(B=1, T=9, center=True, pad_mode="reflect", normalized=False),
     dict(B=3, T=41, center=True, pad_mode="circular", normalized=False),
+    dict(B=7, T=120, center=True, pad_mode="reflect", normalized=False, n_fft=512),
+    dict(B=3, T=61, center=True, pad_mode="circular", normalized=True, n_fft=512),
+    dict(B=4, T=33, center=False, pad_mode="reflect", normalized=False, n_fft=512),
+    dict(B=1, T=7, center=True, pad_mode="constant", normalized=False, n_fft=512),
     dict(B=9, T=50, center=True, pad_mode="replicate", normalized=False, n_fft=4096),
     dict(B=2, T=33, center=False, pad_mode="reflect", normalized=True, n_fft=4096),
     dict(B=1, T=301, center=True, pad_mode="reflect", normalized=False, n_fft=4096),

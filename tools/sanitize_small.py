@@ -10,7 +10,7 @@ import spectrogram_inversion_b200 as S  # noqa: E402
 
 dev = torch.device("cuda")
 torch.manual_seed(0)
-for n_fft, B, T in ((1024, 3, 21), (2048, 2, 17), (4096, 2, 13)):
+for n_fft, B, T in ((512, 3, 25), (1024, 3, 21), (2048, 2, 17), (4096, 2, 13)):
     w = torch.hann_window(n_fft, device=dev)
     mag = torch.rand(B, n_fft // 2 + 1, T, device=dev) * 5
     y = S.griffin_lim(mag, max_iter=3, tol=0, eva_iter=2, verbose=False, window=w, hop_length=n_fft // 4)
