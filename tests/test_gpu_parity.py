@@ -512,3 +512,38 @@ def test_cuda_graph_replay_of_plain_iterations_is_identical():
         nb = training_loop(b, 23, 0.0, False, 4, "sc", history=hb)
         assert na == nb == 23 and a.iterations == b.iterations == 23 and ha == hb
         assert len(a._graphs) >= 1 and torch.equal(a.signal, b.signal)
+
+
+@pytest.mark.parametrize("n_fft", [512, 1024, 2048, 4096])
+def test_specialised_kernels_on_tiny_frame_counts(n_fft, monkeypatch):
+    """T = 1 .. 6 frames (fewer frames than the 3-frame halo, no interior hop, ranges of one frame), several signals:
+    the specialised kernel must agree with the generic one (and not hang on its TMA / mbarrier pipeline)."""
+    from spectrogram_inversion_b200.engine import ADMMSolver, GriffinLimSolver, StftPlan
+    from spectrogram_inversion_b200.stft_args import StftArgs
+    dev = torch.device("cuda")
+    hop, F = n_fft // 4, n_fft // 2 + 1
+    g = torch.Generator(device=dev).manual_seed(n_fft)
+    for center, pad_mode in ((False, "reflect"), (True, "constant"), (True, "replicate")):
+        for T in range(1, 7):
+            if center and T < 2:
+                continue
+            B = 5
+            args = StftArgs(n_fft, hop, n_fft, torch.hamming_window(n_fft, device=dev), center, pad_mode, False, True)
+            plan = StftPlan(args, T, B, torch.float32, dev)
+            mag = torch.rand(B, F, T, device=dev, generator=g) * 4
+            C = mag * torch.exp(2j * torch.pi * torch.rand(B, F, T, device=dev, generator=g))
+            outs = []
+            for force in ("0", "1"):
+                monkeypatch.setenv("SPECINV_FORCE_GENERIC", force)
+                for Cls, coef in ((GriffinLimSolver, 0.99), (ADMMSolver, 0.1)):
+                    s_ = Cls(plan, plan.pack(C), plan.pack(mag), coef)
+                    sums = [s_.step(evaluate=True) for _ in range(2)]
+                    outs.append((s_.signal.clone(), sums))
+            for (xa, sa), (xb, sb) in zip(outs[:2], outs[2:]):
+                fin = torch.isfinite(xb)
+                assert (torch.isfinite(xa) == fin).all(), (center, T)
+                scale = max(1.0, float(xb[fin].abs().max())) if fin.any() else 1.0
+                assert float((xa[fin] - xb[fin]).abs().max()) <= 5e-5 * scale, (n_fft, center, pad_mode, T)
+                for (d0, e0), (d1, e1) in zip(sa, sb):
+                    if np.isfinite(d1) and np.isfinite(e1):
+                        assert abs(d0 - d1) <= 1e-4 * abs(d1) + 1e-6 and abs(e0 - e1) <= 1e-4 * abs(e1) + 1e-6
