@@ -37,39 +37,60 @@ __device__ __forceinline__ T mag_at(const T* __restrict__ main, const T* __restr
 // (one IEEE division), the two neighbours' results arrive by warp shuffle.  Consecutive lanes handle consecutive
 // bins, so the loads / stores of a time step are coalesced in the frame-major layout.  (signal, 30-bin segment)
 // pairs are numbered linearly over the warps so that the batched shapes fit one wave of resident blocks.
+//
+// Small batches do not have enough (signal, segment) pairs to fill the machine, so time is split into `chunks`
+// ranges that run in parallel (MODE 1 / 2; MODE 0 is the single pass):
+//   MODE 1: every (signal, segment, chunk) warp sums its chunk's phase advances (no output yet) and leaves the
+//           double in the 8 / 16 output bytes of (first frame of the chunk, bin);
+//   scan  : an exclusive scan over the chunks of every (signal, bin), in place;
+//   MODE 2: the warp reads ITS start phase from that slot and then writes C for its frames (the slot is overwritten
+//           by the first of them).
+// The double accumulation is then associated per chunk instead of strictly left to right: ~1e-16 relative, which
+// the rounding of the phase to the real type absorbs.
 constexpr int PI_SEG = 30;
 
 template <typename T>
-__global__ void __launch_bounds__(128) phase_init_kernel(Dims dm, int F, int segs, T hop, T inv_n_fft,
-                                                         const T* __restrict__ mag_main, const T* __restrict__ mag_nyq,
-                                                         cx_t<T>* __restrict__ c_main, cx_t<T>* __restrict__ c_nyq,
-                                                         const double* __restrict__ phase_in, double* __restrict__ phase_out) {
+__device__ __forceinline__ double* chunk_slot(const Dims& dm, cx_t<T>* c_main, cx_t<T>* c_nyq, long long fr, int k) {
+    return reinterpret_cast<double*>((dm.onesided && k == dm.M) ? c_nyq + fr : c_main + fr * dm.row + k);
+}
+
+template <typename T, int MODE>
+__global__ void __launch_bounds__(128) phase_init_kernel(Dims dm, int F, int segs, int chunks, int chunk_len, T hop,
+                                                         T inv_n_fft, const T* __restrict__ mag_main,
+                                                         const T* __restrict__ mag_nyq, cx_t<T>* __restrict__ c_main,
+                                                         cx_t<T>* __restrict__ c_nyq, const double* __restrict__ phase_in,
+                                                         double* __restrict__ phase_out) {
     const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;      // global warp
     const int lane = threadIdx.x & 31;
-    if (w >= (long long)dm.B * segs) return;                                           // whole warp
-    const int b = (int)(w / segs);
-    const int k = (int)(w - (long long)b * segs) * PI_SEG - 1 + lane;                  // lanes 0 and 31: halo bins
+    if (w >= (long long)dm.B * segs * chunks) return;                                  // whole warp
+    const int chunk = (int)(w % chunks);
+    const long long ws = w / chunks;
+    const int b = (int)(ws / segs);
+    const int k = (int)(ws - (long long)b * segs) * PI_SEG - 1 + lane;                 // lanes 0 and 31: halo bins
+    const int ta = chunk * chunk_len, tb = min(dm.T, ta + chunk_len);                  // this warp's frames
     const bool in_spec = k >= 0 && k < F;
     const bool owner = in_spec && lane >= 1 && lane <= PI_SEG;
     const bool can_peak = k >= 1 && k <= F - 2;       // strict local maxima exist for 1 <= k <= F-2 only (:597-598)
     const T pi2 = (T)6.283185307179586476925286766559;
     // torch's CPU cumsum accumulates float32 in float64 and rounds each output; phase_in (frame-range
     // sharding) is the phase accumulated by the frames before this range
-    double phase = (owner && phase_in) ? phase_in[(long long)b * F + k] : 0.0;
+    double phase = 0.0;
+    if (MODE == 0) phase = (owner && phase_in) ? phase_in[(long long)b * F + k] : 0.0;
+    if (MODE == 2 && owner) phase = *chunk_slot<T>(dm, c_main, c_nyq, (long long)b * dm.T + ta, k);
     // The running phase is the only loop-carried value: the loads of U consecutive frames are issued together.
     constexpr int U = 4;
-    for (int t0 = 0; t0 < dm.T; t0 += U) {
+    for (int t0 = ta; t0 < tb; t0 += U) {
         T m[U][3];                      // mag[k-1 .. k+1] of frames t0 .. t0+U-1
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const long long fr = (long long)b * dm.T + min(t0 + u, dm.T - 1);
+            const long long fr = (long long)b * dm.T + min(t0 + u, tb - 1);
             m[u][1] = in_spec ? mag_at(mag_main, mag_nyq, dm, fr, k) : T(0);
             m[u][0] = can_peak ? mag_at(mag_main, mag_nyq, dm, fr, k - 1) : T(0);
             m[u][2] = can_peak ? mag_at(mag_main, mag_nyq, dm, fr, k + 1) : T(0);
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            if (t0 + u < dm.T) {        // warp-uniform
+            if (t0 + u < tb) {          // warp-uniform
                 const long long fr = (long long)b * dm.T + t0 + u;
                 const T lo = m[u][0], mid = m[u][1], hi = m[u][2];
                 // own peak: interpolated angular frequency * hop (:604-605), or -1 (omega is never negative).
@@ -88,17 +109,36 @@ __global__ void __launch_bounds__(128) phase_init_kernel(Dims dm, int F, int seg
                 if (dn >= T(0)) omega = dn;
                 if (owner) {
                     phase += (double)omega;
-                    const T ph = (T)phase;
-                    T sn, cs;
-                    sincos_t<T>(ph, &sn, &cs);
-                    const cx_t<T> v = mk<T>(mid * cs, mid * sn);
-                    if (dm.onesided && k == dm.M) c_nyq[fr] = v;
-                    else c_main[fr * dm.row + k] = v;
+                    if (MODE != 1) {
+                        const T ph = (T)phase;
+                        T sn, cs;
+                        sincos_t<T>(ph, &sn, &cs);
+                        const cx_t<T> v = mk<T>(mid * cs, mid * sn);
+                        if (dm.onesided && k == dm.M) c_nyq[fr] = v;
+                        else c_main[fr * dm.row + k] = v;
+                    }
                 }
             }
         }
     }
-    if (owner && phase_out) phase_out[(long long)b * F + k] = phase;
+    if (MODE == 1) { if (owner) *chunk_slot<T>(dm, c_main, c_nyq, (long long)b * dm.T + ta, k) = phase; }
+    else if (owner && phase_out && tb == dm.T) phase_out[(long long)b * F + k] = phase;
+}
+
+// exclusive scan of the chunk sums of every (signal, bin), in place, starting from phase_in
+template <typename T>
+__global__ void phase_scan_kernel(Dims dm, int F, int chunks, int chunk_len, cx_t<T>* c_main, cx_t<T>* c_nyq,
+                                  const double* __restrict__ phase_in) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)dm.B * F) return;
+    const int b = (int)(i / F), k = (int)(i - (long long)b * F);
+    double run = phase_in ? phase_in[i] : 0.0;
+    for (int c = 0; c < chunks; ++c) {
+        double* slot = chunk_slot<T>(dm, c_main, c_nyq, (long long)b * dm.T + (long long)c * chunk_len, k);
+        const double v = *slot;
+        *slot = run;
+        run += v;
+    }
 }
 
 template <typename T>
@@ -114,11 +154,30 @@ static int phase_init_t(const Dims& dm, const void* mag_main, const void* mag_ny
                         const double* phase_in, double* phase_out, cudaStream_t st) {
     const int F = dm.onesided ? dm.M + 1 : dm.N;
     const int segs = (F + PI_SEG - 1) / PI_SEG;
-    const long long blocks = ((long long)dm.B * segs + 3) / 4;          // 4 warps per block
+    // split time only when the (signal, segment) pairs leave more than half of the 148 x 64 warp slots idle (the
+    // split costs a second pass over the magnitudes); chunks of at least 32 frames
+    const long long pairs = (long long)dm.B * segs;
+    long long chunks = (148LL * 64) / pairs;
+    if (chunks > dm.T / 32) chunks = dm.T / 32;
+    if (chunks < 1) chunks = 1;
+    const int chunk_len = (int)((dm.T + chunks - 1) / chunks);
+    chunks = (dm.T + chunk_len - 1) / chunk_len;
+    const long long blocks = (pairs * chunks + 3) / 4;                  // 4 warps per block
     if (blocks > 0x7fffffffLL) return SPECINV_ERR_UNSUPPORTED;
-    phase_init_kernel<T><<<(unsigned)blocks, 128, 0, st>>>(dm, F, segs, (T)dm.hop, (T)(1.0 / dm.N), (const T*)mag_main,
-                                                           (const T*)mag_nyq, (cx_t<T>*)c_main, (cx_t<T>*)c_nyq, phase_in,
-                                                           phase_out);
+    const T hop = (T)dm.hop, inv_n = (T)(1.0 / dm.N);
+    const T* mm = (const T*)mag_main; const T* mn = (const T*)mag_nyq;
+    cx_t<T>* cm = (cx_t<T>*)c_main; cx_t<T>* cn = (cx_t<T>*)c_nyq;
+    if (chunks == 1) {
+        phase_init_kernel<T, 0><<<(unsigned)blocks, 128, 0, st>>>(dm, F, segs, 1, dm.T, hop, inv_n, mm, mn, cm, cn, phase_in,
+                                                                  phase_out);
+    } else {
+        phase_init_kernel<T, 1><<<(unsigned)blocks, 128, 0, st>>>(dm, F, segs, (int)chunks, chunk_len, hop, inv_n, mm, mn, cm,
+                                                                  cn, nullptr, nullptr);
+        const long long nbf = (long long)dm.B * F;
+        phase_scan_kernel<T><<<(unsigned)((nbf + 127) / 128), 128, 0, st>>>(dm, F, (int)chunks, chunk_len, cm, cn, phase_in);
+        phase_init_kernel<T, 2><<<(unsigned)blocks, 128, 0, st>>>(dm, F, segs, (int)chunks, chunk_len, hop, inv_n, mm, mn, cm,
+                                                                  cn, nullptr, phase_out);
+    }
     return (int)cudaGetLastError();
 }
 
