@@ -95,12 +95,7 @@ def _run_host_pipelined(spec, n_chunks, make_solver, max_iter, eva_iter, metric,
     cur = torch.cuda.current_stream(dev)
     s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
     B = spec.shape[0]
-    # the first copy in and the last copy out cannot overlap anything: make the first and the last chunk small
-    weights = [1, 3, 3, 1] if n_chunks == 4 and B >= 16 else [1] * n_chunks
-    bounds, acc = [0], 0
-    for w in weights:
-        acc += w
-        bounds.append((B * acc) // sum(weights))
+    bounds = [(B * k) // n_chunks for k in range(n_chunks + 1)]
 
     def stage(k):
         with torch.cuda.stream(s_in):
