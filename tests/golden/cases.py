@@ -131,3 +131,15 @@ GRAD_CASES = [
 def probe_like(shape, seed):
     """Fixed weights of the scalar loss sum(y * probe)."""
     return np.random.RandomState(1000 + seed).randn(*shape)
+
+
+# the specialised kernels' shapes (hop = n_fft / 4, onesided, float32), run through the reference itself ------------
+FASTREF_CASES = [
+    _c("fastref_512", n_fft=512, window="hann", hop_length=128, T=13, B=3, dtype="float32", seed=21),
+    _c("fastref_1024", n_fft=1024, window="hann", hop_length=256, T=11, B=2, dtype="float32", seed=22),
+    _c("fastref_1024_nocenter", n_fft=1024, window="hamming", hop_length=256, T=9, B=2, dtype="float32", seed=23,
+       center=False),
+    _c("fastref_2048", n_fft=2048, window="hann", hop_length=512, T=10, B=2, dtype="float32", seed=24),
+    _c("fastref_4096", n_fft=4096, window="hann", hop_length=1024, T=9, B=1, dtype="float32", seed=25,
+       pad_mode="constant"),
+]

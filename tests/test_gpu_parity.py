@@ -547,3 +547,28 @@ def test_specialised_kernels_on_tiny_frame_counts(n_fft, monkeypatch):
                 for (d0, e0), (d1, e1) in zip(sa, sb):
                     if np.isfinite(d1) and np.isfinite(e1):
                         assert abs(d0 - d1) <= 1e-4 * abs(d1) + 1e-6 and abs(e0 - e1) <= 1e-4 * abs(e1) + 1e-6
+
+
+FASTREF = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fast.npz"))
+
+
+@pytest.mark.parametrize("case", cases.FASTREF_CASES, ids=lambda c: c["name"])
+def test_specialised_kernels_match_the_reference_itself(case):
+    """The specialised kernels' shapes against outputs of the UNMODIFIED reference (tests/golden/fast.npz, written by
+    tests/golden/make_golden_fast.py): one and two iterations from the same complex start, the magnitude entry
+    (phase_init inside) and RTISI-LA."""
+    import spectrogram_inversion_b200 as S
+    inp = cases.make_case_inputs(case)
+    kw = {k: (torch.from_numpy(v).cuda() if isinstance(v, np.ndarray) else v) for k, v in inp["kwargs"].items()}
+    C, mag, name = torch.from_numpy(inp["C"]).cuda(), torch.from_numpy(inp["mag"]).cuda(), case["name"]
+    y = S.griffin_lim(C, max_iter=1, tol=0, alpha=0.99, verbose=False, eva_iter=1, **kw)
+    close(y, FASTREF[f"{name}/gl_k1"], 1e-5, "GL 1 iteration vs reference")       # north_star: <= 1e-5 in fp32
+    y = S.griffin_lim(C, max_iter=2, tol=0, alpha=0.99, verbose=False, eva_iter=1, **kw)
+    close(y, FASTREF[f"{name}/gl_k2"], 5e-5, "GL 2 iterations vs reference")
+    y = S.ADMM(C, max_iter=1, tol=0, rho=0.1, verbose=False, eva_iter=1, **kw)
+    close(y, FASTREF[f"{name}/admm_k1"], 1e-5, "ADMM 1 iteration vs reference")
+    y = S.griffin_lim(mag, max_iter=2, tol=0, alpha=0.99, verbose=False, **kw)
+    close(y, FASTREF[f"{name}/gl_mag_k2"], 2e-3, "griffin_lim(mag) vs reference")
+    if f"{name}/rtisi_la3_k1" in FASTREF:
+        y = S.RTISI_LA(mag, look_ahead=3, max_iter=1, alpha=0.99, verbose=0, **kw)
+        close(y, FASTREF[f"{name}/rtisi_la3_k1"], 5e-3, "RTISI-LA vs reference")
