@@ -198,7 +198,7 @@ class _Solver:
             side = torch.cuda.Stream(self.plan.device)
             side.wait_stream(main)
             with torch.cuda.stream(side):
-                graph.capture_begin()
+                graph.capture_begin(capture_error_mode="thread_local")
                 for _ in range(n):
                     self.step()
                 graph.capture_end()
