@@ -124,6 +124,8 @@ int specinv_istft(const specinv_desc* d, const void* plan, const void* main_in, 
  * specinv_gl_iter : one closure call of griffin_lim, methods.py:237-250:
  *      s = STFT(x_in); q_out = s - lr*q_in; x_out = ISTFT(q_out*mag/(|q_out|+1e-16))
  *   q_in/q_out and x_in/x_out must not alias (neighbouring tiles re-read the old state).
+ *   Plain Griffin-Lim (alpha = 0, so lr = 0 and q_out == s): pass all four q pointers as NULL and the
+ *   momentum state is neither read nor written (4 instead of 20 bytes of traffic per bin).
  *   sums (may be NULL): two doubles to which sum (|s|-mag)^2 and sum |s|^2 over all
  *   B*F*T bins are ADDED (the fused metric epilogue for methods.py:181-182).
  * specinv_admm_iter : one closure call of ADMM, methods.py:458-483 with Y == X + U:

@@ -82,6 +82,18 @@ def gl_iter(plan: Tensor, x_in: Tensor, x_out: Tensor, q_in_main: Tensor, q_in_n
             _p(mag_main), _p(mag_nyq), float(lr), _p(sums), _stream(x_in)), "gl_iter")
 
 
+@torch.library.custom_op("specinv_b200::gl_plain_iter", mutates_args=("x_out", "sums"), device_types="cuda")
+def gl_plain_iter(plan: Tensor, x_in: Tensor, x_out: Tensor, mag_main: Tensor, mag_nyq: Tensor, sums: Tensor,
+                  n_fft: int, hop: int, center: bool, pad_mode: int, normalized: bool, onesided: bool) -> None:
+    """griffin_lim's closure with alpha = 0 (methods.py:243 with lr = 0): no momentum state (NULL q pointers)."""
+    _need_cuda(plan, x_in, x_out, mag_main, mag_nyq, sums)
+    d = _desc(x_in, n_fft, hop, mag_main.shape[1], mag_main.shape[0], center, pad_mode, normalized, onesided)
+    with torch.cuda.device(x_in.device):
+        _ok(_lib.lib().specinv_gl_iter(
+            C.byref(d), _p(plan), _p(x_in), _p(x_out), None, None, None, None,
+            _p(mag_main), _p(mag_nyq), 0.0, _p(sums), _stream(x_in)), "gl_iter")
+
+
 @torch.library.custom_op("specinv_b200::admm_iter",
                          mutates_args=("x_out", "X_out_main", "X_out_nyq", "U_out_main", "U_out_nyq", "sums"),
                          device_types="cuda")

@@ -30,7 +30,9 @@
 namespace specinv {
 namespace wfast {
 
-enum { OP_GL = 0, OP_ADMM = 1, OP_ISTFT = 2 };   // OP_ISTFT: stand-alone inverse transform + overlap-add (methods.py:233)
+// OP_ISTFT: stand-alone inverse transform + overlap-add (methods.py:233); OP_GLP: plain Griffin-Lim (alpha = 0:
+// q_n = STFT(x_{n-1}), so no momentum state is read or written)
+enum { OP_GL = 0, OP_ADMM = 1, OP_ISTFT = 2, OP_GLP = 3 };
 
 // complex products on the packed FP32x2 pipe (fft_regs.cuh): 2 instructions each
 SPX_HD float2 cmulf(float2 a, float2 b) { return cmul2(a, b); }
@@ -200,7 +202,9 @@ SPX_HD float2 bin_update(float2 s, float2 a0, float2 a1, float m, float coef, fl
         dsum += (r - m) * (r - m);
         esum += r * r;
     }
-    if constexpr (OP == OP_GL) {
+    if constexpr (OP == OP_GLP) {
+        return project_rsq(s, m);
+    } else if constexpr (OP == OP_GL) {
         const float2 q = pfma(f2(-coef, -coef), a0, s);             // s - lr * q_prev
         o0 = q;
         return project_rsq(q, m);
@@ -229,9 +233,9 @@ SPX_HD void pointwise(int l, float2* A, float2* B, const float2* twr, IO& io, fl
     auto upd = [&](auto ec, float2 sv) {
         constexpr int e = decltype(ec)::value;
         float2 o0 = f2(0.f, 0.f), o1 = f2(0.f, 0.f);
-        const float2 h = bin_update<OP, SUMS>(sv, io.s0(e), OP == OP_ADMM ? io.s1(e) : f2(0.f, 0.f), io.mag(e), coef, coef2,
-                                              o0, o1, dsum, esum);
-        io.put(e, o0, o1);
+        const float2 h = bin_update<OP, SUMS>(sv, OP == OP_GLP ? f2(0.f, 0.f) : io.s0(e),
+                                              OP == OP_ADMM ? io.s1(e) : f2(0.f, 0.f), io.mag(e), coef, coef2, o0, o1, dsum, esum);
+        if constexpr (OP != OP_GLP) io.put(e, o0, o1);
         return h;
     };
     // slot 0

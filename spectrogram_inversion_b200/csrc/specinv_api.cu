@@ -20,6 +20,7 @@ int fastw_gl_iter(const specinv_desc*, const void*, const void*, void*, const vo
 int fastw_admm_iter(const specinv_desc*, const void*, const void*, void*, const void*, const void*, const void*,
                     const void*, void*, void*, void*, void*, const void*, const void*, double, double*, void*);
 int fastw_istft(const specinv_desc*, const void*, const void*, const void*, void*, void*);
+int fastw_gl_plain_iter(const specinv_desc*, const void*, const void*, void*, const void*, const void*, double*, void*);
 
 // SPECINV_FORCE_GENERIC=1 routes everything through the generic tile kernels (testing / A-B timing)
 static bool force_generic() {
@@ -316,8 +317,17 @@ int specinv_istft(const specinv_desc* d, const void* plan, const void* main_in, 
 int specinv_gl_iter(const specinv_desc* d, const void* plan, const void* x_in, void* x_out,
                     const void* q_in_main, const void* q_in_nyq, void* q_out_main, void* q_out_nyq,
                     const void* mag_main, const void* mag_nyq, double lr, double* sums, void* stream) {
-    if (!d || !plan || !x_in || !x_out || !q_in_main || !q_out_main || !mag_main) return SPECINV_ERR_INVALID;
-    if (x_in == x_out || q_in_main == q_out_main) return SPECINV_ERR_INVALID;
+    if (!d || !plan || !x_in || !x_out || !mag_main || x_in == x_out) return SPECINV_ERR_INVALID;
+    if (!q_in_main && !q_out_main) {
+        // plain Griffin-Lim: with lr == 0 the momentum state is neither needed nor produced
+        if (lr != 0.0 || q_in_nyq || q_out_nyq) return SPECINV_ERR_INVALID;
+        if (!force_generic() && d->onesided && mag_nyq) {
+            const int rc = fastw_gl_plain_iter(d, plan, x_in, x_out, mag_main, mag_nyq, sums, stream);
+            if (rc != SPECINV_ERR_UNSUPPORTED) return rc;
+        }
+        return generic_gl_iter(d, plan, x_in, x_out, nullptr, nullptr, nullptr, nullptr, mag_main, mag_nyq, 0.0, sums, stream);
+    }
+    if (!q_in_main || !q_out_main || q_in_main == q_out_main) return SPECINV_ERR_INVALID;
     if (!force_generic() && d->onesided && q_in_nyq && q_out_nyq && mag_nyq) {
         const int rc = fastw_gl_iter(d, plan, x_in, x_out, q_in_main, q_in_nyq, q_out_main, q_out_nyq, mag_main, mag_nyq,
                                      lr, sums, stream);

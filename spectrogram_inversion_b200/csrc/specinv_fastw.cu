@@ -225,8 +225,8 @@ __device__ __forceinline__ void stage_rows(const WArgs& a, long long row, int l,
     constexpr int M = Cfg<LANES, VV>::M;
     if (l < 32) {
         if (elect_one()) {
-            mbar_expect_tx(bar, OP == OP_ISTFT ? M * 8 : M * 8 + M * 4);
-            bulk_g2s(qstage_s, a.s0_in + row * M, M * 8, bar);
+            mbar_expect_tx(bar, OP == OP_ISTFT ? M * 8 : OP == OP_GLP ? M * 4 : M * 8 + M * 4);
+            if constexpr (OP != OP_GLP) bulk_g2s(qstage_s, a.s0_in + row * M, M * 8, bar);
             if constexpr (OP != OP_ISTFT) bulk_g2s(mstage_s, a.mag + row * M, M * 4, bar);
         }
     }
@@ -364,7 +364,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) warp_iter_kernel(const WArgs a)
         float mgn_next = 0.f;
         if (l == 0) {
             const long long r0 = (long long)b * a.T + tf0;
-            s0n_next = __ldg(a.s0_in_nyq + r0);
+            if constexpr (OP != OP_GLP) s0n_next = __ldg(a.s0_in_nyq + r0);
             if constexpr (OP != OP_ISTFT) mgn_next = __ldg(a.mag_nyq + r0);
             if constexpr (OP == OP_ADMM) s1n_next = __ldg(a.s1_in_nyq + r0);
         }
@@ -457,7 +457,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) warp_iter_kernel(const WArgs a)
                             if constexpr (OP == OP_ADMM) o1[bin(e)] = v1;
                         }
                     }
-                } io{qstage, mstage, e1, a.s0_out + row * M,
+                } io{qstage, mstage, e1, OP == OP_GLP ? nullptr : a.s0_out + row * M,
                      OP == OP_ADMM ? a.s1_out + row * M : nullptr, a.s0_out_nyq + row,
                      OP == OP_ADMM ? a.s1_out_nyq + row : nullptr, l, l + hi_adj, M - l, M - l - hi_adj, kq0, owned,
                      s0n, s1n, mgn};
@@ -475,7 +475,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) warp_iter_kernel(const WArgs a)
             if (t + 1 < t1) {
                 stage_rows<OP, LANES, VV>(a, row + 1, l, qstage_s, mstage_s, sbar);
                 if (l == 0) {
-                    s0n_next = __ldg(a.s0_in_nyq + row + 1);
+                    if constexpr (OP != OP_GLP) s0n_next = __ldg(a.s0_in_nyq + row + 1);
                     if constexpr (OP != OP_ISTFT) mgn_next = __ldg(a.mag_nyq + row + 1);
                     if constexpr (OP == OP_ADMM) s1n_next = __ldg(a.s1_in_nyq + row + 1);
                 }
@@ -554,7 +554,7 @@ static int launch(const WArgs& a0, cudaStream_t st) {
         if (cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return SPECINV_ERR_NO_DEVICE;
     }
     // the TMA bulk copies need 16-byte aligned rows
-    if ((((uintptr_t)a.x_in | (uintptr_t)a.s0_in | (uintptr_t)a.mag) & 15) != 0) return SPECINV_ERR_UNSUPPORTED;
+    if ((((uintptr_t)a.x_in | (uintptr_t)a.s0_in | (uintptr_t)a.mag) & 15) != 0) return SPECINV_ERR_UNSUPPORTED;   // (s0_in is NULL for OP_GLP)
     if (OP == OP_ISTFT && a.sums) return SPECINV_ERR_INVALID;
     a.frames_total = (long long)a.B * a.T;
     constexpr int GROUPS = WARPS / (LANES / 32);
@@ -619,6 +619,19 @@ int fastw_gl_iter(const specinv_desc* d, const void* plan, const void* x_in, voi
     a.mag = (const float*)mag_main; a.mag_nyq = (const float*)mag_nyq;
     a.coef = (float)lr; a.sums = sums;
     return wfast::launch_any<wfast::OP_GL>(a, d->n_fft, (cudaStream_t)stream);
+}
+
+// Plain Griffin-Lim (alpha = 0, methods.py:243 with lr = 0): x_out = ISTFT(proj(STFT(x_in))), no momentum state.
+int fastw_gl_plain_iter(const specinv_desc* d, const void* plan, const void* x_in, void* x_out, const void* mag_main,
+                        const void* mag_nyq, double* sums, void* stream) {
+    if (!fastw_applicable(d)) return SPECINV_ERR_UNSUPPORTED;
+    Dims dm; int rc = make_dims(d, &dm); if (rc) return rc;
+    wfast::WArgs a{};
+    fill_common(a, dm, d, plan);
+    a.x_in = (const float*)x_in; a.x_out = (float*)x_out;
+    a.mag = (const float*)mag_main; a.mag_nyq = (const float*)mag_nyq;
+    a.sums = sums;
+    return wfast::launch_any<wfast::OP_GLP>(a, d->n_fft, (cudaStream_t)stream);
 }
 
 // x_out = ISTFT(spectrum) (methods.py:135-150) with the same kernel: inverse half of the frame pipeline only.

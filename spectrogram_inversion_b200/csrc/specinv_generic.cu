@@ -71,11 +71,15 @@ __device__ __forceinline__ cx_t<T> bin_update(const TileArgs& a, const BinIO<T>&
     } else if constexpr (OP == OP_GL) {
         // methods.py:243-247
         const T lr = (T)a.coef;
-        cx_t<T> qp = io.ldc(a.s0_in_main, a.s0_in_nyq, kk);
+        const bool momentum = a.s0_in_main != nullptr;     // NULL state: plain Griffin-Lim (lr == 0), q_n = s
         T m = io.ldm(kk);
-        cx_t<T> q = mk<T>(s.x - qp.x * lr, s.y - qp.y * lr);
+        cx_t<T> q = s;
+        if (momentum) {
+            cx_t<T> qp = io.ldc(a.s0_in_main, a.s0_in_nyq, kk);
+            q = mk<T>(s.x - qp.x * lr, s.y - qp.y * lr);
+        }
         if (owned) {
-            io.stc(a.s0_out_main, a.s0_out_nyq, kk, q);
+            if (momentum) io.stc(a.s0_out_main, a.s0_out_nyq, kk, q);
             if (want_sums) {
                 T r = fast_sqrt(s.x * s.x + s.y * s.y);
                 dsum += (r - m) * (r - m);
@@ -324,9 +328,10 @@ int generic_gl_iter(const specinv_desc* d, const void* plan, const void* x_in, v
                     const void* q_in_main, const void* q_in_nyq, void* q_out_main, void* q_out_nyq,
                     const void* mag_main, const void* mag_nyq, double lr, double* sums, void* stream) {
     Dims dm; int rc = make_dims(d, &dm); if (rc) return rc;
-    if (!plan || !x_in || !x_out || !q_in_main || !q_out_main || !mag_main) return SPECINV_ERR_INVALID;
-    if (dm.onesided && (!q_in_nyq || !q_out_nyq || !mag_nyq)) return SPECINV_ERR_INVALID;
-    if (x_in == x_out || q_in_main == q_out_main) return SPECINV_ERR_INVALID;
+    if (!plan || !x_in || !x_out || !mag_main || x_in == x_out) return SPECINV_ERR_INVALID;
+    if (!q_in_main != !q_out_main || (!q_in_main && lr != 0.0)) return SPECINV_ERR_INVALID;
+    if (q_in_main && q_in_main == q_out_main) return SPECINV_ERR_INVALID;
+    if (dm.onesided && (!mag_nyq || (q_in_main && (!q_in_nyq || !q_out_nyq)))) return SPECINV_ERR_INVALID;
     TileArgs a{}; fill_plan(a, dm, d->dtype, plan);
     a.x_in = x_in; a.x_out = x_out;
     a.s0_in_main = q_in_main; a.s0_in_nyq = q_in_nyq; a.s0_out_main = q_out_main; a.s0_out_nyq = q_out_nyq;

@@ -218,16 +218,23 @@ class GriffinLimSolver(_Solver):
     def __init__(self, plan: StftPlan, C: SplitSpec, mag: SplitSpec, alpha: float):
         super().__init__(plan, mag)
         self.lr = alpha / (1 + alpha)                     # methods.py:235
-        self.q = [C, C.like()]
+        # alpha = 0 is plain Griffin-Lim: q_n = STFT(x_{n-1}) needs no momentum state, so none is kept or moved
+        self.plain = self.lr == 0
+        self.q = None if self.plain else [C, C.like()]
         plan.istft(C, self.x[0])                          # methods.py:233
 
     def _launch(self, sums: torch.Tensor) -> None:
         p, i, o = self.plan, self.cur, self.cur ^ 1
+        if self.plain:
+            _ops.gl_plain_iter(p.buf, self.x[i], self.x[o], self.mag.main, self.mag.nyq, sums, *p._k)
+            return
         _ops.gl_iter(p.buf, self.x[i], self.x[o], self.q[i].main, self.q[i].nyq, self.q[o].main, self.q[o].nyq,
                      self.mag.main, self.mag.nyq, sums, self.lr, *p._k)
 
     @property
     def q_state(self) -> SplitSpec:
+        if self.plain:
+            raise RuntimeError("plain Griffin-Lim (alpha = 0) keeps no momentum state")
         return self.q[self.cur]
 
 

@@ -83,12 +83,14 @@ def test_griffin_lim_iterations_from_identical_state(case):
         for k in (1, 2, 3):
             # restart the CUDA step from the ORACLE's state so every step is a single-iteration test
             solver.x[solver.cur].copy_(torch.from_numpy(st.x))
-            solver.q[solver.cur] = plan.pack(torch.from_numpy(st.q))
-            solver.q[solver.cur ^ 1] = solver.q[solver.cur].like()
+            if not solver.plain:      # alpha = 0: no momentum state at all (NULL q pointers through the ABI)
+                solver.q[solver.cur] = plan.pack(torch.from_numpy(st.q))
+                solver.q[solver.cur ^ 1] = solver.q[solver.cur].like()
             d, e = solver.step(evaluate=True)
             st = O.gl_step(st, mag, alpha / (1 + alpha), oa)
             close(solver.signal, st.x, tol, f"x after step {k} alpha {alpha}")
-            close(plan.unpack(solver.q_state), st.q, tol * 10, f"q after step {k}")
+            if not solver.plain:
+                close(plan.unpack(solver.q_state), st.q, tol * 10, f"q after step {k}")
             do, eo, go = O.metric_sums(st.out_mag, mag)
             rel = 1e-4 if case["dtype"] == "float32" else 1e-10
             assert abs(d - do) <= rel * max(do, 1e-30) + 1e-12 and abs(e - eo) <= rel * eo
@@ -466,6 +468,18 @@ def test_fast_path_2048_against_oracle(fc):
         if out is not None:
             do, eo, _ = O.metric_sums(st.out_mag, mag)
             assert abs(out[0] - do) <= 1e-4 * do and abs(out[1] - eo) <= 1e-4 * eo
+    # plain Griffin-Lim (alpha = 0): the no-momentum variant of the kernel (NULL q pointers), 2 steps + sums
+    solver = GriffinLimSolver(plan, plan.pack(torch.from_numpy(C)), plan.pack(magt), 0.0)
+    assert solver.plain and solver.q is None
+    st = O.gl_init(C, oa)
+    for k in range(2):
+        solver.x[solver.cur].copy_(torch.from_numpy(st.x))
+        out = solver.step(evaluate=(k == 1))
+        st = O.gl_step(st, mag, 0.0, oa)
+        close(solver.signal, st.x, 1e-5, f"plain GL x step {k}")
+        if out is not None:
+            do, eo, _ = O.metric_sums(st.out_mag, mag)
+            assert abs(out[0] - do) <= 1e-4 * do and abs(out[1] - eo) <= 1e-4 * eo
     solver = ADMMSolver(plan, plan.pack(torch.from_numpy(C)), plan.pack(magt), 0.1)
     st = O.admm_init(C, oa)
     solver.step(evaluate=True)
@@ -535,11 +549,11 @@ def test_specialised_kernels_on_tiny_frame_counts(n_fft, monkeypatch):
             outs = []
             for force in ("0", "1"):
                 monkeypatch.setenv("SPECINV_FORCE_GENERIC", force)
-                for Cls, coef in ((GriffinLimSolver, 0.99), (ADMMSolver, 0.1)):
+                for Cls, coef in ((GriffinLimSolver, 0.99), (ADMMSolver, 0.1), (GriffinLimSolver, 0.0)):
                     s_ = Cls(plan, plan.pack(C), plan.pack(mag), coef)
                     sums = [s_.step(evaluate=True) for _ in range(2)]
                     outs.append((s_.signal.clone(), sums))
-            for (xa, sa), (xb, sb) in zip(outs[:2], outs[2:]):
+            for (xa, sa), (xb, sb) in zip(outs[:3], outs[3:]):
                 fin = torch.isfinite(xb)
                 assert (torch.isfinite(xa) == fin).all(), (center, T)
                 scale = max(1.0, float(xb[fin].abs().max())) if fin.any() else 1.0

@@ -18,6 +18,8 @@ CFG = {
     "cfg2": dict(algo="gl", B=512, N=240000, sr=24000, n_fft=1024, hop=256, iters=64, alpha=0.99),
     "cfg3": dict(algo="rtisi", B=256, N=240000, sr=24000, n_fft=1024, hop=256, iters=25, alpha=0.99, la=3),
     "cfg4": dict(algo="admm", B=128, N=882000, sr=44100, n_fft=2048, hop=512, iters=100, rho=0.1),
+    "cfg2p": dict(algo="gl", B=512, N=240000, sr=24000, n_fft=1024, hop=256, iters=64, alpha=0.0),      # plain GL
+    "cfg5p": dict(algo="gl", B=1, N=172800000, sr=48000, n_fft=4096, hop=1024, iters=10, alpha=0.0),
     "cfg5": dict(algo="gl", B=1, N=172800000, sr=48000, n_fft=4096, hop=1024, iters=10, alpha=0.99),
 }
 names = [a for a in sys.argv[1:] if a in CFG] or list(CFG)
@@ -60,7 +62,7 @@ for name in names:
     solver.run_plain(n)
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / n
-    per_bin = 20 if c["algo"] == "gl" else 36
+    per_bin = (20 if c["alpha"] > 0 else 4) if c["algo"] == "gl" else 36
     gb = (per_bin * B * F * T + 8 * B * plan.length) / 1e9
     print(f"{name}: {c['algo']} B={B} T={T} {n_fft}/{hop}: {ms:.4f} ms/iter, {gb / ms * 1e3:.0f} GB/s algorithmic "
           f"({gb / ms * 1e3 / PEAK * 100:.1f} % of {PEAK:.0f}), {audio / ms * 1e3:.0f} audio-s*it/s")
