@@ -1,13 +1,13 @@
-// RTISI-LA (torch_specinv/methods.py:273-412) for n_fft = 1024, hop = 256, look_ahead <= 3, onesided fp32 -- the
-// shape of BASELINE.json's cfg3 -- as ONE persistent kernel built from the register FFT pipeline of
-// gl_warp_core.cuh (16 complex values per lane, one warp per frame).
+// RTISI-LA (torch_specinv/methods.py:273-412) for n_fft = 1024 / hop = 256 (the shape of BASELINE.json's cfg3) and
+// n_fft = 512 / hop = 128, look_ahead <= 3, onesided fp32, as ONE persistent kernel built from the register FFT
+// pipeline of gl_warp_core.cuh (16 or 8 complex values per lane, one warp per frame).
 //
 // A signal is owned by LA+1 warps, one per ACTIVE frame; a frame stays in its warp's registers for its whole
 // life (LA+1 outer steps x max_iter inner iterations), together with its momentum spectrum (tensor memory) and
 // its magnitude row (tensor memory, fetched once when the frame is born).  Per inner iteration (methods.py:365-398)
 // every warp
 //   * publishes its synthesis-windowed frame u = frame * w * c in shared memory (rows of 32 lanes),
-//   * rebuilds ITS frame of the overlap-add y: a hop is 4 of a lane's 16 sample pairs, so the contributions of the
+//   * rebuilds ITS frame of the overlap-add y: a hop is a quarter of a lane's sample pairs, so the contributions of the
 //     other frames are the same lane's rows shifted by 4 per frame; the kept frames' part is constant over the
 //     inner iterations and waits in tensor memory,
 //   * windows it (asym_window1/2 for the newest frame when asked), runs the forward FFT, the momentum update
@@ -18,6 +18,7 @@
 // the signal once.
 #include "specinv_common.cuh"
 #include "gl_warp_core.cuh"
+#include "sm100_ptx.cuh"
 
 namespace specinv {
 namespace rfast {
@@ -25,9 +26,7 @@ namespace rfast {
 using namespace wfast;
 
 constexpr int LANES = 32;
-constexpr int M = 512, N = 1024, HOP = 256, KEEP = 3, NAMAX = 4;
-constexpr int SIGS = 2;                       // signals per CTA (2 x 4 warps)
-constexpr int WARPS = SIGS * NAMAX;
+constexpr int KEEP = 3, NAMAX = 4;            // kept frames (n_fft = 4 hop), at most LA + 1 = 4 active frames
 
 struct RArgs {
     const float* mag; const float* mag_nyq;
@@ -41,70 +40,36 @@ struct RArgs {
     long long L;
 };
 
-// ---- tensor memory helpers (same conventions as specinv_fastw.cu) -----------------------------------------
-__device__ __forceinline__ void tmem_alloc(unsigned* smem_dst, int ncols) {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(d), "r"(ncols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(unsigned taddr, int ncols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tmem_ld16(unsigned taddr, float* r) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n\t"
-                 "tcgen05.wait::ld.sync.aligned;"
-                 : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7]),
-                   "=f"(r[8]), "=f"(r[9]), "=f"(r[10]), "=f"(r[11]), "=f"(r[12]), "=f"(r[13]), "=f"(r[14]), "=f"(r[15])
-                 : "r"(taddr) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(unsigned taddr, float* r) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n\t"
-                 "tcgen05.wait::ld.sync.aligned;"
-                 : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7]),
-                   "=f"(r[8]), "=f"(r[9]), "=f"(r[10]), "=f"(r[11]), "=f"(r[12]), "=f"(r[13]), "=f"(r[14]), "=f"(r[15]),
-                   "=f"(r[16]), "=f"(r[17]), "=f"(r[18]), "=f"(r[19]), "=f"(r[20]), "=f"(r[21]), "=f"(r[22]), "=f"(r[23]),
-                   "=f"(r[24]), "=f"(r[25]), "=f"(r[26]), "=f"(r[27]), "=f"(r[28]), "=f"(r[29]), "=f"(r[30]), "=f"(r[31])
-                 : "r"(taddr) : "memory");
-}
-__device__ __forceinline__ void tmem_st16(unsigned taddr, const float* r) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
-                 ::"r"(taddr), "f"(r[0]), "f"(r[1]), "f"(r[2]), "f"(r[3]), "f"(r[4]), "f"(r[5]), "f"(r[6]), "f"(r[7]),
-                   "f"(r[8]), "f"(r[9]), "f"(r[10]), "f"(r[11]), "f"(r[12]), "f"(r[13]), "f"(r[14]), "f"(r[15]) : "memory");
-}
-__device__ __forceinline__ void tmem_st32(unsigned taddr, const float* r) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-                 "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
-                 ::"r"(taddr), "f"(r[0]), "f"(r[1]), "f"(r[2]), "f"(r[3]), "f"(r[4]), "f"(r[5]), "f"(r[6]), "f"(r[7]),
-                   "f"(r[8]), "f"(r[9]), "f"(r[10]), "f"(r[11]), "f"(r[12]), "f"(r[13]), "f"(r[14]), "f"(r[15]),
-                   "f"(r[16]), "f"(r[17]), "f"(r[18]), "f"(r[19]), "f"(r[20]), "f"(r[21]), "f"(r[22]), "f"(r[23]),
-                   "f"(r[24]), "f"(r[25]), "f"(r[26]), "f"(r[27]), "f"(r[28]), "f"(r[29]), "f"(r[30]), "f"(r[31]) : "memory");
-}
-
 // TMEM columns per lane: constant tables (identical in the four sub-partitions), then per-warp state
 constexpr int TC_WA = 0, TC_WSC = 32, TC_TW1 = 64, TC_TW2 = 96, TC_TWR = 112, TC_AS1 = 128, TC_AS2 = 160, TC_WARP = 192;
 constexpr int TC_PRE = 0, TC_YK = 32, TC_MAG = 64, TC_PER_WARP = 80;
 constexpr int TMEM_COLS = 512;
 // float2 of shared memory per signal: u of the active frames (double buffered), u of the kept frames, the output
-// carry, and the two FFT exchange buffers of every warp
-constexpr int ROWS = V * LANES;                                     // one frame = 16 rows of 32 lanes = 512 float2
-constexpr int SIG_F2 = 2 * NAMAX * ROWS + KEEP * ROWS + ROWS + NAMAX * 2 * M;
+// carry (one frame = VV rows of 32 lanes = M float2 each), and the two FFT exchange buffers of every warp
+constexpr int sig_f2(int m) { return 2 * NAMAX * m + KEEP * m + m + NAMAX * 2 * m; }
 
 __device__ __forceinline__ void sig_sync(int bar_id, int threads) {
     asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(threads) : "memory");
 }
 
-// bin offsets of the lane's 16 bins (gl_warp_core.cuh: slot j -> bins l + 64 j and 512 - l - 64 j; lane 0 special)
-struct Bins {
-    int pl, ph, ql, qh, q0;
-    __device__ __forceinline__ int operator()(int e) const {
-        const int j = e >> 1;
-        return (e & 1) ? (j == 0 ? q0 : (j >= 4 ? qh : ql) - 2 * LANES * j) : (j >= 4 ? ph : pl) + 2 * LANES * j;
-    }
-};
-
-__global__ void __launch_bounds__(WARPS * 32, 1) rtisi_fast_kernel(const RArgs a) {
+// VV complex values per lane (16: n_fft = 1024, 8: n_fft = 512), SIGS signals per CTA (SIGS x 4 warps)
+template <int VV, int SIGS>
+__global__ void __launch_bounds__(SIGS * NAMAX * 32, 1) rtisi_fast_kernel(const RArgs a) {
+    using C = Cfg<LANES, VV>;
+    constexpr int V = VV;                          // shadows wfast::V
+    constexpr int M = C::M, HOP = C::HOP, RC = C::RC, HP = VV / 4;
+    constexpr int ROWS = M;                        // float2 per frame: VV rows of 32 lanes
+    constexpr int SIG_F2 = sig_f2(M);
+    constexpr int WARPS = SIGS * NAMAX;
+    static_assert(TC_WARP + ((WARPS + 3) / 4) * TC_PER_WARP <= TMEM_COLS, "TMEM columns");
+    // bin offsets of the lane's VV bins (gl_warp_core.cuh: slot j -> bins l + 64 j and M - l - 64 j; lane 0 special)
+    struct Bins {
+        int pl, ph, ql, qh, q0;
+        __device__ __forceinline__ int operator()(int e) const {
+            const int j = e >> 1;
+            return (e & 1) ? (j == 0 ? q0 : (j >= RC / 2 ? qh : ql) - 2 * LANES * j) : (j >= RC / 2 ? ph : pl) + 2 * LANES * j;
+        }
+    };
     extern __shared__ __align__(16) float2 sm[];
     __shared__ unsigned s_tmem_base;
     __shared__ float2 s_ws[ROWS];                  // synthesis window pairs [row][lane] (commit only)
@@ -115,7 +80,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) rtisi_fast_kernel(const RArgs a
     if (warp == 0) tmem_alloc(&s_tmem_base, TMEM_COLS);
     for (int i = tid; i < ROWS; i += WARPS * 32) {
         const int row = i >> 5, ll = i & 31;
-        s_ws[i] = f2(a.ws[64 * row + 2 * ll], a.ws[64 * row + 2 * ll + 1]);
+        s_ws[i] = f2(a.ws[2 * LANES * row + 2 * ll], a.ws[2 * LANES * row + 2 * ll + 1]);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -123,39 +88,38 @@ __global__ void __launch_bounds__(WARPS * 32, 1) rtisi_fast_kernel(const RArgs a
     const unsigned tlane = s_tmem_base + ((unsigned)(32 * (warp & 3)) << 16);
     if (warp < 4) {
         float t[32];
+        auto window_pairs = [&](const float* w, float scale, unsigned col) {
 #pragma unroll
-        for (int i = 0; i < V; ++i) { t[2 * i] = 0.5f * a.wa[64 * i + 2 * l]; t[2 * i + 1] = 0.5f * a.wa[64 * i + 2 * l + 1]; }
-        tmem_st32(tlane + TC_WA, t);
-#pragma unroll
-        for (int i = 0; i < V; ++i) { t[2 * i] = a.ws[64 * i + 2 * l] * a.coef; t[2 * i + 1] = a.ws[64 * i + 2 * l + 1] * a.coef; }
-        tmem_st32(tlane + TC_WSC, t);
+            for (int i = 0; i < V; ++i) { t[2 * i] = scale * w[2 * LANES * i + 2 * l]; t[2 * i + 1] = scale * w[2 * LANES * i + 2 * l + 1]; }
+            tmem_stw<2 * V>(tlane + col, t);
+        };
+        window_pairs(a.wa, 0.5f, TC_WA);
+        window_pairs(a.ws, a.coef, TC_WSC);
 #pragma unroll
         for (int i = 0; i < V; ++i) {
-            const float2 w = a.tw[((l + 32 * (i >> 3)) * (i & 7)) & (M - 1)];
+            const float2 w = a.tw[((l + LANES * (i / C::R1)) * (i % C::R1)) & (M - 1)];
             t[2 * i] = w.x; t[2 * i + 1] = w.y;
         }
-        tmem_st32(tlane + TC_TW1, t);
+        tmem_stw<2 * V>(tlane + TC_TW1, t);
+        static_assert(C::R2 == 8, "pass-2 twiddles: 8 per lane");
 #pragma unroll
         for (int kb = 0; kb < 8; ++kb) {
-            const float2 w = a.tw[(8 * (l & 7) * kb) & (M - 1)];
+            const float2 w = a.tw[(C::R1 * (l & (RC - 1)) * kb) & (M - 1)];
             t[2 * kb] = w.x; t[2 * kb + 1] = w.y;
         }
+        tmem_st16(tlane + TC_TW2, t);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int k = slot_bin_rt<LANES>(l, j);
+        for (int j = 0; j < RC; ++j) {
+            const int k = slot_bin_rt<LANES, VV>(l, j);
             float2 w;
             if (k <= M / 2) w = a.twr[k];
             else { w = a.twr[M - k]; w.x = -w.x; }
-            t[16 + 2 * j] = w.x; t[16 + 2 * j + 1] = w.y;
+            t[2 * j] = w.x; t[2 * j + 1] = w.y;
         }
-        tmem_st32(tlane + TC_TW2, t);              // TW2 and TWR are adjacent
+        tmem_stw<2 * RC>(tlane + TC_TWR, t);
         if (a.asymmetric) {
-#pragma unroll
-            for (int i = 0; i < V; ++i) { t[2 * i] = 0.5f * a.asym1[64 * i + 2 * l]; t[2 * i + 1] = 0.5f * a.asym1[64 * i + 2 * l + 1]; }
-            tmem_st32(tlane + TC_AS1, t);
-#pragma unroll
-            for (int i = 0; i < V; ++i) { t[2 * i] = 0.5f * a.asym2[64 * i + 2 * l]; t[2 * i + 1] = 0.5f * a.asym2[64 * i + 2 * l + 1]; }
-            tmem_st32(tlane + TC_AS2, t);
+            window_pairs(a.asym1, 0.5f, TC_AS1);
+            window_pairs(a.asym2, 0.5f, TC_AS2);
         }
         tmem_wait_st();
     }
@@ -173,7 +137,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) rtisi_fast_kernel(const RArgs a
         float2* e1 = carry + ROWS + p * 2 * M;
         float2* e2 = e1 + M;
         const int bar_id = 1 + sig, bar_threads = 32 * NA;
-        const Bins bin{l, l == 0 ? -7 * LANES : l, M - l, M - l + (l == 0 ? 7 * LANES : 0), l == 0 ? M / 2 : M - l};
+        const int hi_adj = l == 0 ? -(RC - 1) * LANES : 0;
+        const Bins bin{l, l + hi_adj, M - l, M - l - hi_adj, l == 0 ? M / 2 : M - l};
         float* xo = a.x_out + (long long)b * a.L;
 
         // ---- everything zero (methods.py:353-358)
@@ -184,8 +149,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) rtisi_fast_kernel(const RArgs a
             float z[32];
 #pragma unroll
             for (int i = 0; i < 32; ++i) z[i] = 0.f;
-            tmem_st32(twarp + TC_PRE, z);
-            tmem_st16(twarp + TC_MAG, z);              // frames that precede the spectrogram have zero magnitude (:339)
+            tmem_stw<2 * V>(twarp + TC_PRE, z);
+            tmem_stw<V>(twarp + TC_MAG, z);            // frames that precede the spectrogram have zero magnitude (:339)
         }
         float2 pre_nyq = f2(0.f, 0.f);
         for (int i = p * 32 + l; i < KEEP * ROWS + ROWS; i += 32 * NA) Uk[i] = f2(0.f, 0.f);    // kept frames and carry
@@ -200,51 +165,51 @@ __global__ void __launch_bounds__(WARPS * 32, 1) rtisi_fast_kernel(const RArgs a
             const bool newest = la == a.LA;
             if (newest) {
                 // a new frame is born in this warp: fetch its magnitude row (zero outside the spectrogram, :339)
-                float mg[16];
+                float mg[V];
                 const bool inside = t_frame >= 0 && t_frame < a.T;
                 const float* mrow = a.mag + ((long long)b * a.T + (inside ? t_frame : 0)) * M;
 #pragma unroll
-                for (int e = 0; e < 16; ++e) mg[e] = inside ? __ldg(mrow + bin(e)) : 0.f;
+                for (int e = 0; e < V; ++e) mg[e] = inside ? __ldg(mrow + bin(e)) : 0.f;
                 mag_nyq = (inside && l == 0) ? __ldg(a.mag_nyq + (long long)b * a.T + t_frame) : 0.f;
-                tmem_st16(twarp + TC_MAG, mg);
+                tmem_stw<V>(twarp + TC_MAG, mg);
                 if (i == 0) {
                     // zero-phase start: the newest frame = irfft(first magnitude frame + 0j) (:353-358)
-                    float2 A[8], Bv[8], twr[8];
-                    tmem_ld16(tlane + TC_TWR, reinterpret_cast<float*>(twr));
+                    float2 A[RC], Bv[RC], twr[RC];
+                    tmem_ldw<2 * RC>(tlane + TC_TWR, reinterpret_cast<float*>(twr));
                     struct IO0 {
                         const float* mg; float mn;
                         __device__ __forceinline__ float2 s0(int e) const { return f2(e < 0 ? mn : mg[e], 0.f); }
                     } io0{mg, mag_nyq};
-                    spectrum_pairs(l, A, Bv, twr, io0);
-                    inv_pass3<LANES>(l, A, Bv, e2);
+                    spectrum_pairs<VV>(l, A, Bv, twr, io0);
+                    inv_pass3<LANES, VV>(l, A, Bv, e2);
                     __syncwarp();
                     float2 tw2[8];
                     tmem_ld16(tlane + TC_TW2, reinterpret_cast<float*>(tw2));
-                    inv_pass2<LANES>(l, e2, tw2, e1);
+                    inv_pass2<LANES, VV>(l, e2, tw2, e1);
                     __syncwarp();
                     float2 tw1[V];
-                    tmem_ld32(tlane + TC_TW1, reinterpret_cast<float*>(tw1));
-                    inv_pass1<LANES>(l, e1, tw1, v);
+                    tmem_ldw<2 * V>(tlane + TC_TW1, reinterpret_cast<float*>(tw1));
+                    inv_pass1<LANES, VV>(l, e1, tw1, v);
                     __syncwarp();
                 }
             }
             // ---- part of this frame's y that comes from the kept frames: constant over the inner iterations.
             // kept frame f (0 = oldest) starts (KEEP - f) hops before active frame 0: row i' of this frame is row
-            // i' + 4 (la + KEEP - f) of the kept frame.
+            // i' + HP (la + KEEP - f) of the kept frame (HP = rows per hop).
             {
                 float2 yk[V];
 #pragma unroll
                 for (int r = 0; r < V; ++r) yk[r] = f2(0.f, 0.f);
 #pragma unroll
                 for (int f = 0; f < KEEP; ++f) {
-                    const int shift = 4 * (la + KEEP - f);           // warp-uniform
+                    const int shift = HP * (la + KEEP - f);          // warp-uniform
                     const float2* src = Uk + ((kslot + f) % KEEP) * ROWS + l;
 #pragma unroll
-                    for (int r = 0; r < V - 4; ++r)                 // a kept frame is at least one hop older
+                    for (int r = 0; r < V - HP; ++r)                // a kept frame is at least one hop older
                         if (r + shift < V) yk[r] = yk[r] + src[(r + shift) * LANES];
                 }
                 tmem_wait_st();
-                tmem_st32(twarp + TC_YK, reinterpret_cast<const float*>(yk));
+                tmem_stw<2 * V>(twarp + TC_YK, reinterpret_cast<const float*>(yk));
                 tmem_wait_st();
             }
 
@@ -254,7 +219,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) rtisi_fast_kernel(const RArgs a
                 float2 y[V];
                 {
                     float2 w[V];
-                    tmem_ld32(tlane + TC_WSC, reinterpret_cast<float*>(w));
+                    tmem_ldw<2 * V>(tlane + TC_WSC, reinterpret_cast<float*>(w));
 #pragma unroll
                     for (int r = 0; r < V; ++r) {
                         y[r] = pmul(v[r], w[r]);
@@ -262,11 +227,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) rtisi_fast_kernel(const RArgs a
                     }
                 }
                 sig_sync(bar_id, bar_threads);
-                // ---- this frame of the overlap-add: own u + kept part + the other active frames, shifted by 4
-                // rows per frame of distance (row r of this frame = row r - 4 d of the frame d positions later)
+                // ---- this frame of the overlap-add: own u + kept part + the other active frames, shifted by HP
+                // rows per frame of distance (row r of this frame = row r - HP d of the frame d positions later)
                 {
                     float2 yk[V];
-                    tmem_ld32(twarp + TC_YK, reinterpret_cast<float*>(yk));
+                    tmem_ldw<2 * V>(twarp + TC_YK, reinterpret_cast<float*>(yk));
 #pragma unroll
                     for (int r = 0; r < V; ++r) y[r] = y[r] + yk[r];
                 }
@@ -279,38 +244,38 @@ __global__ void __launch_bounds__(WARPS * 32, 1) rtisi_fast_kernel(const RArgs a
                     const float2* src = Ub + po * ROWS + l;
 #pragma unroll
                     for (int r = 0; r < V; ++r)
-                        if (r - 4 * d >= 0 && r - 4 * d < V) y[r] = y[r] + src[(r - 4 * d) * LANES];
+                        if (r - HP * d >= 0 && r - HP * d < V) y[r] = y[r] + src[(r - HP * d) * LANES];
                 }
                 // ---- analysis window (:371-385)
                 {
                     float2 w[V];
                     const unsigned wcol = (a.asymmetric && newest) ? (j ? TC_AS2 : TC_AS1) : TC_WA;
-                    tmem_ld32(tlane + wcol, reinterpret_cast<float*>(w));
+                    tmem_ldw<2 * V>(tlane + wcol, reinterpret_cast<float*>(w));
 #pragma unroll
                     for (int r = 0; r < V; ++r) y[r] = pmul(y[r], w[r]);
                 }
                 {
                     float2 tw1[V];
-                    tmem_ld32(tlane + TC_TW1, reinterpret_cast<float*>(tw1));
-                    fwd_pass1<LANES>(l, y, tw1, e1);
+                    tmem_ldw<2 * V>(tlane + TC_TW1, reinterpret_cast<float*>(tw1));
+                    fwd_pass1<LANES, VV>(l, y, tw1, e1);
                 }
                 __syncwarp();
                 {
                     float2 tw2[8];
                     tmem_ld16(tlane + TC_TW2, reinterpret_cast<float*>(tw2));
-                    fwd_pass2<LANES>(l, e1, tw2, e2);
+                    fwd_pass2<LANES, VV>(l, e1, tw2, e2);
                 }
                 __syncwarp();
-                float2 A[8], Bv[8];
-                fwd_pass3<LANES>(l, e2, A, Bv);
+                float2 A[RC], Bv[RC];
+                fwd_pass3<LANES, VV>(l, e2, A, Bv);
                 // ---- momentum (:387-392), pre <- S, projection (:394-396)
                 {
                     const bool mom = j > 0 || (i > 0 && !newest);
                     float2 pre[V];
-                    float mg[16];
+                    float mg[V];
                     tmem_wait_st();
-                    tmem_ld32(twarp + TC_PRE, reinterpret_cast<float*>(pre));
-                    tmem_ld16(twarp + TC_MAG, mg);
+                    tmem_ldw<2 * V>(twarp + TC_PRE, reinterpret_cast<float*>(pre));
+                    tmem_ldw<V>(twarp + TC_MAG, mg);
                     struct IO {
                         float2* pre; const float* mg; float2 pn; float mn;
                         __device__ __forceinline__ float2 s0(int e) const { return e < 0 ? pn : pre[e]; }
@@ -318,26 +283,26 @@ __global__ void __launch_bounds__(WARPS * 32, 1) rtisi_fast_kernel(const RArgs a
                         __device__ __forceinline__ float mag(int e) const { return e < 0 ? mn : mg[e]; }
                         __device__ __forceinline__ void put(int e, float2 q, float2) { if (e < 0) pn = q; else pre[e] = q; }
                     } io{pre, mg, pre_nyq, mag_nyq};
-                    float2 twr[8];
-                    tmem_ld16(tlane + TC_TWR, reinterpret_cast<float*>(twr));
+                    float2 twr[RC];
+                    tmem_ldw<2 * RC>(tlane + TC_TWR, reinterpret_cast<float*>(twr));
                     float ds = 0.f, es = 0.f;
-                    pointwise<OP_GL, false>(l, A, Bv, twr, io, mom ? a.lr : 0.f, 0.f, ds, es);
+                    pointwise<OP_GL, false, VV>(l, A, Bv, twr, io, mom ? a.lr : 0.f, 0.f, ds, es);
                     pre_nyq = io.pn;
-                    tmem_st32(twarp + TC_PRE, reinterpret_cast<const float*>(pre));
+                    tmem_stw<2 * V>(twarp + TC_PRE, reinterpret_cast<const float*>(pre));
                 }
                 __syncwarp();
-                inv_pass3<LANES>(l, A, Bv, e2);
+                inv_pass3<LANES, VV>(l, A, Bv, e2);
                 __syncwarp();
                 {
                     float2 tw2[8];
                     tmem_ld16(tlane + TC_TW2, reinterpret_cast<float*>(tw2));
-                    inv_pass2<LANES>(l, e2, tw2, e1);
+                    inv_pass2<LANES, VV>(l, e2, tw2, e1);
                 }
                 __syncwarp();
                 {
                     float2 tw1[V];
-                    tmem_ld32(tlane + TC_TW1, reinterpret_cast<float*>(tw1));
-                    inv_pass1<LANES>(l, e1, tw1, v);
+                    tmem_ldw<2 * V>(tlane + TC_TW1, reinterpret_cast<float*>(tw1));
+                    inv_pass1<LANES, VV>(l, e1, tw1, v);
                 }
                 __syncwarp();
             }
@@ -359,21 +324,21 @@ __global__ void __launch_bounds__(WARPS * 32, 1) rtisi_fast_kernel(const RArgs a
                             const long long m0 = (long long)(t + k) * HOP - a.P;
                             if (m0 >= 0 && m0 + HOP <= a.L) {
 #pragma unroll
-                                for (int r = 0; r < 4; ++r) {
-                                    const float2 ie = __ldg(reinterpret_cast<const float2*>(a.inv_env + m0 + 64 * r + 2 * l));
-                                    const float2 val = c[4 * k + r];
-                                    *reinterpret_cast<float2*>(xo + m0 + 64 * r + 2 * l) = pmul(val, ie);
+                                for (int r = 0; r < HP; ++r) {
+                                    const float2 ie = __ldg(reinterpret_cast<const float2*>(a.inv_env + m0 + 2 * LANES * r + 2 * l));
+                                    const float2 val = c[HP * k + r];
+                                    *reinterpret_cast<float2*>(xo + m0 + 2 * LANES * r + 2 * l) = pmul(val, ie);
                                 }
                             }
                         }
                     }
 #pragma unroll
-                    for (int r = 0; r < V; ++r) carry[r * LANES + l] = r + 4 < V ? c[r + 4] : f2(0.f, 0.f);
+                    for (int r = 0; r < V; ++r) carry[r * LANES + l] = r + HP < V ? c[r + HP] : f2(0.f, 0.f);
                 }
                 // the committed frame replaces the oldest kept frame (stored as u = frame * w * c)
                 {
                     float2 w[V];
-                    tmem_ld32(tlane + TC_WSC, reinterpret_cast<float*>(w));
+                    tmem_ldw<2 * V>(tlane + TC_WSC, reinterpret_cast<float*>(w));
                     float2* dst = Uk + kslot * ROWS + l;
 #pragma unroll
                     for (int r = 0; r < V; ++r) dst[r * LANES] = pmul(v[r], w[r]);
@@ -392,13 +357,23 @@ __global__ void __launch_bounds__(WARPS * 32, 1) rtisi_fast_kernel(const RArgs a
     if (warp == 0) tmem_dealloc(s_tmem_base, TMEM_COLS);
 }
 
+template <int VV, int SIGS>
+static int launch(const RArgs& a, cudaStream_t st) {
+    const size_t smem = (size_t)SIGS * sig_f2(Cfg<LANES, VV>::M) * sizeof(float2);
+    cudaError_t e = cudaFuncSetAttribute(rtisi_fast_kernel<VV, SIGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    rtisi_fast_kernel<VV, SIGS><<<(a.B + SIGS - 1) / SIGS, SIGS * NAMAX * 32, smem, st>>>(a);
+    return (int)cudaGetLastError();
+}
+
 }  // namespace rfast
 
 // Returns SPECINV_ERR_UNSUPPORTED when the shape is not the one this kernel is specialised for.
 int rtisi_fast(const specinv_desc* d, const Dims& dm, const void* plan, const void* mag_main, const void* mag_nyq,
                void* x_out, const void* asym1, const void* asym2, int look_ahead, int asymmetric, int max_iter,
                double alpha, double synth_coeff, cudaStream_t st) {
-    if (d->dtype != SPECINV_F32 || !d->onesided || d->n_fft != 1024 || d->hop != 256) return SPECINV_ERR_UNSUPPORTED;
+    if (d->dtype != SPECINV_F32 || !d->onesided || d->hop * 4 != d->n_fft || (d->n_fft != 1024 && d->n_fft != 512))
+        return SPECINV_ERR_UNSUPPORTED;
     const int LA = look_ahead < 0 ? dm.K : look_ahead;
     if (LA > 3 || dm.K != rfast::KEEP) return SPECINV_ERR_UNSUPPORTED;
     rfast::RArgs a{};
@@ -410,11 +385,13 @@ int rtisi_fast(const specinv_desc* d, const Dims& dm, const void* plan, const vo
     a.mag = (const float*)mag_main; a.mag_nyq = (const float*)mag_nyq; a.x_out = (float*)x_out;
     a.coef = (float)synth_coeff; a.lr = (float)(alpha / (1.0 + alpha));
     a.B = dm.B; a.T = dm.T; a.P = dm.P; a.LA = LA; a.max_iter = max_iter; a.asymmetric = asymmetric; a.L = dm.L;
-    const size_t smem = (size_t)rfast::SIGS * rfast::SIG_F2 * sizeof(float2);
-    cudaError_t e = cudaFuncSetAttribute(rfast::rtisi_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    rfast::rtisi_fast_kernel<<<(dm.B + rfast::SIGS - 1) / rfast::SIGS, rfast::WARPS * 32, smem, st>>>(a);
-    return (int)cudaGetLastError();
+    // Signals per CTA: as few as still fit the batch into one wave of CTAs (the kernel is latency-bound, so a signal
+    // runs fastest when its warps share an SM with as few others as possible).
+    int sms = 0, dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+        return SPECINV_ERR_NO_DEVICE;
+    if (d->n_fft == 1024) return dm.B <= sms ? rfast::launch<16, 1>(a, st) : rfast::launch<16, 2>(a, st);
+    return dm.B <= sms ? rfast::launch<8, 1>(a, st) : dm.B <= 2 * sms ? rfast::launch<8, 2>(a, st) : rfast::launch<8, 4>(a, st);
 }
 
 }  // namespace specinv

@@ -376,28 +376,39 @@ RTISI_FAST_CASES = [
     dict(B=5, T=8, look_ahead=0, asym=False, max_iter=2, alpha=0.0, center=True, normalized=False, window="hann"),
     dict(B=2, T=8, look_ahead=2, asym=False, max_iter=2, alpha=0.99, center=True, normalized=False, window=None, win_length=700),
     dict(B=3, T=14, look_ahead=3, asym=False, max_iter=3, alpha=0.99, center=True, normalized=False, window="hann"),
+    # n_fft = 512 / hop = 128: 8 values per lane, four signals per CTA
+    dict(B=5, T=9, look_ahead=3, asym=False, max_iter=2, alpha=0.99, center=True, normalized=False, window="hann", n_fft=512),
+    dict(B=4, T=7, look_ahead=-1, asym=True, max_iter=2, alpha=0.99, center=True, normalized=False, window="hann", n_fft=512),
+    dict(B=1, T=8, look_ahead=1, asym=True, max_iter=3, alpha=0.5, center=False, normalized=True, window="hamming", n_fft=512),
+    dict(B=9, T=8, look_ahead=0, asym=False, max_iter=2, alpha=0.0, center=True, normalized=False, window="hann", n_fft=512),
+    dict(B=2, T=12, look_ahead=2, asym=False, max_iter=2, alpha=0.99, center=True, normalized=False, window=None, win_length=300, n_fft=512),
+    # batches beyond one signal per SM (148): two / four signals share a CTA
+    dict(B=151, T=6, look_ahead=3, asym=False, max_iter=2, alpha=0.99, center=True, normalized=False, window="hann"),
+    dict(B=151, T=6, look_ahead=3, asym=True, max_iter=2, alpha=0.99, center=True, normalized=False, window="hann", n_fft=512),
+    dict(B=299, T=6, look_ahead=2, asym=False, max_iter=2, alpha=0.99, center=True, normalized=False, window="hann", n_fft=512),
 ]
 
 
-@pytest.mark.parametrize("rc", RTISI_FAST_CASES, ids=lambda c: f"B{c['B']}_T{c['T']}_la{c['look_ahead']}_asym{int(c['asym'])}_it{c['max_iter']}")
+@pytest.mark.parametrize("rc", RTISI_FAST_CASES, ids=lambda c: f"n{c.get('n_fft', 1024)}_B{c['B']}_T{c['T']}_la{c['look_ahead']}_asym{int(c['asym'])}_it{c['max_iter']}")
 def test_rtisi_fast_kernel_1024_against_oracle(rc, monkeypatch):
-    """The register-FFT RTISI-LA kernel (n_fft = 1024, hop = 256) against the oracle in float64.  fp32 trajectories of
+    """The register-FFT RTISI-LA kernel (n_fft = 1024 / hop = 256 and 512 / 128) against the oracle in float64.  fp32 trajectories of
     RTISI-LA drift apart quickly (the projection divides by |S|; SURVEY.md section 7: fp32 vs fp64 of the REFERENCE
     decorrelate over a full run), so the yardstick is the drift of two other fp32 implementations from the same fp64
     run -- the oracle in float32 and the generic shared-memory kernel: an indexing mistake gives O(1) errors."""
     import spectrogram_inversion_b200 as S
     rs = np.random.RandomState(rc["T"])
-    n_fft, hop = 1024, 256
+    n_fft = rc.get("n_fft", 1024)
+    hop = n_fft // 4
     kw = dict(hop_length=hop, center=rc["center"], normalized=rc["normalized"])
     wl = rc.get("win_length", n_fft)
     if rc["window"] is not None:
         kw["window"] = cases.window_of(rc["window"], wl, np.float32)
     if wl != n_fft:
         kw["win_length"] = wl
-    oa = O.args_helper(513, np.float32, **kw)
+    oa = O.args_helper(n_fft // 2 + 1, np.float32, **kw)
     n_samples = (rc["T"] - 1) * hop + (0 if rc["center"] else n_fft)
     mag = np.abs(O.stft(rs.randn(rc["B"], n_samples).astype(np.float32), oa)).astype(np.float32)
-    assert mag.shape == (rc["B"], 513, rc["T"])
+    assert mag.shape == (rc["B"], n_fft // 2 + 1, rc["T"])
     run = dict(look_ahead=rc["look_ahead"], asymmetric_window=rc["asym"], max_iter=rc["max_iter"], alpha=rc["alpha"])
     y32 = O.RTISI_LA(mag, **run, **kw)
     kw64 = {k: (v.astype(np.float64) if isinstance(v, np.ndarray) else v) for k, v in kw.items()}
