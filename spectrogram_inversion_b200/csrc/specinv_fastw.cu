@@ -49,7 +49,10 @@ struct WArgs {
 constexpr int TC_WA = 0, TC_WS = 32, TC_TW1 = 64, TC_TW2 = 96, TC_TWR = 128, TC_IE = 144, TC_WARP = 152;
 constexpr int TC_PER_WARP = 48;     // ring: 3 blocks x 8 words, carry: 24 words
 constexpr int TMEM_COLS = 512;
-constexpr int WARPS = 12;           // 12 warps x 168 registers (no spills); 12 x 15 KB of staging fills the shared memory
+// 12 warps x 168 registers (no spills), 12 x 15 KB of staging fills the shared memory; the 8-values-per-lane variant
+// needs <= 128 registers and half the staging: 16 warps (measured at B = 512, T = 1251: GL 0.722 -> 0.678 ms; ADMM,
+// whose 36 B/bin are already HBM-bound, is faster with 12: 1.07 vs 1.12 ms)
+constexpr int warps_of(int vv, int op) { return vv == 8 && op != OP_ADMM ? 16 : 12; }
 // float2 of shared memory per frame group: E1, E2 (M float2 each), staged input block (HOP floats = M/4 float2),
 // magnitude row (M floats = M/2 float2), q / X row (M float2)
 constexpr int group_f2(int m) { return 2 * m + m / 4 + m / 2 + m; }
@@ -135,7 +138,7 @@ __device__ __forceinline__ void stage_rows(const WArgs& a, long long row, int l,
 }
 
 template <int OP, bool SUMS, int LANES, int VV>
-__global__ void __launch_bounds__(WARPS * 32, 1) warp_iter_kernel(const WArgs a) {
+__global__ void __launch_bounds__(warps_of(VV, OP) * 32, 1) warp_iter_kernel(const WArgs a) {
     using C = Cfg<LANES, VV>;
     constexpr int M = C::M;
     constexpr int V = VV;                         // complex values per lane (shadows wfast::V)
@@ -143,6 +146,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) warp_iter_kernel(const WArgs a)
     constexpr int RC = C::RC;                     // pair slots per lane
     constexpr int GROUP_F2 = group_f2(M);
     constexpr int G = LANES / 32;                 // warps per frame group
+    constexpr int WARPS = warps_of(VV, OP);
     constexpr int GROUPS = WARPS / G;
     static_assert(TC_WARP + ((WARPS + 3) / 4) * TC_PER_WARP <= TMEM_COLS, "TMEM columns");
     extern __shared__ __align__(16) float2 sm[];
@@ -459,6 +463,7 @@ static int launch(const WArgs& a0, cudaStream_t st) {
     if ((((uintptr_t)a.x_in | (uintptr_t)a.s0_in | (uintptr_t)a.mag) & 15) != 0) return SPECINV_ERR_UNSUPPORTED;   // (s0_in is NULL for OP_GLP)
     if (OP == OP_ISTFT && a.sums) return SPECINV_ERR_INVALID;
     a.frames_total = (long long)a.B * a.T;
+    constexpr int WARPS = warps_of(VV, OP);
     constexpr int GROUPS = WARPS / (LANES / 32);
     const int slots = g_sms * GROUPS;
     // One frame range per group slot.  A range re-computes 3 halo frames, which costs ~1.5 % when the ranges are
