@@ -594,6 +594,8 @@ def test_specialised_kernels_match_the_reference_itself(case):
     close(y, FASTREF[f"{name}/admm_k1"], 1e-5, "ADMM 1 iteration vs reference")
     y = S.griffin_lim(mag, max_iter=2, tol=0, alpha=0.99, verbose=False, **kw)
     close(y, FASTREF[f"{name}/gl_mag_k2"], 2e-3, "griffin_lim(mag) vs reference")
+    y = S.griffin_lim(C, max_iter=2, tol=0, alpha=0.0, verbose=False, eva_iter=1, **kw)
+    close(y, FASTREF[f"{name}/gl_plain_k2"], 5e-5, "plain GL (alpha = 0) 2 iterations vs reference")
     if f"{name}/rtisi_la3_k1" in FASTREF:
         y = S.RTISI_LA(mag, look_ahead=3, max_iter=1, alpha=0.99, verbose=0, **kw)
         close(y, FASTREF[f"{name}/rtisi_la3_k1"], 5e-3, "RTISI-LA vs reference")
