@@ -95,13 +95,21 @@ __device__ __forceinline__ void tmem_st4(unsigned taddr, const float* r) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
                  ::"r"(taddr), "f"(r[0]), "f"(r[1]), "f"(r[2]), "f"(r[3]) : "memory");
 }
-// W words per lane (4, 8, 16 or 32)
+__device__ __forceinline__ void tmem_ld2(unsigned taddr, float* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];\n\t"
+                 "tcgen05.wait::ld.sync.aligned;"
+                 : "=f"(r[0]), "=f"(r[1]) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_st2(unsigned taddr, const float* r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr), "f"(r[0]), "f"(r[1]) : "memory");
+}
+// W words per lane (2, 4, 8, 16 or 32)
 template <int W> __device__ __forceinline__ void tmem_ldw(unsigned taddr, float* r) {
-    if constexpr (W == 4) tmem_ld4(taddr, r); else if constexpr (W == 8) tmem_ld8(taddr, r);
+    if constexpr (W == 2) tmem_ld2(taddr, r); else if constexpr (W == 4) tmem_ld4(taddr, r); else if constexpr (W == 8) tmem_ld8(taddr, r);
     else if constexpr (W == 16) tmem_ld16(taddr, r); else tmem_ld32(taddr, r);
 }
 template <int W> __device__ __forceinline__ void tmem_stw(unsigned taddr, const float* r) {
-    if constexpr (W == 4) tmem_st4(taddr, r); else if constexpr (W == 8) tmem_st8(taddr, r);
+    if constexpr (W == 2) tmem_st2(taddr, r); else if constexpr (W == 4) tmem_st4(taddr, r); else if constexpr (W == 8) tmem_st8(taddr, r);
     else if constexpr (W == 16) tmem_st16(taddr, r); else tmem_st32(taddr, r);
 }
 

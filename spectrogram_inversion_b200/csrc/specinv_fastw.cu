@@ -1,506 +1,24 @@
-// Fused iteration kernels for hop = n_fft/4, onesided, fp32 with 16 complex values per lane (gl_warp_core.cuh):
-//   n_fft =  512 / hop = 128  : one warp per frame, 8 values per lane (LANES = 32, VV = 8)
-//   n_fft = 1024 / hop = 256  : one warp per frame    (LANES = 32)   -- the headline shape (cfg2)
-//   n_fft = 2048 / hop = 512  : two warps per frame   (LANES = 64)   -- cfg1, cfg4
-//   n_fft = 4096 / hop = 1024 : four warps per frame  (LANES = 128)  -- cfg5
-//
-// One launch = one whole Griffin-Lim (or ADMM) iteration.  Every group of LANES/32 warps walks through a
-// contiguous range of the B*T frames (crossing signal boundaries if need be) and for each frame does,
-// entirely on chip:
-//   window -> real FFT (M-point complex FFT in three passes, gl_warp_core.cuh) -> momentum / ADMM update and
-//   magnitude projection on the FFT outputs in registers -> inverse FFT -> windowed overlap-add.
-//   * 16 complex values per lane: <= 168 registers, 12 free-running warps per SM (no CTA-wide barriers; the
-//     warps of a frame group meet at a named barrier per exchange), and the unrolled frame body fits the
-//     instruction cache;
-//   * the lane-constant tables (windows, twiddles), the lane-private input ring and the overlap-add carry
-//     live in TENSOR MEMORY and move with tcgen05.ld / tcgen05.st (one instruction per 8..32 registers, no
-//     shared-memory bandwidth); shared memory only carries the four FFT exchanges (swizzled, conflict free);
-//   * the q / X and magnitude rows of the NEXT frame and the next hop of input samples are fetched by the TMA
-//     (cp.async.bulk, one elected lane, mbarrier completion) into per-group staging rows one frame ahead, so
-//     the compute never waits on DRAM; the new state is written straight from registers, 256 contiguous
-//     bytes per warp instruction.
-// A range re-computes the 3 frames before it as a halo (state not written, output not stored), so ranges are
-// independent: no atomics, deterministic.  State arrays are ping-ponged (q_in != q_out).
-#include <cstdlib>
-
-#include "specinv_common.cuh"
-#include "gl_warp_core.cuh"
-#include "sm100_ptx.cuh"
+// Entry points of the specialised fused kernels (specinv_fastw_kernel.cuh) and the hop = n_fft/4 instances; the
+// hop = n_fft/2 and n_fft/8 instances live in specinv_fastw_ov2.cu / specinv_fastw_ov8.cu.
+#include "specinv_fastw_kernel.cuh"
 
 namespace specinv {
 namespace wfast {
+SPECINV_FASTW_DEFINE_LAUNCH(4)
 
-struct WArgs {
-    const float* x_in; float* x_out;
-    const float2* s0_in;  const float2* s0_in_nyq;  float2* s0_out; float2* s0_out_nyq;
-    const float2* s1_in;  const float2* s1_in_nyq;  float2* s1_out; float2* s1_out_nyq;
-    const float* mag;     const float* mag_nyq;
-    const float2* tw;     const float2* twr;        // plan tables: W_M^j (M entries), W_N^k (k <= M/2)
-    const float* wa; const float* ws; const float* inv_env;
-    double* sums;
-    float coef, coef2;
-    int B, T, P, pad_mode;
-    long long L;
-    long long frames_total;     // B * T
-    int ranges;                 // number of warp groups that get a frame range
-};
-
-// TMEM columns (per lane): constant tables shared by the warps of one sub-partition, then per-warp state
-constexpr int TC_WA = 0, TC_WS = 32, TC_TW1 = 64, TC_TW2 = 96, TC_TWR = 128, TC_IE = 144, TC_WARP = 152;
-constexpr int TC_PER_WARP = 48;     // ring: 3 blocks x 8 words, carry: 24 words
-constexpr int TMEM_COLS = 512;
-// 12 warps x 168 registers (no spills), 12 x 15 KB of staging fills the shared memory; the 8-values-per-lane variant
-// needs <= 128 registers and half the staging: 16 warps (measured at B = 512, T = 1251: GL 0.722 -> 0.678 ms; ADMM,
-// whose 36 B/bin are already HBM-bound, is faster with 12: 1.07 vs 1.12 ms)
-constexpr int warps_of(int vv, int op) { return vv == 8 && op != OP_ADMM ? 16 : 12; }
-// float2 of shared memory per frame group: E1, E2 (M float2 each), staged input block (HOP floats = M/4 float2),
-// magnitude row (M floats = M/2 float2), q / X row (M float2)
-constexpr int group_f2(int m) { return 2 * m + m / 4 + m / 2 + m; }
-
-// Synchronise the warps that share a frame (named barrier per group) or just the warp.
-template <int LANES>
-__device__ __forceinline__ void group_sync(int bar_id) {
-    if constexpr (LANES == 32) __syncwarp();
-    else asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(LANES) : "memory");
-}
-
-// Fetch block u (padded samples [HOP u, HOP u + HOP)) of signal x: lane l gets the pairs at 2 LANES j + 2 l.
-template <int LANES, int VV>
-__device__ __forceinline__ void fetch_block_regs(const WArgs& a, const float* __restrict__ x, int u, int l, float2* nb) {
-    constexpr int HOP = Cfg<LANES, VV>::HOP, HP = VV / 4;
-    const long long base = (long long)u * HOP - a.P;
-    if (base >= 0 && base + HOP <= a.L) {
-#pragma unroll
-        for (int j = 0; j < HP; ++j) nb[j] = __ldg(reinterpret_cast<const float2*>(x + base + 2 * LANES * j + 2 * l));
-    } else {
-#pragma unroll
-        for (int j = 0; j < HP; ++j) {
-            const long long pp = (long long)u * HOP + 2 * LANES * j + 2 * l;
-            const long long i0 = pad_index(pp, a.P, a.L, a.pad_mode), i1 = pad_index(pp + 1, a.P, a.L, a.pad_mode);
-            nb[j] = f2(i0 >= 0 ? x[i0] : 0.f, i1 >= 0 ? x[i1] : 0.f);
-        }
-    }
-}
-// Same into the staging buffer xs[LANES j + l] (= the block's bytes in memory order): interior blocks by one TMA
-// bulk copy issued by the group's first warp (returns true: the data arrives on `bar`), padded edge blocks
-// element by element.
-template <int LANES, int VV>
-__device__ __forceinline__ bool fetch_block_staged(const WArgs& a, const float* __restrict__ x, int u, int l, float2* xs,
-                                                   unsigned xs_s, unsigned bar) {
-    constexpr int HOP = Cfg<LANES, VV>::HOP, HP = VV / 4;
-    const long long base = (long long)u * HOP - a.P;
-    if (base >= 0 && base + HOP <= a.L) {
-        if (l < 32) { if (elect_one()) { mbar_expect_tx(bar, HOP * 4); bulk_g2s(xs_s, x + base, HOP * 4, bar); } }
-        return true;
-    }
-#pragma unroll
-    for (int j = 0; j < HP; ++j) {
-        const long long pp = (long long)u * HOP + 2 * LANES * j + 2 * l;
-        const long long i0 = pad_index(pp, a.P, a.L, a.pad_mode), i1 = pad_index(pp + 1, a.P, a.L, a.pad_mode);
-        xs[LANES * j + l] = f2(i0 >= 0 ? x[i0] : 0.f, i1 >= 0 ? x[i1] : 0.f);
-    }
-    return false;
-}
-template <int LANES, int VV>
-__device__ __forceinline__ bool block_valid(const WArgs& a, int u) {
-    const long long base = (long long)u * Cfg<LANES, VV>::HOP - a.P;
-    return base >= 0 && base + Cfg<LANES, VV>::HOP <= a.L;
-}
-template <int LANES, int VV>
-__device__ __forceinline__ void load_inv_env(const WArgs& a, int u, int l, float2* ie) {
-    const long long base = (long long)u * Cfg<LANES, VV>::HOP - a.P;
-#pragma unroll
-    for (int j = 0; j < VV / 4; ++j) {
-        // volatile + "memory": the compiler must not sink these loads down to their use
-        asm volatile("ld.global.nc.v2.f32 {%0, %1}, [%2];" : "=f"(ie[j].x), "=f"(ie[j].y)
-                     : "l"(a.inv_env + base + 2 * LANES * j + 2 * l) : "memory");
-    }
-}
-template <int LANES, int VV>
-__device__ __forceinline__ void store_block_ie(const WArgs& a, float* __restrict__ xo, int u, int l, const float2* blk,
-                                               const float2* ie) {
-    const long long base = (long long)u * Cfg<LANES, VV>::HOP - a.P;
-#pragma unroll
-    for (int j = 0; j < VV / 4; ++j)
-        *reinterpret_cast<float2*>(xo + base + 2 * LANES * j + 2 * l) = pmul(blk[j], ie[j]);
-}
-// Fetch the q / X row and the magnitude row of frame `row` into the staging rows (one elected lane, TMA).
-template <int OP, int LANES, int VV>
-__device__ __forceinline__ void stage_rows(const WArgs& a, long long row, int l, unsigned qstage_s, unsigned mstage_s, unsigned bar) {
-    constexpr int M = Cfg<LANES, VV>::M;
-    if (l < 32) {
-        if (elect_one()) {
-            mbar_expect_tx(bar, OP == OP_ISTFT ? M * 8 : OP == OP_GLP ? M * 4 : M * 8 + M * 4);
-            if constexpr (OP != OP_GLP) bulk_g2s(qstage_s, a.s0_in + row * M, M * 8, bar);
-            if constexpr (OP != OP_ISTFT) bulk_g2s(mstage_s, a.mag + row * M, M * 4, bar);
-        }
-    }
-}
-
-template <int OP, bool SUMS, int LANES, int VV>
-__global__ void __launch_bounds__(warps_of(VV, OP) * 32, 1) warp_iter_kernel(const WArgs a) {
-    using C = Cfg<LANES, VV>;
-    constexpr int M = C::M;
-    constexpr int V = VV;                         // complex values per lane (shadows wfast::V)
-    constexpr int HP = VV / 4;                    // sample pairs per hop and lane
-    constexpr int RC = C::RC;                     // pair slots per lane
-    constexpr int GROUP_F2 = group_f2(M);
-    constexpr int G = LANES / 32;                 // warps per frame group
-    constexpr int WARPS = warps_of(VV, OP);
-    constexpr int GROUPS = WARPS / G;
-    static_assert(TC_WARP + ((WARPS + 3) / 4) * TC_PER_WARP <= TMEM_COLS, "TMEM columns");
-    extern __shared__ __align__(16) float2 sm[];
-    __shared__ unsigned s_tmem_base;
-    __shared__ __align__(8) unsigned long long s_bar[GROUPS][3];   // per group: input block, state rows, ADMM U row
-    const int tid = threadIdx.x, warp = tid >> 5;
-    const int grp = warp / G;                     // frame group inside the CTA
-    const int l = tid - grp * LANES;              // lane inside the group, 0 .. LANES-1
-    const int bar_id = 1 + grp;
-    if (warp == 0) tmem_alloc(&s_tmem_base, TMEM_COLS);
-    const unsigned xbar = (unsigned)__cvta_generic_to_shared(&s_bar[grp][0]), sbar = xbar + 8, ubar = xbar + 16;
-    if (l == 0) { mbar_init(xbar, 1); mbar_init(sbar, 1); mbar_init(ubar, 1); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    // this warp's TMEM window: lanes 32 * (warp % 4) .. +31.  A group's warps sit on consecutive sub-partitions
-    // (G divides 4), so the position inside the group, hence the lane-constant tables, depend on warp % 4 only.
-    const unsigned tlane = s_tmem_base + ((unsigned)(32 * (warp & 3)) << 16);
-    if (warp < 4) {
-        const int tl = 32 * (warp % G) + (tid & 31);       // group lane served by this sub-partition
-        float t[32];
-#pragma unroll
-        for (int i = 0; i < V; ++i) { t[2 * i] = 0.5f * a.wa[2 * LANES * i + 2 * tl]; t[2 * i + 1] = 0.5f * a.wa[2 * LANES * i + 2 * tl + 1]; }
-        tmem_stw<2 * V>(tlane + TC_WA, t);
-#pragma unroll
-        for (int i = 0; i < V; ++i) { t[2 * i] = a.ws[2 * LANES * i + 2 * tl]; t[2 * i + 1] = a.ws[2 * LANES * i + 2 * tl + 1]; }
-        tmem_stw<2 * V>(tlane + TC_WS, t);
-#pragma unroll
-        for (int i = 0; i < V; ++i) {       // [R1 s + ka]: W_M^((tl + LANES s) ka)
-            const float2 w = a.tw[((tl + LANES * (i / C::R1)) * (i % C::R1)) & (M - 1)];
-            t[2 * i] = w.x; t[2 * i + 1] = w.y;
-        }
-        tmem_stw<2 * V>(tlane + TC_TW1, t);
-#pragma unroll
-        for (int kb = 0; kb < 16; ++kb) {   // W_(RC R2)^(c kb) = W_M^(R1 c kb), c = tl & (RC - 1)
-            const float2 w = a.tw[(C::R1 * (tl & (RC - 1)) * (kb % C::R2)) & (M - 1)];
-            t[2 * kb] = w.x; t[2 * kb + 1] = w.y;
-        }
-        tmem_st32(tlane + TC_TW2, t);
-#pragma unroll
-        for (int j = 0; j < RC; ++j) {
-            const int k = slot_bin_rt<LANES, VV>(tl, j);
-            float2 w;
-            if (k <= M / 2) w = a.twr[k];
-            else { w = a.twr[M - k]; w.x = -w.x; }                  // W_N^k = -conj(W_N^(M-k))
-            t[2 * j] = w.x; t[2 * j + 1] = w.y;
-        }
-        tmem_stw<2 * RC>(tlane + TC_TWR, t);
-        // 1/envelope of an INTERIOR hop (4 overlapping frames): the envelope is periodic with the hop there, so
-        // blocks 3 .. T-1 take it from here instead of streaming it from memory (block 3 is the first such block)
-        if (a.T >= 4) {
-#pragma unroll
-            for (int j = 0; j < HP; ++j) {
-                const float2 e = *reinterpret_cast<const float2*>(a.inv_env + (3LL * C::HOP - a.P) + 2 * LANES * j + 2 * tl);
-                t[2 * j] = e.x; t[2 * j + 1] = e.y;
-            }
-            tmem_stw<2 * HP>(tlane + TC_IE, t);
-        }
-        tmem_wait_st();
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-
-    const unsigned twarp = tlane + TC_WARP + TC_PER_WARP * (warp >> 2);   // ring (24 columns) then carry (24)
-    float2* e1 = sm + grp * GROUP_F2;
-    float2* e2 = e1 + M;
-    float2* xs = e2 + M;                                            // HOP floats = M / 4 float2
-    float* mstage = reinterpret_cast<float*>(xs + M / 4);           // magnitudes of the coming frame (M floats)
-    float2* qstage = xs + M / 4 + M / 2;                            // q / X row of the coming frame
-    const unsigned grp_s = (unsigned)__cvta_generic_to_shared(sm) + grp * (GROUP_F2 * 8);   // shared-window addresses
-    const unsigned xs_s = grp_s + 2 * M * 8, mstage_s = xs_s + (M / 4) * 8, qstage_s = mstage_s + (M / 2) * 8;
-    unsigned xpar = 0, spar = 0, upar = 0;                          // mbarrier phase parities
-
-    // bin offsets of the lane's pair slots inside a main row
-    const int hi_adj = l == 0 ? -(RC - 1) * LANES : 0;  // lane 0, slots j >= RC/2: LANES + 2 LANES (j - RC/2)
-    const int kq0 = l == 0 ? M / 2 : M - l;
-
-    double dacc = 0.0, eacc = 0.0;
-    const int gg = blockIdx.x + gridDim.x * grp;                    // global group index
-    long long g = 0, g1 = 0;
-    if (gg < a.ranges) {
-        g = a.frames_total * gg / a.ranges;
-        g1 = a.frames_total * (gg + 1) / a.ranges;
-    }
-    while (g < g1) {
-        const int b = (int)(g / a.T);
-        const int t0 = (int)(g - (long long)b * a.T);
-        const int t1 = (int)min((long long)a.T, t0 + (g1 - g));
-        g += t1 - t0;
-        const int tf0 = max(0, t0 - 3);
-        const float* x = a.x_in + (long long)b * a.L;
-        float* xo = a.x_out + (long long)b * a.L;
-
-        // ---- prologue: empty carry, ring = blocks tf0 .. tf0 + 2, block tf0 + 3 and the first rows on their way
-        tmem_wait_st();
-        {
-            float z[6 * HP];
-#pragma unroll
-            for (int i = 0; i < 6 * HP; ++i) z[i] = 0.f;
-            tmem_stw<4 * HP>(twarp + 24, z); tmem_stw<2 * HP>(twarp + 24 + 4 * HP, z + 4 * HP);
-        }
-        int m = tf0 % 3;                                            // ring slot of block t
-        if constexpr (OP != OP_ISTFT) {
-            int mm = m;
-#pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                float2 nb[HP];
-                fetch_block_regs<LANES, VV>(a, x, tf0 + i, l, nb);
-                tmem_stw<2 * HP>(twarp + 2 * HP * mm, reinterpret_cast<const float*>(nb));
-                mm = mm == 2 ? 0 : mm + 1;
-            }
-        }
-        group_sync<LANES>(bar_id);                 // nobody still reads the staging rows of an earlier range
-        bool x_async = false;
-        if constexpr (OP != OP_ISTFT) x_async = fetch_block_staged<LANES, VV>(a, x, tf0 + 3, l, xs, xs_s, xbar);
-        stage_rows<OP, LANES, VV>(a, (long long)b * a.T + tf0, l, qstage_s, mstage_s, sbar);
-        // Nyquist scalars of the coming frame (lane 0), fetched one frame ahead like the rows
-        float2 s0n_next = f2(0.f, 0.f), s1n_next = f2(0.f, 0.f);
-        float mgn_next = 0.f;
-        if (l == 0) {
-            const long long r0 = (long long)b * a.T + tf0;
-            if constexpr (OP != OP_GLP) s0n_next = __ldg(a.s0_in_nyq + r0);
-            if constexpr (OP != OP_ISTFT) mgn_next = __ldg(a.mag_nyq + r0);
-            if constexpr (OP == OP_ADMM) s1n_next = __ldg(a.s1_in_nyq + r0);
-        }
-        if constexpr (OP == OP_ADMM) {             // U rows are read straight from global memory: pull them into L2
-            const char* u0 = reinterpret_cast<const char*>(a.s1_in + ((long long)b * a.T + tf0) * M);
-            if (128 * l < M * 8) prefetch_l2(u0 + 128 * l);
-        }
-
-        for (int t = tf0; t < t1; ++t) {
-            const long long row = (long long)b * a.T + t;
-            const bool owned = t >= t0;
-            float2 v[V];
-            float2 A[RC], Bv[RC];
-            if constexpr (OP != OP_ISTFT) {
-            // ---- assemble the frame: blocks t .. t+2 from the ring, block t+3 from the staging buffer
-            {
-                const int m1 = m == 2 ? 0 : m + 1, m2 = m1 == 2 ? 0 : m1 + 1;
-                tmem_wait_st();
-                tmem_ldw<2 * HP>(twarp + 2 * HP * m, reinterpret_cast<float*>(v));
-                tmem_ldw<2 * HP>(twarp + 2 * HP * m1, reinterpret_cast<float*>(v + HP));
-                tmem_ldw<2 * HP>(twarp + 2 * HP * m2, reinterpret_cast<float*>(v + 2 * HP));
-                if (x_async) { mbar_wait(xbar, xpar); xpar ^= 1; }
-#pragma unroll
-                for (int j = 0; j < HP; ++j) v[3 * HP + j] = xs[LANES * j + l];
-                tmem_stw<2 * HP>(twarp + 2 * HP * m, reinterpret_cast<const float*>(v + 3 * HP));   // block t+3 replaces block t
-                m = m1;
-            }
-            group_sync<LANES>(bar_id);             // xs consumed by every lane; the previous frame's reads of E1 are done
-            if (t + 1 < t1) {
-                x_async = fetch_block_staged<LANES, VV>(a, x, t + 4, l, xs, xs_s, xbar);
-                if constexpr (OP == OP_ADMM) {
-                    const char* u1 = reinterpret_cast<const char*>(a.s1_in + (row + 1) * M);
-                    if (128 * l < M * 8) prefetch_l2(u1 + 128 * l);
-                }
-            }
-            {
-                float2 w[V];
-                tmem_ldw<2 * V>(tlane + TC_WA, reinterpret_cast<float*>(w));
-#pragma unroll
-                for (int i = 0; i < V; ++i) v[i] = pmul(v[i], w[i]);
-            }
-            {
-                float2 tw1[V];
-                tmem_ldw<2 * V>(tlane + TC_TW1, reinterpret_cast<float*>(tw1));
-                fwd_pass1<LANES, VV>(l, v, tw1, e1);
-            }
-            group_sync<LANES>(bar_id);
-            {
-                float2 tw2[C::R2];
-                if constexpr (C::R2 == 8) tmem_ld16(tlane + TC_TW2, reinterpret_cast<float*>(tw2));
-                else tmem_ld32(tlane + TC_TW2, reinterpret_cast<float*>(tw2));
-                fwd_pass2<LANES, VV>(l, e1, tw2, e2);
-            }
-            group_sync<LANES>(bar_id);
-            if constexpr (OP == OP_ADMM) {
-                // E1 is idle until the inverse pass 2: stage this frame's U row (L2-prefetched a frame ago) in it
-                if (l < 32) { if (elect_one()) { mbar_expect_tx(ubar, M * 8); bulk_g2s(grp_s, a.s1_in + row * M, M * 8, ubar); } }
-            }
-            fwd_pass3<LANES, VV>(l, e2, A, Bv);
-            }  // OP != OP_ISTFT
-            const float2 s0n = s0n_next, s1n = s1n_next;
-            const float mgn = mgn_next;
-            mbar_wait(sbar, spar); spar ^= 1;      // this frame's staged rows have landed
-            if constexpr (OP == OP_ADMM) { mbar_wait(ubar, upar); upar ^= 1; }
-            {
-                // ---- point-wise stage on the lane's 16 bins (+ Nyquist for lane 0), state fetched where it is used.
-                // Element e = 2 j / 2 j + 1 is the P / Q bin of slot j: bins l + 2 LANES j and M - l - 2 LANES j, except
-                // for lane 0 (slots 4..7: 2 LANES j - 7 LANES and its mirror; slot 0: bins 0 and M/2).  Four per-lane
-                // base offsets turn every access into base + compile-time offset.
-                struct IO {
-                    const float2* q; const float* mg; const float2* u; float2* o0; float2* o1;
-                    float2* o0n; float2* o1n;
-                    int pl, ph, ql, qh, q0; bool owned;
-                    float2 s0n, s1n; float mgn;
-                    __device__ __forceinline__ int bin(int e) const {
-                        const int j = e >> 1;
-                        return (e & 1) ? (j == 0 ? q0 : (j >= RC / 2 ? qh : ql) - 2 * LANES * j)
-                                       : (j >= RC / 2 ? ph : pl) + 2 * LANES * j;
-                    }
-                    __device__ __forceinline__ float2 s0(int e) const { return e < 0 ? s0n : q[bin(e)]; }
-                    __device__ __forceinline__ float2 s1(int e) const { return e < 0 ? s1n : u[bin(e)]; }
-                    __device__ __forceinline__ float mag(int e) const { return e < 0 ? mgn : mg[bin(e)]; }
-                    __device__ __forceinline__ void put(int e, float2 v0, float2 v1) const {
-                        if (!owned) return;
-                        if (e < 0) {
-                            *o0n = v0;
-                            if constexpr (OP == OP_ADMM) *o1n = v1;
-                        } else {
-                            o0[bin(e)] = v0;
-                            if constexpr (OP == OP_ADMM) o1[bin(e)] = v1;
-                        }
-                    }
-                } io{qstage, mstage, e1, OP == OP_GLP ? nullptr : a.s0_out + row * M,
-                     OP == OP_ADMM ? a.s1_out + row * M : nullptr, a.s0_out_nyq + row,
-                     OP == OP_ADMM ? a.s1_out_nyq + row : nullptr, l, l + hi_adj, M - l, M - l - hi_adj, kq0, owned,
-                     s0n, s1n, mgn};
-                float2 twr[RC];
-                tmem_ldw<2 * RC>(tlane + TC_TWR, reinterpret_cast<float*>(twr));
-                if constexpr (OP == OP_ISTFT) {
-                    spectrum_pairs<VV>(l, A, Bv, twr, io);
-                } else {
-                    float dsum = 0.f, esum = 0.f;
-                    pointwise<OP, SUMS, VV>(l, A, Bv, twr, io, a.coef, a.coef2, dsum, esum);
-                    if constexpr (SUMS) { if (owned) { dacc += (double)dsum; eacc += (double)esum; } }
-                }
-            }
-            group_sync<LANES>(bar_id);             // every lane has read its classes from E2 and its staged state
-            if (t + 1 < t1) {
-                stage_rows<OP, LANES, VV>(a, row + 1, l, qstage_s, mstage_s, sbar);
-                if (l == 0) {
-                    if constexpr (OP != OP_GLP) s0n_next = __ldg(a.s0_in_nyq + row + 1);
-                    if constexpr (OP != OP_ISTFT) mgn_next = __ldg(a.mag_nyq + row + 1);
-                    if constexpr (OP == OP_ADMM) s1n_next = __ldg(a.s1_in_nyq + row + 1);
-                }
-            }
-            inv_pass3<LANES, VV>(l, A, Bv, e2);
-            group_sync<LANES>(bar_id);
-            const bool emit = owned && block_valid<LANES, VV>(a, t);
-            float2 ie[HP];
-            if (emit && t < 3) load_inv_env<LANES, VV>(a, t, l, ie);    // edge blocks; early: hidden behind the last two passes
-            {
-                float2 tw2[C::R2];
-                if constexpr (C::R2 == 8) tmem_ld16(tlane + TC_TW2, reinterpret_cast<float*>(tw2));
-                else tmem_ld32(tlane + TC_TW2, reinterpret_cast<float*>(tw2));
-                inv_pass2<LANES, VV>(l, e2, tw2, e1);
-            }
-            group_sync<LANES>(bar_id);
-            {
-                float2 tw1[V];
-                tmem_ldw<2 * V>(tlane + TC_TW1, reinterpret_cast<float*>(tw1));
-                inv_pass1<LANES, VV>(l, e1, tw1, v);
-            }
-            // ---- windowed overlap-add: out = carry (3 hops from earlier frames) + ws * v; the first hop
-            // (4 pairs) of `out` is a finished block, the other 12 pairs are the new carry
-            {
-                float2 w[V], carry[3 * HP];
-                tmem_ldw<2 * V>(tlane + TC_WS, reinterpret_cast<float*>(w));
-                tmem_ldw<4 * HP>(twarp + 24, reinterpret_cast<float*>(carry));
-                tmem_ldw<2 * HP>(twarp + 24 + 4 * HP, reinterpret_cast<float*>(carry + 2 * HP));
-#pragma unroll
-                for (int i = 0; i < V; ++i) v[i] = i < 3 * HP ? pfma(w[i], v[i], carry[i]) : pmul(w[i], v[i]);
-                tmem_stw<4 * HP>(twarp + 24, reinterpret_cast<const float*>(v + HP));
-                tmem_stw<2 * HP>(twarp + 24 + 4 * HP, reinterpret_cast<const float*>(v + 3 * HP));
-                if (emit) {
-                    if (t >= 3) tmem_ldw<2 * HP>(tlane + TC_IE, reinterpret_cast<float*>(ie));   // interior: periodic envelope
-                    store_block_ie<LANES, VV>(a, xo, t, l, v, ie);
-                }
-            }
-        }
-        if (t1 == a.T) {      // tail of the signal: blocks T, T+1, T+2 are complete now
-            float2 carry[3 * HP];
-            tmem_wait_st();
-            tmem_ldw<4 * HP>(twarp + 24, reinterpret_cast<float*>(carry));
-            tmem_ldw<2 * HP>(twarp + 24 + 4 * HP, reinterpret_cast<float*>(carry + 2 * HP));
-#pragma unroll
-            for (int k = 0; k < 3; ++k)
-                if (block_valid<LANES, VV>(a, a.T + k)) {
-                    float2 ie[HP];
-                    load_inv_env<LANES, VV>(a, a.T + k, l, ie);
-                    store_block_ie<LANES, VV>(a, xo, a.T + k, l, carry + HP * k, ie);
-                }
-        }
-    }
-
-    if constexpr (SUMS) {
-        double d = dacc, e = eacc;
-        for (int o = 16; o > 0; o >>= 1) {
-            d += __shfl_xor_sync(0xffffffffu, d, o);
-            e += __shfl_xor_sync(0xffffffffu, e, o);
-        }
-        if ((tid & 31) == 0 && (d != 0.0 || e != 0.0)) { atomicAdd(a.sums, d); atomicAdd(a.sums + 1, e); }
-    }
-    tmem_wait_st();
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    if (warp == 0) tmem_dealloc(s_tmem_base, TMEM_COLS);
-}
-
-static int g_sms = 0;
-
-template <int OP, int LANES, int VV = V>
-static int launch(const WArgs& a0, cudaStream_t st) {
-    WArgs a = a0;
-    if (g_sms == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess) return SPECINV_ERR_NO_DEVICE;
-        if (cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return SPECINV_ERR_NO_DEVICE;
-    }
-    // the TMA bulk copies need 16-byte aligned rows
-    if ((((uintptr_t)a.x_in | (uintptr_t)a.s0_in | (uintptr_t)a.mag) & 15) != 0) return SPECINV_ERR_UNSUPPORTED;   // (s0_in is NULL for OP_GLP)
-    if (OP == OP_ISTFT && a.sums) return SPECINV_ERR_INVALID;
-    a.frames_total = (long long)a.B * a.T;
-    constexpr int WARPS = warps_of(VV, OP);
-    constexpr int GROUPS = WARPS / (LANES / 32);
-    const int slots = g_sms * GROUPS;
-    // One frame range per group slot.  A range re-computes 3 halo frames, which costs ~1.5 % when the ranges are
-    // long (the batched configs) and buys parallelism when the problem is small (one short signal).
-    long long ranges = a.frames_total < slots ? a.frames_total : slots;
-    a.ranges = (int)ranges;
-    const int grid = (int)min((long long)g_sms, ranges);
-    // with fewer ranges than group slots, spread them over all CTAs of the grid: range index = blockIdx + grid * group
-    const size_t smem = (size_t)GROUPS * group_f2(Cfg<LANES, VV>::M) * sizeof(float2);
-    cudaError_t e;
-    if (a.sums) {
-        e = cudaFuncSetAttribute(warp_iter_kernel<OP, true, LANES, VV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        warp_iter_kernel<OP, true, LANES, VV><<<grid, WARPS * 32, smem, st>>>(a);
-    } else {
-        e = cudaFuncSetAttribute(warp_iter_kernel<OP, false, LANES, VV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        warp_iter_kernel<OP, false, LANES, VV><<<grid, WARPS * 32, smem, st>>>(a);
-    }
-    return (int)cudaGetLastError();
-}
-
-template <int OP>
-static int launch_any(const WArgs& a, int n_fft, cudaStream_t st) {
-    switch (n_fft) {
-        case 512: return launch<OP, 32, 8>(a, st);
-        case 1024: return launch<OP, 32>(a, st);
-        case 2048: return launch<OP, 64>(a, st);
-        case 4096: return launch<OP, 128>(a, st);
+static int launch_op(int op, const WArgs& a, const specinv_desc* d, cudaStream_t st) {
+    switch (d->n_fft / d->hop) {
+        case 2: return fastw_launch_ov2(op, a, d->n_fft, st);
+        case 4: return fastw_launch_ov4(op, a, d->n_fft, st);
+        case 8: return fastw_launch_ov8(op, a, d->n_fft, st);
         default: return SPECINV_ERR_UNSUPPORTED;
     }
 }
-
 }  // namespace wfast
 
 static bool fastw_applicable(const specinv_desc* d) {
-    return d->dtype == SPECINV_F32 && d->onesided && d->hop * 4 == d->n_fft &&
+    return d->dtype == SPECINV_F32 && d->onesided &&
+           (d->hop * 2 == d->n_fft || d->hop * 4 == d->n_fft || d->hop * 8 == d->n_fft) &&
            (d->n_fft == 512 || d->n_fft == 1024 || d->n_fft == 2048 || d->n_fft == 4096);
 }
 
@@ -525,7 +43,7 @@ int fastw_gl_iter(const specinv_desc* d, const void* plan, const void* x_in, voi
     a.s0_out = (float2*)q_out_main; a.s0_out_nyq = (float2*)q_out_nyq;
     a.mag = (const float*)mag_main; a.mag_nyq = (const float*)mag_nyq;
     a.coef = (float)lr; a.sums = sums;
-    return wfast::launch_any<wfast::OP_GL>(a, d->n_fft, (cudaStream_t)stream);
+    return wfast::launch_op(wfast::OP_GL, a, d, (cudaStream_t)stream);
 }
 
 // Plain Griffin-Lim (alpha = 0, methods.py:243 with lr = 0): x_out = ISTFT(proj(STFT(x_in))), no momentum state.
@@ -538,7 +56,7 @@ int fastw_gl_plain_iter(const specinv_desc* d, const void* plan, const void* x_i
     a.x_in = (const float*)x_in; a.x_out = (float*)x_out;
     a.mag = (const float*)mag_main; a.mag_nyq = (const float*)mag_nyq;
     a.sums = sums;
-    return wfast::launch_any<wfast::OP_GLP>(a, d->n_fft, (cudaStream_t)stream);
+    return wfast::launch_op(wfast::OP_GLP, a, d, (cudaStream_t)stream);
 }
 
 // x_out = ISTFT(spectrum) (methods.py:135-150) with the same kernel: inverse half of the frame pipeline only.
@@ -550,7 +68,7 @@ int fastw_istft(const specinv_desc* d, const void* plan, const void* main_in, co
     fill_common(a, dm, d, plan);
     a.x_out = (float*)x_out;
     a.s0_in = (const float2*)main_in; a.s0_in_nyq = (const float2*)nyq_in;
-    return wfast::launch_any<wfast::OP_ISTFT>(a, d->n_fft, (cudaStream_t)stream);
+    return wfast::launch_op(wfast::OP_ISTFT, a, d, (cudaStream_t)stream);
 }
 
 int fastw_admm_iter(const specinv_desc* d, const void* plan, const void* x_in, void* x_out,
@@ -568,7 +86,7 @@ int fastw_admm_iter(const specinv_desc* d, const void* plan, const void* x_in, v
     a.s1_out = (float2*)U_out_main; a.s1_out_nyq = (float2*)U_out_nyq;
     a.mag = (const float*)mag_main; a.mag_nyq = (const float*)mag_nyq;
     a.coef = (float)rho; a.coef2 = (float)(1.0 / (1.0 + rho)); a.sums = sums;
-    return wfast::launch_any<wfast::OP_ADMM>(a, d->n_fft, (cudaStream_t)stream);
+    return wfast::launch_op(wfast::OP_ADMM, a, d, (cudaStream_t)stream);
 }
 
 }  // namespace specinv

@@ -1,0 +1,8 @@
+// hop = n_fft/2 instances of the specialised fused kernels (specinv_fastw_kernel.cuh).
+#include "specinv_fastw_kernel.cuh"
+
+namespace specinv {
+namespace wfast {
+SPECINV_FASTW_DEFINE_LAUNCH(2)
+}  // namespace wfast
+}  // namespace specinv

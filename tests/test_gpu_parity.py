@@ -445,17 +445,29 @@ FAST2048_CASES = [
     dict(B=9, T=50, center=True, pad_mode="replicate", normalized=False, n_fft=4096),
     dict(B=2, T=33, center=False, pad_mode="reflect", normalized=True, n_fft=4096),
     dict(B=1, T=301, center=True, pad_mode="reflect", normalized=False, n_fft=4096),
+    # hop = n_fft / 2 and n_fft / 8 (ov = frames overlapping on a sample)
+    dict(B=5, T=90, center=True, pad_mode="reflect", normalized=False, n_fft=1024, ov=2),
+    dict(B=5, T=90, center=True, pad_mode="reflect", normalized=False, n_fft=1024, ov=8),
+    dict(B=3, T=40, center=False, pad_mode="reflect", normalized=True, n_fft=1024, ov=8),
+    dict(B=6, T=70, center=True, pad_mode="constant", normalized=False, n_fft=512, ov=2),
+    dict(B=6, T=70, center=True, pad_mode="circular", normalized=False, n_fft=512, ov=8),
+    dict(B=2, T=17, center=False, pad_mode="reflect", normalized=False, n_fft=512, ov=2),
+    dict(B=4, T=50, center=True, pad_mode="replicate", normalized=False, n_fft=2048, ov=2),
+    dict(B=4, T=50, center=True, pad_mode="reflect", normalized=True, n_fft=2048, ov=8),
+    dict(B=2, T=40, center=True, pad_mode="reflect", normalized=False, n_fft=4096, ov=2),
+    dict(B=2, T=40, center=False, pad_mode="reflect", normalized=False, n_fft=4096, ov=8),
+    dict(B=1, T=300, center=True, pad_mode="reflect", normalized=False, n_fft=1024, ov=2),
 ]
 
 
 @pytest.mark.parametrize("fc", FAST2048_CASES,
-                         ids=lambda c: f"n{c.get('n_fft', 2048)}_B{c['B']}_T{c['T']}_{c['pad_mode']}_c{int(c['center'])}")
+                         ids=lambda c: f"n{c.get('n_fft', 2048)}_ov{c.get('ov', 4)}_B{c['B']}_T{c['T']}_{c['pad_mode']}_c{int(c['center'])}")
 def test_fast_path_2048_against_oracle(fc):
     from spectrogram_inversion_b200.engine import ADMMSolver, GriffinLimSolver, StftPlan
     from spectrogram_inversion_b200.stft_args import args_helper
     rs = np.random.RandomState(fc["T"])
     n_fft = fc.get("n_fft", 2048)
-    hop, F = n_fft // 4, n_fft // 2 + 1
+    hop, F = n_fft // fc.get("ov", 4), n_fft // 2 + 1
     B, T = fc["B"], fc["T"]
     w = cases.window_of("hann" if fc["center"] else "hamming", n_fft, np.float32)
     kw = dict(hop_length=hop, center=fc["center"], pad_mode=fc["pad_mode"], normalized=fc["normalized"], window=w)
@@ -539,17 +551,18 @@ def test_cuda_graph_replay_of_plain_iterations_is_identical():
         assert len(a._graphs) >= 1 and torch.equal(a.signal, b.signal)
 
 
+@pytest.mark.parametrize("ov", [4, 2, 8])
 @pytest.mark.parametrize("n_fft", [512, 1024, 2048, 4096])
-def test_specialised_kernels_on_tiny_frame_counts(n_fft, monkeypatch):
+def test_specialised_kernels_on_tiny_frame_counts(n_fft, ov, monkeypatch):
     """T = 1 .. 6 frames (fewer frames than the 3-frame halo, no interior hop, ranges of one frame), several signals:
     the specialised kernel must agree with the generic one (and not hang on its TMA / mbarrier pipeline)."""
     from spectrogram_inversion_b200.engine import ADMMSolver, GriffinLimSolver, StftPlan
     from spectrogram_inversion_b200.stft_args import StftArgs
     dev = torch.device("cuda")
-    hop, F = n_fft // 4, n_fft // 2 + 1
+    hop, F = n_fft // ov, n_fft // 2 + 1
     g = torch.Generator(device=dev).manual_seed(n_fft)
     for center, pad_mode in ((False, "reflect"), (True, "constant"), (True, "replicate")):
-        for T in range(1, 7):
+        for T in (range(1, 7) if ov == 4 else sorted({1, 2, 3, ov - 1, ov, ov + 1, 2 * ov + 1})):
             if center and T < 2:
                 continue
             B = 5
