@@ -20,6 +20,7 @@ ap.add_argument("--n_fft", type=int, default=1024)
 ap.add_argument("--hop", type=int, default=256)
 ap.add_argument("--samples", type=int, default=240000)
 ap.add_argument("--sums", action="store_true")
+ap.add_argument("--alpha", type=float, default=0.99, help="0 = plain Griffin-Lim (no momentum state)")
 a = ap.parse_args()
 
 dev = torch.device("cuda")
@@ -34,7 +35,7 @@ mag.main.copy_(S.main.abs()); mag.nyq.copy_(S.nyq.abs())
 ph = torch.exp(2j * torch.pi * torch.rand(S.main.shape, device=dev))
 S.main.copy_(mag.main * ph)
 del ph, x
-solver = GriffinLimSolver(plan, S, mag, 0.99) if a.algo == "gl" else ADMMSolver(plan, S, mag, 0.1)
+solver = GriffinLimSolver(plan, S, mag, a.alpha) if a.algo == "gl" else ADMMSolver(plan, S, mag, 0.1)
 for _ in range(3):
     solver.step(evaluate=a.sums)
 torch.cuda.synchronize()
@@ -46,7 +47,7 @@ e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / a.iters
 F = a.n_fft // 2 + 1
-per_bin = 20 if a.algo == "gl" else 36
+per_bin = (20 if a.alpha > 0 else 4) if a.algo == "gl" else 36
 gb = (per_bin * a.batch * F * T + 8 * a.batch * plan.length) / 1e9
 print(f"{a.algo} n_fft={a.n_fft} hop={a.hop} B={a.batch} T={T}: {ms:.4f} ms/iter, {gb / ms * 1e3:.1f} GB/s algorithmic, "
       f"{a.batch * a.samples / 24000 / ms * 1e3:.0f} audio-s*it/s (24 kHz)")
