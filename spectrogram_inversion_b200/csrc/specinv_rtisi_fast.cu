@@ -1,6 +1,7 @@
-// RTISI-LA (torch_specinv/methods.py:273-412) for n_fft = 1024 / hop = 256 (the shape of BASELINE.json's cfg3) and
-// n_fft = 512 / hop = 128, look_ahead <= 3, onesided fp32, as ONE persistent kernel built from the register FFT
-// pipeline of gl_warp_core.cuh (16 or 8 complex values per lane, one warp per frame).
+// RTISI-LA (torch_specinv/methods.py:273-412) for n_fft = 1024 / hop = 256 (the shape of BASELINE.json's cfg3),
+// n_fft = 512 / hop = 128 and n_fft = 2048 / hop = 512, look_ahead <= 3, onesided fp32, as ONE persistent kernel built
+// from the register FFT pipeline of gl_warp_core.cuh (16 or 8 complex values per lane, one warp -- two for 2048 --
+// per frame).
 //
 // A signal is owned by LA+1 warps, one per ACTIVE frame; a frame stays in its warp's registers for its whole
 // life (LA+1 outer steps x max_iter inner iterations), together with its momentum spectrum (tensor memory) and
@@ -25,7 +26,6 @@ namespace rfast {
 
 using namespace wfast;
 
-constexpr int LANES = 32;
 constexpr int KEEP = 3, NAMAX = 4;            // kept frames (n_fft = 4 hop), at most LA + 1 = 4 active frames
 
 struct RArgs {
@@ -41,8 +41,8 @@ struct RArgs {
 };
 
 // TMEM columns per lane: constant tables (identical in the four sub-partitions), then per-warp state
-constexpr int TC_WA = 0, TC_WSC = 32, TC_TW1 = 64, TC_TW2 = 96, TC_TWR = 112, TC_AS1 = 128, TC_AS2 = 160, TC_WARP = 192;
-constexpr int TC_PRE = 0, TC_YK = 32, TC_MAG = 64, TC_PER_WARP = 80;
+constexpr int TC_WA = 0, TC_WSC = 32, TC_TW1 = 64, TC_TW2 = 96, TC_TWR = 128, TC_AS1 = 144, TC_AS2 = 176, TC_WARP = 208;
+// per warp (VV = values per lane): momentum spectrum `pre` 2 VV words, kept part of y 2 VV, magnitude row VV
 constexpr int TMEM_COLS = 512;
 // float2 of shared memory per signal: u of the active frames (double buffered), u of the kept frames, the output
 // carry (one frame = VV rows of 32 lanes = M float2 each), and the two FFT exchange buffers of every warp
@@ -52,16 +52,27 @@ __device__ __forceinline__ void sig_sync(int bar_id, int threads) {
     asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(threads) : "memory");
 }
 
-// VV complex values per lane (16: n_fft = 1024, 8: n_fft = 512), SIGS signals per CTA (SIGS x 4 warps)
-template <int VV, int SIGS>
-__global__ void __launch_bounds__(SIGS * NAMAX * 32, 1) rtisi_fast_kernel(const RArgs a) {
+// Synchronise the warps that share a frame (named barrier) or just the warp.
+template <int LANES>
+__device__ __forceinline__ void frame_sync(int bar_id) {
+    if constexpr (LANES == 32) __syncwarp();
+    else asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(LANES) : "memory");
+}
+
+// LANES lanes (LANES / 32 warps) per frame and VV complex values per lane: <32, 16> n_fft = 1024, <32, 8> n_fft = 512,
+// <64, 16> n_fft = 2048; SIGS signals per CTA (SIGS x 4 frame slots)
+template <int LANES, int VV, int SIGS>
+__global__ void __launch_bounds__(SIGS * NAMAX * LANES, 1) rtisi_fast_kernel(const RArgs a) {
     using C = Cfg<LANES, VV>;
     constexpr int V = VV;                          // shadows wfast::V
     constexpr int M = C::M, HOP = C::HOP, RC = C::RC, HP = VV / 4;
-    constexpr int ROWS = M;                        // float2 per frame: VV rows of 32 lanes
+    constexpr int ROWS = M;                        // float2 per frame: VV rows of LANES lanes
     constexpr int SIG_F2 = sig_f2(M);
-    constexpr int WARPS = SIGS * NAMAX;
+    constexpr int G = LANES / 32;                  // warps per frame
+    constexpr int WARPS = SIGS * NAMAX * G;
+    constexpr int TC_PRE = 0, TC_YK = 2 * V, TC_MAG = 4 * V, TC_PER_WARP = 5 * V;
     static_assert(TC_WARP + ((WARPS + 3) / 4) * TC_PER_WARP <= TMEM_COLS, "TMEM columns");
+    static_assert(1 + SIGS + SIGS * NAMAX <= 16 || G == 1, "named barriers");
     // bin offsets of the lane's VV bins (gl_warp_core.cuh: slot j -> bins l + 64 j and M - l - 64 j; lane 0 special)
     struct Bins {
         int pl, ph, ql, qh, q0;
@@ -73,13 +84,16 @@ __global__ void __launch_bounds__(SIGS * NAMAX * 32, 1) rtisi_fast_kernel(const 
     extern __shared__ __align__(16) float2 sm[];
     __shared__ unsigned s_tmem_base;
     __shared__ float2 s_ws[ROWS];                  // synthesis window pairs [row][lane] (commit only)
-    const int tid = threadIdx.x, warp = tid >> 5, l = tid & 31;
-    const int sig = warp >> 2;                     // signal slot inside the CTA
-    const int p = warp & 3;                        // physical frame slot of this warp
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int sig = warp / (NAMAX * G);            // signal slot inside the CTA
+    const int wf = warp % (NAMAX * G);             // warp inside the signal
+    const int p = wf / G;                          // physical frame slot of this warp's frame group
+    const int l = 32 * (wf % G) + (tid & 31);      // lane inside the frame group, 0 .. LANES-1 (wf % G == warp % G)
     const int NA = a.LA + 1;
+    const int fbar = 1 + SIGS + sig * NAMAX + p;   // named barrier of the frame group (G > 1)
     if (warp == 0) tmem_alloc(&s_tmem_base, TMEM_COLS);
     for (int i = tid; i < ROWS; i += WARPS * 32) {
-        const int row = i >> 5, ll = i & 31;
+        const int row = i / LANES, ll = i % LANES;
         s_ws[i] = f2(a.ws[2 * LANES * row + 2 * ll], a.ws[2 * LANES * row + 2 * ll + 1]);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -101,13 +115,12 @@ __global__ void __launch_bounds__(SIGS * NAMAX * 32, 1) rtisi_fast_kernel(const 
             t[2 * i] = w.x; t[2 * i + 1] = w.y;
         }
         tmem_stw<2 * V>(tlane + TC_TW1, t);
-        static_assert(C::R2 == 8, "pass-2 twiddles: 8 per lane");
 #pragma unroll
-        for (int kb = 0; kb < 8; ++kb) {
+        for (int kb = 0; kb < C::R2; ++kb) {
             const float2 w = a.tw[(C::R1 * (l & (RC - 1)) * kb) & (M - 1)];
             t[2 * kb] = w.x; t[2 * kb + 1] = w.y;
         }
-        tmem_st16(tlane + TC_TW2, t);
+        tmem_stw<2 * C::R2>(tlane + TC_TW2, t);
 #pragma unroll
         for (int j = 0; j < RC; ++j) {
             const int k = slot_bin_rt<LANES, VV>(l, j);
@@ -136,7 +149,7 @@ __global__ void __launch_bounds__(SIGS * NAMAX * 32, 1) rtisi_fast_kernel(const 
         float2* carry = Uk + KEEP * ROWS;              // [ROWS]
         float2* e1 = carry + ROWS + p * 2 * M;
         float2* e2 = e1 + M;
-        const int bar_id = 1 + sig, bar_threads = 32 * NA;
+        const int bar_id = 1 + sig, bar_threads = LANES * NA;
         const int hi_adj = l == 0 ? -(RC - 1) * LANES : 0;
         const Bins bin{l, l + hi_adj, M - l, M - l - hi_adj, l == 0 ? M / 2 : M - l};
         float* xo = a.x_out + (long long)b * a.L;
@@ -153,7 +166,7 @@ __global__ void __launch_bounds__(SIGS * NAMAX * 32, 1) rtisi_fast_kernel(const 
             tmem_stw<V>(twarp + TC_MAG, z);            // frames that precede the spectrogram have zero magnitude (:339)
         }
         float2 pre_nyq = f2(0.f, 0.f);
-        for (int i = p * 32 + l; i < KEEP * ROWS + ROWS; i += 32 * NA) Uk[i] = f2(0.f, 0.f);    // kept frames and carry
+        for (int i = p * LANES + l; i < KEEP * ROWS + ROWS; i += LANES * NA) Uk[i] = f2(0.f, 0.f);  // kept frames and carry
         sig_sync(bar_id, bar_threads);
         int kslot = 0;                                 // kept ring: logical kept frame f (0 = oldest) = slot (kslot + f) % KEEP
         float mag_nyq = 0.f;
@@ -182,15 +195,15 @@ __global__ void __launch_bounds__(SIGS * NAMAX * 32, 1) rtisi_fast_kernel(const 
                     } io0{mg, mag_nyq};
                     spectrum_pairs<VV>(l, A, Bv, twr, io0);
                     inv_pass3<LANES, VV>(l, A, Bv, e2);
-                    __syncwarp();
-                    float2 tw2[8];
-                    tmem_ld16(tlane + TC_TW2, reinterpret_cast<float*>(tw2));
+                    frame_sync<LANES>(fbar);
+                    float2 tw2[C::R2];
+                    tmem_ldw<2 * C::R2>(tlane + TC_TW2, reinterpret_cast<float*>(tw2));
                     inv_pass2<LANES, VV>(l, e2, tw2, e1);
-                    __syncwarp();
+                    frame_sync<LANES>(fbar);
                     float2 tw1[V];
                     tmem_ldw<2 * V>(tlane + TC_TW1, reinterpret_cast<float*>(tw1));
                     inv_pass1<LANES, VV>(l, e1, tw1, v);
-                    __syncwarp();
+                    frame_sync<LANES>(fbar);
                 }
             }
             // ---- part of this frame's y that comes from the kept frames: constant over the inner iterations.
@@ -259,13 +272,13 @@ __global__ void __launch_bounds__(SIGS * NAMAX * 32, 1) rtisi_fast_kernel(const 
                     tmem_ldw<2 * V>(tlane + TC_TW1, reinterpret_cast<float*>(tw1));
                     fwd_pass1<LANES, VV>(l, y, tw1, e1);
                 }
-                __syncwarp();
+                frame_sync<LANES>(fbar);
                 {
-                    float2 tw2[8];
-                    tmem_ld16(tlane + TC_TW2, reinterpret_cast<float*>(tw2));
+                    float2 tw2[C::R2];
+                    tmem_ldw<2 * C::R2>(tlane + TC_TW2, reinterpret_cast<float*>(tw2));
                     fwd_pass2<LANES, VV>(l, e1, tw2, e2);
                 }
-                __syncwarp();
+                frame_sync<LANES>(fbar);
                 float2 A[RC], Bv[RC];
                 fwd_pass3<LANES, VV>(l, e2, A, Bv);
                 // ---- momentum (:387-392), pre <- S, projection (:394-396)
@@ -290,21 +303,21 @@ __global__ void __launch_bounds__(SIGS * NAMAX * 32, 1) rtisi_fast_kernel(const 
                     pre_nyq = io.pn;
                     tmem_stw<2 * V>(twarp + TC_PRE, reinterpret_cast<const float*>(pre));
                 }
-                __syncwarp();
+                frame_sync<LANES>(fbar);
                 inv_pass3<LANES, VV>(l, A, Bv, e2);
-                __syncwarp();
+                frame_sync<LANES>(fbar);
                 {
-                    float2 tw2[8];
-                    tmem_ld16(tlane + TC_TW2, reinterpret_cast<float*>(tw2));
+                    float2 tw2[C::R2];
+                    tmem_ldw<2 * C::R2>(tlane + TC_TW2, reinterpret_cast<float*>(tw2));
                     inv_pass2<LANES, VV>(l, e2, tw2, e1);
                 }
-                __syncwarp();
+                frame_sync<LANES>(fbar);
                 {
                     float2 tw1[V];
                     tmem_ldw<2 * V>(tlane + TC_TW1, reinterpret_cast<float*>(tw1));
                     inv_pass1<LANES, VV>(l, e1, tw1, v);
                 }
-                __syncwarp();
+                frame_sync<LANES>(fbar);
             }
 
             // ---- commit the oldest active frame (:401-404) and fuse the final overlap-add (:406-408)
@@ -357,12 +370,12 @@ __global__ void __launch_bounds__(SIGS * NAMAX * 32, 1) rtisi_fast_kernel(const 
     if (warp == 0) tmem_dealloc(s_tmem_base, TMEM_COLS);
 }
 
-template <int VV, int SIGS>
+template <int LANES, int VV, int SIGS>
 static int launch(const RArgs& a, cudaStream_t st) {
     const size_t smem = (size_t)SIGS * sig_f2(Cfg<LANES, VV>::M) * sizeof(float2);
-    cudaError_t e = cudaFuncSetAttribute(rtisi_fast_kernel<VV, SIGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(rtisi_fast_kernel<LANES, VV, SIGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    rtisi_fast_kernel<VV, SIGS><<<(a.B + SIGS - 1) / SIGS, SIGS * NAMAX * 32, smem, st>>>(a);
+    rtisi_fast_kernel<LANES, VV, SIGS><<<(a.B + SIGS - 1) / SIGS, SIGS * NAMAX * LANES, smem, st>>>(a);
     return (int)cudaGetLastError();
 }
 
@@ -372,7 +385,8 @@ static int launch(const RArgs& a, cudaStream_t st) {
 int rtisi_fast(const specinv_desc* d, const Dims& dm, const void* plan, const void* mag_main, const void* mag_nyq,
                void* x_out, const void* asym1, const void* asym2, int look_ahead, int asymmetric, int max_iter,
                double alpha, double synth_coeff, cudaStream_t st) {
-    if (d->dtype != SPECINV_F32 || !d->onesided || d->hop * 4 != d->n_fft || (d->n_fft != 1024 && d->n_fft != 512))
+    if (d->dtype != SPECINV_F32 || !d->onesided || d->hop * 4 != d->n_fft ||
+        (d->n_fft != 2048 && d->n_fft != 1024 && d->n_fft != 512))
         return SPECINV_ERR_UNSUPPORTED;
     const int LA = look_ahead < 0 ? dm.K : look_ahead;
     if (LA > 3 || dm.K != rfast::KEEP) return SPECINV_ERR_UNSUPPORTED;
@@ -390,8 +404,10 @@ int rtisi_fast(const specinv_desc* d, const Dims& dm, const void* plan, const vo
     int sms = 0, dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
         return SPECINV_ERR_NO_DEVICE;
-    if (d->n_fft == 1024) return dm.B <= sms ? rfast::launch<16, 1>(a, st) : rfast::launch<16, 2>(a, st);
-    return dm.B <= sms ? rfast::launch<8, 1>(a, st) : dm.B <= 2 * sms ? rfast::launch<8, 2>(a, st) : rfast::launch<8, 4>(a, st);
+    if (d->n_fft == 2048) return rfast::launch<64, 16, 1>(a, st);       // two warps per frame, one signal per CTA
+    if (d->n_fft == 1024) return dm.B <= sms ? rfast::launch<32, 16, 1>(a, st) : rfast::launch<32, 16, 2>(a, st);
+    return dm.B <= sms ? rfast::launch<32, 8, 1>(a, st) : dm.B <= 2 * sms ? rfast::launch<32, 8, 2>(a, st)
+                                                                          : rfast::launch<32, 8, 4>(a, st);
 }
 
 }  // namespace specinv

@@ -36,7 +36,7 @@ def main():
             out[f"{name}/admm_k1"] = ref.ADMM(C, max_iter=1, tol=0, rho=0.1, verbose=False, eva_iter=1, **kw).numpy()
             out[f"{name}/gl_mag_k2"] = ref.griffin_lim(mag, max_iter=2, tol=0, alpha=0.99, verbose=False, **kw).numpy()
             out[f"{name}/gl_plain_k2"] = ref.griffin_lim(C, max_iter=2, tol=0, alpha=0.0, verbose=False, eva_iter=1, **kw).numpy()
-            if case["n_fft"] in (512, 1024):
+            if case["n_fft"] in (512, 1024, 2048):
                 out[f"{name}/rtisi_la3_k1"] = ref.RTISI_LA(mag, look_ahead=3, max_iter=1, alpha=0.99, verbose=0, **kw).numpy()
             print(name, {k.split("/")[1]: v.shape for k, v in out.items() if k.startswith(name)})
     np.savez_compressed(os.path.join(HERE, "fast.npz"), **out)

@@ -382,6 +382,12 @@ RTISI_FAST_CASES = [
     dict(B=1, T=8, look_ahead=1, asym=True, max_iter=3, alpha=0.5, center=False, normalized=True, window="hamming", n_fft=512),
     dict(B=9, T=8, look_ahead=0, asym=False, max_iter=2, alpha=0.0, center=True, normalized=False, window="hann", n_fft=512),
     dict(B=2, T=12, look_ahead=2, asym=False, max_iter=2, alpha=0.99, center=True, normalized=False, window=None, win_length=300, n_fft=512),
+    # n_fft = 2048 / hop = 512: two warps per frame
+    dict(B=3, T=7, look_ahead=3, asym=False, max_iter=2, alpha=0.99, center=True, normalized=False, window="hann", n_fft=2048),
+    dict(B=2, T=6, look_ahead=-1, asym=True, max_iter=2, alpha=0.99, center=True, normalized=False, window="hann", n_fft=2048),
+    dict(B=1, T=6, look_ahead=1, asym=True, max_iter=3, alpha=0.5, center=False, normalized=True, window="hamming", n_fft=2048),
+    dict(B=4, T=6, look_ahead=0, asym=False, max_iter=2, alpha=0.0, center=True, normalized=False, window="hann", n_fft=2048),
+    dict(B=2, T=9, look_ahead=2, asym=False, max_iter=2, alpha=0.99, center=True, normalized=False, window=None, win_length=1500, n_fft=2048),
     # batches beyond one signal per SM (148): two / four signals share a CTA
     dict(B=151, T=6, look_ahead=3, asym=False, max_iter=2, alpha=0.99, center=True, normalized=False, window="hann"),
     dict(B=151, T=6, look_ahead=3, asym=True, max_iter=2, alpha=0.99, center=True, normalized=False, window="hann", n_fft=512),
@@ -391,7 +397,7 @@ RTISI_FAST_CASES = [
 
 @pytest.mark.parametrize("rc", RTISI_FAST_CASES, ids=lambda c: f"n{c.get('n_fft', 1024)}_B{c['B']}_T{c['T']}_la{c['look_ahead']}_asym{int(c['asym'])}_it{c['max_iter']}")
 def test_rtisi_fast_kernel_1024_against_oracle(rc, monkeypatch):
-    """The register-FFT RTISI-LA kernel (n_fft = 1024 / hop = 256 and 512 / 128) against the oracle in float64.  fp32 trajectories of
+    """The register-FFT RTISI-LA kernel (n_fft = 1024 / hop = 256, 512 / 128, 2048 / 512) against the oracle in float64.  fp32 trajectories of
     RTISI-LA drift apart quickly (the projection divides by |S|; SURVEY.md section 7: fp32 vs fp64 of the REFERENCE
     decorrelate over a full run), so the yardstick is the drift of two other fp32 implementations from the same fp64
     run -- the oracle in float32 and the generic shared-memory kernel: an indexing mistake gives O(1) errors."""

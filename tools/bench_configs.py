@@ -18,6 +18,7 @@ CFG = {
     "cfg2": dict(algo="gl", B=512, N=240000, sr=24000, n_fft=1024, hop=256, iters=64, alpha=0.99),
     "cfg3": dict(algo="rtisi", B=256, N=240000, sr=24000, n_fft=1024, hop=256, iters=25, alpha=0.99, la=3),
     "cfg3s": dict(algo="rtisi", B=256, N=160000, sr=16000, n_fft=512, hop=128, iters=25, alpha=0.99, la=3),
+    "cfg3l": dict(algo="rtisi", B=128, N=441000, sr=44100, n_fft=2048, hop=512, iters=25, alpha=0.99, la=3),
     "cfg4": dict(algo="admm", B=128, N=882000, sr=44100, n_fft=2048, hop=512, iters=100, rho=0.1),
     "cfg2p": dict(algo="gl", B=512, N=240000, sr=24000, n_fft=1024, hop=256, iters=64, alpha=0.0),      # plain GL
     "cfg5p": dict(algo="gl", B=1, N=172800000, sr=48000, n_fft=4096, hop=1024, iters=10, alpha=0.0),

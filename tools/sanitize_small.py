@@ -21,7 +21,7 @@ for n_fft, B, T in ((512, 3, 25), (1024, 3, 21), (2048, 2, 17), (4096, 2, 13)):
         torch.cuda.synchronize()
         print(n_fft, ov, tuple(y.shape), tuple(z.shape),
               bool(torch.isfinite(y).all()), bool(torch.isfinite(y0).all()), bool(torch.isfinite(z).all()))
-for n_fft in (1024, 512):
+for n_fft in (1024, 512, 2048):
     y = S.RTISI_LA(torch.rand(3, n_fft // 2 + 1, 9, device=dev), look_ahead=3, max_iter=2, verbose=0,
                    window=torch.hann_window(n_fft, device=dev), hop_length=n_fft // 4, asymmetric_window=True)
     torch.cuda.synchronize()
