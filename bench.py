@@ -38,7 +38,9 @@ WORKLOADS = {
     # name: (B, samples, sample_rate, n_fft, hop, iters, alpha)
     "cfg2": dict(B=512, N=240000, sr=24000, n_fft=1024, hop=256, iters=64, alpha=0.99,
                  desc="batched griffin_lim B=512 x 10 s @ 24 kHz, n_fft=1024 hop=256 hann, 64 iters, alpha=0.99, "
-                      "tol=0, eva_iter=10, real-magnitude input (phase_init inside)"),
+                      "tol=0, eva_iter=10 (the metric sums are computed on every 10th iteration as in the reference; at "
+                      "tol=0 with verbose off nothing can observe them, so the host does not wait for them), "
+                      "real-magnitude input (phase_init inside)"),
     "cfg1": dict(B=1, N=661500, sr=22050, n_fft=2048, hop=512, iters=100, alpha=0.3,
                  desc="griffin_lim one 30 s @ 22.05 kHz signal, n_fft=2048 hop=512 hann, 100 iters, alpha=0.3"),
 }

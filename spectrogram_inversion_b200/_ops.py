@@ -41,6 +41,25 @@ def _need_cuda(*ts: Tensor) -> None:
             raise RuntimeError("specinv_b200 ops need contiguous buffers")
 
 
+def pointers(tensors):
+    """Device pointers for `iter_direct` (None / empty tensor = NULL)."""
+    return [t.data_ptr() if t is not None and t.numel() else None for t in tensors]
+
+
+def iter_direct(fn, what: str, device: torch.device, desc_ref, ptrs, coef: float, sums_ptr) -> None:
+    """The engine's per-iteration launch: the same C entry point as the `gl_iter` / `admm_iter` custom ops below,
+    called straight through ctypes on buffers the solver owns.  (The torch.library dispatch of a custom op costs
+    ~40 us per call -- more than a whole iteration of a small problem, 24 us at BASELINE cfg1.)
+    ``ptrs``: the pointer arguments between the descriptor and the coefficient (`pointers`)."""
+    stream = torch.cuda.current_stream(device).cuda_stream
+    if torch.cuda.current_device() == device.index:
+        code = fn(desc_ref, *ptrs, coef, sums_ptr, stream)
+    else:
+        with torch.cuda.device(device):
+            code = fn(desc_ref, *ptrs, coef, sums_ptr, stream)
+    _ok(code, what)
+
+
 @torch.library.custom_op("specinv_b200::plan_init", mutates_args=("plan",), device_types="cuda")
 def plan_init(plan: Tensor, window: Tensor, n_fft: int, hop: int, n_frames: int, batch: int, center: bool,
               pad_mode: int, normalized: bool, onesided: bool) -> None:
@@ -80,18 +99,6 @@ def gl_iter(plan: Tensor, x_in: Tensor, x_out: Tensor, q_in_main: Tensor, q_in_n
         _ok(_lib.lib().specinv_gl_iter(
             C.byref(d), _p(plan), _p(x_in), _p(x_out), _p(q_in_main), _p(q_in_nyq), _p(q_out_main), _p(q_out_nyq),
             _p(mag_main), _p(mag_nyq), float(lr), _p(sums), _stream(x_in)), "gl_iter")
-
-
-@torch.library.custom_op("specinv_b200::gl_plain_iter", mutates_args=("x_out", "sums"), device_types="cuda")
-def gl_plain_iter(plan: Tensor, x_in: Tensor, x_out: Tensor, mag_main: Tensor, mag_nyq: Tensor, sums: Tensor,
-                  n_fft: int, hop: int, center: bool, pad_mode: int, normalized: bool, onesided: bool) -> None:
-    """griffin_lim's closure with alpha = 0 (methods.py:243 with lr = 0): no momentum state (NULL q pointers)."""
-    _need_cuda(plan, x_in, x_out, mag_main, mag_nyq, sums)
-    d = _desc(x_in, n_fft, hop, mag_main.shape[1], mag_main.shape[0], center, pad_mode, normalized, onesided)
-    with torch.cuda.device(x_in.device):
-        _ok(_lib.lib().specinv_gl_iter(
-            C.byref(d), _p(plan), _p(x_in), _p(x_out), None, None, None, None,
-            _p(mag_main), _p(mag_nyq), 0.0, _p(sums), _stream(x_in)), "gl_iter")
 
 
 @torch.library.custom_op("specinv_b200::admm_iter",

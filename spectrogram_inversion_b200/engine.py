@@ -64,10 +64,11 @@ class StftPlan:
         self.n_bins = args.n_bins
         self._k = (n, args.hop_length, args.center, self.pad_mode, args.normalized, args.onesided)
         self.buf = None
-        if not tables:          # layout conversion / phase_init only
-            return
         d = _lib.make_desc(n, args.hop_length, self.T, self.B, args.center, self.pad_mode, args.normalized,
                            args.onesided, _ops._DT[dtype])
+        self.desc, self.desc_ref = d, _lib.C.byref(d)      # struct specinv_desc of this plan (kept alive here)
+        if not tables:          # layout conversion / phase_init only
+            return
         nbytes = _lib.C.c_size_t(0)
         _lib.check(_lib.lib().specinv_plan_bytes(_lib.C.byref(d), _lib.C.byref(nbytes)), "plan_bytes")
         self.buf = torch.empty(nbytes.value, dtype=torch.uint8, device=device)
@@ -149,10 +150,20 @@ class _Solver:
         self.n_bins_total = plan.B * plan.n_bins * plan.T
         self.g = float(spec_sums(mag, mag)[2].item())   # sum mag^2 (constant per call)
         self.iterations = 0
-        # Small problems are launch bound (cfg1: 24 us of kernel vs 45 us of Python + custom-op dispatch per
-        # iteration): runs of non-evaluating iterations are then replayed from a CUDA graph.
+        # Iterations are launched straight through ctypes (`_ops.iter_direct`, ~6 us of host time each), which keeps
+        # even the smallest config GPU-bound (cfg1: 24 us of kernel per iteration).  Replaying runs of iterations
+        # from a CUDA graph is available (`use_graphs = True`) for a solver that lives long enough to pay for the
+        # capture: measured 2.6-4 ms per captured graph, more than a whole 100-iteration cfg1 job.
         self._graphs = {}
-        self.use_graphs = plan.B * plan.T * plan.args.n_fft <= (1 << 24)
+        self.use_graphs = False
+        self._ptrs = [None, None]      # per ping-pong parity: (tensors, their device pointers)
+
+    def _launch_direct(self, what: str, tensors: tuple, coef: float, sums: torch.Tensor) -> None:
+        c = self._ptrs[self.cur]
+        if c is None or len(c[0]) != len(tensors) or any(a is not b for a, b in zip(c[0], tensors)):
+            c = self._ptrs[self.cur] = (tensors, _ops.pointers(tensors))      # (re)built when a buffer was replaced
+        _ops.iter_direct(self._fn, what, self.plan.device, self.plan.desc_ref, c[1], coef,
+                         sums.data_ptr() if sums.numel() else None)
 
     @property
     def signal(self) -> torch.Tensor:
@@ -161,11 +172,12 @@ class _Solver:
     def _launch(self, sums: torch.Tensor) -> None:
         raise NotImplementedError
 
-    def step(self, evaluate: bool = False) -> Optional[Tuple[float, float]]:
+    def step(self, evaluate: bool = False, read: bool = True) -> Optional[Tuple[float, float]]:
         """One fused iteration.  With ``evaluate`` returns (d, e) = (sum (|s|-mag)^2, sum |s|^2) of
         the spectrogram the iteration started from -- exactly the ``output`` the reference's closure
         returns (methods.py:242, :465) -- which costs one device->host sync like the reference's
-        ``.item()`` calls (methods.py:181-182)."""
+        ``.item()`` calls (methods.py:181-182).  ``read=False`` leaves the two sums on the device
+        (``self.sums``): the evaluation is computed but the host does not wait for it."""
         if evaluate:
             self.sums.zero_()
             self._launch(self.sums)
@@ -173,7 +185,7 @@ class _Solver:
             self._launch(self._nosums)
         self.cur ^= 1
         self.iterations += 1
-        if evaluate:
+        if evaluate and read:
             d, e = self.sums.tolist()
             return d, e
         return None
@@ -181,13 +193,19 @@ class _Solver:
 
     def run_plain(self, n: int) -> None:
         """``n`` iterations without evaluation (no host synchronisation)."""
+        self.run_pattern((False,) * n)
+
+    def run_pattern(self, flags: Tuple[bool, ...]) -> None:
+        """One iteration per flag, evaluating (fused metric sums left on the device, not read) where the flag is
+        set; never synchronises with the host.  Small problems replay the whole pattern from a CUDA graph."""
+        n = len(flags)
         if n <= 0:
             return
         if n == 1 or not self.use_graphs:
-            for _ in range(n):
-                self.step()
+            for f in flags:
+                self.step(evaluate=f, read=False)
             return
-        key = (n, self.cur)
+        key = (flags if any(flags) else n, self.cur)
         graph = self._graphs.get(key)
         if graph is None:
             # record n ping-pong launches starting from the current parity (the buffers are fixed for the
@@ -199,8 +217,8 @@ class _Solver:
             side.wait_stream(main)
             with torch.cuda.stream(side):
                 graph.capture_begin(capture_error_mode="thread_local")
-                for _ in range(n):
-                    self.step()
+                for f in flags:
+                    self.step(evaluate=f, read=False)
                 graph.capture_end()
             main.wait_stream(side)
             self.cur, self.iterations, _ops.LAUNCHES[0] = cur, its, launches
@@ -221,15 +239,13 @@ class GriffinLimSolver(_Solver):
         # alpha = 0 is plain Griffin-Lim: q_n = STFT(x_{n-1}) needs no momentum state, so none is kept or moved
         self.plain = self.lr == 0
         self.q = None if self.plain else [C, C.like()]
+        self._fn = _lib.lib().specinv_gl_iter
         plan.istft(C, self.x[0])                          # methods.py:233
 
     def _launch(self, sums: torch.Tensor) -> None:
         p, i, o = self.plan, self.cur, self.cur ^ 1
-        if self.plain:
-            _ops.gl_plain_iter(p.buf, self.x[i], self.x[o], self.mag.main, self.mag.nyq, sums, *p._k)
-            return
-        _ops.gl_iter(p.buf, self.x[i], self.x[o], self.q[i].main, self.q[i].nyq, self.q[o].main, self.q[o].nyq,
-                     self.mag.main, self.mag.nyq, sums, self.lr, *p._k)
+        qi = (None, None, None, None) if self.plain else (self.q[i].main, self.q[i].nyq, self.q[o].main, self.q[o].nyq)
+        self._launch_direct("gl_iter", (p.buf, self.x[i], self.x[o], *qi, self.mag.main, self.mag.nyq), self.lr, sums)
 
     @property
     def q_state(self) -> SplitSpec:
@@ -246,13 +262,15 @@ class ADMMSolver(_Solver):
         self.rho = float(rho)
         self.X = [C, C.like()]
         self.U = [C.zeros_like(), C.like()]
+        self._fn = _lib.lib().specinv_admm_iter
         plan.istft(C, self.x[0])                          # methods.py:453
 
     def _launch(self, sums: torch.Tensor) -> None:
         p, i, o = self.plan, self.cur, self.cur ^ 1
-        _ops.admm_iter(p.buf, self.x[i], self.x[o], self.X[i].main, self.X[i].nyq, self.U[i].main, self.U[i].nyq,
-                       self.X[o].main, self.X[o].nyq, self.U[o].main, self.U[o].nyq, self.mag.main, self.mag.nyq,
-                       sums, self.rho, *p._k)
+        self._launch_direct("admm_iter",
+                            (p.buf, self.x[i], self.x[o], self.X[i].main, self.X[i].nyq, self.U[i].main, self.U[i].nyq,
+                             self.X[o].main, self.X[o].nyq, self.U[o].main, self.U[o].nyq, self.mag.main, self.mag.nyq),
+                            self.rho, sums)
 
 
 def metric_value(name: str, d: float, e: float, g: float) -> float:
@@ -290,6 +308,17 @@ def training_loop(solver, max_iter: int, tol: float, verbose, eva_iter: int, met
     previous_loss = None
     done = 0
     run_plain = getattr(solver, "run_plain", None)
+    run_pattern = getattr(solver, "run_pattern", None)
+    if tol == 0 and not verbose and history is None and reduce_sums is None and run_pattern is not None:
+        # With tol == 0 the stopping rule `(previous - loss) / init < 0 and previous > loss` (methods.py:187) can
+        # never fire and nothing displays the metric: the evaluations are still computed at the reference's cadence
+        # (the fused epilogue runs on the same iterations) but the host does not wait for the two sums.
+        i = 0
+        while i < max_iter:
+            n = min(eva_iter, max_iter - i)
+            run_pattern(tuple((i + k) % eva_iter == eva_iter - 1 for k in range(n)))
+            i += n
+        return max_iter
     with tqdm(total=max_iter, disable=not verbose) as pbar:
         i = 0
         while i < max_iter:

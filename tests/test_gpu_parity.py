@@ -536,8 +536,8 @@ def test_host_batches_are_pipelined_in_chunks_with_identical_results():
 
 
 def test_cuda_graph_replay_of_plain_iterations_is_identical():
-    """Small problems replay the iterations between evaluations from a CUDA graph (engine._Solver.run_plain): same
-    kernels on the same buffers, so the result must equal the step-by-step run bit for bit, for odd and even runs."""
+    """A solver with `use_graphs` replays the iterations between evaluations from a CUDA graph (engine._Solver.run_plain):
+    same kernels on the same buffers, so the result must equal the step-by-step run bit for bit, for odd and even runs."""
     import spectrogram_inversion_b200 as S
     from spectrogram_inversion_b200.engine import ADMMSolver, GriffinLimSolver, StftPlan, training_loop
     from spectrogram_inversion_b200.stft_args import args_helper
@@ -548,13 +548,22 @@ def test_cuda_graph_replay_of_plain_iterations_is_identical():
     pm = plan.pack(mag)
     for make in (lambda: GriffinLimSolver(plan, plan.phase_init(pm), pm, 0.99), lambda: ADMMSolver(plan, plan.phase_init(pm), pm, 0.1)):
         a, b = make(), make()
-        assert a.use_graphs
-        b.use_graphs = False
+        a.use_graphs = True
+        assert not b.use_graphs                       # default: direct launches (the capture costs more than a short job)
         ha, hb = [], []
         na = training_loop(a, 23, 0.0, False, 4, "sc", history=ha)       # runs of 3 plain iterations, tail of 3
         nb = training_loop(b, 23, 0.0, False, 4, "sc", history=hb)
         assert na == nb == 23 and a.iterations == b.iterations == 23 and ha == hb
         assert len(a._graphs) >= 1 and torch.equal(a.signal, b.signal)
+        # tol == 0, nothing watching the metric: the evaluations run at the same iterations (whole eva_iter blocks from
+        # one graph) but the host never waits for the sums -- same signal, and the last sums are on the device
+        for use_graphs in (True, False):
+            c = make()
+            c.use_graphs = use_graphs
+            nc = training_loop(c, 23, 0.0, False, 4, "sc")
+            assert nc == 23 and c.iterations == 23 and torch.equal(c.signal, a.signal)
+            d_last = float(c.sums[0].item())
+            assert abs(d_last / c.n_bins_total - ha[-1][2]) <= 1e-12 * abs(ha[-1][2])
 
 
 @pytest.mark.parametrize("ov", [4, 2, 8])
