@@ -20,7 +20,7 @@
 //     (cp.async.bulk, one elected lane, mbarrier completion) into per-group staging rows one frame ahead, so
 //     the compute never waits on DRAM; the new state is written straight from registers, 256 contiguous
 //     bytes per warp instruction.
-// A range re-computes the 3 frames before it as a halo (state not written, output not stored), so ranges are
+// A range re-computes the OV - 1 frames before it as a halo (state not written, output not stored), so ranges are
 // independent: no atomics, deterministic.  State arrays are ping-ponged (q_in != q_out).
 #pragma once
 #include <cstdlib>
