@@ -48,8 +48,15 @@ constexpr int TMEM_COLS = 512;
 // carry (one frame = VV rows of 32 lanes = M float2 each), and the two FFT exchange buffers of every warp
 constexpr int sig_f2(int m) { return 2 * NAMAX * m + KEEP * m + m + NAMAX * 2 * m; }
 
-__device__ __forceinline__ void sig_sync(int bar_id, int threads) {
-    asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(threads) : "memory");
+// Named barrier over the `na` active frame groups of a signal (na * LANES threads; immediate thread counts).
+template <int LANES>
+__device__ __forceinline__ void sig_sync(int bar_id, int na) {
+    switch (na) {
+        case 1: asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(LANES) : "memory"); break;
+        case 2: asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(2 * LANES) : "memory"); break;
+        case 3: asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(3 * LANES) : "memory"); break;
+        default: asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(4 * LANES) : "memory"); break;
+    }
 }
 
 // Synchronise the warps that share a frame (named barrier) or just the warp.
@@ -83,6 +90,9 @@ __global__ void __launch_bounds__(SIGS * NAMAX * LANES, 1) rtisi_fast_kernel(con
     };
     extern __shared__ __align__(16) float2 sm[];
     __shared__ unsigned s_tmem_base;
+    // compute-sanitizer's synccheck (12.9) reports "Missing init, barrier at shared address 0x0" for a kernel that
+    // uses tcgen05.alloc but owns no mbarrier; this initialised, otherwise unused one keeps the tool usable here
+    __shared__ __align__(8) unsigned long long s_tool_bar;
     __shared__ float2 s_ws[ROWS];                  // synthesis window pairs [row][lane] (commit only)
     const int tid = threadIdx.x, warp = tid >> 5;
     const int sig = warp / (NAMAX * G);            // signal slot inside the CTA
@@ -91,6 +101,7 @@ __global__ void __launch_bounds__(SIGS * NAMAX * LANES, 1) rtisi_fast_kernel(con
     const int l = 32 * (wf % G) + (tid & 31);      // lane inside the frame group, 0 .. LANES-1 (wf % G == warp % G)
     const int NA = a.LA + 1;
     const int fbar = 1 + SIGS + sig * NAMAX + p;   // named barrier of the frame group (G > 1)
+    if (threadIdx.x == 0) mbar_init((unsigned)__cvta_generic_to_shared(&s_tool_bar), 1);
     if (warp == 0) tmem_alloc(&s_tmem_base, TMEM_COLS);
     for (int i = tid; i < ROWS; i += WARPS * 32) {
         const int row = i / LANES, ll = i % LANES;
@@ -149,7 +160,7 @@ __global__ void __launch_bounds__(SIGS * NAMAX * LANES, 1) rtisi_fast_kernel(con
         float2* carry = Uk + KEEP * ROWS;              // [ROWS]
         float2* e1 = carry + ROWS + p * 2 * M;
         float2* e2 = e1 + M;
-        const int bar_id = 1 + sig, bar_threads = LANES * NA;
+        const int bar_id = 1 + sig;
         const int hi_adj = l == 0 ? -(RC - 1) * LANES : 0;
         const Bins bin{l, l + hi_adj, M - l, M - l - hi_adj, l == 0 ? M / 2 : M - l};
         float* xo = a.x_out + (long long)b * a.L;
@@ -167,7 +178,7 @@ __global__ void __launch_bounds__(SIGS * NAMAX * LANES, 1) rtisi_fast_kernel(con
         }
         float2 pre_nyq = f2(0.f, 0.f);
         for (int i = p * LANES + l; i < KEEP * ROWS + ROWS; i += LANES * NA) Uk[i] = f2(0.f, 0.f);  // kept frames and carry
-        sig_sync(bar_id, bar_threads);
+        sig_sync<LANES>(bar_id, NA);
         int kslot = 0;                                 // kept ring: logical kept frame f (0 = oldest) = slot (kslot + f) % KEEP
         float mag_nyq = 0.f;
 
@@ -239,7 +250,7 @@ __global__ void __launch_bounds__(SIGS * NAMAX * LANES, 1) rtisi_fast_kernel(con
                         Ub[p * ROWS + r * LANES + l] = y[r];
                     }
                 }
-                sig_sync(bar_id, bar_threads);
+                sig_sync<LANES>(bar_id, NA);
                 // ---- this frame of the overlap-add: own u + kept part + the other active frames, shifted by HP
                 // rows per frame of distance (row r of this frame = row r - HP d of the frame d positions later)
                 {
@@ -361,7 +372,7 @@ __global__ void __launch_bounds__(SIGS * NAMAX * LANES, 1) rtisi_fast_kernel(con
                 for (int r = 0; r < V; ++r) v[r] = f2(0.f, 0.f);
             }
             kslot = (kslot + 1) % KEEP;
-            sig_sync(bar_id, bar_threads);              // the kept ring and the carry are in place for the next step
+            sig_sync<LANES>(bar_id, NA);              // the kept ring and the carry are in place for the next step
         }
         tmem_wait_st();
     }

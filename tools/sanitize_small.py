@@ -26,3 +26,9 @@ for n_fft in (1024, 512, 2048):
                    window=torch.hann_window(n_fft, device=dev), hop_length=n_fft // 4, asymmetric_window=True)
     torch.cuda.synchronize()
     print("rtisi", n_fft, tuple(y.shape))
+# batches beyond one signal per SM: two / four signals share a CTA (1024: B > 148 -> 2; 512: B > 296 -> 4)
+for n_fft, B in ((1024, 150), (512, 150), (512, 298)):
+    y = S.RTISI_LA(torch.rand(B, n_fft // 2 + 1, 5, device=dev), look_ahead=2, max_iter=2, verbose=0,
+                   window=torch.hann_window(n_fft, device=dev), hop_length=n_fft // 4)
+    torch.cuda.synchronize()
+    print("rtisi", n_fft, tuple(y.shape), bool(torch.isfinite(y).all()))
