@@ -78,7 +78,7 @@ def _finish(x: torch.Tensor, spec: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def _pipeline_chunks(spec: torch.Tensor, tol: float, verbose) -> int:
+def _pipeline_chunks(spec: torch.Tensor, tol: float, verbose, state_arrays: int = 1) -> int:
     """Host (non-CUDA) batches are processed in batch chunks so that the host->device copy of the next chunk and
     the device->host copy of the previous result overlap the iterations of the current one.  The signals of a
     batch only interact through the batch-global early-stop test (methods.py:186-190), which can never fire with
@@ -86,8 +86,15 @@ def _pipeline_chunks(spec: torch.Tensor, tol: float, verbose) -> int:
     with ``tol == 0`` and no progress bar the chunked run returns exactly what the whole-batch run returns."""
     if spec.is_cuda or len(spec.shape) != 3 or tol != 0 or verbose:
         return 1
-    B, _, T = spec.shape
-    return int(max(1, min(4, B, (B * T) // 60000)))
+    B, F, T = spec.shape
+    n = int(max(1, min(4, B, (B * T) // 60000)))
+    # ... and small enough for the device: a chunk holds its input, the magnitudes, the ping-pong state (two complex
+    # arrays for Griffin-Lim, four for ADMM) and two signals; keep that within 80 % of the free memory
+    per_signal = F * T * spec.element_size() * (2 if not spec.is_complex() else 1) * (1 + 0.5 + 2 * state_arrays + 1)
+    free = torch.cuda.mem_get_info(compute_device(spec))[0] if torch.cuda.is_available() else 0
+    if free > 0:
+        n = max(n, min(B, -(-int(B * per_signal) // int(0.8 * free))))
+    return n
 
 
 def _run_host_pipelined(spec, n_chunks, make_solver, max_iter, eva_iter, metric, stft_kwargs):
@@ -176,7 +183,7 @@ def ADMM(spec, max_iter=1000, tol=1e-6, rho=0.1, verbose=1, eva_iter=10, metric=
     if autograd.wants_grad(spec):
         work, args = _diff_setup(spec, stft_kwargs)
         return _diff_finish(autograd.admm_diff(work, args, max_iter, tol, rho, verbose, eva_iter, metric), spec)
-    n_chunks = _pipeline_chunks(spec, tol, verbose)
+    n_chunks = _pipeline_chunks(spec, tol, verbose, state_arrays=2)
     if n_chunks > 1:
         return _run_host_pipelined(spec, n_chunks, lambda p, c, m: ADMMSolver(p, c, m, rho), max_iter, eva_iter, metric,
                                    stft_kwargs)

@@ -527,6 +527,12 @@ def test_host_batches_are_pipelined_in_chunks_with_identical_results():
     mag = torch.from_numpy((np.abs(rs.randn(B, 129, T)) * 3).astype(np.float32))
     assert methods._pipeline_chunks(mag, 0.0, False) == 2
     assert methods._pipeline_chunks(mag, 1e-6, False) == 1 and methods._pipeline_chunks(mag.cuda(), 0.0, False) == 1
+    # a host batch too large for the device is cut into as many chunks as it takes to fit 80 % of the free memory
+    free = torch.cuda.mem_get_info()[0]
+    big = torch.empty(1, dtype=torch.float32).expand(40000, 513, 938)           # 77 GB of magnitudes, stride 0
+    need = 40000 * 513 * 938 * 4 * 9
+    assert methods._pipeline_chunks(big, 0.0, False) == max(4, -(-need // int(0.8 * free)))
+    assert methods._pipeline_chunks(big, 0.0, False, state_arrays=2) > methods._pipeline_chunks(big, 0.0, False)
     w = torch.hann_window(256)
     for fn, kw in ((S.griffin_lim, dict(alpha=0.99)), (S.ADMM, dict(rho=0.1))):
         y_host = fn(mag.pin_memory(), max_iter=3, tol=0, verbose=False, eva_iter=2, window=w, hop_length=64, **kw)
