@@ -633,3 +633,18 @@ def test_specialised_kernels_match_the_reference_itself(case):
     if f"{name}/rtisi_la3_k1" in FASTREF:
         y = S.RTISI_LA(mag, look_ahead=3, max_iter=1, alpha=0.99, verbose=0, **kw)
         close(y, FASTREF[f"{name}/rtisi_la3_k1"], 5e-3, "RTISI-LA vs reference")
+
+
+def test_random_configurations_specialised_vs_fp64_generic():
+    """tools/fuzz_fast_vs_generic.py: random (n_fft, hop, B, T, padding, window length, algorithm) draws; the specialised
+    fp32 kernels must stay within 4x the generic fp32 kernel's distance (+1e-5) from the generic fp64 result."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_fast_vs_generic.py"), "100", "3"],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = r.stdout.strip().splitlines()
+    assert len(lines) == 101 and lines[-1].startswith("worst"), r.stdout[-1000:]
+    bad = [ln for ln in lines if "MISMATCH" in ln]
+    assert not bad, "\n".join(bad)

@@ -1,5 +1,5 @@
-"""Random shapes / options: the specialised fused kernels against the generic tile kernel (SPECINV_FORCE_GENERIC=1),
-two evaluated iterations each.  python tools/fuzz_fast_vs_generic.py [n_cases] [seed]"""
+"""Random shapes / options: the specialised fused kernels (fp32) against the generic tile kernel in fp64, with the
+generic fp32 kernel as the yardstick for fp32 conditioning; two evaluated iterations each.  python tools/fuzz_fast_vs_generic.py [n_cases] [seed]"""
 import os
 import random
 import sys
@@ -39,21 +39,43 @@ for case in range(n_cases):
     F = n_fft // 2 + 1
     mag = torch.rand(B, F, T, device=dev, generator=g) * 4
     C = mag * torch.exp(2j * torch.pi * torch.rand(B, F, T, device=dev, generator=g))
-    outs = []
-    for force in ("0", "1"):
+    # three runs: the specialised kernels (fp32), the generic kernel in fp32, and the generic kernel in fp64 as the
+    # yardstick.  Step 1 starts from identical state; step 2 runs free (the projection q / |q| amplifies differences
+    # at bins with |q| ~ 0, in BOTH fp32 runs): the specialised kernel may be at most 4x further from the fp64 result
+    # than the generic fp32 kernel is (plus 1e-5).
+    plan64 = StftPlan(StftArgs(n_fft, hop, n_fft, w.double(), center, pad_mode, normalized, True), T, B, torch.float64, dev)
+    Cls = GriffinLimSolver if algo == "gl" else ADMMSolver
+    runs = {}
+    for name, force, pl, cast in (("fast", "0", plan, lambda t: t), ("gen32", "1", plan, lambda t: t),
+                                  ("gen64", "1", plan64, lambda t: t.to(torch.complex128 if t.is_complex() else torch.float64))):
         os.environ["SPECINV_FORCE_GENERIC"] = force
-        s = (GriffinLimSolver if algo == "gl" else ADMMSolver)(plan, plan.pack(C), plan.pack(mag), coef)
-        sums = [s.step(evaluate=True) for _ in range(2)]
-        outs.append((s.signal.clone(), sums))
-    (xa, sa), (xb, sb) = outs
-    fin = torch.isfinite(xb)
-    ok = bool((torch.isfinite(xa) == fin).all())
-    scale = max(1.0, float(xb[fin].abs().max())) if fin.any() else 1.0
-    err = float((xa[fin] - xb[fin]).abs().max()) / scale if fin.any() else 0.0
-    serr = max(abs(d0 - d1) / max(abs(d1), 1e-6) for (d0, _), (d1, _) in zip(sa, sb) if d1 == d1 and abs(d1) != float("inf")) \
-        if any(d1 == d1 for (_, _), (d1, _) in zip(sa, sb)) else 0.0
-    worst = max(worst, err)
-    flag = "" if ok and err <= 5e-5 and serr <= 1e-3 else "   <-- MISMATCH"
+        try:
+            runs[name] = (force, Cls(pl, pl.pack(cast(C)), pl.pack(cast(mag)), coef))
+        except NotImplementedError:      # fp64 tiles of n_fft = 4096 with a 7-frame halo exceed the shared memory
+            assert name == "gen64"
+            runs[name] = runs["gen32"]
+    good, line = True, []
+    for step in range(2):
+        x, sums = {}, {}
+        for name, (force, solver) in runs.items():
+            if name == "gen64" and solver is runs["gen32"][1]:
+                sums[name], x[name] = sums["gen32"], x["gen32"]
+                continue
+            os.environ["SPECINV_FORCE_GENERIC"] = force
+            sums[name] = solver.step(evaluate=True)
+            x[name] = solver.signal.double()
+        fin = torch.isfinite(x["gen64"])
+        good = good and bool((torch.isfinite(x["fast"]) == fin).all())
+        scale = max(1.0, float(x["gen64"][fin].abs().max())) if fin.any() else 1.0
+        ef = float((x["fast"][fin] - x["gen64"][fin]).abs().max()) / scale if fin.any() else 0.0
+        eg = float((x["gen32"][fin] - x["gen64"][fin]).abs().max()) / scale if fin.any() else 0.0
+        d64 = sums["gen64"][0]
+        es = abs(sums["fast"][0] - d64) / max(abs(d64), 1e-6) if d64 == d64 and abs(d64) != float("inf") else 0.0
+        if runs["gen64"][1] is runs["gen32"][1]:
+            eg = 2.5e-5 * (step + 1) ** 3            # no fp64 yardstick: fixed allowance (1e-4 step 1, 8e-4 step 2)
+        good = good and ef <= 4 * eg + 1e-5 and es <= 1e-3
+        worst = max(worst, ef / (4 * eg + 1e-5))
+        line.append(f"step{step + 1} fast {ef:.1e} generic {eg:.1e} sums {es:.1e}")
     print(f"{case:3d} n_fft={n_fft} hop={hop} B={B} T={T} center={int(center)} {pad_mode:9s} norm={int(normalized)} wl={wl} "
-          f"{algo} {coef}: err {err:.2e} sums {serr:.1e}{flag}")
-print("worst", worst)
+          f"{algo} {coef}: {', '.join(line)}{'' if good else '   <-- MISMATCH'}")
+print("worst error / allowance", worst)
