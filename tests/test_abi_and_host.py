@@ -154,3 +154,48 @@ def test_bench_reference_arm_prints_the_contract_line():
         assert key in line, key
     assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and "workload" in line["config"]
+
+
+class _FakeSolver:
+    """Records what the host loop asks for (no GPU): loss decreases geometrically."""
+
+    def __init__(self):
+        self.g, self.n_bins_total, self.calls, self.loss = 1.0, 10, [], 1.0
+
+    def step(self, evaluate=False, read=True):
+        self.calls.append(bool(evaluate))
+        self.loss *= 0.9
+        return (self.loss, 1.0) if evaluate and read else None
+
+    def run_pattern(self, flags):
+        for f in flags:
+            self.step(evaluate=f, read=False)
+
+    def run_plain(self, n):
+        self.run_pattern((False,) * n)
+
+
+@pytest.mark.parametrize("max_iter,eva_iter", [(23, 4), (10, 10), (7, 10), (30, 1), (1, 1)])
+def test_training_loop_keeps_the_reference_cadence_with_and_without_host_reads(max_iter, eva_iter):
+    """methods.py:153-190: iteration i is evaluated iff i % eva_iter == eva_iter - 1.  With tol == 0, no progress bar and
+    no history the loop does not read the sums back, but must evaluate on exactly the same iterations."""
+    from spectrogram_inversion_b200.engine import training_loop
+    want = [i % eva_iter == eva_iter - 1 for i in range(max_iter)]
+    blind, watched = _FakeSolver(), _FakeSolver()
+    assert training_loop(blind, max_iter, 0.0, False, eva_iter, "sc") == max_iter
+    hist = []
+    assert training_loop(watched, max_iter, 0.0, False, eva_iter, "sc", history=hist) == max_iter
+    assert blind.calls == want and watched.calls == want
+    assert [h[0] for h in hist] == [i for i in range(max_iter) if want[i]]
+
+
+def test_training_loop_stops_early_like_the_reference():
+    """methods.py:186-190: stop when (previous - loss) / init < tol and previous > loss (checked from the second
+    evaluation on); the returned count is the number of iterations done."""
+    from spectrogram_inversion_b200.engine import training_loop
+    s = _FakeSolver()
+    # losses at evaluations: 0.9^2, 0.9^4, ... ; relative improvement (l_{k-1} - l_k) / l_0 falls below 0.1 at k = 2
+    n = training_loop(s, 100, 0.1, False, 2, "snr")
+    l = [0.9 ** (2 * (k + 1)) / 10 for k in range(50)]
+    k_stop = next(k for k in range(1, 50) if (l[k - 1] - l[k]) / l[0] < 0.1 and l[k - 1] > l[k])
+    assert n == 2 * (k_stop + 1) and len(s.calls) == n
