@@ -126,7 +126,10 @@ int run() {
         cd a0(s0_in[k].x, s0_in[k].y), a1(s1_in[k].x, s1_in[k].y), o0(s0_out[k].x, s0_out[k].y), o1(s1_out[k].x, s1_out[k].y);
         double m = mag[k];
         dref += (std::abs(s[k]) - m) * (std::abs(s[k]) - m); eref += std::norm(s[k]);
-        if (OP == OP_GL) {
+        if (OP == OP_GLP) {             // plain Griffin-Lim: q = s, no state read or written
+            h[k] = s[k] * m / (std::abs(s[k]) + 1e-16);
+            err_state = fmax(err_state, std::abs(o0) + std::abs(o1));       // outputs untouched (still zero)
+        } else if (OP == OP_GL) {
             cd q = s[k] - (double)coef * a0;
             err_state = fmax(err_state, std::abs(q - o0));
             h[k] = q * m / (std::abs(q) + 1e-16);
@@ -156,5 +159,6 @@ int main() {
     rc |= run<32, OP_GL>() | run<32, OP_ADMM>();
     rc |= run<64, OP_GL>() | run<64, OP_ADMM>();
     rc |= run<128, OP_GL>() | run<128, OP_ADMM>();
+    rc |= run<32, OP_GLP, 8>() | run<32, OP_GLP>() | run<64, OP_GLP>() | run<128, OP_GLP>();
     return rc;
 }
