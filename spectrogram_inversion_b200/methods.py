@@ -3,14 +3,11 @@
 from __future__ import annotations
 
 import math
-from typing import Optional, Tuple
-
 import torch
 
 from . import _ops, autograd
-from .engine import (ADMMSolver, GriffinLimSolver, METRIC_NAMES, SplitSpec, StftPlan, compute_device,
-                     training_loop)
-from .stft_args import StftArgs, args_helper, real_dtype_of
+from .engine import ADMMSolver, GriffinLimSolver, METRIC_NAMES, StftPlan, compute_device, training_loop
+from .stft_args import args_helper, real_dtype_of
 
 __all__ = ["griffin_lim", "RTISI_LA", "ADMM", "L_BFGS", "phase_init"]
 

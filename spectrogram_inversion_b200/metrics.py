@@ -2,8 +2,6 @@
 fused CUDA reduction ``specinv_metric_sums`` (one pass instead of the reference's three)."""
 from __future__ import annotations
 
-import math
-
 import torch
 
 from . import _ops

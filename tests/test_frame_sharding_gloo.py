@@ -7,7 +7,6 @@ phase_init scan over ranks, the all-reduced metric sums, the gather -- is the pr
 spectrogram_inversion_b200/sharding.py.  Result must equal the oracle's whole-signal griffin_lim."""
 import os
 import socket
-from dataclasses import replace
 from types import SimpleNamespace
 
 import numpy as np

@@ -11,7 +11,6 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 import cases
-from oracle import specinv_oracle as O
 
 pytestmark = pytest.mark.gpu
 

@@ -5,12 +5,9 @@ import os
 import socket
 
 import numpy as np
-import pytest
-import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from oracle import specinv_oracle as O
 
 
 def _free_port():
