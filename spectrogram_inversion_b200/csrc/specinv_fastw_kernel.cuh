@@ -235,6 +235,12 @@ __global__ void __launch_bounds__(warps_of(VV, OP) * 32, 1) warp_iter_kernel(con
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // Programmatic dependent launch: everything above touched only this CTA's own resources and the immutable plan
+    // tables, so it may run under the tail of the previous kernel of the stream (the previous iteration).  Let the
+    // next launch start as early as SM resources allow, then wait until the previous grid has completed and its
+    // writes are visible before the first access to the ping-pong state (which that grid may still be reading).
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     const unsigned twarp = tlane + TC_WARP + TC_PER_WARP * (warp >> 2);   // ring (RING_W columns) then carry (RING_W)
     float2* e1 = sm + grp * GROUP_F2;
@@ -496,17 +502,25 @@ static int launch(const WArgs& a0, cudaStream_t st) {
     const int grid = (int)min((long long)g_sms, ranges);
     // with fewer ranges than group slots, spread them over all CTAs of the grid: range index = blockIdx + grid * group
     const size_t smem = (size_t)GROUPS * group_f2(Cfg<LANES, VV>::M, OV) * sizeof(float2);
+    // launched with programmatic stream serialization: the kernel's prologue may overlap the previous kernel's tail
+    // (see griddepcontrol.wait in the kernel)
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(WARPS * 32); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
     cudaError_t e;
     if (a.sums) {
         e = cudaFuncSetAttribute(warp_iter_kernel<OP, true, LANES, VV, OV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
-        warp_iter_kernel<OP, true, LANES, VV, OV><<<grid, WARPS * 32, smem, st>>>(a);
+        e = cudaLaunchKernelEx(&cfg, warp_iter_kernel<OP, true, LANES, VV, OV>, a);
     } else {
         e = cudaFuncSetAttribute(warp_iter_kernel<OP, false, LANES, VV, OV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
-        warp_iter_kernel<OP, false, LANES, VV, OV><<<grid, WARPS * 32, smem, st>>>(a);
+        e = cudaLaunchKernelEx(&cfg, warp_iter_kernel<OP, false, LANES, VV, OV>, a);
     }
-    return (int)cudaGetLastError();
+    return (int)e;
 }
 
 template <int OP, int OV>
