@@ -220,27 +220,32 @@ __global__ void __launch_bounds__(warps_of(VV, OP) * 32, 1) warp_iter_kernel(con
             t[2 * j] = w.x; t[2 * j + 1] = w.y;
         }
         tmem_stw<2 * RC>(tlane + TC_TWR, t);
-        // 1/envelope of an INTERIOR hop (OV overlapping frames): the envelope is periodic with the hop there, so
-        // blocks OV-1 .. T-1 take it from here instead of streaming it from memory (block OV-1 is the first such block)
-        if (a.T >= OV) {
+        tmem_wait_st();
+    }
+    // Programmatic dependent launch: everything above touched only this CTA's own resources and the plan's window /
+    // twiddle tables -- written by the first kernel of specinv_plan_init, which is never the kernel right before
+    // this one in the stream (the envelope kernel follows it) -- so it may run under the tail of the previous
+    // kernel of the stream (the previous iteration).  Let the next launch start as early as SM resources allow, then
+    // wait until the previous grid has completed and its writes are visible before the first access to anything it
+    // may have written (the 1/envelope, the signal, the state) or may still be reading (the ping-pong buffers).
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    // 1/envelope of an INTERIOR hop (OV overlapping frames): the envelope is periodic with the hop there, so
+    // blocks OV-1 .. T-1 take it from here instead of streaming it from memory (block OV-1 is the first such block)
+    if (warp < 4 && a.T >= OV) {
+        const int tl = 32 * (warp % G) + (tid & 31);
+        float t[2 * HP];
 #pragma unroll
-            for (int j = 0; j < HP; ++j) {
-                const float2 e = *reinterpret_cast<const float2*>(a.inv_env + ((long long)NR * HOP - a.P) + 2 * LANES * j + 2 * tl);
-                t[2 * j] = e.x; t[2 * j + 1] = e.y;
-            }
-            tmem_stw<2 * HP>(tlane + TC_IE, t);
+        for (int j = 0; j < HP; ++j) {
+            const float2 e = *reinterpret_cast<const float2*>(a.inv_env + ((long long)NR * HOP - a.P) + 2 * LANES * j + 2 * tl);
+            t[2 * j] = e.x; t[2 * j + 1] = e.y;
         }
+        tmem_stw<2 * HP>(tlane + TC_IE, t);
         tmem_wait_st();
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    // Programmatic dependent launch: everything above touched only this CTA's own resources and the immutable plan
-    // tables, so it may run under the tail of the previous kernel of the stream (the previous iteration).  Let the
-    // next launch start as early as SM resources allow, then wait until the previous grid has completed and its
-    // writes are visible before the first access to the ping-pong state (which that grid may still be reading).
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     const unsigned twarp = tlane + TC_WARP + TC_PER_WARP * (warp >> 2);   // ring (RING_W columns) then carry (RING_W)
     float2* e1 = sm + grp * GROUP_F2;
