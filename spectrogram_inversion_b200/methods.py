@@ -94,10 +94,26 @@ def _pipeline_chunks(spec: torch.Tensor, tol: float, verbose, state_arrays: int 
     return n
 
 
+_SIDE_STREAMS = {}
+
+
+def _side_streams(dev: torch.device):
+    """The copy-in / copy-out streams of the host pipeline, created ONCE per device.  torch hands out side streams
+    round-robin from a pool of 32 and its caching allocator keeps freed blocks per stream: with fresh streams per call
+    the staged input chunks (3 x 236 MiB at cfg2) could not be reused until the pool wrapped around 16 calls later --
+    every call paid three cudaMallocs, some of them 100-250 ms (measured, tools/e2e_tail.py)."""
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    st = _SIDE_STREAMS.get(key)
+    if st is None:
+        st = _SIDE_STREAMS[key] = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+    return st
+
+
 def _run_host_pipelined(spec, n_chunks, make_solver, max_iter, eva_iter, metric, stft_kwargs):
     dev = compute_device(spec)
     cur = torch.cuda.current_stream(dev)
-    s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    s_in, s_out = _side_streams(dev)
+    s_in.wait_stream(cur)
     B = spec.shape[0]
     bounds = [(B * k) // n_chunks for k in range(n_chunks + 1)]
 

@@ -8,9 +8,16 @@ the oracle is too slow to run: every warp group of every SM is busy, ranges cros
     and with a loose max bound, because the projection q*mag/|q| is ill-conditioned for the few bins (out of
     2.5e8) whose |q| is tiny: two fp32 evaluations of the same q legitimately disagree there
   * the specialised and the generic kernel agree on one iteration
+  * ORACLE SLICES: a few signals sliced out of the full batch (cfg2, cfg4) -- for the one-hour signal of cfg5 a few
+    200-frame windows at the start, the middle and the end -- are pushed through one iteration of the numpy oracle
+    (oracle/specinv_oracle.py gl_step / admm_step, pinned to the reference) from the very same state, and the rows /
+    samples the full-size launch produced for them must match to 1e-5 absolute (the signals are unit scale)
 """
+import numpy as np
 import pytest
 import torch
+
+from oracle import specinv_oracle as O
 
 pytestmark = pytest.mark.gpu
 
@@ -27,6 +34,66 @@ def _rel(a, b):
 
 def _rel_rms(a, b):
     return float((a - b).pow(2).mean().sqrt() / b.pow(2).mean().sqrt().clamp_min(1e-30))
+
+
+def _rows(s, b, t0=0, t1=None):
+    """(F, T') numpy array of signal b, frames [t0, t1) of a split frame-major spectrum."""
+    main = s.main[b, t0:t1].cpu().numpy()
+    nyq = s.nyq[b, t0:t1].cpu().numpy()
+    return np.ascontiguousarray(np.concatenate([main, nyq[:, None]], axis=1).T)
+
+
+def _oracle_slices(c, plan, x0, C, mag, solver, coef):
+    """One oracle iteration on slices of the full-size problem, from the state the kernel started from.
+
+    Forward half: the kernel's new state against the oracle's (tight).  Inverse half: the kernel's signal against the
+    ORACLE's ISTFT of the kernel's own new state (1e-5 absolute; the signals are unit scale).  End to end (kernel's
+    signal against the oracle's whole step): 2e-6 in RMS, 1e-4 max -- among the ~1e6 bins of a slice a few have
+    |q| ~ 1e-2 (|q| is Rayleigh with sigma ~ 20), where q*mag/|q| turns the 1e-5 round-off of q into a 1e-3 relative
+    change of that bin, i.e. a few 1e-5 in the signal; the two half-step checks are free of that."""
+    n_fft, hop = c["n_fft"], c["n_fft"] // 4
+    w = torch.hann_window(n_fft).numpy()
+    F = n_fft // 2 + 1
+
+    def check(tag, xs, Cs, ms, a, env, state_k, x_k, sl):
+        if c["algo"] == "gl":
+            st = O.gl_step(O.GLState(x=xs, q=Cs, env=env), ms, coef / (1 + coef), a)
+            (qk,) = state_k
+            assert np.abs(qk - st.q).max() <= 2e-4, (tag, "q", np.abs(qk - st.q).max())            # |q| up to ~250
+            own, _ = O.istft(O.project(qk, ms), a, env)
+        else:
+            st = O.admm_step(O.ADMMState(x=xs, X=Cs, U=np.zeros_like(Cs), env=env), ms, coef, a)
+            Xk, Uk = state_k
+            assert np.abs(Uk - st.U).max() <= 2e-4, (tag, "U", np.abs(Uk - st.U).max())
+            assert np.sqrt(np.mean(np.abs(Xk - st.X) ** 2)) <= 1e-5 * np.sqrt(np.mean(np.abs(st.X) ** 2)), (tag, "X")
+            own, _ = O.istft(Xk + Uk, a, env)
+        e_inv = np.abs(x_k - own[:, sl]).max()
+        assert e_inv <= 1e-5, (tag, "inverse half", e_inv)
+        d = x_k - st.x[:, sl]
+        assert np.sqrt(np.mean(d * d)) <= 2e-6 * np.sqrt(np.mean(st.x[:, sl] ** 2)) and np.abs(d).max() <= 1e-4, \
+            (tag, "end to end", np.sqrt(np.mean(d * d)), np.abs(d).max())
+
+    if plan.B > 1:
+        a = O.args_helper(F, np.float32, window=w, hop_length=hop)
+        env = O.ola_envelope(plan.T, a, dtype=np.float32)
+        for b in (0, plan.B // 2 - 1, plan.B - 1):
+            state_k = (_rows(solver.q_state, b)[None],) if c["algo"] == "gl" else \
+                (_rows(solver.X[solver.cur], b)[None], _rows(solver.U[solver.cur], b)[None])
+            check(f"signal {b}", x0[b:b + 1].cpu().numpy(), _rows(C, b)[None], _rows(mag, b)[None], a, env, state_k,
+                  solver.signal[b:b + 1].cpu().numpy(), slice(None))
+        return
+    # one long signal: un-centred windows of W frames; the samples at least n_fft away from the window's ends see
+    # the same frames (and the same envelope) as in the full problem
+    W = 200
+    a = O.args_helper(F, np.float32, window=w, hop_length=hop, center=False)
+    env = O.ola_envelope(W, a, dtype=np.float32)
+    P = n_fft // 2
+    for t0 in (3, plan.T // 2, plan.T - W - 3):
+        lo = t0 * hop - P                                   # first sample of frame t0 in the unpadded signal
+        n = (W - 1) * hop + n_fft
+        check(f"frames {t0}..{t0 + W}", x0[:, lo:lo + n].cpu().numpy(), _rows(C, 0, t0, t0 + W)[None],
+              _rows(mag, 0, t0, t0 + W)[None], a, env, (_rows(solver.q_state, 0, t0, t0 + W)[None],),
+              solver.signal[:, lo + n_fft:lo + n - n_fft].cpu().numpy(), slice(n_fft, n - n_fft))
 
 
 @pytest.mark.parametrize("name", list(CONFIGS))
@@ -75,6 +142,7 @@ def test_full_size_properties(name, monkeypatch):
         del own_x
         want_x = plan.istft(SplitSpec(proj(q.main, mag.main), proj(q.nyq, mag.nyq)))
         assert _rel_rms(solver.signal, want_x) <= 2e-6 and _rel(solver.signal, want_x) <= 1e-4
+        _oracle_slices(c, plan, x0, C, mag, solver, 0.99)
     else:
         rho = 0.1
         solver = ADMMSolver(plan, SplitSpec(C.main.clone(), C.nyq.clone()), mag, rho)
@@ -97,6 +165,7 @@ def test_full_size_properties(name, monkeypatch):
         del own_x
         want_x = plan.istft(SplitSpec(outs[0][0] + outs[0][1], outs[1][0] + outs[1][1]))
         assert _rel_rms(solver.signal, want_x) <= 2e-6 and _rel(solver.signal, want_x) <= 1e-4
+        _oracle_slices(c, plan, x0, C, mag, solver, rho)
     fused = solver.signal.clone()
     del solver, want_x
     torch.cuda.empty_cache()
