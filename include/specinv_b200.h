@@ -163,7 +163,10 @@ int specinv_fill_padding(int dtype, void* x, int64_t ld, int rows, int64_t padde
  * handle to hand to the neighbours through any channel) and maps its neighbours' areas with specinv_ipc_open.
  * specinv_halo_exchange pushes this rank's partial sums of the first / last `ov` samples of every row of x into the
  * left / right neighbour's area (NULL: no neighbour), raises their flags to `seq` (1, 2, 3, ... per exchange), waits
- * for its own flags and adds left partial + right partial in place. */
+ * for its own flags and adds left partial + right partial in place.  The wait is bounded (SPECINV_P2P_TIMEOUT_MS,
+ * default 10000): after a timeout the kernel records the exchange number in the area's status word and this and all
+ * later exchanges return without adding; specinv_halo_status copies that word to the host (synchronising `stream`):
+ * 0 = every exchange so far found its neighbour. */
 size_t specinv_halo_area_bytes(int dtype, int rows, int64_t ov);
 int specinv_ipc_alloc(size_t bytes, void** dptr, void* handle64);
 int specinv_ipc_open(const void* handle64, void** dptr);
@@ -171,6 +174,7 @@ int specinv_ipc_close(void* dptr);
 int specinv_ipc_free(void* dptr);
 int specinv_halo_exchange(int dtype, void* x, int64_t ld, int rows, int64_t local_len, int64_t ov, void* recv_self,
                           void* recv_left_peer, void* recv_right_peer, uint32_t seq, void* stream);
+int specinv_halo_status(int dtype, const void* recv_self, int rows, int64_t ov, uint32_t* status, void* stream);
 
 /* ---- metrics (metrics.py:4-43, F.mse_loss at methods.py:182) ---------------------------------
  * out[0] += sum (a-b)^2, out[1] += sum a^2, out[2] += sum b^2 over n contiguous reals. */

@@ -227,3 +227,25 @@ def fill_padding(x: Tensor, padded_offset: int, pad: int, signal_len: int, pad_m
     with torch.cuda.device(x.device):
         _ok(_lib.lib().specinv_fill_padding(_DT[x.dtype], _p(x), x.stride(0), x.shape[0], int(padded_offset), x.shape[1],
                                             int(pad), int(signal_len), int(pad_mode), _stream(x)), "fill_padding")
+
+
+# ---- fake (meta) kernels --------------------------------------------------------------------------------------
+# Every op writes into caller-owned buffers and returns nothing, so its FakeTensor / meta implementation is "check
+# the arguments, do nothing": torch.compile, FakeTensorMode and torch.export can trace through code that calls them
+# (SURVEY.md section 8b).  The checks are the ones that do not need data: shapes that the C entry point derives
+# sizes from.
+def _fake_nothing(*args, **kwargs) -> None:
+    return None
+
+
+def _fake_iter(plan, x_in, x_out, *rest) -> None:
+    if x_in.shape != x_out.shape:
+        raise RuntimeError("specinv_b200: x_in / x_out shape mismatch")
+    return None
+
+
+ALL_OPS = (plan_init, stft, istft, gl_iter, admm_iter, pack, unpack, metric_sums, phase_init, spec_abs, rtisi_la,
+           plan_init_ranged, phase_init_ex, halo_sum, fill_padding)
+for _op in ALL_OPS:
+    _op.register_fake(_fake_iter if _op in (gl_iter, admm_iter) else _fake_nothing)
+del _op

@@ -1,10 +1,24 @@
 // extern "C" entry points of libspecinv_b200.so (see include/specinv_b200.h), the plan
 // initialisation kernels, layout conversion and the standalone metric reduction.
+#include <atomic>
 #include <cstdlib>
 
 #include "specinv_common.cuh"
 
 namespace specinv {
+
+// ---------------------------------------------------------------- PDL guard (see specinv_common.cuh)
+static const uintptr_t kNoStream = ~(uintptr_t)0;
+static std::atomic<uintptr_t> g_tables_last_on{kNoStream};   // stream whose latest library launch wrote plan tables
+void note_tables_launch(cudaStream_t st) { g_tables_last_on.store((uintptr_t)st, std::memory_order_release); }
+void note_other_launch(cudaStream_t st) {
+    uintptr_t expect = (uintptr_t)st;                        // only the same stream's mark is cleared
+    g_tables_last_on.compare_exchange_strong(expect, kNoStream, std::memory_order_acq_rel);
+}
+bool pdl_prologue_safe(cudaStream_t st) {
+    uintptr_t expect = (uintptr_t)st;
+    return !g_tables_last_on.compare_exchange_strong(expect, kNoStream, std::memory_order_acq_rel);
+}
 
 // implemented in specinv_generic.cu
 int generic_stft(const specinv_desc*, const void*, const void*, void*, void*, void*);
@@ -82,9 +96,11 @@ static int plan_init_t(const Dims& dm, const specinv_desc* d, const void* window
     plan_tables_kernel<T><<<(n + 255) / 256, 256, 0, st>>>(dm.N, dm.M, d->normalized, (const T*)window,
                                                            (cx_t<T>*)(p + pl.tw), (cx_t<T>*)(p + pl.twr),
                                                            (T*)(p + pl.wa), (T*)(p + pl.ws));
+    note_tables_launch(st);       // an iteration kernel launched right behind this one must not overlap it
     plan_envelope_kernel<T><<<(unsigned)((dm.L + 255) / 256), 256, 0, st>>>(dm, frame_offset, total_frames,
                                                                             (const T*)window, (T*)(p + pl.env),
                                                                             (T*)(p + pl.inv_env));
+    note_other_launch(st);        // the envelope kernel does not touch the tables: overlap behind it is safe
     return (int)cudaGetLastError();
 }
 
@@ -371,6 +387,18 @@ int specinv_fill_padding(int dtype, void* x, int64_t ld, int rows, int64_t padde
                          int64_t signal_len, int pad_mode, void* stream) {
     if (!x || rows < 1 || pad < 0 || local_len < 1 || signal_len < 1) return SPECINV_ERR_INVALID;
     if (pad == 0) return SPECINV_OK;
+    // A buffer that holds padding samples must also hold their sources: reflect padding mirrors sample P + k onto
+    // P - k (and L + P - 1 - k onto L + P - 1 + k), so an edge range needs 2 * pad + 1 samples; otherwise the kernel
+    // would have to leave stale padding behind (the source lives on the neighbouring rank).
+    if (pad_mode == SPECINV_PAD_REFLECT) {
+        const long long end = padded_offset + local_len;                       // buffer = padded samples [offset, end)
+        const bool has_left = padded_offset < pad, has_right = end > pad + signal_len;
+        // farthest sources: of the first left-pad sample in the buffer (2 pad - offset) and of the last right-pad one
+        if (has_left && 2LL * pad - padded_offset >= end) return SPECINV_ERR_INVALID;
+        if (has_right && 2LL * signal_len - 2 + 2LL * pad - (end - 1) < padded_offset) return SPECINV_ERR_INVALID;
+    }
+    if (pad_mode == SPECINV_PAD_CIRCULAR && (padded_offset > 0 || padded_offset + local_len < signal_len + 2LL * pad))
+        return SPECINV_ERR_UNSUPPORTED;   // wraps around the whole signal: single-range buffers only
     dim3 grid((unsigned)((2LL * pad + 255) / 256), rows);
     if (dtype == SPECINV_F64)
         fill_padding_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>((double*)x, ld, rows, padded_offset, local_len,

@@ -97,6 +97,16 @@ inline int make_dims(const specinv_desc* d, Dims* o) {
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// Programmatic-dependent-launch guard (defined in specinv_api.cu).  The fused iteration kernels read the plan's
+// window / twiddle tables in their prologue, BEFORE griddepcontrol.wait, i.e. possibly while the previous kernel of
+// the stream is still running.  That is only safe when that previous kernel does not write those tables:
+// `note_tables_launch(st)` records that the tables kernel was the library's latest launch on stream `st`,
+// `note_other_launch(st)` that some other library kernel followed it, and `pdl_prologue_safe(st)` -- called by the
+// iteration launchers -- returns false (launch fully serialised) in the first case and clears the mark.
+void note_tables_launch(cudaStream_t st);
+void note_other_launch(cudaStream_t st);
+bool pdl_prologue_safe(cudaStream_t st);
+
 inline PlanLayout plan_layout(const Dims& dm, int dtype) {
     const size_t es = dtype == SPECINV_F64 ? 8 : 4;
     PlanLayout p; size_t off = 0;

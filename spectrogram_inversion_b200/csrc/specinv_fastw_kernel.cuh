@@ -223,9 +223,9 @@ __global__ void __launch_bounds__(warps_of(VV, OP) * 32, 1) warp_iter_kernel(con
         tmem_wait_st();
     }
     // Programmatic dependent launch: everything above touched only this CTA's own resources and the plan's window /
-    // twiddle tables -- written by the first kernel of specinv_plan_init, which is never the kernel right before
-    // this one in the stream (the envelope kernel follows it) -- so it may run under the tail of the previous
-    // kernel of the stream (the previous iteration).  Let the next launch start as early as SM resources allow, then
+    // twiddle tables, so it may run under the tail of the previous kernel of the stream (the previous iteration).
+    // The tables are written by plan_tables_kernel only; the host side enforces that this kernel is never launched
+    // with the programmatic attribute right behind it (note_tables_launch / pdl_prologue_safe, specinv_common.cuh).  Let the next launch start as early as SM resources allow, then
     // wait until the previous grid has completed and its writes are visible before the first access to anything it
     // may have written (the 1/envelope, the signal, the state) or may still be reading (the ping-pong buffers).
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -494,7 +494,8 @@ static int launch(const WArgs& a0, cudaStream_t st) {
         if (cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return SPECINV_ERR_NO_DEVICE;
     }
     // the TMA bulk copies need 16-byte aligned rows
-    if ((((uintptr_t)a.x_in | (uintptr_t)a.s0_in | (uintptr_t)a.mag) & 15) != 0) return SPECINV_ERR_UNSUPPORTED;   // (s0_in is NULL for OP_GLP)
+    // (s0_in is NULL for OP_GLP, s1_in for everything but ADMM, whose U rows are bulk-copied too)
+    if ((((uintptr_t)a.x_in | (uintptr_t)a.s0_in | (uintptr_t)a.s1_in | (uintptr_t)a.mag) & 15) != 0) return SPECINV_ERR_UNSUPPORTED;
     if (OP == OP_ISTFT && a.sums) return SPECINV_ERR_INVALID;
     a.frames_total = (long long)a.B * a.T;
     constexpr int WARPS = warps_of(VV, OP);
@@ -511,9 +512,11 @@ static int launch(const WArgs& a0, cudaStream_t st) {
     // (see griddepcontrol.wait in the kernel)
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(WARPS * 32); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    // ... unless the library's last launch on this stream was the kernel that WRITES the plan tables the prologue reads
+    // (specinv_common.cuh: pdl_prologue_safe); then this launch is fully serialised behind it.
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_prologue_safe(st) ? 1 : 0;
     cfg.attrs = attr; cfg.numAttrs = 1;
     cudaError_t e;
     if (a.sums) {

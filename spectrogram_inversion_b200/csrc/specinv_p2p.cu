@@ -11,6 +11,12 @@
 // Slots are double buffered by the parity of the iteration number: a rank can only be one exchange ahead of its
 // neighbour (it needs the neighbour's flag k to finish exchange k), so the slot of iteration k+2 is free.
 // No collective library call, no host synchronisation; a rank that arrives early spins on its flag only.
+// The spin is BOUNDED (SPECINV_P2P_TIMEOUT_MS, default 10 s, measured with %globaltimer): a neighbour that died or
+// took another code path must not leave this GPU in an uninterruptible kernel.  On a timeout the kernel writes the
+// iteration number into the status word of its own receive area, skips the add, and every later exchange returns at
+// once; the host reads the word where it synchronises anyway (specinv_halo_status) and raises.
+#include <cstdlib>
+
 #include "specinv_common.cuh"
 
 namespace specinv {
@@ -29,7 +35,15 @@ struct HaloArgs {
     char* recv_self;                 // this rank's receive area
     char* recv_peer[2];              // the left / right neighbour's receive area (nullptr: no neighbour)
     unsigned seq;
+    unsigned long long timeout_ns;   // bound of the wait for the neighbour's push
 };
+
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+constexpr int FLAG_STATUS = 2;       // word index (after the two arrival flags): 0 = fine, else the exchange that timed out
 
 // byte offsets inside a receive area: slot(parity, from_side) then the two flags
 __host__ __device__ inline size_t slot_off(int parity, int from_side, int rows, long long ov, size_t es) {
@@ -56,12 +70,23 @@ __global__ void __launch_bounds__(1024) halo_exchange_kernel(const HaloArgs a) {
     __syncthreads();
     unsigned* peer_flags = (unsigned*)(peer + flags_off(a.rows, a.ov, sizeof(T)));
     unsigned* my_flags = (unsigned*)(a.recv_self + flags_off(a.rows, a.ov, sizeof(T)));
+    __shared__ int s_ok;
     if (threadIdx.x == 0) {
         st_release_sys(peer_flags + (side == 0 ? 1 : 0), a.seq);
-        // 2. wait for the neighbour's push of this iteration
-        while ((int)(ld_acquire_sys(my_flags + side) - a.seq) < 0) __nanosleep(100);
+        // 2. wait for the neighbour's push of this iteration -- bounded; a rank that already failed does not wait again
+        bool ok = ld_acquire_sys(my_flags + FLAG_STATUS) == 0;
+        if (ok) {
+            const unsigned long long t0 = global_timer_ns();
+            while ((int)(ld_acquire_sys(my_flags + side) - a.seq) < 0) {
+                __nanosleep(100);
+                if (global_timer_ns() - t0 > a.timeout_ns) { ok = false; break; }
+            }
+            if (!ok) atomicCAS(my_flags + FLAG_STATUS, 0u, a.seq);
+        }
+        s_ok = ok;
     }
     __syncthreads();
+    if (!s_ok) return;               // the host will see the status word; the samples keep this rank's partial sums
     // 3. left partial + right partial
     const T* src = (const T*)(a.recv_self + slot_off(parity, side, a.rows, a.ov, sizeof(T)));
     for (long long i = threadIdx.x; i < n; i += blockDim.x) {
@@ -104,11 +129,34 @@ int specinv_ipc_open(const void* handle64, void** dptr) {
 int specinv_ipc_close(void* dptr) { return dptr ? (int)cudaIpcCloseMemHandle(dptr) : SPECINV_OK; }
 int specinv_ipc_free(void* dptr) { return dptr ? (int)cudaFree(dptr) : SPECINV_OK; }
 
+static unsigned long long halo_timeout_ns() {
+    static unsigned long long ns = 0;
+    if (ns == 0) {
+        const char* e = getenv("SPECINV_P2P_TIMEOUT_MS");
+        long long ms = e ? atoll(e) : 0;
+        if (ms <= 0) ms = 10000;
+        ns = (unsigned long long)ms * 1000000ull;
+    }
+    return ns;
+}
+
+// *status = 0 while every exchange found its neighbour; otherwise the number of the first exchange that timed out.
+// Synchronises `stream` (call it where the host waits anyway: evaluations, the end of the run).
+int specinv_halo_status(int dtype, const void* recv_self, int rows, int64_t ov, uint32_t* status, void* stream) {
+    if (!recv_self || !status || rows < 1 || ov < 1) return SPECINV_ERR_INVALID;
+    const size_t es = dtype == SPECINV_F64 ? 8 : 4;
+    const char* p = (const char*)recv_self + flags_off(rows, ov, es) + FLAG_STATUS * sizeof(unsigned);
+    cudaError_t e = cudaMemcpyAsync(status, p, sizeof(unsigned), cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+    if (e != cudaSuccess) return (int)e;
+    return (int)cudaStreamSynchronize((cudaStream_t)stream);
+}
+
 int specinv_halo_exchange(int dtype, void* x, int64_t ld, int rows, int64_t local_len, int64_t ov, void* recv_self,
                           void* recv_left_peer, void* recv_right_peer, uint32_t seq, void* stream) {
     if (!x || !recv_self || rows < 1 || ov < 1 || local_len < 2 * ov || seq == 0) return SPECINV_ERR_INVALID;
     if (!recv_left_peer && !recv_right_peer) return SPECINV_OK;
-    HaloArgs a{x, ld, rows, local_len, ov, (char*)recv_self, {(char*)recv_left_peer, (char*)recv_right_peer}, seq};
+    HaloArgs a{x, ld, rows, local_len, ov, (char*)recv_self, {(char*)recv_left_peer, (char*)recv_right_peer}, seq,
+               halo_timeout_ns()};
     if (dtype == SPECINV_F64) halo_exchange_kernel<double><<<2, 1024, 0, (cudaStream_t)stream>>>(a);
     else if (dtype == SPECINV_F32) halo_exchange_kernel<float><<<2, 1024, 0, (cudaStream_t)stream>>>(a);
     else return SPECINV_ERR_INVALID;

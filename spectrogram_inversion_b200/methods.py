@@ -12,6 +12,8 @@ from .stft_args import args_helper, real_dtype_of
 __all__ = ["griffin_lim", "RTISI_LA", "ADMM", "L_BFGS", "phase_init"]
 
 pi2 = 2 * math.pi
+_TORCH_STFT_KEYS = frozenset(("hop_length", "win_length", "window", "center", "pad_mode", "normalized", "onesided",
+                              "return_complex", "align_to_window"))
 
 
 def _pop_aliases(kw: dict, max_iter, eva_iter):
@@ -213,6 +215,12 @@ def RTISI_LA(spec, look_ahead=-1, asymmetric_window=False, max_iter=25, alpha=0.
     assert alpha >= 0
     assert not spec.is_complex()
     assert 4 > len(spec.shape) > 1
+    if not asymmetric_window:
+        # the reference hands the caller's kwargs to torch.stft on this path (methods.py:308-310, :385), so an unknown
+        # key is a TypeError there (griffin_lim / ADMM and the asymmetric path silently ignore it, :42-46)
+        for key in stft_kwargs:
+            if key not in _TORCH_STFT_KEYS:
+                raise TypeError(f"stft() got an unexpected keyword argument '{key}'")
     if autograd.wants_grad(spec):
         work, args = _diff_setup(spec, stft_kwargs)
         return _diff_finish(autograd.rtisi_diff(work, args, look_ahead, asymmetric_window, max_iter, alpha, verbose), spec)

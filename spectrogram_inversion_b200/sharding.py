@@ -168,7 +168,11 @@ class CudaRangeEngine:
 class PeerHalo:
     """NVLink peer-memory plumbing of the one-kernel halo exchange (csrc/specinv_p2p.cu): this rank's receive area
     (cudaMalloc + CUDA IPC handle), the mapped areas of its two neighbours, and the exchange counter.  The 64-byte
-    handles travel through ``dist.all_gather_object``; nothing else uses the process group afterwards."""
+    handles travel through ``dist.all_gather_object``; nothing else uses the process group afterwards.
+
+    ``PeerHalo.create`` is the collective constructor: every rank tries to set its side up and the ranks agree
+    (all-reduce of an ok flag) whether ALL of them succeeded; otherwise everyone releases what it got and the caller
+    falls back to the NCCL send/recv exchange -- no rank is left waiting on a peer that took the other path."""
 
     def __init__(self, rows: int, ov: int, dtype, device, group, rank: int, world: int):
         import ctypes as C
@@ -176,20 +180,52 @@ class PeerHalo:
         self._lib, self._C = _lib, C
         self.dt = _ops._DT[dtype]
         self.rows, self.ov, self.device, self.seq = rows, ov, device, 0
+        self.area, self.peers = None, [C.c_void_p(), C.c_void_p()]
+        self.error = None
         L = _lib.lib()
-        with torch.cuda.device(device):
-            nbytes = L.specinv_halo_area_bytes(self.dt, rows, ov)
-            self.area = C.c_void_p()
-            handle = C.create_string_buffer(64)
-            _lib.check(L.specinv_ipc_alloc(nbytes, C.byref(self.area), handle), "ipc_alloc")
-            handles = [None] * world
-            dist.all_gather_object(handles, bytes(handle.raw), group=group)
-            self.peers = [C.c_void_p(), C.c_void_p()]
-            for side, r in ((0, rank - 1), (1, rank + 1)):
-                if 0 <= r < world:
-                    _lib.check(L.specinv_ipc_open(C.create_string_buffer(handles[r], 64), C.byref(self.peers[side])),
-                               "ipc_open")
-        dist.barrier(group=group)
+        handle = C.create_string_buffer(64)
+        try:
+            with torch.cuda.device(device):
+                nbytes = L.specinv_halo_area_bytes(self.dt, rows, ov)
+                area = C.c_void_p()
+                _lib.check(L.specinv_ipc_alloc(nbytes, C.byref(area), handle), "ipc_alloc")
+                self.area = area
+        except Exception as ex:            # keep going: the other ranks are waiting in the all_gather below
+            self.error = ex
+        infos = [None] * world
+        dist.all_gather_object(infos, (bytes(handle.raw), torch.cuda.current_device(), self.error is None), group=group)
+        if self.error is None and not all(ok for _, _, ok in infos):
+            self.error = RuntimeError("a peer rank could not allocate its halo area")
+        if self.error is None:
+            try:
+                with torch.cuda.device(device):
+                    me = torch.cuda.current_device()
+                    for side, r in ((0, rank - 1), (1, rank + 1)):
+                        if not 0 <= r < world:
+                            continue
+                        peer_dev = infos[r][1]
+                        # (with one visible device per process both are device 0 and the question cannot be asked here:
+                        # cudaIpcOpenMemHandle then decides)
+                        if peer_dev != me and not torch.cuda.can_device_access_peer(me, peer_dev):
+                            raise RuntimeError(f"cuda:{me} cannot access its neighbour cuda:{peer_dev} (no P2P)")
+                        _lib.check(L.specinv_ipc_open(C.create_string_buffer(infos[r][0], 64), C.byref(self.peers[side])),
+                                   "ipc_open")
+            except Exception as ex:
+                self.error = ex
+
+    @classmethod
+    def create(cls, rows, ov, dtype, device, group, rank, world, comm_device):
+        """Collective over ``group``: a working PeerHalo on every rank, or None on every rank."""
+        ph = cls(rows, ov, dtype, device, group, rank, world)
+        ok = torch.tensor([0.0 if ph.error is not None else 1.0], device=comm_device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)      # also the barrier: every mapping is in place
+        if ok.item() == 1.0:
+            return ph
+        if ph.error is not None:
+            import warnings
+            warnings.warn(f"NVLink peer-memory halo exchange unavailable ({ph.error}); using NCCL send/recv")
+        ph.close()
+        return None
 
     def exchange(self, x: torch.Tensor) -> None:
         C, L = self._C, self._lib.lib()
@@ -200,15 +236,32 @@ class PeerHalo:
                                                     self.ov, self.area, self.peers[0], self.peers[1], self.seq, stream),
                             "halo_exchange")
 
+    def check(self) -> None:
+        """Raise when an exchange timed out waiting for a neighbour (synchronises the current stream; called where
+        the host waits anyway: evaluations and the end of the run)."""
+        C, L = self._C, self._lib.lib()
+        if self.area is None:
+            return
+        status = C.c_uint32(0)
+        stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        with torch.cuda.device(self.device):
+            self._lib.check(L.specinv_halo_status(self.dt, self.area, self.rows, self.ov, C.byref(status), stream),
+                            "halo_status")
+        if status.value:
+            raise RuntimeError(f"halo exchange {status.value} timed out waiting for a neighbouring rank "
+                               "(SPECINV_P2P_TIMEOUT_MS); the result is incomplete")
+
     def close(self) -> None:
-        if getattr(self, "area", None) is None:
+        if getattr(self, "area", None) is None and not any(bool(p) for p in getattr(self, "peers", [])):
             return
         L = self._lib.lib()
         torch.cuda.synchronize(self.device)
-        for p in self.peers:
+        for i, p in enumerate(self.peers):
             if p:
                 L.specinv_ipc_close(p)
-        L.specinv_ipc_free(self.area)
+                self.peers[i] = self._C.c_void_p()
+        if self.area is not None:
+            L.specinv_ipc_free(self.area)
         self.area = None
 
     def __del__(self):
@@ -234,6 +287,10 @@ class FrameShardedGriffinLim:
         a = engine.args_global
         self.ov = a.n_fft - a.hop_length
         assert engine.local_len >= 2 * self.ov, "every rank needs at least ceil(n_fft/hop) frames"
+        if a.center and a.pad_mode == "reflect" and self.rank in (0, self.world - 1):
+            # the reflect sources of an edge rank's padding must live in its own buffer (specinv_fill_padding would
+            # otherwise have to leave stale padding behind): 2 * pad + 1 samples, i.e. at least two frames
+            assert engine.local_len >= 2 * a.pad + 1, "the first / last rank needs at least 2 frames with reflect padding"
         self.lr = alpha / (1 + alpha)
         self.mag = mag_local
         self.q = [C_local, engine.like(C_local)]
@@ -251,8 +308,8 @@ class FrameShardedGriffinLim:
         self.peer = None
         if (self.world > 1 and self.x[0].is_cuda and dist.get_backend(group) == "nccl"
                 and os.environ.get("SPECINV_P2P", "1") != "0"):
-            self.peer = PeerHalo(self.x[0].shape[0], self.ov, self.x[0].dtype, self.x[0].device, group, self.rank,
-                                 self.world)
+            self.peer = PeerHalo.create(self.x[0].shape[0], self.ov, self.x[0].dtype, self.x[0].device, group,
+                                        self.rank, self.world, self.x[0].device)
         engine.istft_partial(C_local, self.x[0])                  # x_0 = ISTFT(C)  (methods.py:233)
         self._exchange(self.x[0])
         self.iterations = 0
@@ -307,6 +364,8 @@ class FrameShardedGriffinLim:
         self.iterations += 1
         if evaluate:
             d, e = self.sums.tolist()
+            if self.peer is not None:
+                self.peer.check()
             return d, e
         return None
 
@@ -316,6 +375,8 @@ class FrameShardedGriffinLim:
 
     def owned_piece(self):
         """(start index in the global unpadded signal, tensor) of the samples this rank owns."""
+        if self.peer is not None:
+            self.peer.check()
         a, e = self.e.args_global, self.e
         hop, P, L = a.hop_length, a.pad, e.signal_len
         off = e.padded_offset

@@ -96,6 +96,15 @@ def test_assertions_fire_before_any_gpu_work():
         S.RTISI_LA(spec.to(torch.complex64))
 
 
+def test_rtisi_unknown_kwargs_raise_like_the_reference():
+    """methods.py:308-310, :385: on the non-asymmetric path the caller's kwargs reach torch.stft, so an unknown key
+    is a TypeError (before any device work); the asymmetric path ignores it like griffin_lim / ADMM (:42-46)."""
+    import spectrogram_inversion_b200 as S
+    spec = torch.rand(65, 20)
+    with pytest.raises(TypeError, match="unexpected keyword argument 'foo'"):
+        S.RTISI_LA(spec, max_iter=1, verbose=0, foo=1)
+
+
 @pytest.mark.skipif(torch.cuda.is_available(), reason="only meaningful on a box without a GPU")
 def test_no_cpu_fallback():
     import spectrogram_inversion_b200 as S
@@ -141,7 +150,8 @@ def test_package_exports_the_reference_names_and_lbfgs_runs():
 
 
 def test_bench_reference_arm_prints_the_contract_line():
-    """`bench.py --impl reference` (the oracle port on the host cores) prints one JSON line with the contract keys."""
+    """`bench.py --impl reference` (the unmodified reference from baseline/_ref on the host cores, or the oracle port
+    when it is not installed) prints one JSON line with the contract keys."""
     import json
     import subprocess
     import sys
@@ -152,8 +162,42 @@ def test_bench_reference_arm_prints_the_contract_line():
     for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
                 "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert key in line, key
-    assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
+    installed = os.path.exists(os.path.join(ROOT, "baseline", "_ref", "torch_specinv", "methods.py"))
+    assert line["impl"] == "reference" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == ("reference" if installed else "port")
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and "workload" in line["config"]
+
+
+def test_every_custom_op_has_a_fake_kernel():
+    """SURVEY.md section 8b: each specinv_b200:: op carries a register_fake implementation, so FakeTensorMode /
+    torch.compile can trace through callers without a device (the ops mutate caller-owned buffers, return nothing)."""
+    from torch._subclasses.fake_tensor import FakeTensorMode
+    from spectrogram_inversion_b200 import _ops
+    assert len(_ops.ALL_OPS) == 15
+    with FakeTensorMode():
+        f = lambda *shape, dt=torch.float32: torch.empty(*shape, dtype=dt, device="cuda")
+        B, T, M, L = 2, 9, 64, 8 * 32
+        plan = torch.empty(4096, dtype=torch.uint8, device="cuda")
+        x0, x1 = f(B, L), f(B, L)
+        qm, qn = f(B, T, M, dt=torch.complex64), f(B, T, dt=torch.complex64)
+        mm, mn = f(B, T, M), f(B, T)
+        sums = f(2, dt=torch.float64)
+        k = (128, 32, True, 0, False, True)
+        assert _ops.plan_init(plan, f(128), 128, 32, T, B, True, 0, False, True) is None
+        assert _ops.stft(plan, x0, qm, qn, *k) is None and _ops.istft(plan, qm, qn, x0, *k) is None
+        assert _ops.gl_iter(plan, x0, x1, qm, qn, qm.clone(), qn.clone(), mm, mn, sums, 0.5, *k) is None
+        assert _ops.admm_iter(plan, x0, x1, qm, qn, qm, qn, qm.clone(), qn.clone(), qm.clone(), qn.clone(), mm, mn, sums,
+                              0.1, *k) is None
+        with pytest.raises(RuntimeError):
+            _ops.gl_iter(plan, x0, f(B, L + 1), qm, qn, qm.clone(), qn.clone(), mm, mn, sums, 0.5, *k)
+        assert _ops.pack(f(B, M + 1, T), mm, mn, 128, True) is None
+        assert _ops.unpack(qm, qn, f(B, M + 1, T, dt=torch.complex64), 128, True) is None
+        assert _ops.metric_sums(mm, mm, f(3, dt=torch.float64)) is None
+        assert _ops.phase_init(mm, mn, qm, qn, 128, 32, True) is None and _ops.spec_abs(qm, qn, mm, mn, 128, True) is None
+        assert _ops.rtisi_la(plan, f(128), mm, mn, x0, f(256), 3, False, 4, 0.99, 0.1, *k) is None
+        assert _ops.plan_init_ranged(plan, f(128), 128, 32, T, B, False, True, 0, 20) is None
+        assert _ops.phase_init_ex(mm, mn, qm, qn, f(0, dt=torch.float64), f(B, M + 1, dt=torch.float64), 128, 32, True) is None
+        assert _ops.halo_sum(f(B, 96), f(B, 96), f(B, 96)) is None and _ops.fill_padding(x0, 0, 64, L, 0) is None
 
 
 class _FakeSolver:
