@@ -176,6 +176,25 @@ int specinv_halo_exchange(int dtype, void* x, int64_t ld, int rows, int64_t loca
                           void* recv_left_peer, void* recv_right_peer, uint32_t seq, void* stream);
 int specinv_halo_status(int dtype, const void* recv_self, int rows, int64_t ov, uint32_t* status, void* stream);
 
+/* ---- small problems: a whole run of fast Griffin-Lim iterations in ONE persistent kernel ---------------------
+ * (csrc/specinv_resident.cu; replaces n_iters calls of specinv_gl_iter, i.e. n_iters passes of the closure
+ * methods.py:237-250 under the loop methods.py:178-190).  When B * T frames fit the shared memory of the SMs
+ * (hop = n_fft/4, n_fft 1024 / 2048 / 4096, fp32, onesided, not circular padding, at most one signal per SM) the
+ * momentum spectra, magnitudes and signal stay on chip for all iterations; HBM sees the state once in, once out.
+ *   specinv_gl_run_workspace_bytes: SPECINV_ERR_UNSUPPORTED when the problem does not fit -- use specinv_gl_iter.
+ *   specinv_gl_run: iterations iter0 .. iter0 + n_iters - 1; those with (i % eva_iter) == eva_iter - 1 add their
+ *     metric sums (as specinv_gl_iter's `sums`) to sums[2 k], sums[2 k + 1], k = 0, 1, ... in order (sums == NULL:
+ *     no evaluation).  q_in / q_out and x_in / x_out may alias.  `workspace` (16-byte aligned, caller-owned, device)
+ *     carries the neighbour exchange of the CTAs; nothing is allocated, nothing synchronises.
+ *   specinv_gl_run_status: 0, or the iteration at which a CTA timed out waiting for a neighbour
+ *     (SPECINV_RESIDENT_TIMEOUT_MS, default 5000; the result is then invalid).  Synchronises `stream`. */
+int specinv_gl_run_workspace_bytes(const specinv_desc* d, size_t* bytes);
+int specinv_gl_run(const specinv_desc* d, const void* plan, const void* x_in, void* x_out,
+                   const void* q_in_main, const void* q_in_nyq, void* q_out_main, void* q_out_nyq,
+                   const void* mag_main, const void* mag_nyq, double lr, int n_iters, int iter0, int eva_iter,
+                   double* sums, void* workspace, void* stream);
+int specinv_gl_run_status(const specinv_desc* d, const void* workspace, uint32_t* status, void* stream);
+
 /* ---- metrics (metrics.py:4-43, F.mse_loss at methods.py:182) ---------------------------------
  * out[0] += sum (a-b)^2, out[1] += sum a^2, out[2] += sum b^2 over n contiguous reals. */
 int specinv_metric_sums(int dtype, const void* a, const void* b, int64_t n, double* out3, void* stream);

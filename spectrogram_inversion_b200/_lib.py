@@ -26,6 +26,7 @@ EXPORTS = (
     "specinv_phase_init_ex", "specinv_halo_sum", "specinv_fill_padding", "specinv_plan_unit_envelope",
     "specinv_halo_area_bytes", "specinv_ipc_alloc", "specinv_ipc_open", "specinv_ipc_close", "specinv_ipc_free",
     "specinv_halo_exchange", "specinv_halo_status",
+    "specinv_gl_run_workspace_bytes", "specinv_gl_run", "specinv_gl_run_status",
 )
 
 
@@ -56,6 +57,9 @@ def _declare(lib: C.CDLL) -> None:
         "specinv_ipc_close": [vp],
         "specinv_ipc_free": [vp],
         "specinv_halo_exchange": [C.c_int, vp, i64, C.c_int, i64, i64, vp, vp, vp, C.c_uint32, vp],
+        "specinv_gl_run_workspace_bytes": [dp, C.POINTER(C.c_size_t)],
+        "specinv_gl_run": [dp, vp, vp, vp, vp, vp, vp, vp, vp, vp, dbl, C.c_int, C.c_int, C.c_int, vp, vp, vp],
+        "specinv_gl_run_status": [dp, vp, C.POINTER(C.c_uint32), vp],
         "specinv_halo_status": [C.c_int, vp, C.c_int, i64, C.POINTER(C.c_uint32), vp],
         "specinv_plan_envelope": [dp, vp, vp, vp],
         "specinv_plan_init_ranged": [dp, vp, vp, i64, i64, vp],

@@ -6,6 +6,7 @@ keeps in ``_training_loop`` (torch_specinv/methods.py:153-190)."""
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass
 from typing import Callable, List, Optional, Tuple
 
@@ -193,7 +194,19 @@ class _Solver:
 
     def run_plain(self, n: int) -> None:
         """``n`` iterations without evaluation (no host synchronisation)."""
-        self.run_pattern((False,) * n)
+        self.run_many(n, self.iterations, 1, evaluate=False)
+
+    def run_many(self, n: int, iter0: int, eva_iter: int, evaluate: bool = True) -> None:
+        """Iterations iter0 .. iter0 + n - 1 of the reference loop (methods.py:178-190) without host synchronisation:
+        those with ``i % eva_iter == eva_iter - 1`` run the fused metric epilogue when ``evaluate`` (the last pair of
+        sums stays in ``self.sums``)."""
+        if not evaluate:
+            return self.run_pattern((False,) * n)
+        i = 0
+        while i < n:
+            m = min(eva_iter, n - i)
+            self.run_pattern(tuple((iter0 + i + k) % eva_iter == eva_iter - 1 for k in range(m)))
+            i += m
 
     def run_pattern(self, flags: Tuple[bool, ...]) -> None:
         """One iteration per flag, evaluating (fused metric sums left on the device, not read) where the flag is
@@ -241,6 +254,43 @@ class GriffinLimSolver(_Solver):
         self.q = None if self.plain else [C, C.like()]
         self._fn = _lib.lib().specinv_gl_iter
         plan.istft(C, self.x[0])                          # methods.py:233
+        # Small problems (B * T frames fit the SMs' shared memory): runs of iterations go through ONE persistent kernel
+        # with the state resident on chip (csrc/specinv_resident.cu) instead of one launch per iteration.
+        self._resident_ws = None
+        if not self.plain and plan.dtype == torch.float32 and os.environ.get("SPECINV_RESIDENT", "1") != "0":
+            nbytes = _lib.C.c_size_t(0)
+            if _lib.lib().specinv_gl_run_workspace_bytes(plan.desc_ref, _lib.C.byref(nbytes)) == 0:
+                self._resident_ws = torch.empty(nbytes.value, dtype=torch.uint8, device=plan.device)
+
+    def run_many(self, n: int, iter0: int, eva_iter: int, evaluate: bool = True) -> None:
+        if self._resident_ws is None or n < 2 or self.use_graphs:
+            return super().run_many(n, iter0, eva_iter, evaluate)
+        p, i, o = self.plan, self.cur, self.cur ^ 1
+        n_eval = sum(1 for k in range(n) if (iter0 + k) % eva_iter == eva_iter - 1) if evaluate else 0
+        sums = torch.zeros(2 * n_eval, dtype=torch.float64, device=p.device) if n_eval else None
+        stream = torch.cuda.current_stream(p.device).cuda_stream
+        with torch.cuda.device(p.device):
+            code = _lib.lib().specinv_gl_run(
+                p.desc_ref, p.buf.data_ptr(), self.x[i].data_ptr(), self.x[o].data_ptr(), self.q[i].main.data_ptr(),
+                self.q[i].nyq.data_ptr(), self.q[o].main.data_ptr(), self.q[o].nyq.data_ptr(), self.mag.main.data_ptr(),
+                self.mag.nyq.data_ptr(), self.lr, int(n), int(iter0), int(eva_iter),
+                sums.data_ptr() if sums is not None else None, self._resident_ws.data_ptr(), stream)
+        _ops._ok(code, "gl_run")
+        if sums is not None:
+            self.sums.copy_(sums[-2:])
+        self.cur ^= 1
+        self.iterations += n
+
+    def check_resident(self) -> None:
+        """Raise if a CTA of the last persistent run timed out waiting for a neighbour (synchronises)."""
+        if self._resident_ws is None:
+            return
+        status = _lib.C.c_uint32(0)
+        with torch.cuda.device(self.plan.device):
+            _ops._ok(_lib.lib().specinv_gl_run_status(self.plan.desc_ref, self._resident_ws.data_ptr(), _lib.C.byref(status),
+                                                      torch.cuda.current_stream(self.plan.device).cuda_stream), "gl_run_status", 0)
+        if status.value:
+            raise RuntimeError(f"persistent Griffin-Lim kernel: neighbour wait timed out at iteration {status.value}")
 
     def _launch(self, sums: torch.Tensor) -> None:
         p, i, o = self.plan, self.cur, self.cur ^ 1
@@ -313,6 +363,10 @@ def training_loop(solver, max_iter: int, tol: float, verbose, eva_iter: int, met
         # With tol == 0 the stopping rule `(previous - loss) / init < 0 and previous > loss` (methods.py:187) can
         # never fire and nothing displays the metric: the evaluations are still computed at the reference's cadence
         # (the fused epilogue runs on the same iterations) but the host does not wait for the two sums.
+        run_many = getattr(solver, "run_many", None)
+        if run_many is not None:
+            run_many(max_iter, 0, eva_iter)
+            return max_iter
         i = 0
         while i < max_iter:
             n = min(eva_iter, max_iter - i)

@@ -165,6 +165,9 @@ class CudaRangeEngine:
         self._ops.fill_padding(x, self.padded_offset, self.pad, self.signal_len, self.pad_mode)
 
 
+PEER_EXCHANGES = [0]      # halo exchanges done by the peer-memory kernel in this process (tests / bench look at it)
+
+
 class PeerHalo:
     """NVLink peer-memory plumbing of the one-kernel halo exchange (csrc/specinv_p2p.cu): this rank's receive area
     (cudaMalloc + CUDA IPC handle), the mapped areas of its two neighbours, and the exchange counter.  The 64-byte
@@ -230,6 +233,7 @@ class PeerHalo:
     def exchange(self, x: torch.Tensor) -> None:
         C, L = self._C, self._lib.lib()
         self.seq += 1
+        PEER_EXCHANGES[0] += 1
         stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
         with torch.cuda.device(self.device):
             self._lib.check(L.specinv_halo_exchange(self.dt, C.c_void_p(x.data_ptr()), x.stride(0), self.rows, x.shape[1],
@@ -304,12 +308,15 @@ class FrameShardedGriffinLim:
             red = _all_reduce_floats([self.g, float(self.n_bins_total)], group, self._comm_device())
             self.g, self.n_bins_total = red[0], int(round(red[1]))
         # NCCL ranks on their own GPUs: the exchange is ONE kernel over NVLink peer memory (SPECINV_P2P=0 keeps the
-        # NCCL send/recv path); gloo groups / ranks sharing a GPU use the host-staged path below
+        # NCCL send/recv path); gloo groups / ranks sharing a GPU use the host-staged path below, unless
+        # SPECINV_P2P=force asks for the peer-memory kernel there too (CUDA IPC also maps another process's buffer on
+        # the SAME device: how a single-GPU box exercises the kernel, tests/test_gpu_sharding.py)
         self.peer = None
-        if (self.world > 1 and self.x[0].is_cuda and dist.get_backend(group) == "nccl"
-                and os.environ.get("SPECINV_P2P", "1") != "0"):
+        mode = os.environ.get("SPECINV_P2P", "1")
+        if (self.world > 1 and self.x[0].is_cuda and mode != "0"
+                and (dist.get_backend(group) == "nccl" or mode == "force")):
             self.peer = PeerHalo.create(self.x[0].shape[0], self.ov, self.x[0].dtype, self.x[0].device, group,
-                                        self.rank, self.world, self.x[0].device)
+                                        self.rank, self.world, self._comm_device())
         engine.istft_partial(C_local, self.x[0])                  # x_0 = ISTFT(C)  (methods.py:233)
         self._exchange(self.x[0])
         self.iterations = 0
