@@ -419,7 +419,8 @@ def measure_cfg5_sharded(cx, w, n_iter=100, n_check=3):
     Tg = hi - lo
 
     def local(s):
-        return SplitSpec(s.main[:, lo:hi].contiguous(), s.nyq[:, lo:hi].contiguous())
+        # clone: the solver owns (and ping-pongs into) what it is given; a prefix slice is already contiguous
+        return SplitSpec(s.main[:, lo:hi].clone(), s.nyq[:, lo:hi].clone())
 
     engine = CudaRangeEngine(args, Tg, 1, torch.float32, cx.dev, lo, T)
     solver = FrameShardedGriffinLim(engine, local(C), local(mag), w["coef"])

@@ -40,6 +40,7 @@ struct RArgs {
     double* sums;            // 2 doubles per evaluating iteration of this run, or nullptr
     float2* xb;              // exchange area [cta][parity][side][3 * HOP / 2] float2
     unsigned* flags;         // [cta] epoch flags (zeroed before the launch) + [grid] status word
+    unsigned long long* prof;  // [cta][8] clock cycles per phase, summed over the run (thread 0; tools/resident_profile.py)
     float coef;
     int B, T, P, pad_mode;
     long long L;
@@ -246,6 +247,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) resident_gl_kernel(const RArgs a)
     int n_eval = 0;
     bool failed = false;
 
+    // phase timers (thread 0): frames, overlap-add, exchange write, neighbour wait, exchange read, normalise, padding
+    unsigned long long pt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tk = clock64();
+    auto tick = [&](int phase) {
+        if (tid == 0) { const long long now = clock64(); pt[phase] += (unsigned long long)(now - tk); tk = now; }
+    };
+    tick(7);
     for (int it = 0; it < a.n_iters; ++it) {
         const bool eval = a.sums != nullptr && ((a.iter0 + it) % a.eva_iter) == a.eva_iter - 1;
         for (int f0 = 0; f0 < nf; f0 += GROUPS) {
@@ -324,6 +332,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) resident_gl_kernel(const RArgs a)
                 }
             }
             __syncthreads();
+            tick(0);
             // ---- overlap-add of this round's frames (f0 .. fl), in frame order, on top of the earlier rounds
             {
                 const int fl = min(nf, f0 + GROUPS) - 1;
@@ -337,6 +346,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) resident_gl_kernel(const RArgs a)
                 }
             }
             __syncthreads();
+            tick(1);
         }
         if (eval) {
             double d = dacc, ee = eacc;
@@ -363,6 +373,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) resident_gl_kernel(const RArgs a)
                 s_wait_ok = 1;
             }
             __syncthreads();
+            tick(2);
             if ((tid == 0 && has_left) || (tid == 32 && has_right)) {
                 const unsigned* fp = a.flags + (tid == 0 ? blockIdx.x - 1 : blockIdx.x + 1);
                 if (!failed) {
@@ -373,6 +384,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) resident_gl_kernel(const RArgs a)
                 }
             }
             __syncthreads();
+            tick(3);
             if (!s_wait_ok && !failed) {
                 failed = true;                                // a neighbour never arrived: report, keep going without it
                 if (tid == 0) atomicExch(a.flags + gridDim.x, epoch);
@@ -388,6 +400,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) resident_gl_kernel(const RArgs a)
                 }
             }
             __syncthreads();
+            tick(4);
         }
         // ---- x = sums / envelope -> next input; accumulator cleared
         for (int ps = tid; ps < span / 2; ps += NTHREADS) {
@@ -403,6 +416,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) resident_gl_kernel(const RArgs a)
             xa2[ps] = f2(0.f, 0.f);
         }
         __syncthreads();
+        tick(5);
         // ---- centre padding of the signal's ends (sources inside this CTA's span)
         if (a.P > 0 && (c == 0 || c == a.cps - 1)) {
             for (int j = tid; j < 2 * a.P; j += NTHREADS) {
@@ -414,7 +428,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) resident_gl_kernel(const RArgs a)
                 XC[sp] = src >= 0 ? XC[src + a.P - (long long)t0 * HOP] : 0.f;
             }
             __syncthreads();
+            tick(6);
         }
+    }
+    if (tid == 0 && a.prof) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a.prof[(size_t)blockIdx.x * 8 + k] = pt[k];
     }
 
     // ---- results: owned samples (a CTA's last 3 hops belong to its right neighbour), state rows
@@ -447,7 +466,7 @@ static int device_limits() {
     return SPECINV_OK;
 }
 
-struct Shape { int lanes, cps, fpc, grid; size_t smem, xb_bytes, ws_bytes; };
+struct Shape { int lanes, cps, fpc, grid; size_t smem, xb_bytes, flag_bytes, ws_bytes; };
 
 // How a (B, T) problem maps onto the CTAs, or SPECINV_ERR_UNSUPPORTED when it does not fit on chip.
 static int plan_shape(const specinv_desc* d, const Dims& dm, Shape* s) {
@@ -467,7 +486,8 @@ static int plan_shape(const specinv_desc* d, const Dims& dm, Shape* s) {
     s->fpc = (dm.T + cps - 1) / cps;
     s->smem = smem_bytes(s->lanes, s->fpc);
     s->xb_bytes = (size_t)s->grid * 2 * 2 * NR * (d->hop / 2) * sizeof(float2);
-    s->ws_bytes = s->xb_bytes + ((size_t)s->grid + 1) * sizeof(unsigned);
+    s->flag_bytes = (((size_t)s->grid + 1) * sizeof(unsigned) + 15) / 16 * 16;
+    s->ws_bytes = s->xb_bytes + s->flag_bytes + (size_t)s->grid * 8 * sizeof(unsigned long long);
     return SPECINV_OK;
 }
 
@@ -521,6 +541,7 @@ int specinv_gl_run(const specinv_desc* d, const void* plan, const void* x_in, vo
     a.sums = sums;
     a.xb = (float2*)workspace;
     a.flags = (unsigned*)((char*)workspace + s.xb_bytes);
+    a.prof = (unsigned long long*)((char*)workspace + s.xb_bytes + s.flag_bytes);
     a.coef = (float)lr;
     a.B = dm.B; a.T = dm.T; a.P = dm.P; a.pad_mode = dm.pad_mode; a.L = dm.L;
     a.cps = s.cps; a.fpc = s.fpc;

@@ -60,7 +60,7 @@ def test_resident_run_matches_per_iteration_kernels(n_fft, B, T, kw, monkeypatch
     a.run_many(n, 0, 3)                       # evaluations at iterations 2 and 5
     b.run_many(n, 0, 3)
     a.check_resident()
-    assert a.cur == b.cur and a.iterations == b.iterations == n
+    assert a.iterations == b.iterations == n          # (a ping-ponged once, b six times)
     xa, xb = a.signal.cpu().numpy(), b.signal.cpu().numpy()
     scale = max(1.0, float(np.abs(xb).max()))
     assert np.isfinite(xa).all()
