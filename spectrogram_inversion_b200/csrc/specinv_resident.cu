@@ -247,6 +247,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) resident_gl_kernel(const RArgs a)
     int n_eval = 0;
     bool failed = false;
 
+    constexpr int XH = NR * HP2;                              // float2 per shared region
+    // frame schedule (see the loop): head = first 3 frames, tail = last 3 (not counted twice), then the interior
+    const int head = min(NR, nf), tail0 = max(head, nf - NR), tailc = nf - tail0;
+    const int k_send = ((head + tailc - 1) / GROUPS) * GROUPS;   // first schedule position of the round that completes them
     // phase timers (thread 0): frames, overlap-add, exchange write, neighbour wait, exchange read, normalise, padding
     unsigned long long pt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long tk = clock64();
@@ -256,10 +260,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) resident_gl_kernel(const RArgs a)
     tick(7);
     for (int it = 0; it < a.n_iters; ++it) {
         const bool eval = a.sums != nullptr && ((a.iter0 + it) % a.eva_iter) == a.eva_iter - 1;
-        for (int f0 = 0; f0 < nf; f0 += GROUPS) {
-            const int f = f0 + grp;
-            if (f < nf) {
-                float2 v[V];
+        for (int k0 = 0; k0 < nf; k0 += GROUPS) {
+            // schedule position -> frame: the frames that touch a shared region (first 3, last 3) come first, so that
+            // their partial sums are on their way to the neighbours while the interior frames are transformed
+            const int k = k0 + grp;
+            const int f = k < head ? k : (k - head < tailc ? tail0 + (k - head) : head + (k - head - tailc));
+            float2 v[V];
+            if (k < nf) {
 #pragma unroll
                 for (int i = 0; i < V; ++i) v[i] = xc2[f * HP2 + LANES * i + l];
                 {
@@ -323,30 +330,40 @@ __global__ void __launch_bounds__(NTHREADS, 1) resident_gl_kernel(const RArgs a)
                     tmem_ldw<2 * V>(tlane + TC_TW1, reinterpret_cast<float*>(tw1));
                     inv_pass1<LANES, V>(l, e, tw1, v);
                 }
-                group_sync<LANES>(bar_id);                      // E1 consumed: the buffer now takes the windowed frame
                 {
                     float2 w[V];
                     tmem_ldw<2 * V>(tlane + TC_WS, reinterpret_cast<float*>(w));
 #pragma unroll
-                    for (int i = 0; i < V; ++i) e[LANES * i + l] = pmul(w[i], v[i]);      // pair LANES i + l of the frame
+                    for (int i = 0; i < V; ++i) v[i] = pmul(w[i], v[i]);                  // pair LANES i + l of the frame
                 }
             }
-            __syncthreads();
             tick(0);
-            // ---- overlap-add of this round's frames (f0 .. fl), in frame order, on top of the earlier rounds
-            {
-                const int fl = min(nf, f0 + GROUPS) - 1;
-                const int p1 = fl * HP2 + M;
-                for (int ps = f0 * HP2 + tid; ps < p1; ps += NTHREADS) {
-                    const int hb = ps / HP2;
-                    float2 acc = xa2[ps];
-                    const int fa = max(f0, hb - NR), fb = min(fl, hb);
-                    for (int ff = fa; ff <= fb; ++ff) acc = acc + E[(ff - f0) * M + (ps - ff * HP2)];
-                    xa2[ps] = acc;
+            // ---- overlap-add straight from the registers, in four steps: in step s every frame adds its hop 3 - s, so
+            // the frames of a round never meet on a sample within a step and a hop block receives its frames in
+            // increasing order (frame b-3 first); a CTA barrier separates the steps.  Deterministic, no atomics.
+#pragma unroll
+            for (int st = 0; st < 4; ++st) {
+                constexpr int HPL = V / 4;                    // sample pairs per hop and lane
+                const int j = 3 - st;
+                if (k < nf) {
+                    float2* dst = xa2 + (f + j) * HP2 + l;
+#pragma unroll
+                    for (int r = 0; r < HPL; ++r) dst[LANES * r] = dst[LANES * r] + v[HPL * j + r];
                 }
+                __syncthreads();
             }
-            __syncthreads();
             tick(1);
+            // ---- the shared regions are complete (as far as this CTA's frames go): send them to the neighbours
+            if (k0 == k_send && (has_left || has_right)) {
+                float4* mine = reinterpret_cast<float4*>(a.xb + ((size_t)blockIdx.x * 2 + (it & 1)) * 2 * XH);
+                const float4* xa4 = reinterpret_cast<const float4*>(XA);
+                if (has_left) for (int i = tid; i < XH / 2; i += NTHREADS) __stcg(mine + i, xa4[i]);
+                if (has_right) for (int i = tid; i < XH / 2; i += NTHREADS) __stcg(mine + XH / 2 + i, xa4[nf * HP2 / 2 + i]);
+                __syncthreads();
+                // release by ONE thread after the CTA barrier: cumulative over the other threads' stores
+                if (tid == 0) st_release_gpu(a.flags + blockIdx.x, (unsigned)it + 1u);
+                tick(2);
+            }
         }
         if (eval) {
             double d = dacc, ee = eacc;
@@ -359,21 +376,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) resident_gl_kernel(const RArgs a)
         }
         dacc = 0.0; eacc = 0.0;
 
-        // ---- exchange the partial sums of the 3 hops shared with each neighbour (L2, epoch flags, parity slots)
-        constexpr int XH = NR * HP2;                          // float2 per shared region
+        // ---- partial sums of the 3 hops shared with each neighbour (L2, epoch flags, parity slots): wait, add
         if (has_left || has_right) {
             const unsigned epoch = (unsigned)it + 1u;
-            float2* mine = a.xb + ((size_t)blockIdx.x * 2 + (it & 1)) * 2 * XH;
-            if (has_left) for (int i = tid; i < XH; i += NTHREADS) __stcg(mine + i, xa2[i]);
-            if (has_right) for (int i = tid; i < XH; i += NTHREADS) __stcg(mine + XH + i, xa2[nf * HP2 + i]);
-            __threadfence();
+            if (tid == 0) s_wait_ok = 1;
             __syncthreads();
-            if (tid == 0) {
-                st_release_gpu(a.flags + blockIdx.x, epoch);
-                s_wait_ok = 1;
-            }
-            __syncthreads();
-            tick(2);
             if ((tid == 0 && has_left) || (tid == 32 && has_right)) {
                 const unsigned* fp = a.flags + (tid == 0 ? blockIdx.x - 1 : blockIdx.x + 1);
                 if (!failed) {
@@ -390,13 +397,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) resident_gl_kernel(const RArgs a)
                 if (tid == 0) atomicExch(a.flags + gridDim.x, epoch);
             }
             if (!failed) {
+                float4* xa4 = reinterpret_cast<float4*>(XA);
+                auto add4 = [](float4 p, float4 q) { return make_float4(p.x + q.x, p.y + q.y, p.z + q.z, p.w + q.w); };
+                // both sides add "left partial + right partial": bit-identical samples in the two CTAs
                 if (has_left) {
-                    const float2* nb = a.xb + ((size_t)(blockIdx.x - 1) * 2 + (it & 1)) * 2 * XH + XH;     // its tail
-                    for (int i = tid; i < XH; i += NTHREADS) xa2[i] = __ldcg(nb + i) + xa2[i];
+                    const float4* nb = reinterpret_cast<const float4*>(a.xb + ((size_t)(blockIdx.x - 1) * 2 + (it & 1)) * 2 * XH + XH);
+                    for (int i = tid; i < XH / 2; i += NTHREADS) xa4[i] = add4(__ldcg(nb + i), xa4[i]);                     // its tail
                 }
                 if (has_right) {
-                    const float2* nb = a.xb + ((size_t)(blockIdx.x + 1) * 2 + (it & 1)) * 2 * XH;          // its head
-                    for (int i = tid; i < XH; i += NTHREADS) xa2[nf * HP2 + i] = xa2[nf * HP2 + i] + __ldcg(nb + i);
+                    const float4* nb = reinterpret_cast<const float4*>(a.xb + ((size_t)(blockIdx.x + 1) * 2 + (it & 1)) * 2 * XH);
+                    for (int i = tid; i < XH / 2; i += NTHREADS)
+                        xa4[nf * HP2 / 2 + i] = add4(xa4[nf * HP2 / 2 + i], __ldcg(nb + i));                                   // its head
                 }
             }
             __syncthreads();
