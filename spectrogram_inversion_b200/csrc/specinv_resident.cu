@@ -251,6 +251,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) resident_gl_kernel(const RArgs a)
     // frame schedule (see the loop): head = first 3 frames, tail = last 3 (not counted twice), then the interior
     const int head = min(NR, nf), tail0 = max(head, nf - NR), tailc = nf - tail0;
     const int k_send = ((head + tailc - 1) / GROUPS) * GROUPS;   // first schedule position of the round that completes them
+    const int k_last = ((nf - 1) / GROUPS) * GROUPS;             // first schedule position of the last round
+    // the last warp is idle in the last round, and the send happened in an earlier one
+    const bool early_recv = (has_left || has_right) && k_send < k_last && k_last + GROUPS - 1 >= nf;
     // phase timers (thread 0): frames, overlap-add, exchange write, neighbour wait, exchange read, normalise, padding
     unsigned long long pt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long tk = clock64();
@@ -266,6 +269,38 @@ __global__ void __launch_bounds__(NTHREADS, 1) resident_gl_kernel(const RArgs a)
             const int k = k0 + grp;
             const int f = k < head ? k : (k - head < tailc ? tail0 + (k - head) : head + (k - head - tailc));
             float2 v[V];
+            if (early_recv && k0 == k_last && warp == WARPS - 1) {
+                // this warp has no frame in the last round: it takes the neighbours' partial sums in the meantime
+                // (sent a round ago: the flags are normally up already) -- the shared regions are not touched by the
+                // interior frames, and the barriers of the overlap-add below publish the result to the CTA
+                const unsigned epoch = (unsigned)it + 1u;
+                const int ln = tid & 31;
+                bool ok = !failed;
+                if (ok && ((ln == 0 && has_left) || (ln == 1 && has_right))) {
+                    const unsigned* fp = a.flags + (ln == 0 ? blockIdx.x - 1 : blockIdx.x + 1);
+                    const unsigned long long tstart = global_timer_ns();
+                    while (ld_acquire_gpu(fp) < epoch) {
+                        if (global_timer_ns() - tstart > a.timeout_ns) { ok = false; break; }
+                    }
+                }
+                ok = __all_sync(0xffffffffu, ok);
+                if (!ok && !failed) {
+                    failed = true;
+                    if (ln == 0) atomicExch(a.flags + gridDim.x, epoch);
+                }
+                if (!failed) {
+                    float4* xa4 = reinterpret_cast<float4*>(XA);
+                    auto add4 = [](float4 p, float4 q) { return make_float4(p.x + q.x, p.y + q.y, p.z + q.z, p.w + q.w); };
+                    if (has_left) {
+                        const float4* nb = reinterpret_cast<const float4*>(a.xb + ((size_t)(blockIdx.x - 1) * 2 + (it & 1)) * 2 * XH + XH);
+                        for (int i = ln; i < XH / 2; i += 32) xa4[i] = add4(__ldcg(nb + i), xa4[i]);
+                    }
+                    if (has_right) {
+                        const float4* nb = reinterpret_cast<const float4*>(a.xb + ((size_t)(blockIdx.x + 1) * 2 + (it & 1)) * 2 * XH);
+                        for (int i = ln; i < XH / 2; i += 32) xa4[nf * HP2 / 2 + i] = add4(xa4[nf * HP2 / 2 + i], __ldcg(nb + i));
+                    }
+                }
+            }
             if (k < nf) {
 #pragma unroll
                 for (int i = 0; i < V; ++i) v[i] = xc2[f * HP2 + LANES * i + l];
@@ -360,8 +395,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) resident_gl_kernel(const RArgs a)
                 if (has_left) for (int i = tid; i < XH / 2; i += NTHREADS) __stcg(mine + i, xa4[i]);
                 if (has_right) for (int i = tid; i < XH / 2; i += NTHREADS) __stcg(mine + XH / 2 + i, xa4[nf * HP2 / 2 + i]);
                 __syncthreads();
-                // release by ONE thread after the CTA barrier: cumulative over the other threads' stores
-                if (tid == 0) st_release_gpu(a.flags + blockIdx.x, (unsigned)it + 1u);
+                // release by ONE thread after the CTA barrier: cumulative over the other threads' stores.  It waits for
+                // those stores to be performed, so it is issued by the last warp, which is idle in the next round
+                // whenever the frames do not fill the groups.
+                if (tid == NTHREADS - 32) st_release_gpu(a.flags + blockIdx.x, (unsigned)it + 1u);
                 tick(2);
             }
         }
@@ -377,7 +414,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) resident_gl_kernel(const RArgs a)
         dacc = 0.0; eacc = 0.0;
 
         // ---- partial sums of the 3 hops shared with each neighbour (L2, epoch flags, parity slots): wait, add
-        if (has_left || has_right) {
+        // (unless the idle warp of the last round has done it already)
+        if ((has_left || has_right) && !early_recv) {
             const unsigned epoch = (unsigned)it + 1u;
             if (tid == 0) s_wait_ok = 1;
             __syncthreads();
