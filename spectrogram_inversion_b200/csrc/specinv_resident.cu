@@ -289,15 +289,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) resident_gl_kernel(const RArgs a)
                     if (ln == 0) atomicExch(a.flags + gridDim.x, epoch);
                 }
                 if (!failed) {
+                    // all loads of a chunk in flight before the first add (8 x 16 bytes per lane)
                     float4* xa4 = reinterpret_cast<float4*>(XA);
-                    auto add4 = [](float4 p, float4 q) { return make_float4(p.x + q.x, p.y + q.y, p.z + q.z, p.w + q.w); };
-                    if (has_left) {
-                        const float4* nb = reinterpret_cast<const float4*>(a.xb + ((size_t)(blockIdx.x - 1) * 2 + (it & 1)) * 2 * XH + XH);
-                        for (int i = ln; i < XH / 2; i += 32) xa4[i] = add4(__ldcg(nb + i), xa4[i]);
-                    }
-                    if (has_right) {
-                        const float4* nb = reinterpret_cast<const float4*>(a.xb + ((size_t)(blockIdx.x + 1) * 2 + (it & 1)) * 2 * XH);
-                        for (int i = ln; i < XH / 2; i += 32) xa4[nf * HP2 / 2 + i] = add4(xa4[nf * HP2 / 2 + i], __ldcg(nb + i));
+                    constexpr int PER = XH / 2 / 32, CH = 6;                        // float4 per lane and side (6, 12, 24); chunk
+                    static_assert(PER % CH == 0, "chunking");
+                    for (int side = 0; side < 2; ++side) {
+                        if (side == 0 ? !has_left : !has_right) continue;
+                        const float4* nb = reinterpret_cast<const float4*>(
+                            a.xb + ((size_t)(side == 0 ? blockIdx.x - 1 : blockIdx.x + 1) * 2 + (it & 1)) * 2 * XH + (side == 0 ? XH : 0));
+                        float4* dst = xa4 + (side == 0 ? 0 : nf * HP2 / 2);
+                        for (int c0 = 0; c0 < PER; c0 += CH) {
+                            float4 t[CH];
+#pragma unroll
+                            for (int u = 0; u < CH; ++u) t[u] = __ldcg(nb + (c0 + u) * 32 + ln);
+#pragma unroll
+                            for (int u = 0; u < CH; ++u) {
+                                const float4 m4 = dst[(c0 + u) * 32 + ln];
+                                // left partial + right partial, the same order in both CTAs
+                                dst[(c0 + u) * 32 + ln] = side == 0 ? make_float4(t[u].x + m4.x, t[u].y + m4.y, t[u].z + m4.z, t[u].w + m4.w)
+                                                                    : make_float4(m4.x + t[u].x, m4.y + t[u].y, m4.z + t[u].z, m4.w + t[u].w);
+                            }
+                        }
                     }
                 }
             }

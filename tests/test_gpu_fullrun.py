@@ -47,10 +47,15 @@ FULL_RUNS = [
 ]
 
 
+@pytest.mark.parametrize("resident", ["0", "1"], ids=["per_iteration_kernels", "default_path"])
 @pytest.mark.parametrize("fr", FULL_RUNS, ids=lambda c: c["id"])
-def test_full_run_final_sc_within_1pct_specialised(fr):
-    """Public API (default launch path: direct ctypes launches with programmatic dependent launch over the ping-pong
-    buffers) and the same run replayed from CUDA graphs: final SC within 1 % of the oracle's fp32 run."""
+def test_full_run_final_sc_within_1pct_specialised(fr, resident, monkeypatch):
+    """Public API and the same run replayed from CUDA graphs: final SC within 1 % of the oracle's fp32 run.
+    `per_iteration_kernels` (SPECINV_RESIDENT=0): one launch of the fused kernel per iteration (direct ctypes
+    launches with programmatic dependent launch over the ping-pong buffers) -- what the batched configs run.
+    `default_path`: these test problems are small enough for the persistent kernel of csrc/specinv_resident.cu, which
+    the public API then prefers for fast Griffin-Lim (ADMM and plain GL always use the per-iteration kernels)."""
+    monkeypatch.setenv("SPECINV_RESIDENT", resident)
     import spectrogram_inversion_b200 as S
     from spectrogram_inversion_b200 import methods
     from spectrogram_inversion_b200.engine import ADMMSolver, GriffinLimSolver, training_loop
@@ -70,18 +75,24 @@ def test_full_run_final_sc_within_1pct_specialised(fr):
     solver = Solver(plan, Cs, ms, coef)
     hist = []
     training_loop(solver, fr["iters"], 0.0, False, 10, "sc", history=hist)
-    assert torch.equal(solver.signal, yg), "evaluating loop and fire-and-forget loop differ"
+    if resident == "0" or fr["algo"] != "griffin_lim" or fr["kw"].get("alpha") == 0.0:
+        assert torch.equal(solver.signal, yg), "evaluating loop and fire-and-forget loop differ"
+    else:   # chunks of 9 iterations through the persistent kernel + the evaluating one through the per-iteration kernel
+        assert abs(_sc(solver.signal.cpu().numpy(), a, mag) - sco) <= ONE_PERCENT_DB
     # the fused epilogue's metric (of the spectrogram the LAST evaluated iteration started from) tracks the oracle's
     _, log = getattr(O, fr["algo"])(C, max_iter=fr["iters"], tol=0, window=w, hop_length=hop, return_log=True,
                                     **fr["kw"])
     assert len(hist) == len(log.evaluations) and hist[-1][0] == log.evaluations[-1][0]
     assert abs(hist[-1][1] - log.evaluations[-1][1]) <= ONE_PERCENT_DB, (hist[-1], log.evaluations[-1])
-    # CUDA-graph replay of the same iterations
+    # CUDA-graph replay of the same iterations (always the per-iteration kernels)
     plan, Cs, ms = methods._setup(Ct, dict(window=wt, hop_length=hop))
     solver = Solver(plan, Cs, ms, coef)
     solver.use_graphs = True
     training_loop(solver, fr["iters"], 0.0, False, 10, "sc")
-    assert torch.equal(solver.signal, yg), "graph replay differs from direct launches"
+    if resident == "0" or fr["algo"] != "griffin_lim" or fr["kw"].get("alpha") == 0.0:
+        assert torch.equal(solver.signal, yg), "graph replay differs from direct launches"
+    else:
+        assert abs(_sc(solver.signal.cpu().numpy(), a, mag) - sco) <= ONE_PERCENT_DB
 
 
 def test_full_run_rtisi_la_final_sc_within_1pct():
