@@ -147,6 +147,25 @@ int specinv_rtisi_la(const specinv_desc* d, const void* plan, const void* window
                      const void* mag_nyq, void* x_out, void* scratch, int look_ahead, int asymmetric_window,
                      int max_iter, double alpha, double synth_coeff, void* stream);
 
+/* The same run cut at outer-step boundaries (the `for i in range(steps + look_ahead)` loop, methods.py:363): outer
+ * steps [step_begin, step_end) of the T + look_ahead steps, each with its max_iter inner iterations, its commit and
+ * its block of x_out.  `state` (specinv_rtisi_state_bytes, caller-owned device memory) receives the sliding state
+ * before step step_end when step_end < T + look_ahead and provides it when step_begin > 0; per signal, in the real
+ * type of the run:
+ *   frames [LA+1][n_fft]   active frames, oldest first, as the kernels hold them: the un-normalised inverse FFT
+ *                          (= irfft frame of methods.py:398 times n_fft, or times n_fft^1/2 when `normalized`)
+ *   pre    [LA+1][F] cplx  momentum spectra of the active frames (methods.py:392; index LA is not used: zero)
+ *   kept   [K][n_fft]      kept frames, oldest first, already multiplied by window * synth_coeff (methods.py:365-368)
+ *   carry  [n_fft]         overlap-add of the committed frames * window beyond the samples already written (:407)
+ * Running [0, s) and [s, T + LA) with the state in between gives bit-identical x_out to one run: this is how the
+ * Python layer shows the reference's per-step progress bar (methods.py:362,400), and what the per-step parity tests
+ * feed with the oracle's state. */
+int specinv_rtisi_state_bytes(const specinv_desc* d, int look_ahead, size_t* bytes);
+int specinv_rtisi_la_steps(const specinv_desc* d, const void* plan, const void* window, const void* mag_main,
+                           const void* mag_nyq, void* x_out, void* scratch, int look_ahead, int asymmetric_window,
+                           int max_iter, double alpha, double synth_coeff, int step_begin, int step_end, void* state,
+                           void* stream);
+
 /* ---- frame-range sharding helpers (single long signal over several GPUs) --------------------------
  * specinv_halo_sum    : out = left + right over rows x n strided views -- the per-iteration combination of
  *                       the two partial overlap-add sums of the (n_fft - hop)-sample region two neighbouring

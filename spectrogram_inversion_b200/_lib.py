@@ -27,6 +27,7 @@ EXPORTS = (
     "specinv_halo_area_bytes", "specinv_ipc_alloc", "specinv_ipc_open", "specinv_ipc_close", "specinv_ipc_free",
     "specinv_halo_exchange", "specinv_halo_status",
     "specinv_gl_run_workspace_bytes", "specinv_gl_run", "specinv_gl_run_status",
+    "specinv_rtisi_state_bytes", "specinv_rtisi_la_steps",
 )
 
 
@@ -72,6 +73,8 @@ def _declare(lib: C.CDLL) -> None:
         "specinv_phase_init": [dp, vp, vp, vp, vp, vp],
         "specinv_spec_abs": [dp, vp, vp, vp, vp, vp],
         "specinv_rtisi_la": [dp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, dbl, dbl, vp],
+        "specinv_rtisi_state_bytes": [dp, C.c_int, C.POINTER(C.c_size_t)],
+        "specinv_rtisi_la_steps": [dp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, dbl, dbl, C.c_int, C.c_int, vp, vp],
         "specinv_stft": [dp, vp, vp, vp, vp, vp],
         "specinv_istft": [dp, vp, vp, vp, vp, vp],
         "specinv_gl_iter": [dp, vp, vp, vp, vp, vp, vp, vp, vp, vp, dbl, vp, vp],

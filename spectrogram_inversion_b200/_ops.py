@@ -185,6 +185,30 @@ def rtisi_la(plan: Tensor, window: Tensor, mag_main: Tensor, mag_nyq: Tensor, x_
                                         float(alpha), float(synth_coeff), _stream(x_out)), "rtisi_la", 2)
 
 
+@torch.library.custom_op("specinv_b200::rtisi_la_steps", mutates_args=("x_out", "scratch", "state"), device_types="cuda")
+def rtisi_la_steps(plan: Tensor, window: Tensor, mag_main: Tensor, mag_nyq: Tensor, x_out: Tensor, scratch: Tensor,
+                   state: Tensor, look_ahead: int, asymmetric: bool, max_iter: int, alpha: float, synth_coeff: float,
+                   step_begin: int, step_end: int, n_fft: int, hop: int, center: bool, pad_mode: int, normalized: bool,
+                   onesided: bool) -> None:
+    """Outer steps [step_begin, step_end) of RTISI_LA (methods.py:363-404) with the sliding state in `state`
+    (`rtisi_state_bytes` bytes; read when step_begin > 0, written when step_end < T + look_ahead)."""
+    _need_cuda(plan, window, mag_main, mag_nyq, x_out, scratch, state)
+    d = _desc(x_out, n_fft, hop, mag_main.shape[1], mag_main.shape[0], center, pad_mode, normalized, onesided)
+    with torch.cuda.device(x_out.device):
+        _ok(_lib.lib().specinv_rtisi_la_steps(C.byref(d), _p(plan), _p(window), _p(mag_main), _p(mag_nyq), _p(x_out),
+                                              _p(scratch), int(look_ahead), int(bool(asymmetric)), int(max_iter),
+                                              float(alpha), float(synth_coeff), int(step_begin), int(step_end), _p(state),
+                                              _stream(x_out)), "rtisi_la_steps", 2)
+
+
+def rtisi_state_bytes(ref: Tensor, n_fft: int, hop: int, n_frames: int, batch: int, normalized: bool, onesided: bool,
+                      look_ahead: int) -> int:
+    d = _desc(ref, n_fft, hop, n_frames, batch, False, 0, normalized, onesided)
+    n = C.c_size_t(0)
+    _lib.check(_lib.lib().specinv_rtisi_state_bytes(C.byref(d), int(look_ahead), C.byref(n)), "rtisi_state_bytes")
+    return int(n.value)
+
+
 @torch.library.custom_op("specinv_b200::plan_init_ranged", mutates_args=("plan",), device_types="cuda")
 def plan_init_ranged(plan: Tensor, window: Tensor, n_fft: int, hop: int, n_frames: int, batch: int, normalized: bool,
                      onesided: bool, frame_offset: int, total_frames: int) -> None:
@@ -245,7 +269,7 @@ def _fake_iter(plan, x_in, x_out, *rest) -> None:
 
 
 ALL_OPS = (plan_init, stft, istft, gl_iter, admm_iter, pack, unpack, metric_sums, phase_init, spec_abs, rtisi_la,
-           plan_init_ranged, phase_init_ex, halo_sum, fill_padding)
+           rtisi_la_steps, plan_init_ranged, phase_init_ex, halo_sum, fill_padding)
 for _op in ALL_OPS:
     _op.register_fake(_fake_iter if _op in (gl_iter, admm_iter) else _fake_nothing)
 del _op

@@ -24,7 +24,16 @@ namespace specinv {
 // implemented in specinv_rtisi_fast.cu; returns SPECINV_ERR_UNSUPPORTED when the shape is not its own
 int rtisi_fast(const specinv_desc* d, const Dims& dm, const void* plan, const void* mag_main, const void* mag_nyq,
                void* x_out, const void* asym1, const void* asym2, int look_ahead, int asymmetric, int max_iter,
-               double alpha, double synth_coeff, cudaStream_t st);
+               double alpha, double synth_coeff, int step_begin, int step_end, void* state, cudaStream_t st);
+
+// Elements (of the real type) of the sliding state of ONE signal between two outer steps, the layout both kernels
+// save / restore (include/specinv_b200.h: specinv_rtisi_la_steps): active frames [NA][N] (logical order, oldest
+// first; the kernels' unscaled inverse-FFT samples), momentum spectra [NA][F] complex, kept frames [K][N] already
+// multiplied by window * synth_coeff, output overlap-add carry [N].
+size_t rtisi_state_elems(const Dims& dm, int LA) {
+    const size_t NA = LA + 1, F = dm.onesided ? dm.M + 1 : dm.N;
+    return NA * dm.N + 2 * NA * F + (size_t)dm.K * dm.N + dm.N;
+}
 
 struct RtisiArgs {
     const void* mag_main; const void* mag_nyq;
@@ -35,6 +44,9 @@ struct RtisiArgs {
     double lr;                                // alpha / (1 + alpha)
     Dims dm;
     int LA, max_iter, asymmetric, Mp;
+    int step_begin, step_end;                 // outer steps [step_begin, step_end) of the T + LA steps of a run
+    void* state;                              // per-signal sliding state in / out (rtisi_state_elems), or nullptr
+    size_t state_elems;
 };
 
 template <typename T>
@@ -85,7 +97,24 @@ __global__ void __launch_bounds__(256) rtisi_kernel(const RtisiArgs a) {
     for (int i = tid; i < K * N; i += NT) kept[i] = T(0);
     for (int i = tid; i < N; i += NT) carry[i] = T(0);
     __syncthreads();
-    {
+    T* st_frames = a.state ? (T*)a.state + (size_t)b * a.state_elems : nullptr;
+    T* st_pre = st_frames + (size_t)NA * N;
+    T* st_kept = st_pre + 2 * (size_t)NA * F;
+    T* st_carry = st_kept + (size_t)K * N;
+    if (a.step_begin > 0) {
+        // ---- resume: the state another launch saved before outer step step_begin
+        for (int idx = tid; idx < NA * N; idx += NT) {
+            const int aa = idx / N, n = idx - aa * N;
+            workf[2 * ((size_t)((aa + a.step_begin) % NA) * Mp + padidx(n >> 1)) + (n & 1)] = st_frames[idx];
+        }
+        for (int idx = tid; idx < NA * F; idx += NT) {
+            const int aa = idx / F, k = idx - aa * F;
+            pre[(size_t)((aa + a.step_begin) % NA) * F + k] = mk<T>(st_pre[2 * idx], st_pre[2 * idx + 1]);
+        }
+        for (int i = tid; i < K * N; i += NT) kept[i] = st_kept[i];
+        for (int i = tid; i < N; i += NT) carry[i] = st_carry[i];
+        __syncthreads();
+    } else {
         // logical frame LA at step 0 lives in slot (LA + 0) % NA = LA
         C* v = work + (size_t)LA * Mp;
         for (int k = tid; k <= M / 2; k += NT) {
@@ -107,14 +136,13 @@ __global__ void __launch_bounds__(256) rtisi_kernel(const RtisiArgs a) {
     }
 
     int kslot = 0;   // kept ring: logical kept frame f (0 = oldest) lives in slot (kslot + f) % K
-    const int steps = dm.T + LA;
-    for (int i = 0; i < steps; ++i) {
+    for (int i = a.step_begin; i < a.step_end; ++i) {
         // part of y contributed by the kept frames: constant over the inner iterations
         for (int p = tid; p < ylen; p += NT) {
             T acc = T(0);
             for (int f = 0; f < K; ++f) {
                 const int idx = p + (K - f) * hop;          // index inside kept frame f
-                if (idx < N) acc += kept[(size_t)((kslot + f) % K) * N + idx] * (ws[idx] * coef);
+                if (idx < N) acc += kept[(size_t)((kslot + f) % K) * N + idx];   // stored as frame * (ws * coef)
             }
             ykept[p] = acc;
         }
@@ -219,13 +247,30 @@ __global__ void __launch_bounds__(256) rtisi_kernel(const RtisiArgs a) {
         if (K > 0) {
             // the committed frame replaces the oldest kept frame
             T* dst = kept + (size_t)kslot * N;
-            for (int n = tid; n < N; n += NT) dst[n] = wsample(s0, n);
+            for (int n = tid; n < N; n += NT) dst[n] = wsample(s0, n) * (ws[n] * coef);
             kslot = (kslot + 1) % K;
         }
         __syncthreads();
         // slot s0 becomes the newest (all-zero) active frame of the next step
         for (int n = tid; n < Mp; n += NT) work[(size_t)s0 * Mp + n] = mk<T>(T(0), T(0));
         __syncthreads();
+    }
+    if (a.state && a.step_end < dm.T + LA) {
+        // ---- save the state before outer step step_end (logical order; the newest frame's momentum is not used)
+        for (int idx = tid; idx < NA * N; idx += NT) {
+            const int aa = idx / N, n = idx - aa * N;
+            st_frames[idx] = wsample((aa + a.step_end) % NA, n);
+        }
+        for (int idx = tid; idx < NA * F; idx += NT) {
+            const int aa = idx / F, k = idx - aa * F;
+            const C v = aa == LA ? mk<T>(T(0), T(0)) : pre[(size_t)((aa + a.step_end) % NA) * F + k];
+            st_pre[2 * idx] = v.x; st_pre[2 * idx + 1] = v.y;
+        }
+        for (int idx = tid; idx < K * N; idx += NT) {
+            const int f = idx / N, n = idx - f * N;
+            st_kept[idx] = kept[(size_t)((kslot + f) % K) * N + n];
+        }
+        for (int i = tid; i < N; i += NT) st_carry[i] = carry[i];
     }
 }
 
@@ -251,7 +296,7 @@ __global__ void rtisi_windows_kernel(int N, int hop, int K, const T* __restrict_
 template <typename T>
 static int rtisi_t(const specinv_desc* d, const Dims& dm, const void* plan, const void* window, const void* mag_main,
                    const void* mag_nyq, void* x_out, void* scratch, int look_ahead, int asymmetric, int max_iter,
-                   double alpha, double synth_coeff, cudaStream_t st) {
+                   double alpha, double synth_coeff, int step_begin, int step_end, void* state, cudaStream_t st) {
     RtisiArgs a{};
     const PlanLayout pl = plan_layout(dm, d->dtype);
     const char* p = (const char*)plan;
@@ -262,6 +307,7 @@ static int rtisi_t(const specinv_desc* d, const Dims& dm, const void* plan, cons
     a.synth_coeff = synth_coeff; a.lr = alpha / (1.0 + alpha);
     a.mag_main = mag_main; a.mag_nyq = mag_nyq; a.x_out = x_out;
     a.Mp = dm.M + (dm.M >> 4);
+    a.step_begin = step_begin; a.step_end = step_end; a.state = state; a.state_elems = rtisi_state_elems(dm, a.LA);
     T* asym = (T*)scratch;
     a.asym1 = asym; a.asym2 = asym + dm.N;
     const double fscale = d->normalized ? 1.0 / sqrt((double)dm.N) : 1.0;
@@ -272,7 +318,7 @@ static int rtisi_t(const specinv_desc* d, const Dims& dm, const void* plan, cons
         const char* fg = getenv("SPECINV_FORCE_GENERIC");
         if (!(fg && fg[0] == '1')) {
             const int rf = rtisi_fast(d, dm, plan, mag_main, mag_nyq, x_out, asym, asym + dm.N, look_ahead, asymmetric,
-                                      max_iter, alpha, synth_coeff, st);
+                                      max_iter, alpha, synth_coeff, step_begin, step_end, state, st);
             if (rf != SPECINV_ERR_UNSUPPORTED) return rf;
         }
     }
@@ -293,15 +339,40 @@ static int rtisi_t(const specinv_desc* d, const Dims& dm, const void* plan, cons
 
 using namespace specinv;
 
-extern "C" int specinv_rtisi_la(const specinv_desc* d, const void* plan, const void* window, const void* mag_main,
-                                const void* mag_nyq, void* x_out, void* scratch, int look_ahead, int asymmetric_window,
-                                int max_iter, double alpha, double synth_coeff, void* stream) {
+extern "C" {
+
+int specinv_rtisi_state_bytes(const specinv_desc* d, int look_ahead, size_t* bytes) {
+    Dims dm; int rc = make_dims(d, &dm); if (rc) return rc;
+    if (!bytes) return SPECINV_ERR_INVALID;
+    const int LA = look_ahead < 0 ? dm.K : look_ahead;
+    *bytes = (size_t)dm.B * rtisi_state_elems(dm, LA) * (d->dtype == SPECINV_F64 ? 8 : 4);
+    return SPECINV_OK;
+}
+
+int specinv_rtisi_la_steps(const specinv_desc* d, const void* plan, const void* window, const void* mag_main,
+                           const void* mag_nyq, void* x_out, void* scratch, int look_ahead, int asymmetric_window,
+                           int max_iter, double alpha, double synth_coeff, int step_begin, int step_end, void* state,
+                           void* stream) {
     Dims dm; int rc = make_dims(d, &dm); if (rc) return rc;
     if (!plan || !window || !mag_main || !x_out || !scratch || (dm.onesided && !mag_nyq)) return SPECINV_ERR_INVALID;
     if (max_iter < 1 || alpha < 0) return SPECINV_ERR_INVALID;
+    const int steps = dm.T + (look_ahead < 0 ? dm.K : look_ahead);
+    if (step_begin < 0 || step_end > steps || step_begin >= step_end) return SPECINV_ERR_INVALID;
+    if ((step_begin > 0 || step_end < steps) && !state) return SPECINV_ERR_INVALID;
     return d->dtype == SPECINV_F64
                ? rtisi_t<double>(d, dm, plan, window, mag_main, mag_nyq, x_out, scratch, look_ahead, asymmetric_window,
-                                 max_iter, alpha, synth_coeff, (cudaStream_t)stream)
+                                 max_iter, alpha, synth_coeff, step_begin, step_end, state, (cudaStream_t)stream)
                : rtisi_t<float>(d, dm, plan, window, mag_main, mag_nyq, x_out, scratch, look_ahead, asymmetric_window,
-                                max_iter, alpha, synth_coeff, (cudaStream_t)stream);
+                                max_iter, alpha, synth_coeff, step_begin, step_end, state, (cudaStream_t)stream);
 }
+
+int specinv_rtisi_la(const specinv_desc* d, const void* plan, const void* window, const void* mag_main,
+                     const void* mag_nyq, void* x_out, void* scratch, int look_ahead, int asymmetric_window,
+                     int max_iter, double alpha, double synth_coeff, void* stream) {
+    Dims dm; int rc = make_dims(d, &dm); if (rc) return rc;
+    return specinv_rtisi_la_steps(d, plan, window, mag_main, mag_nyq, x_out, scratch, look_ahead, asymmetric_window,
+                                  max_iter, alpha, synth_coeff, 0, dm.T + (look_ahead < 0 ? dm.K : look_ahead), nullptr,
+                                  stream);
+}
+
+}  // extern "C"

@@ -38,6 +38,9 @@ struct RArgs {
     float lr;                                 // alpha / (1 + alpha)
     int B, T, P, LA, max_iter, asymmetric;
     long long L;
+    int step_begin, step_end;                 // outer steps [step_begin, step_end) of the T + LA steps of a run
+    float* state;                             // per-signal sliding state in / out (specinv_rtisi.cu: rtisi_state_elems)
+    size_t state_elems;
 };
 
 // TMEM columns per lane: constant tables (identical in the four sub-partitions), then per-warp state
@@ -182,8 +185,45 @@ __global__ void __launch_bounds__(SIGS * NAMAX * LANES, 1) rtisi_fast_kernel(con
         int kslot = 0;                                 // kept ring: logical kept frame f (0 = oldest) = slot (kslot + f) % KEEP
         float mag_nyq = 0.f;
 
-        const int steps = a.T + a.LA;
-        for (int i = 0; i < steps; ++i) {
+        // canonical state of this signal (natural sample / bin order, logical frame order)
+        constexpr int N = 2 * M, F = M + 1;
+        float* st_frames = a.state ? a.state + (size_t)b * a.state_elems : nullptr;
+        float* st_pre = st_frames + (size_t)NA * N;
+        float* st_kept = st_pre + 2 * (size_t)NA * F;
+        float* st_carry = st_kept + (size_t)KEEP * N;
+        if (a.step_begin > 0) {
+            // ---- resume before outer step step_begin: this warp's frame, its momentum spectrum and magnitude row
+            int la0 = (p - a.step_begin) % NA; if (la0 < 0) la0 += NA;
+            const float2* fr = reinterpret_cast<const float2*>(st_frames + (size_t)la0 * N);
+#pragma unroll
+            for (int r = 0; r < V; ++r) v[r] = fr[r * LANES + l];                  // pair LANES r + l
+            {
+                float pre[2 * V];
+                const float2* pr = reinterpret_cast<const float2*>(st_pre + 2 * (size_t)la0 * F);
+#pragma unroll
+                for (int e = 0; e < V; ++e) { const float2 q = pr[bin(e)]; pre[2 * e] = q.x; pre[2 * e + 1] = q.y; }
+                tmem_stw<2 * V>(twarp + TC_PRE, pre);
+                pre_nyq = l == 0 ? pr[M] : f2(0.f, 0.f);
+            }
+            if (la0 != a.LA) {            // (the newest frame fetches its row when the step starts)
+                const int t_frame = a.step_begin + la0 - a.LA;
+                float mg[V];
+                const bool inside = t_frame >= 0 && t_frame < a.T;
+                const float* mrow = a.mag + ((long long)b * a.T + (inside ? t_frame : 0)) * M;
+#pragma unroll
+                for (int e = 0; e < V; ++e) mg[e] = inside ? __ldg(mrow + bin(e)) : 0.f;
+                mag_nyq = (inside && l == 0) ? __ldg(a.mag_nyq + (long long)b * a.T + t_frame) : 0.f;
+                tmem_stw<V>(twarp + TC_MAG, mg);
+            }
+            const float2* kp = reinterpret_cast<const float2*>(st_kept);
+            for (int i = p * LANES + l; i < KEEP * ROWS; i += LANES * NA) Uk[i] = kp[i];
+            const float2* cp = reinterpret_cast<const float2*>(st_carry);
+            for (int i = p * LANES + l; i < ROWS; i += LANES * NA) carry[i] = cp[i];
+            tmem_wait_st();
+            sig_sync<LANES>(bar_id, NA);
+        }
+
+        for (int i = a.step_begin; i < a.step_end; ++i) {
             int la = (p - i) % NA; if (la < 0) la += NA;          // logical index of this warp's frame
             const int t_frame = i + la - a.LA;                    // spectrogram frame it reconstructs
             const bool newest = la == a.LA;
@@ -374,6 +414,30 @@ __global__ void __launch_bounds__(SIGS * NAMAX * LANES, 1) rtisi_fast_kernel(con
             kslot = (kslot + 1) % KEEP;
             sig_sync<LANES>(bar_id, NA);              // the kept ring and the carry are in place for the next step
         }
+        if (a.state && a.step_end < a.T + a.LA) {
+            // ---- save the state before outer step step_end
+            int la1 = (p - a.step_end) % NA; if (la1 < 0) la1 += NA;
+            float2* fr = reinterpret_cast<float2*>(st_frames + (size_t)la1 * N);
+#pragma unroll
+            for (int r = 0; r < V; ++r) fr[r * LANES + l] = v[r];
+            {
+                float pre[2 * V];
+                tmem_wait_st();
+                tmem_ldw<2 * V>(twarp + TC_PRE, pre);
+                float2* pr = reinterpret_cast<float2*>(st_pre + 2 * (size_t)la1 * F);
+                const bool keep = la1 != a.LA;        // the newest frame's momentum is never used: saved as zero
+#pragma unroll
+                for (int e = 0; e < V; ++e) pr[bin(e)] = keep ? f2(pre[2 * e], pre[2 * e + 1]) : f2(0.f, 0.f);
+                if (l == 0) pr[M] = keep ? pre_nyq : f2(0.f, 0.f);
+            }
+            float2* kp = reinterpret_cast<float2*>(st_kept);
+            for (int i = p * LANES + l; i < KEEP * ROWS; i += LANES * NA) {
+                const int f = i / ROWS, r = i - f * ROWS;
+                kp[i] = Uk[((kslot + f) % KEEP) * ROWS + r];
+            }
+            float2* cp = reinterpret_cast<float2*>(st_carry);
+            for (int i = p * LANES + l; i < ROWS; i += LANES * NA) cp[i] = carry[i];
+        }
         tmem_wait_st();
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -395,7 +459,7 @@ static int launch(const RArgs& a, cudaStream_t st) {
 // Returns SPECINV_ERR_UNSUPPORTED when the shape is not the one this kernel is specialised for.
 int rtisi_fast(const specinv_desc* d, const Dims& dm, const void* plan, const void* mag_main, const void* mag_nyq,
                void* x_out, const void* asym1, const void* asym2, int look_ahead, int asymmetric, int max_iter,
-               double alpha, double synth_coeff, cudaStream_t st) {
+               double alpha, double synth_coeff, int step_begin, int step_end, void* state, cudaStream_t st) {
     if (d->dtype != SPECINV_F32 || !d->onesided || d->hop * 4 != d->n_fft ||
         (d->n_fft != 2048 && d->n_fft != 1024 && d->n_fft != 512))
         return SPECINV_ERR_UNSUPPORTED;
@@ -410,6 +474,8 @@ int rtisi_fast(const specinv_desc* d, const Dims& dm, const void* plan, const vo
     a.mag = (const float*)mag_main; a.mag_nyq = (const float*)mag_nyq; a.x_out = (float*)x_out;
     a.coef = (float)synth_coeff; a.lr = (float)(alpha / (1.0 + alpha));
     a.B = dm.B; a.T = dm.T; a.P = dm.P; a.LA = LA; a.max_iter = max_iter; a.asymmetric = asymmetric; a.L = dm.L;
+    a.step_begin = step_begin; a.step_end = step_end; a.state = (float*)state;
+    a.state_elems = (size_t)(LA + 1) * dm.N + 2 * (size_t)(LA + 1) * (dm.M + 1) + (size_t)dm.K * dm.N + dm.N;
     // Signals per CTA: as few as still fit the batch into one wave of CTAs (the kernel is latency-bound, so a signal
     // runs fastest when its warps share an SM with as few others as possible).
     int sms = 0, dev = 0;

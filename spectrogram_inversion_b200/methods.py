@@ -4,6 +4,7 @@ from __future__ import annotations
 
 import math
 import torch
+from tqdm import tqdm
 
 from . import _ops, autograd
 from .engine import ADMMSolver, GriffinLimSolver, METRIC_NAMES, StftPlan, compute_device, training_loop
@@ -237,8 +238,24 @@ def RTISI_LA(spec, look_ahead=-1, asymmetric_window=False, max_iter=25, alpha=0.
     synth_coeff = float(args.hop_length / (window @ window))                 # methods.py:318
     x = plan.empty_signal()
     scratch = torch.empty(2 * args.n_fft, dtype=work.dtype, device=dev)
-    _ops.rtisi_la(plan.buf, window, mag.main, mag.nyq, x, scratch, int(look_ahead), bool(asymmetric_window),
-                  int(max_iter), float(alpha), synth_coeff, *plan._k)
+    if not verbose:
+        _ops.rtisi_la(plan.buf, window, mag.main, mag.nyq, x, scratch, int(look_ahead), bool(asymmetric_window),
+                      int(max_iter), float(alpha), synth_coeff, *plan._k)
+        return _finish(x, spec)
+    # the reference's progress bar counts outer steps (methods.py:362, :400): the persistent kernel is cut at step
+    # boundaries, its sliding state parked in HBM in between (bit-identical to the uncut run)
+    LA = (args.n_fft - 1) // args.hop_length if look_ahead < 0 else int(look_ahead)
+    steps = T + LA
+    state = torch.empty(_ops.rtisi_state_bytes(x, args.n_fft, args.hop_length, T, B, args.normalized, args.onesided, LA),
+                        dtype=torch.uint8, device=dev)
+    chunk = max(1, -(-steps // 40))
+    with tqdm(total=steps, disable=not verbose) as pbar:
+        for s0 in range(0, steps, chunk):
+            s1 = min(steps, s0 + chunk)
+            _ops.rtisi_la_steps(plan.buf, window, mag.main, mag.nyq, x, scratch, state, LA, bool(asymmetric_window),
+                                int(max_iter), float(alpha), synth_coeff, s0, s1, *plan._k)
+            torch.cuda.current_stream(dev).synchronize()          # the bar shows work that is done
+            pbar.update(s1 - s0)
     return _finish(x, spec)
 
 

@@ -173,7 +173,7 @@ def test_every_custom_op_has_a_fake_kernel():
     torch.compile can trace through callers without a device (the ops mutate caller-owned buffers, return nothing)."""
     from torch._subclasses.fake_tensor import FakeTensorMode
     from spectrogram_inversion_b200 import _ops
-    assert len(_ops.ALL_OPS) == 15
+    assert len(_ops.ALL_OPS) == 16
     with FakeTensorMode():
         f = lambda *shape, dt=torch.float32: torch.empty(*shape, dtype=dt, device="cuda")
         B, T, M, L = 2, 9, 64, 8 * 32
