@@ -166,3 +166,64 @@ def test_one_outer_step_from_the_oracles_state(c, monkeypatch):
                 ("pre", i, max_iter, np.abs(pre_c[:, :LA] - parts["pre"][:, :LA]).max(), ps)
             assert np.abs(kept_g - parts["kept"]).max() <= tol * max(1.0, np.abs(parts["kept"]).max()), ("kept", i, max_iter)
             assert np.abs(carry_g - parts["carry"]).max() <= tol * max(1.0, np.abs(parts["carry"]).max()), ("carry", i, max_iter)
+
+
+@pytest.mark.parametrize("seed", range(14))
+def test_random_configurations_one_step_from_oracle_state(seed, monkeypatch):
+    """The configurations tools/fuzz_rtisi.py draws (n_fft, look_ahead, asymmetric, alpha, win_length, normalized,
+    centre, batch sizes that put 1 / 2 / 4 signals on a CTA), judged per OUTER STEP from the oracle's state instead of
+    over whole runs.  Round 1's whole-run fuzz saw the register kernel up to 6.5x further from the fp64 run than the
+    generic kernel in two cases (n_fft=2048 la=0 wl=1866; n_fft=512 la=0 alpha=0): whole runs amplify every rounding
+    difference step after step (the projection S * mag / |S| divides by |S|, and |S| ~ 0 bins are common when the
+    look-ahead is 0), so two correct fp32 implementations can differ by 1e-2 after three inner iterations of a dozen
+    steps.  From identical state one step agrees to 1e-5; those two configurations are seeds 0 and 1 here."""
+    import random
+    rnd = random.Random(seed)
+    if seed == 0:
+        n_fft, la, asym, alpha, wl, normalized, center, B, T = 2048, 0, False, 0.99, 1866, False, True, 3, 9
+    elif seed == 1:
+        n_fft, la, asym, alpha, wl, normalized, center, B, T = 512, 0, False, 0.0, 512, False, True, 5, 8
+    else:
+        n_fft = rnd.choice([512, 1024, 2048, 256])
+        la = rnd.choice([-1, 0, 1, 2, 3])
+        asym = rnd.random() < 0.4
+        alpha = rnd.choice([0.99, 0.99, 0.5, 0.0])
+        wl = n_fft if rnd.random() < 0.6 else rnd.randrange(n_fft // 2 + 1, n_fft)
+        normalized = rnd.random() < 0.3
+        center = rnd.random() < 0.7
+        B = rnd.choice([1, 2, 3, 5, 150, 299] if n_fft in (512, 1024) else [1, 2, 3])
+        T = rnd.choice([6, 9, 14])
+    hop = n_fft // 4
+    dtype = np.dtype(np.float32)
+    rs = np.random.RandomState(seed)
+    w = cases.window_of("hann" if center else "hamming", wl, dtype)
+    okw = dict(window=w, hop_length=hop, center=center, normalized=normalized)
+    if wl != n_fft:
+        okw["win_length"] = wl
+    oa = O.args_helper(n_fft // 2 + 1, dtype, **okw)
+    mag = np.abs(O.stft(rs.randn(B, (T - 1) * hop + (0 if center else n_fft)).astype(dtype), oa)).astype(dtype)
+    plan, pm, window, coeff, LA, nbytes, args = _gpu_objects(mag, okw, la)
+    steps = T + LA
+    max_iter = rnd.choice([1, 2])
+    su = O.rtisi_setup(mag, look_ahead=la, asymmetric_window=asym, max_iter=max_iter, alpha=alpha, **okw)
+    st = O.rtisi_init(su)
+    i0 = rnd.randrange(1, steps - 1)
+    for i in range(i0):
+        for j in range(max_iter):
+            st = O.rtisi_inner(su, st, j)
+        st = O.rtisi_commit(su, st)
+    flat, _ = _canonical(su, st, dtype)
+    for j in range(max_iter):
+        st = O.rtisi_inner(su, st, j)
+    st = O.rtisi_commit(su, st)
+    _, parts = _canonical(su, st, np.float64)
+    state = torch.from_numpy(np.ascontiguousarray(flat)).cuda().view(torch.uint8).reshape(-1)
+    assert state.numel() == nbytes
+    x = torch.zeros(B, plan.length, dtype=torch.float32, device="cuda")
+    _run_steps(plan, pm, window, coeff, LA, args, x, state, [i0, i0 + 1], asym, max_iter, alpha)
+    got = state.view(torch.float32).reshape(B, -1).cpu().numpy().astype(np.float64)
+    N, NA = n_fft, LA + 1
+    inv_scale = N ** -0.5 if normalized else 1.0 / N
+    fr_g = got[:, :NA * N].reshape(B, NA, N) * inv_scale
+    err = np.abs(fr_g - parts["frames"]).max()
+    assert err <= 1e-5 * 4 ** (max_iter - 1) * max(1.0, np.abs(parts["frames"]).max()), (err, n_fft, la, asym, alpha, wl, i0)
