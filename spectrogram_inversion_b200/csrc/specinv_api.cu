@@ -44,12 +44,12 @@ static bool force_generic() {
 
 // ---------------------------------------------------------------- plan
 template <typename T>
-__global__ void plan_tables_kernel(int N, int M, int normalized, const T* __restrict__ window,
+__global__ void plan_tables_kernel(int N, int M, int pow2, int normalized, const T* __restrict__ window,
                                    cx_t<T>* tw, cx_t<T>* twr, T* wa, T* ws) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < M) {
+    if (pow2 ? i < M : i < N) {
         double s, c;
-        sincospi(2.0 * i / M, &s, &c);
+        sincospi(2.0 * i / (pow2 ? M : N), &s, &c);
         tw[i] = mk<T>((T)c, (T)(-s));
     }
     if (i <= M / 2) {
@@ -93,7 +93,7 @@ static int plan_init_t(const Dims& dm, const specinv_desc* d, const void* window
     const PlanLayout pl = plan_layout(dm, d->dtype);
     char* p = (char*)plan;
     const int n = dm.N;
-    plan_tables_kernel<T><<<(n + 255) / 256, 256, 0, st>>>(dm.N, dm.M, d->normalized, (const T*)window,
+    plan_tables_kernel<T><<<(n + 255) / 256, 256, 0, st>>>(dm.N, dm.M, dm.pow2, d->normalized, (const T*)window,
                                                            (cx_t<T>*)(p + pl.tw), (cx_t<T>*)(p + pl.twr),
                                                            (T*)(p + pl.wa), (T*)(p + pl.ws));
     note_tables_launch(st);       // an iteration kernel launched right behind this one must not overlap it

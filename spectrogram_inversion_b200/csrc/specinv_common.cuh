@@ -47,6 +47,7 @@ struct Dims {
     int N;        // n_fft
     int M;        // N/2: size of the complex FFT used for the real transform
     int logM;
+    int pow2;     // n_fft is a power of two (FFT kernels); otherwise the direct-DFT tile kernel of specinv_generic.cu
     int hop;
     int T;        // frames
     int B;        // batch
@@ -75,12 +76,14 @@ inline int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
 inline int make_dims(const specinv_desc* d, Dims* o) {
     if (!d) return SPECINV_ERR_INVALID;
     const int N = d->n_fft;
-    if (N < 16 || N > 8192 || (N & (N - 1))) return N > 0 && (N & (N - 1)) ? SPECINV_ERR_UNSUPPORTED : SPECINV_ERR_INVALID;
+    if (N < 16 || N > 8192) return SPECINV_ERR_INVALID;
+    if (N & 1) return SPECINV_ERR_UNSUPPORTED;     // odd n_fft (two-sided spectra with an odd bin count only)
     if (d->hop < 1 || d->hop > N) return SPECINV_ERR_INVALID;
     if (d->n_frames < 1 || d->batch < 1) return SPECINV_ERR_INVALID;
     if (d->dtype != SPECINV_F32 && d->dtype != SPECINV_F64) return SPECINV_ERR_INVALID;
     if (d->pad_mode < 0 || d->pad_mode > 3) return SPECINV_ERR_INVALID;
     o->N = N; o->M = N / 2; o->logM = ilog2(N / 2); o->hop = d->hop; o->T = d->n_frames; o->B = d->batch;
+    o->pow2 = (N & (N - 1)) == 0;
     o->P = d->center ? N / 2 : 0;
     o->K = (N - 1) / d->hop;
     o->pad_mode = d->pad_mode;
@@ -110,7 +113,8 @@ bool pdl_prologue_safe(cudaStream_t st);
 inline PlanLayout plan_layout(const Dims& dm, int dtype) {
     const size_t es = dtype == SPECINV_F64 ? 8 : 4;
     PlanLayout p; size_t off = 0;
-    p.tw = off;      off = align_up(off + (size_t)dm.M * 2 * es, 256);
+    // power of two: W_M^j, j < M (the M-point complex FFT); otherwise W_N^j, j < N (direct DFT)
+    p.tw = off;      off = align_up(off + (size_t)(dm.pow2 ? dm.M : dm.N) * 2 * es, 256);
     p.twr = off;     off = align_up(off + (size_t)(dm.M / 2 + 1) * 2 * es, 256);
     p.wa = off;      off = align_up(off + (size_t)dm.N * es, 256);
     p.ws = off;      off = align_up(off + (size_t)dm.N * es, 256);

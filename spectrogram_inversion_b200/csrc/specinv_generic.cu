@@ -249,6 +249,129 @@ __global__ void __launch_bounds__(1024) tile_kernel(const TileArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------
+// Any EVEN n_fft that is not a power of two (the reference infers n_fft from the bin count, methods.py:65-68; 400 is
+// torchaudio's default): the same tile structure with the transforms done as direct DFTs on the W_N table of the
+// plan.  O(N^2) per frame instead of O(N log N) -- a coverage path (about 4x the generic FFT kernel's time at
+// N = 400), never a fallback to another library.  Shared memory per frame: N time samples and N/2+1 bins.
+//   forward : s[k] = sum_n fr[n] W_N^(kn), k <= N/2               (fr = frame * analysis window)
+//   inverse : x[n] = Re h[0] + (-1)^n Re h[N/2] + 2 sum_{0<k<N/2} Re(h[k] conj(W_N^(kn)))   (C2R, unnormalised:
+//             the synthesis window carries 1/N or N^-1/2 like in the FFT kernels)
+// ------------------------------------------------------------------------------------------
+template <typename T, int OP>
+__global__ void __launch_bounds__(512) dft_tile_kernel(const TileArgs a) {
+    using C = cx_t<T>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const Dims& dm = a.dm;
+    const int N = dm.N, H = dm.M + 1, hop = dm.hop;
+    const int b = blockIdx.y;
+    const int t0 = blockIdx.x * a.tile_frames;
+    const int t1 = min(dm.T, t0 + a.tile_frames);
+    const int f0 = (OP == OP_STFT) ? t0 : max(0, t0 - dm.K);
+    const int nfr = t1 - f0;
+    const int tid = threadIdx.x, NT = blockDim.x;
+    C* hb = reinterpret_cast<C*>(smem_raw);                          // [frames][H] half spectra
+    T* fb = reinterpret_cast<T*>(hb + (size_t)(a.tile_frames + dm.K) * H);   // [frames][N] time frames
+    const C* __restrict__ tw = (const C*)a.tw;                       // W_N^j = (cos, -sin)(2 pi j / N)
+    const T* wa = (const T*)a.wa;
+    const T* ws = (const T*)a.ws;
+
+    T dsum = T(0), esum = T(0);
+    const bool want_sums = a.sums != nullptr;
+    if constexpr (OP != OP_ISTFT) {
+        const T* x = (const T*)a.x_in + (long long)b * dm.L;
+        for (int idx = tid; idx < nfr * N; idx += NT) {
+            const int f = idx / N, n = idx - f * N;
+            const long long i0 = pad_index((long long)(f0 + f) * hop + n, dm.P, dm.L, dm.pad_mode);
+            fb[idx] = (i0 >= 0 ? x[i0] : T(0)) * wa[n];
+        }
+        __syncthreads();
+    }
+    // ---- forward DFT of every half-spectrum bin + point-wise stage
+    for (int idx = tid; idx < nfr * H; idx += NT) {
+        const int f = idx / H, k = idx - f * H;
+        const int t = f0 + f;
+        const bool owned = t >= t0;
+        C s = mk<T>(T(0), T(0));
+        if constexpr (OP != OP_ISTFT) {
+            const T* fr = fb + (size_t)f * N;
+            T sr = T(0), si = T(0);
+            int j = 0;                                               // (k n) mod N
+            for (int n = 0; n < N; ++n) {
+                const C w = tw[j];
+                sr += fr[n] * w.x; si += fr[n] * w.y;
+                j += k; if (j >= N) j -= N;
+            }
+            s = mk<T>(sr, si);
+        }
+        const BinIO<T> io(a, (long long)b * dm.T + t);
+        C h = bin_update<T, OP>(a, io, k, s, owned, want_sums, dsum, esum);
+        if (!dm.onesided && k != 0 && k != dm.M) {
+            // two-sided: the mirrored bin N-k holds conj(s) of the real-input STFT; ifft(...).real (methods.py:145-146)
+            // is the C2R transform of the Hermitian part (p[k] + conj p[N-k]) / 2
+            const C m = bin_update<T, OP>(a, io, N - k, mk<T>(s.x, -s.y), owned, want_sums, dsum, esum);
+            h = mk<T>(T(0.5) * (h.x + m.x), T(0.5) * (h.y - m.y));
+        }
+        hb[idx] = h;
+    }
+    if constexpr (OP == OP_GL || OP == OP_ADMM) {
+        if (want_sums) {
+            __shared__ double red[2][32];
+            double d = (double)dsum, e = (double)esum;
+            for (int o = 16; o > 0; o >>= 1) {
+                d += __shfl_xor_sync(0xffffffffu, d, o);
+                e += __shfl_xor_sync(0xffffffffu, e, o);
+            }
+            if ((tid & 31) == 0) { red[0][tid >> 5] = d; red[1][tid >> 5] = e; }
+            __syncthreads();
+            if (tid == 0) {
+                double dd = 0, ee = 0;
+                for (int i = 0; i < (NT >> 5); ++i) { dd += red[0][i]; ee += red[1][i]; }
+                atomicAdd(a.sums, dd);
+                atomicAdd(a.sums + 1, ee);
+            }
+        }
+    }
+    if constexpr (OP == OP_STFT) return;
+    __syncthreads();
+    // ---- inverse (C2R) DFT of every sample
+    for (int idx = tid; idx < nfr * N; idx += NT) {
+        const int f = idx / N, n = idx - f * N;
+        const C* h = hb + (size_t)f * H;
+        T acc = h[0].x + ((n & 1) ? -h[dm.M].x : h[dm.M].x);
+        T part = T(0);
+        int j = n;                                                   // (k n) mod N for k = 1
+        for (int k = 1; k < dm.M; ++k) {
+            const C w = tw[j];
+            part += h[k].x * w.x + h[k].y * w.y;                     // Re(h conj(W))
+            j += n; if (j >= N) j -= N;
+        }
+        fb[idx] = acc + T(2) * part;
+    }
+    __syncthreads();
+    // ---- windowed overlap-add of the owned output range (gather), times 1/envelope
+    {
+        const long long o0 = (long long)t0 * hop;
+        const long long o1 = (t1 == dm.T) ? dm.Lp : (long long)t1 * hop;
+        T* xo = (T*)a.x_out + (long long)b * dm.L;
+        const T* ienv = (const T*)a.inv_env;
+        for (long long pp = o0 + tid; pp < o1; pp += NT) {
+            const long long m = pp - dm.P;
+            if (m < 0 || m >= dm.L) continue;
+            int tlo = pp >= N ? (int)((pp - N) / hop) + 1 : 0;
+            if (tlo < f0) tlo = f0;
+            int thi = (int)(pp / hop);
+            if (thi > t1 - 1) thi = t1 - 1;
+            T acc = T(0);
+            for (int t = tlo; t <= thi; ++t) {
+                const int i = (int)(pp - (long long)t * hop);
+                acc += fb[(size_t)(t - f0) * N + i] * ws[i];
+            }
+            xo[m] = acc * ienv[m];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
 static int g_smem_optin = -1;
@@ -264,8 +387,36 @@ static int smem_optin() {
 }
 
 template <typename T, int OP>
+static int launch_dft_tile(TileArgs& a, cudaStream_t st) {
+    const Dims& dm = a.dm;
+    const size_t frame_bytes = ((size_t)dm.N + 2 * (size_t)(dm.M + 1)) * sizeof(T);
+    const int halo = (OP == OP_STFT) ? 0 : dm.K;
+    const int optin = smem_optin();
+    if (optin <= 0) return SPECINV_ERR_NO_DEVICE;
+    const size_t big = (size_t)optin - 1024;
+    const size_t budget = big < (size_t)100 * 1024 ? big : (size_t)100 * 1024;
+    int cap = (int)(budget / frame_bytes);
+    if (cap - halo < (halo > 1 ? 2 * halo : 2)) cap = (int)(big / frame_bytes);
+    int owned = cap - halo;
+    if (owned < 1) return SPECINV_ERR_UNSUPPORTED;
+    if (owned > dm.T) owned = dm.T;
+    while (owned > 4 * (halo > 0 ? halo : 1) && (long long)dm.B * ((dm.T + owned - 1) / owned) < 2 * 148) owned = (owned + 1) / 2;
+    a.tile_frames = owned;
+    // (the kernel places the time frames behind tile_frames + K half spectra whatever the op)
+    const size_t smem = (size_t)(owned + dm.K) * frame_bytes;
+    if (smem > big) return SPECINV_ERR_UNSUPPORTED;
+    cudaError_t e = cudaFuncSetAttribute(dft_tile_kernel<T, OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    dim3 grid((dm.T + owned - 1) / owned, dm.B);
+    if (grid.y > 65535) return SPECINV_ERR_UNSUPPORTED;
+    dft_tile_kernel<T, OP><<<grid, 512, smem, st>>>(a);
+    return (int)cudaGetLastError();
+}
+
+template <typename T, int OP>
 static int launch_tile(TileArgs& a, cudaStream_t st) {
     const Dims& dm = a.dm;
+    if (!dm.pow2) return launch_dft_tile<T, OP>(a, st);
     const int Mp = dm.M + (dm.M >> 4);
     const size_t frame_bytes = (size_t)Mp * 2 * sizeof(T);
     const int halo = (OP == OP_STFT) ? 0 : dm.K;

@@ -354,6 +354,7 @@ int specinv_rtisi_la_steps(const specinv_desc* d, const void* plan, const void* 
                            int max_iter, double alpha, double synth_coeff, int step_begin, int step_end, void* state,
                            void* stream) {
     Dims dm; int rc = make_dims(d, &dm); if (rc) return rc;
+    if (!dm.pow2) return SPECINV_ERR_UNSUPPORTED;      // the RTISI-LA kernels are built on the power-of-two FFTs
     if (!plan || !window || !mag_main || !x_out || !scratch || (dm.onesided && !mag_nyq)) return SPECINV_ERR_INVALID;
     if (max_iter < 1 || alpha < 0) return SPECINV_ERR_INVALID;
     const int steps = dm.T + (look_ahead < 0 ? dm.K : look_ahead);

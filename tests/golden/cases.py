@@ -143,3 +143,17 @@ FASTREF_CASES = [
     _c("fastref_4096", n_fft=4096, window="hann", hop_length=1024, T=9, B=1, dtype="float32", seed=25,
        pad_mode="constant"),
 ]
+
+
+# n_fft that is not a power of two (the reference infers n_fft from the bin count, methods.py:65-68; 400 is torchaudio's
+# default): the direct-DFT tile kernels.  make_golden_nonpow2.py -> nonpow2.npz
+NONPOW2_CASES = [
+    _c("np2_400_hann_f32", n_fft=400, window="hann", hop_length=100, T=15, B=2, dtype="float32", seed=31),
+    _c("np2_400_hann_f64", n_fft=400, window="hann", hop_length=160, T=11, B=2, dtype="float64", seed=32),
+    _c("np2_120_rect_f64", n_fft=120, T=17, B=3, dtype="float64", seed=33),                              # all defaults
+    _c("np2_600_short_win_f32", n_fft=600, win_length=401, window="hamming", hop_length=150, T=9, B=1, dtype="float32",
+       seed=34, pad_mode="constant", normalized=True),
+    _c("np2_96_twosided_f64", n_fft=96, window="hann", hop_length=24, T=19, B=2, dtype="float64", seed=35, onesided=False),
+    _c("np2_1000_nocenter_f32", n_fft=1000, window="hamming", hop_length=250, T=8, B=2, dtype="float32", seed=36,
+       center=False),
+]
