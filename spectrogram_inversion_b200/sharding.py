@@ -116,6 +116,7 @@ class CudaRangeEngine:
         self.padded_offset = frame_offset * args.hop_length
         self.signal_len = args.signal_length(total_frames)
         self._nosums = torch.empty(0, dtype=torch.float64, device=device)
+        self._gl_fn = _lib.lib().specinv_gl_iter
 
     # -- state -------------------------------------------------------------------------------------
     def pack(self, spec_local):
@@ -151,9 +152,12 @@ class CudaRangeEngine:
         self.plan.istft(c, out)
 
     def gl_iter(self, x_in, x_out, q_in, q_out, mag, lr, sums):
+        # straight through ctypes like the single-GPU solvers (engine._Solver._launch_direct): at 8 ranks an iteration
+        # is ~0.2 ms of kernel time, a torch.library dispatch (~45 us) per launch would show
         p = self.plan
-        self._ops.gl_iter(p.buf, x_in, x_out, q_in.main, q_in.nyq, q_out.main, q_out.nyq, mag.main, mag.nyq,
-                          sums if sums is not None else self._nosums, lr, *p._k)
+        ptrs = self._ops.pointers((p.buf, x_in, x_out, q_in.main, q_in.nyq, q_out.main, q_out.nyq, mag.main, mag.nyq))
+        self._ops.iter_direct(self._gl_fn, "gl_iter", self.device, p.desc_ref, ptrs, lr,
+                              sums.data_ptr() if sums is not None else None)
 
     def new_sums(self):
         return torch.zeros(2, dtype=torch.float64, device=self.device)
@@ -162,7 +166,13 @@ class CudaRangeEngine:
         self._ops.halo_sum(left, right, out)
 
     def fill_padding(self, x):
-        self._ops.fill_padding(x, self.padded_offset, self.pad, self.signal_len, self.pad_mode)
+        from . import _lib
+        C = _lib.C
+        with torch.cuda.device(self.device):
+            self._ops._ok(_lib.lib().specinv_fill_padding(
+                self._ops._DT[x.dtype], C.c_void_p(x.data_ptr()), x.stride(0), x.shape[0], int(self.padded_offset),
+                x.shape[1], int(self.pad), int(self.signal_len), int(self.pad_mode),
+                C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)), "fill_padding")
 
 
 PEER_EXCHANGES = [0]      # halo exchanges done by the peer-memory kernel in this process (tests / bench look at it)
