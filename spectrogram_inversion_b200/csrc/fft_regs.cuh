@@ -89,6 +89,12 @@ SPX_HD float2 operator-(float2 a, float2 b) { return psub(a, b); }
 SPX_HD float2 cmul2(float2 a, float2 w) { return pfma(f2(a.x, a.x), w, pmul(f2(a.y, a.y), f2(-w.y, w.x))); }
 SPX_HD float2 cmulc2(float2 a, float2 w) { return pfma(f2(a.x, a.x), f2(w.x, -w.y), pmul(f2(a.y, a.y), f2(w.y, w.x))); }
 SPX_HD float2 smul2(float2 a, float s) { return pmul(a, f2(s, s)); }
+// The same two products with conj(w) = (w.x, -w.y) supplied by the caller (a table): the packed instructions take a
+// half-swapped or broadcast operand for free, but not a half-NEGATED one -- cmul2 / cmulc2 on a table twiddle cost a
+// scalar negate and a move on top of their two packed instructions (52 + 52 of 1288 instructions per frame at
+// n_fft = 1024, profiles/r02_warp_n1024_ncu_summary.txt); with the conjugate beside the twiddle they cost two.
+SPX_HD float2 cmul2t(float2 a, float2 w, float2 wc) { return pfma(f2(a.x, a.x), w, pmul(f2(a.y, a.y), f2(wc.y, wc.x))); }
+SPX_HD float2 cmulc2t(float2 a, float2 w, float2 wc) { return pfma(f2(a.x, a.x), wc, pmul(f2(a.y, a.y), f2(w.y, w.x))); }
 
 // v * exp(-+ 2 pi i K / N)   (forward: minus sign; INV: plus sign), K, N compile time
 template <int K, int N, bool INV>

@@ -56,6 +56,25 @@ SPX_HD void post_pair(float2 P, float2 Q, float2 w, float2& sP, float2& sQ) {
     const float2 D = E - WO;
     sQ = f2(D.x, -D.y);                                 // (er - wor, woi - ei)
 }
+// (wc = conj(w) from a table, or nullptr-equivalent HC = false: computed on the fly)
+template <bool HC>
+SPX_HD void post_pair_t(float2 P, float2 Q, float2 w, float2 wc, float2& sP, float2& sQ) {
+    const float2 E = P + f2(Q.x, -Q.y);
+    const float2 O = f2(P.y, -P.x) + f2(Q.y, Q.x);
+    const float2 WO = HC ? cmul2t(O, w, wc) : cmul2(O, w);
+    sP = E + WO;
+    const float2 D = E - WO;
+    sQ = f2(D.x, -D.y);
+}
+template <bool HC>
+SPX_HD void pre_pair_t(float2 hP, float2 hQ, float2 w, float2 wc, float2& P, float2& Q) {
+    const float2 A = hP + f2(hQ.x, -hQ.y);
+    const float2 D = hP - f2(hQ.x, -hQ.y);
+    const float2 G = HC ? cmulc2t(D, w, wc) : cmulc2(D, w);
+    P = A + f2(-G.y, G.x);
+    const float2 R = A - f2(-G.y, G.x);
+    Q = f2(R.x, -R.y);
+}
 // inverse pre-process: (h[k], h[M-k]) -> (Z'[k], Z'[M-k]), the inputs of the M-point inverse complex FFT
 SPX_HD void pre_pair(float2 hP, float2 hQ, float2 w, float2& P, float2& Q) {
     const float2 A = hP + f2(hQ.x, -hQ.y);              // (Ar, Ai) = hP + conj(hQ)
@@ -129,8 +148,8 @@ struct LaneTables {
 
 // ---- forward ---------------------------------------------------------------------------------------------
 // v[i] = windowed z[LANES i + l] on entry
-template <int LANES, int VV = V>
-SPX_HD void fwd_pass1(int l, float2* v, const float2* tw1, float2* e1) {
+template <int LANES, int VV = V, bool HC = false>
+SPX_HD void fwd_pass1(int l, float2* v, const float2* tw1, float2* e1, const float2* tw1c = nullptr) {
     using C = Cfg<LANES, VV>;
     const int c = l & (C::RC - 1);
     static_for<C::S1>([&](auto sc) {
@@ -141,14 +160,14 @@ SPX_HD void fwd_pass1(int l, float2* v, const float2* tw1, float2* e1) {
         const int b = (l + LANES * s) >> C::LOGRC;
         static_for<C::R1>([&](auto kc) {
             constexpr int ka = decltype(kc)::value;
-            const float2 y = ka == 0 ? t[0] : cmulf(t[ka], tw1[C::R1 * s + ka]);
+            const float2 y = ka == 0 ? t[0] : (HC ? cmul2t(t[ka], tw1[C::R1 * s + ka], tw1c[C::R1 * s + ka]) : cmulf(t[ka], tw1[C::R1 * s + ka]));
             e1[ex_addr<C::R2, C::RC>(C::RC * ka + c, b)] = y;
         });
     });
 }
 
-template <int LANES, int VV = V>
-SPX_HD void fwd_pass2(int l, const float2* e1, const float2* tw2, float2* e2) {
+template <int LANES, int VV = V, bool HC = false>
+SPX_HD void fwd_pass2(int l, const float2* e1, const float2* tw2, float2* e2, const float2* tw2c = nullptr) {
     using C = Cfg<LANES, VV>;
     const int c = l & (C::RC - 1);
     static_for<C::S2>([&](auto rc) {
@@ -163,7 +182,7 @@ SPX_HD void fwd_pass2(int l, const float2* e1, const float2* tw2, float2* e2) {
         fft_small<C::R2, false>(t);
         static_for<C::R2>([&](auto kc) {
             constexpr int kb = decltype(kc)::value;
-            const float2 y = kb == 0 ? t[0] : cmulf(t[kb], tw2[kb]);
+            const float2 y = kb == 0 ? t[0] : (HC ? cmul2t(t[kb], tw2[kb], tw2c[kb]) : cmulf(t[kb], tw2[kb]));
             e2[ex_addr<C::RC>(ka + C::R1 * kb, c)] = y;
         });
     });
@@ -225,9 +244,9 @@ SPX_HD float2 bin_update(float2 s, float2 a0, float2 a1, float m, float coef, fl
 // bin; lane 0 slot 0: bins 0 and M/2), e = -1: the Nyquist bin (lane 0 only):
 //     float2 io.s0(e), io.s1(e); float io.mag(e); void io.put(e, o0, o1)
 // so that values are fetched right where they are used (no block of 48 live registers).
-template <int OP, bool SUMS, int VV = V, typename IO>
+template <int OP, bool SUMS, int VV = V, bool HC = false, typename IO>
 SPX_HD void pointwise(int l, float2* A, float2* B, const float2* twr, IO& io, float coef, float coef2, float& dsum,
-                      float& esum) {
+                      float& esum, const float2* twrc = nullptr) {
     constexpr int RC = VV / 2, H = RC / 2;      // pair slots per lane; lane 0 pairs inside its two classes
     const bool l0 = l == 0;
     auto upd = [&](auto ec, float2 sv) {
@@ -249,11 +268,11 @@ SPX_HD void pointwise(int l, float2* A, float2* B, const float2* twr, IO& io, fl
         A[H] = f2(2.f * h4.x, -2.f * h4.y);
     } else {
         float2 sP, sQ, P, Q;
-        const float2 w = twr[0];
-        post_pair(A[0], B[RC - 1], w, sP, sQ);
+        const float2 w = twr[0], wc = HC ? twrc[0] : w;
+        post_pair_t<HC>(A[0], B[RC - 1], w, wc, sP, sQ);
         const float2 hP = upd(std::integral_constant<int, 0>{}, sP);
         const float2 hQ = upd(std::integral_constant<int, 1>{}, sQ);
-        pre_pair(hP, hQ, w, P, Q);
+        pre_pair_t<HC>(hP, hQ, w, wc, P, Q);
         A[0] = P; B[RC - 1] = Q;
     }
     // slots 1..RC-1.  general lanes: (A[j], B[RC-1-j]); lane 0, j < H: (A[j], A[RC-j]); lane 0, j >= H:
@@ -263,12 +282,12 @@ SPX_HD void pointwise(int l, float2* A, float2* B, const float2* twr, IO& io, fl
         float2 P, Q;
         if constexpr (j < H) { P = A[j]; Q = l0 ? A[RC - j] : B[RC - 1 - j]; }
         else { P = l0 ? B[j - H] : A[j]; Q = l0 ? B[RC - 1 - (j - H)] : B[RC - 1 - j]; }
-        const float2 w = twr[j];
+        const float2 w = twr[j], wc = HC ? twrc[j] : w;
         float2 sP, sQ;
-        post_pair(P, Q, w, sP, sQ);
+        post_pair_t<HC>(P, Q, w, wc, sP, sQ);
         const float2 hP = upd(std::integral_constant<int, 2 * j>{}, sP);
         const float2 hQ = upd(std::integral_constant<int, 2 * j + 1>{}, sQ);
-        pre_pair(hP, hQ, w, P, Q);
+        pre_pair_t<HC>(hP, hQ, w, wc, P, Q);
         if constexpr (j < H) { A[j] = P; if (l0) A[RC - j] = Q; else B[RC - 1 - j] = Q; }
         else { if (l0) { B[j - H] = P; B[RC - 1 - (j - H)] = Q; } else { A[j] = P; B[RC - 1 - j] = Q; } }
     });
@@ -276,8 +295,8 @@ SPX_HD void pointwise(int l, float2* A, float2* B, const float2* twr, IO& io, fl
 
 // Stand-alone inverse transform (ISTFT): the given spectrum h replaces the point-wise stage; on return A / B hold
 // the inputs of the inverse pass 3.  `io.s0(e)` as above (e = -1: the Nyquist bin).
-template <int VV = V, typename IO>
-SPX_HD void spectrum_pairs(int l, float2* A, float2* B, const float2* twr, IO& io) {
+template <int VV = V, bool HC = false, typename IO>
+SPX_HD void spectrum_pairs(int l, float2* A, float2* B, const float2* twr, IO& io, const float2* twrc = nullptr) {
     constexpr int RC = VV / 2, H = RC / 2;
     const bool l0 = l == 0;
     if (l0) {
@@ -285,12 +304,12 @@ SPX_HD void spectrum_pairs(int l, float2* A, float2* B, const float2* twr, IO& i
         A[0] = f2(h0.x + hM.x, h0.x - hM.x);        // C2R ignores Im(DC), Im(Nyquist)
         A[H] = f2(2.f * h4.x, -2.f * h4.y);
     } else {
-        pre_pair(io.s0(0), io.s0(1), twr[0], A[0], B[RC - 1]);
+        pre_pair_t<HC>(io.s0(0), io.s0(1), twr[0], HC ? twrc[0] : twr[0], A[0], B[RC - 1]);
     }
     static_for<RC - 1>([&](auto jc) {
         constexpr int j = decltype(jc)::value + 1;
         float2 P, Q;
-        pre_pair(io.s0(2 * j), io.s0(2 * j + 1), twr[j], P, Q);
+        pre_pair_t<HC>(io.s0(2 * j), io.s0(2 * j + 1), twr[j], HC ? twrc[j] : twr[j], P, Q);
         if constexpr (j < H) { A[j] = P; if (l0) A[RC - j] = Q; else B[RC - 1 - j] = Q; }
         else { if (l0) { B[j - H] = P; B[RC - 1 - (j - H)] = Q; } else { A[j] = P; B[RC - 1 - j] = Q; } }
     });
@@ -310,8 +329,8 @@ SPX_HD void inv_pass3(int l, float2* A, float2* B, float2* e2) {
     });
 }
 
-template <int LANES, int VV = V>
-SPX_HD void inv_pass2(int l, const float2* e2, const float2* tw2, float2* e1) {
+template <int LANES, int VV = V, bool HC = false>
+SPX_HD void inv_pass2(int l, const float2* e2, const float2* tw2, float2* e1, const float2* tw2c = nullptr) {
     using C = Cfg<LANES, VV>;
     const int c = l & (C::RC - 1);
     static_for<C::S2>([&](auto rc) {
@@ -321,7 +340,7 @@ SPX_HD void inv_pass2(int l, const float2* e2, const float2* tw2, float2* e1) {
         static_for<C::R2>([&](auto kc) {
             constexpr int kb = decltype(kc)::value;
             const float2 y = e2[ex_addr<C::RC>(ka + C::R1 * kb, c)];
-            t[kb] = kb == 0 ? y : cmulcf(y, tw2[kb]);
+            t[kb] = kb == 0 ? y : (HC ? cmulc2t(y, tw2[kb], tw2c[kb]) : cmulcf(y, tw2[kb]));
         });
         fft_small<C::R2, true>(t);   // t[b] = Y1'[ka, b, c] (before the pass-1 twiddle)
         static_for<C::R2 / 2>([&](auto pc) {
@@ -333,8 +352,8 @@ SPX_HD void inv_pass2(int l, const float2* e2, const float2* tw2, float2* e1) {
 }
 
 // v[i] = z'[LANES i + l] (unscaled)
-template <int LANES, int VV = V>
-SPX_HD void inv_pass1(int l, const float2* e1, const float2* tw1, float2* v) {
+template <int LANES, int VV = V, bool HC = false>
+SPX_HD void inv_pass1(int l, const float2* e1, const float2* tw1, float2* v, const float2* tw1c = nullptr) {
     using C = Cfg<LANES, VV>;
     const int c = l & (C::RC - 1);
     static_for<C::S1>([&](auto sc) {
@@ -344,7 +363,7 @@ SPX_HD void inv_pass1(int l, const float2* e1, const float2* tw1, float2* v) {
         static_for<C::R1>([&](auto kc) {
             constexpr int ka = decltype(kc)::value;
             const float2 y = e1[ex_addr<C::R2, C::RC>(C::RC * ka + c, b)];
-            t[ka] = ka == 0 ? y : cmulcf(y, tw1[C::R1 * s + ka]);
+            t[ka] = ka == 0 ? y : (HC ? cmulc2t(y, tw1[C::R1 * s + ka], tw1c[C::R1 * s + ka]) : cmulcf(y, tw1[C::R1 * s + ka]));
         });
         fft_small<C::R1, true>(t);
         static_for<C::R1>([&](auto ac) { constexpr int a = decltype(ac)::value; v[C::S1 * a + s] = t[a]; });

@@ -48,7 +48,12 @@ struct WArgs {
 };
 
 // TMEM columns (per lane): constant tables shared by the warps of one sub-partition, then per-warp state
-constexpr int TC_WA = 0, TC_WS = 32, TC_TW1 = 64, TC_TW2 = 96, TC_TWR = 128, TC_IE = 144, TC_WARP = 160;
+constexpr int TC_WA = 0, TC_WS = 32, TC_TW1 = 64, TC_TW2 = 96, TC_TWR = 128, TC_IE = 144;
+// One-warp-per-frame variants (LANES = 32) also keep the CONJUGATES of the three twiddle tables (fft_regs.cuh: cmul2t):
+// 64 more columns, which is exactly what 12 warps x 96 columns of ring / carry leave of the 512.
+constexpr int TC_TW1C = 160, TC_TW2C = 192, TC_TWRC = 208;
+constexpr bool has_conj_tables(int lanes) { return lanes == 32; }
+constexpr int tc_warp(int lanes) { return has_conj_tables(lanes) ? 224 : 160; }
 // per warp: the input ring (OV - 1 hops) then the overlap-add carry (OV - 1 hops), a hop = 2 VV / OV words per lane
 // (OV = n_fft / hop = 2, 4 or 8 overlapping frames per sample; 48 words for OV = 4 and 16 values per lane)
 constexpr int ring_words(int vv, int ov) { return (ov - 1) * 2 * vv / ov; }
@@ -172,7 +177,9 @@ __global__ void __launch_bounds__(warps_of(VV, OP) * 32, 1) warp_iter_kernel(con
     constexpr int G = LANES / 32;                 // warps per frame group
     constexpr int WARPS = warps_of(VV, OP);
     constexpr int GROUPS = WARPS / G;
-    static_assert(TC_WARP + ((WARPS + 3) / 4) * TC_PER_WARP <= TMEM_COLS && TC_IE + 2 * HP <= TC_WARP, "TMEM columns");
+    constexpr bool HC = has_conj_tables(LANES);
+    constexpr int TC_WARP = tc_warp(LANES);
+    static_assert(TC_WARP + ((WARPS + 3) / 4) * TC_PER_WARP <= TMEM_COLS && TC_IE + 2 * HP <= 160, "TMEM columns");
     extern __shared__ __align__(16) float2 sm[];
     __shared__ unsigned s_tmem_base;
     __shared__ __align__(8) unsigned long long s_bar[GROUPS][3];   // per group: input block, state rows, ADMM U row
@@ -220,6 +227,23 @@ __global__ void __launch_bounds__(warps_of(VV, OP) * 32, 1) warp_iter_kernel(con
             t[2 * j] = w.x; t[2 * j + 1] = w.y;
         }
         tmem_stw<2 * RC>(tlane + TC_TWR, t);
+        if constexpr (HC) {
+#pragma unroll
+            for (int j = 0; j < RC; ++j) t[2 * j + 1] = -t[2 * j + 1];
+            tmem_stw<2 * RC>(tlane + TC_TWRC, t);
+#pragma unroll
+            for (int i = 0; i < V; ++i) {
+                const float2 w = a.tw[((tl + LANES * (i / C::R1)) * (i % C::R1)) & (M - 1)];
+                t[2 * i] = w.x; t[2 * i + 1] = -w.y;
+            }
+            tmem_stw<2 * V>(tlane + TC_TW1C, t);
+#pragma unroll
+            for (int kb = 0; kb < C::R2; ++kb) {
+                const float2 w = a.tw[(C::R1 * (tl & (RC - 1)) * kb) & (M - 1)];
+                t[2 * kb] = w.x; t[2 * kb + 1] = -w.y;
+            }
+            tmem_stw<2 * C::R2>(tlane + TC_TW2C, t);
+        }
         tmem_wait_st();
     }
     // Programmatic dependent launch: everything above touched only this CTA's own resources and the plan's window /
@@ -350,16 +374,18 @@ __global__ void __launch_bounds__(warps_of(VV, OP) * 32, 1) warp_iter_kernel(con
                 for (int i = 0; i < V; ++i) v[i] = pmul(v[i], w[i]);
             }
             {
-                float2 tw1[V];
+                float2 tw1[V], tw1c[HC ? V : 1];
                 tmem_ldw<2 * V>(tlane + TC_TW1, reinterpret_cast<float*>(tw1));
-                fwd_pass1<LANES, VV>(l, v, tw1, e1);
+                if constexpr (HC) tmem_ldw<2 * V>(tlane + TC_TW1C, reinterpret_cast<float*>(tw1c));
+                fwd_pass1<LANES, VV, HC>(l, v, tw1, e1, tw1c);
             }
             group_sync<LANES>(bar_id);
             {
-                float2 tw2[C::R2];
+                float2 tw2[C::R2], tw2c[HC ? C::R2 : 1];
                 if constexpr (C::R2 == 8) tmem_ld16(tlane + TC_TW2, reinterpret_cast<float*>(tw2));
                 else tmem_ld32(tlane + TC_TW2, reinterpret_cast<float*>(tw2));
-                fwd_pass2<LANES, VV>(l, e1, tw2, e2);
+                if constexpr (HC) tmem_ldw<2 * C::R2>(tlane + TC_TW2C, reinterpret_cast<float*>(tw2c));
+                fwd_pass2<LANES, VV, HC>(l, e1, tw2, e2, tw2c);
             }
             group_sync<LANES>(bar_id);
             if constexpr (OP == OP_ADMM) {
@@ -404,13 +430,14 @@ __global__ void __launch_bounds__(warps_of(VV, OP) * 32, 1) warp_iter_kernel(con
                      OP == OP_ADMM ? a.s1_out + row * M : nullptr, a.s0_out_nyq + row,
                      OP == OP_ADMM ? a.s1_out_nyq + row : nullptr, l, l + hi_adj, M - l, M - l - hi_adj, kq0, owned,
                      s0n, s1n, mgn};
-                float2 twr[RC];
+                float2 twr[RC], twrc[HC ? RC : 1];
                 tmem_ldw<2 * RC>(tlane + TC_TWR, reinterpret_cast<float*>(twr));
+                if constexpr (HC) tmem_ldw<2 * RC>(tlane + TC_TWRC, reinterpret_cast<float*>(twrc));
                 if constexpr (OP == OP_ISTFT) {
-                    spectrum_pairs<VV>(l, A, Bv, twr, io);
+                    spectrum_pairs<VV, HC>(l, A, Bv, twr, io, twrc);
                 } else {
                     float dsum = 0.f, esum = 0.f;
-                    pointwise<OP, SUMS, VV>(l, A, Bv, twr, io, a.coef, a.coef2, dsum, esum);
+                    pointwise<OP, SUMS, VV, HC>(l, A, Bv, twr, io, a.coef, a.coef2, dsum, esum, twrc);
                     if constexpr (SUMS) { if (owned) { dacc += (double)dsum; eacc += (double)esum; } }
                 }
             }
@@ -429,16 +456,18 @@ __global__ void __launch_bounds__(warps_of(VV, OP) * 32, 1) warp_iter_kernel(con
             float2 ie[HP];
             if (emit && t < NR) load_inv_env<LANES, VV, OV>(a, t, l, ie);   // edge blocks; early: hidden behind the last two passes
             {
-                float2 tw2[C::R2];
+                float2 tw2[C::R2], tw2c[HC ? C::R2 : 1];
                 if constexpr (C::R2 == 8) tmem_ld16(tlane + TC_TW2, reinterpret_cast<float*>(tw2));
                 else tmem_ld32(tlane + TC_TW2, reinterpret_cast<float*>(tw2));
-                inv_pass2<LANES, VV>(l, e2, tw2, e1);
+                if constexpr (HC) tmem_ldw<2 * C::R2>(tlane + TC_TW2C, reinterpret_cast<float*>(tw2c));
+                inv_pass2<LANES, VV, HC>(l, e2, tw2, e1, tw2c);
             }
             group_sync<LANES>(bar_id);
             {
-                float2 tw1[V];
+                float2 tw1[V], tw1c[HC ? V : 1];
                 tmem_ldw<2 * V>(tlane + TC_TW1, reinterpret_cast<float*>(tw1));
-                inv_pass1<LANES, VV>(l, e1, tw1, v);
+                if constexpr (HC) tmem_ldw<2 * V>(tlane + TC_TW1C, reinterpret_cast<float*>(tw1c));
+                inv_pass1<LANES, VV, HC>(l, e1, tw1, v, tw1c);
             }
             // ---- windowed overlap-add: out = carry (NR hops from earlier frames) + ws * v; the first hop
             // (HP pairs) of `out` is a finished block, the other NR * HP pairs are the new carry

@@ -44,7 +44,10 @@ struct RArgs {
 };
 
 // TMEM columns per lane: constant tables (identical in the four sub-partitions), then per-warp state
-constexpr int TC_WA = 0, TC_WSC = 32, TC_TW1 = 64, TC_TW2 = 96, TC_TWR = 128, TC_AS1 = 144, TC_AS2 = 176, TC_WARP = 208;
+constexpr int TC_WA = 0, TC_WSC = 32, TC_TW1 = 64, TC_TW2 = 96, TC_TWR = 128, TC_AS1 = 144, TC_AS2 = 176;
+// conjugates of the three twiddle tables (fft_regs.cuh: cmul2t), then the per-warp state
+constexpr int TC_TW1C = 208, TC_TW2C = 240, TC_TWRC = 272, TC_WARP = 288;
+constexpr bool HC = true;
 // per warp (VV = values per lane): momentum spectrum `pre` 2 VV words, kept part of y 2 VV, magnitude row VV
 constexpr int TMEM_COLS = 512;
 // float2 of shared memory per signal: u of the active frames (double buffered), u of the kept frames, the output
@@ -144,6 +147,21 @@ __global__ void __launch_bounds__(SIGS * NAMAX * LANES, 1) rtisi_fast_kernel(con
             t[2 * j] = w.x; t[2 * j + 1] = w.y;
         }
         tmem_stw<2 * RC>(tlane + TC_TWR, t);
+#pragma unroll
+        for (int j = 0; j < RC; ++j) t[2 * j + 1] = -t[2 * j + 1];
+        tmem_stw<2 * RC>(tlane + TC_TWRC, t);
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            const float2 w = a.tw[((l + LANES * (i / C::R1)) * (i % C::R1)) & (M - 1)];
+            t[2 * i] = w.x; t[2 * i + 1] = -w.y;
+        }
+        tmem_stw<2 * V>(tlane + TC_TW1C, t);
+#pragma unroll
+        for (int kb = 0; kb < C::R2; ++kb) {
+            const float2 w = a.tw[(C::R1 * (l & (RC - 1)) * kb) & (M - 1)];
+            t[2 * kb] = w.x; t[2 * kb + 1] = -w.y;
+        }
+        tmem_stw<2 * C::R2>(tlane + TC_TW2C, t);
         if (a.asymmetric) {
             window_pairs(a.asym1, 0.5f, TC_AS1);
             window_pairs(a.asym2, 0.5f, TC_AS2);
@@ -319,15 +337,17 @@ __global__ void __launch_bounds__(SIGS * NAMAX * LANES, 1) rtisi_fast_kernel(con
                     for (int r = 0; r < V; ++r) y[r] = pmul(y[r], w[r]);
                 }
                 {
-                    float2 tw1[V];
+                    float2 tw1[V], tw1c[V];
                     tmem_ldw<2 * V>(tlane + TC_TW1, reinterpret_cast<float*>(tw1));
-                    fwd_pass1<LANES, VV>(l, y, tw1, e1);
+                    tmem_ldw<2 * V>(tlane + TC_TW1C, reinterpret_cast<float*>(tw1c));
+                    fwd_pass1<LANES, VV, HC>(l, y, tw1, e1, tw1c);
                 }
                 frame_sync<LANES>(fbar);
                 {
-                    float2 tw2[C::R2];
+                    float2 tw2[C::R2], tw2c[C::R2];
                     tmem_ldw<2 * C::R2>(tlane + TC_TW2, reinterpret_cast<float*>(tw2));
-                    fwd_pass2<LANES, VV>(l, e1, tw2, e2);
+                    tmem_ldw<2 * C::R2>(tlane + TC_TW2C, reinterpret_cast<float*>(tw2c));
+                    fwd_pass2<LANES, VV, HC>(l, e1, tw2, e2, tw2c);
                 }
                 frame_sync<LANES>(fbar);
                 float2 A[RC], Bv[RC];
@@ -347,10 +367,11 @@ __global__ void __launch_bounds__(SIGS * NAMAX * LANES, 1) rtisi_fast_kernel(con
                         __device__ __forceinline__ float mag(int e) const { return e < 0 ? mn : mg[e]; }
                         __device__ __forceinline__ void put(int e, float2 q, float2) { if (e < 0) pn = q; else pre[e] = q; }
                     } io{pre, mg, pre_nyq, mag_nyq};
-                    float2 twr[RC];
+                    float2 twr[RC], twrc[RC];
                     tmem_ldw<2 * RC>(tlane + TC_TWR, reinterpret_cast<float*>(twr));
+                    tmem_ldw<2 * RC>(tlane + TC_TWRC, reinterpret_cast<float*>(twrc));
                     float ds = 0.f, es = 0.f;
-                    pointwise<OP_GL, false, VV>(l, A, Bv, twr, io, mom ? a.lr : 0.f, 0.f, ds, es);
+                    pointwise<OP_GL, false, VV, HC>(l, A, Bv, twr, io, mom ? a.lr : 0.f, 0.f, ds, es, twrc);
                     pre_nyq = io.pn;
                     tmem_stw<2 * V>(twarp + TC_PRE, reinterpret_cast<const float*>(pre));
                 }
@@ -358,15 +379,17 @@ __global__ void __launch_bounds__(SIGS * NAMAX * LANES, 1) rtisi_fast_kernel(con
                 inv_pass3<LANES, VV>(l, A, Bv, e2);
                 frame_sync<LANES>(fbar);
                 {
-                    float2 tw2[C::R2];
+                    float2 tw2[C::R2], tw2c[C::R2];
                     tmem_ldw<2 * C::R2>(tlane + TC_TW2, reinterpret_cast<float*>(tw2));
-                    inv_pass2<LANES, VV>(l, e2, tw2, e1);
+                    tmem_ldw<2 * C::R2>(tlane + TC_TW2C, reinterpret_cast<float*>(tw2c));
+                    inv_pass2<LANES, VV, HC>(l, e2, tw2, e1, tw2c);
                 }
                 frame_sync<LANES>(fbar);
                 {
-                    float2 tw1[V];
+                    float2 tw1[V], tw1c[V];
                     tmem_ldw<2 * V>(tlane + TC_TW1, reinterpret_cast<float*>(tw1));
-                    inv_pass1<LANES, VV>(l, e1, tw1, v);
+                    tmem_ldw<2 * V>(tlane + TC_TW1C, reinterpret_cast<float*>(tw1c));
+                    inv_pass1<LANES, VV, HC>(l, e1, tw1, v, tw1c);
                 }
                 frame_sync<LANES>(fbar);
             }

@@ -72,7 +72,8 @@ static int check_conflicts() {
     return bad;
 }
 
-template <int LANES, int OP, int VV = V>
+// HC: the variants that take the conjugate twiddle tables (cmul2t / cmulc2t), as the one-warp-per-frame kernels do
+template <int LANES, int OP, int VV = V, bool HC = false>
 int run() {
     using C = Cfg<LANES, VV>;
     constexpr int V = VV, RC = C::RC;
@@ -81,6 +82,12 @@ int run() {
     for (int i = 0; i < N; ++i) { x[i] = (float)(4 * frand()); wa[i] = (float)(0.5 - 0.5 * cos(2 * M_PI * i / N)); ws[i] = wa[i] / N; }
     std::vector<LaneTables<LANES, VV>> tb(LANES);
     for (int l = 0; l < LANES; ++l) make_tables<LANES, VV>(l, wa, ws, tb[l]);
+    std::vector<LaneTables<LANES, VV>> tc = tb;                     // conjugates of the three twiddle tables
+    for (int l = 0; l < LANES; ++l) {
+        for (int i = 0; i < VV; ++i) tc[l].tw1[i].y = -tc[l].tw1[i].y;
+        for (int i = 0; i < C::R2; ++i) tc[l].tw2[i].y = -tc[l].tw2[i].y;
+        for (int i = 0; i < VV / 2; ++i) tc[l].twr[i].y = -tc[l].twr[i].y;
+    }
     std::vector<float2> s0_in(M + 1), s1_in(M + 1), s0_out(M + 1), s1_out(M + 1);
     std::vector<float> mag(M + 1);
     for (int k = 0; k <= M; ++k) {
@@ -93,9 +100,9 @@ int run() {
     std::vector<std::vector<float2>> v(LANES, std::vector<float2>(V)), A(LANES, std::vector<float2>(RC)), Bv(LANES, std::vector<float2>(RC));
     for (int l = 0; l < LANES; ++l) {
         for (int i = 0; i < V; ++i) v[l][i] = f2(x[2 * LANES * i + 2 * l] * tb[l].wa[i].x, x[2 * LANES * i + 2 * l + 1] * tb[l].wa[i].y);
-        fwd_pass1<LANES, VV>(l, v[l].data(), tb[l].tw1, e1.data());
+        fwd_pass1<LANES, VV, HC>(l, v[l].data(), tb[l].tw1, e1.data(), tc[l].tw1);
     }
-    for (int l = 0; l < LANES; ++l) fwd_pass2<LANES, VV>(l, e1.data(), tb[l].tw2, e2.data());
+    for (int l = 0; l < LANES; ++l) fwd_pass2<LANES, VV, HC>(l, e1.data(), tb[l].tw2, e2.data(), tc[l].tw2);
     float ds = 0, es = 0;
     for (int l = 0; l < LANES; ++l) fwd_pass3<LANES, VV>(l, e2.data(), A[l].data(), Bv[l].data());
     for (int l = 0; l < LANES; ++l) {
@@ -111,11 +118,11 @@ int run() {
             SPX_HD float mag(int e) const { return mg[bin(e)]; }
             SPX_HD void put(int e, float2 o0, float2 o1) { s0o[bin(e)] = o0; s1o[bin(e)] = o1; }
         } io{l, s0_in.data(), s1_in.data(), mag.data(), s0_out.data(), s1_out.data()};
-        pointwise<OP, true, VV>(l, A[l].data(), Bv[l].data(), tb[l].twr, io, coef, coef2, ds, es);
+        pointwise<OP, true, VV, HC>(l, A[l].data(), Bv[l].data(), tb[l].twr, io, coef, coef2, ds, es, tc[l].twr);
     }
     for (int l = 0; l < LANES; ++l) inv_pass3<LANES, VV>(l, A[l].data(), Bv[l].data(), e2.data());
-    for (int l = 0; l < LANES; ++l) inv_pass2<LANES, VV>(l, e2.data(), tb[l].tw2, e1.data());
-    for (int l = 0; l < LANES; ++l) inv_pass1<LANES, VV>(l, e1.data(), tb[l].tw1, v[l].data());
+    for (int l = 0; l < LANES; ++l) inv_pass2<LANES, VV, HC>(l, e2.data(), tb[l].tw2, e1.data(), tc[l].tw2);
+    for (int l = 0; l < LANES; ++l) inv_pass1<LANES, VV, HC>(l, e1.data(), tb[l].tw1, v[l].data(), tc[l].tw1);
 
     std::vector<cd> s(M + 1), h(M + 1);
     double dref = 0, eref = 0, err_state = 0, err_x = 0;
@@ -148,6 +155,7 @@ int run() {
         const double ours = ((n & 1) ? v[l][i].y : v[l][i].x) / N;
         err_x = fmax(err_x, fabs(ours - acc / N));
     }
+    if (HC) printf("(conjugate tables) ");
     printf("LANES %d V %d OP %d: state err %.3e  frame err %.3e  sums rel err %.3e %.3e\n", LANES, V, OP, err_state, err_x,
            fabs(ds - dref) / dref, fabs(es - eref) / eref);
     return (err_state < 4e-4 && err_x < 2e-5 && fabs(ds - dref) / dref < 1e-4 && fabs(es - eref) / eref < 1e-4) ? 0 : 1;
@@ -160,5 +168,7 @@ int main() {
     rc |= run<64, OP_GL>() | run<64, OP_ADMM>();
     rc |= run<128, OP_GL>() | run<128, OP_ADMM>();
     rc |= run<32, OP_GLP, 8>() | run<32, OP_GLP>() | run<64, OP_GLP>() | run<128, OP_GLP>();
+    rc |= run<32, OP_GL, 16, true>() | run<32, OP_ADMM, 16, true>() | run<32, OP_GLP, 16, true>();
+    rc |= run<32, OP_GL, 8, true>() | run<32, OP_ADMM, 8, true>() | run<64, OP_GL, 16, true>();
     return rc;
 }
