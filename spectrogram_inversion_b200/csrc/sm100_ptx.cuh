@@ -19,9 +19,6 @@ __device__ __forceinline__ void bulk_g2s(unsigned smem_dst, const void* gsrc, un
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_dst), "l"(gsrc), "r"(bytes), "r"(bar) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(unsigned bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
 __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
     unsigned ok;
     do {

@@ -182,37 +182,18 @@ __global__ void __launch_bounds__(warps_of(VV, OP) * 32, 1) warp_iter_kernel(con
     static_assert(TC_WARP + ((WARPS + 3) / 4) * TC_PER_WARP <= TMEM_COLS && TC_IE + 2 * HP <= 160, "TMEM columns");
     extern __shared__ __align__(16) float2 sm[];
     __shared__ unsigned s_tmem_base;
-    // per group: TMA completion of the input block / the state rows / ADMM's U row, then the four "everybody has READ
-    // it" barriers of the multi-warp groups (SW below): staged input block, E1 (inverse pass 1), E2 (forward pass 3),
-    // staged state rows
-    __shared__ __align__(8) unsigned long long s_bar[GROUPS][7];
-    // Frames shared by several warps (LANES > 32): the write-after-read hazards on the exchange and staging buffers
-    // are guarded by split mbarriers -- a warp ARRIVES right after its reads and only whoever overwrites the buffer
-    // WAITS, much later (the TMA-issuing warp, or everybody just before the next pass writes) -- instead of two of the
-    // six blocking named barriers per frame.  The four read-after-write barriers stay bar.sync.  Consecutive arrivals of
-    // a warp on one mbarrier are always separated by a bar.sync of the group, so phases cannot mix.
-    constexpr bool SW = LANES > 32;
+    __shared__ __align__(8) unsigned long long s_bar[GROUPS][3];   // per group: input block, state rows, ADMM U row
     const int tid = threadIdx.x, warp = tid >> 5;
     const int grp = warp / G;                     // frame group inside the CTA
     const int l = tid - grp * LANES;              // lane inside the group, 0 .. LANES-1
     const int bar_id = 1 + grp;
     if (warp == 0) tmem_alloc(&s_tmem_base, TMEM_COLS);
     const unsigned xbar = (unsigned)__cvta_generic_to_shared(&s_bar[grp][0]), sbar = xbar + 8, ubar = xbar + 16;
-    const unsigned xw = xbar + 24, yw = xbar + 32, zw = xbar + 40, rw = xbar + 48;
-    if (l == 0) {
-        mbar_init(xbar, 1); mbar_init(sbar, 1); mbar_init(ubar, 1);
-        mbar_init(xw, G); mbar_init(yw, G); mbar_init(zw, G); mbar_init(rw, G);
-    }
+    if (l == 0) { mbar_init(xbar, 1); mbar_init(sbar, 1); mbar_init(ubar, 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    auto war_arrive = [&](unsigned bar) {            // one arrival per warp, after all its lanes are done reading
-        __syncwarp();
-        if ((tid & 31) == 0) mbar_arrive(bar);
-    };
-    if constexpr (SW) war_arrive(yw);                // "E1 of the frame before the first one has been read"
-    unsigned wpar = 0;                               // phase parity of xw / zw / rw (one phase per frame); yw runs one ahead
     // this warp's TMEM window: lanes 32 * (warp % 4) .. +31.  A group's warps sit on consecutive sub-partitions
     // (G divides 4), so the position inside the group, hence the lane-constant tables, depend on warp % 4 only.
     const unsigned tlane = s_tmem_base + ((unsigned)(32 * (warp & 3)) << 16);
@@ -378,12 +359,7 @@ __global__ void __launch_bounds__(warps_of(VV, OP) * 32, 1) warp_iter_kernel(con
                 tmem_stw<2 * HP>(twarp + 2 * HP * m, reinterpret_cast<const float*>(v + NR * HP));   // block t+NR replaces block t
                 m = m == NR - 1 ? 0 : m + 1;
             }
-            if constexpr (SW) {
-                war_arrive(xw);                    // this warp has consumed xs
-                if (t + 1 < t1 && l < 32) mbar_wait(xw, wpar);        // the warp that re-fills xs waits for all of them
-            } else {
-                group_sync<LANES>(bar_id);         // xs consumed by every lane; the previous frame's reads of E1 are done
-            }
+            group_sync<LANES>(bar_id);             // xs consumed by every lane; the previous frame's reads of E1 are done
             if (t + 1 < t1) {
                 x_async = fetch_block_staged<LANES, VV, OV>(a, x, t + OV, l, xs, xs_s, xbar);
                 if constexpr (OP == OP_ADMM) {
@@ -401,7 +377,6 @@ __global__ void __launch_bounds__(warps_of(VV, OP) * 32, 1) warp_iter_kernel(con
                 float2 tw1[V], tw1c[HC ? V : 1];
                 tmem_ldw<2 * V>(tlane + TC_TW1, reinterpret_cast<float*>(tw1));
                 if constexpr (HC) tmem_ldw<2 * V>(tlane + TC_TW1C, reinterpret_cast<float*>(tw1c));
-                if constexpr (SW) mbar_wait(yw, wpar);             // the previous frame's inverse pass 1 has read E1
                 fwd_pass1<LANES, VV, HC>(l, v, tw1, e1, tw1c);
             }
             group_sync<LANES>(bar_id);
@@ -418,7 +393,6 @@ __global__ void __launch_bounds__(warps_of(VV, OP) * 32, 1) warp_iter_kernel(con
                 if (l < 32) { if (elect_one()) { mbar_expect_tx(ubar, M * 8); bulk_g2s(grp_s, a.s1_in + row * M, M * 8, ubar); } }
             }
             fwd_pass3<LANES, VV>(l, e2, A, Bv);
-            if constexpr (SW) war_arrive(zw);      // this warp has read its classes from E2
             }  // OP != OP_ISTFT
             const float2 s0n = s0n_next, s1n = s1n_next;
             const float mgn = mgn_next;
@@ -467,12 +441,7 @@ __global__ void __launch_bounds__(warps_of(VV, OP) * 32, 1) warp_iter_kernel(con
                     if constexpr (SUMS) { if (owned) { dacc += (double)dsum; eacc += (double)esum; } }
                 }
             }
-            if constexpr (SW) {
-                war_arrive(rw);                    // this warp has read its staged state
-                if (t + 1 < t1 && l < 32) mbar_wait(rw, wpar);        // the warp that re-stages the rows waits for all
-            } else {
-                group_sync<LANES>(bar_id);         // every lane has read its classes from E2 and its staged state
-            }
+            group_sync<LANES>(bar_id);             // every lane has read its classes from E2 and its staged state
             if (t + 1 < t1) {
                 stage_rows<OP, LANES, VV>(a, row + 1, l, qstage_s, mstage_s, sbar);
                 if (l == 0) {
@@ -481,7 +450,6 @@ __global__ void __launch_bounds__(warps_of(VV, OP) * 32, 1) warp_iter_kernel(con
                     if constexpr (OP == OP_ADMM) s1n_next = __ldg(a.s1_in_nyq + row + 1);
                 }
             }
-            if constexpr (SW && OP != OP_ISTFT) mbar_wait(zw, wpar);   // everybody has read E2 (forward pass 3)
             inv_pass3<LANES, VV>(l, A, Bv, e2);
             group_sync<LANES>(bar_id);
             const bool emit = owned && block_valid<LANES, VV, OV>(a, t);
@@ -501,7 +469,6 @@ __global__ void __launch_bounds__(warps_of(VV, OP) * 32, 1) warp_iter_kernel(con
                 if constexpr (HC) tmem_ldw<2 * V>(tlane + TC_TW1C, reinterpret_cast<float*>(tw1c));
                 inv_pass1<LANES, VV, HC>(l, e1, tw1, v, tw1c);
             }
-            if constexpr (SW) { war_arrive(yw); wpar ^= 1; }      // E1 consumed; next frame = next phase
             // ---- windowed overlap-add: out = carry (NR hops from earlier frames) + ws * v; the first hop
             // (HP pairs) of `out` is a finished block, the other NR * HP pairs are the new carry
             {
