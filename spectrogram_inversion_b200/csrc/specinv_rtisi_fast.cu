@@ -592,11 +592,12 @@ int rtisi_fast(const specinv_desc* d, const Dims& dm, const void* plan, const vo
         return SPECINV_ERR_NO_DEVICE;
     if (d->n_fft == 2048) return rfast::launch<64, 16, 1>(a, st);       // two warps per frame, one signal per CTA
     if (d->n_fft == 1024) {
-        // two warps per frame, 8 values per lane (gl_warp_core_1c.cuh): half the instructions on the critical path of
-        // an inner iteration; SPECINV_RTISI_ONE_WARP=1 keeps the one-warp-per-frame variant (A/B timing, tests)
-        const char* e = getenv("SPECINV_RTISI_ONE_WARP");
-        if (e && e[0] == '1') return dm.B <= sms ? rfast::launch<32, 16, 1>(a, st) : rfast::launch<32, 16, 2>(a, st);
-        return dm.B <= sms ? rfast::launch<64, 8, 1>(a, st) : rfast::launch<64, 8, 2>(a, st);
+        // SPECINV_RTISI_TWO_WARPS=1: two warps per frame, 8 values per lane (gl_warp_core_1c.cuh).  Half the
+        // instructions per lane, but the same FP work per SM plus two more frame barriers and the mirror-lane exchange:
+        // measured 62.6 ms against 57.2 ms at cfg3 (the FMA pipe is 59 % busy either way), so it is not the default.
+        const char* e = getenv("SPECINV_RTISI_TWO_WARPS");
+        if (e && e[0] == '1') return dm.B <= sms ? rfast::launch<64, 8, 1>(a, st) : rfast::launch<64, 8, 2>(a, st);
+        return dm.B <= sms ? rfast::launch<32, 16, 1>(a, st) : rfast::launch<32, 16, 2>(a, st);
     }
     return dm.B <= sms ? rfast::launch<32, 8, 1>(a, st) : dm.B <= 2 * sms ? rfast::launch<32, 8, 2>(a, st)
                                                                           : rfast::launch<32, 8, 4>(a, st);
