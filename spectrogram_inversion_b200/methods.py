@@ -118,12 +118,7 @@ def _run_host_pipelined(spec, n_chunks, make_solver, max_iter, eva_iter, metric,
     s_in, s_out = _side_streams(dev)
     s_in.wait_stream(cur)
     B = spec.shape[0]
-    # Only the first chunk's upload and the last chunk's download are exposed (everything in between overlaps the
-    # iterations), so with four chunks the outer two are small: 1/8, 3/8, 3/8, 1/8 of the batch
-    if n_chunks == 4 and B >= 32:
-        bounds = [0, B // 8, B // 2, B - B // 8, B]
-    else:
-        bounds = [(B * k) // n_chunks for k in range(n_chunks + 1)]
+    bounds = [(B * k) // n_chunks for k in range(n_chunks + 1)]
 
     def stage(k):
         with torch.cuda.stream(s_in):

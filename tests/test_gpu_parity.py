@@ -539,12 +539,6 @@ def test_host_batches_are_pipelined_in_chunks_with_identical_results():
         y_dev = fn(mag.cuda(), max_iter=3, tol=0, verbose=False, eva_iter=2, window=w.cuda(), hop_length=64, **kw)
         assert not y_host.is_cuda and y_host.shape == y_dev.shape
         assert torch.equal(y_host, y_dev.cpu())
-    # four chunks of uneven size (1/8, 3/8, 3/8, 1/8 of the batch: small first upload / last download)
-    mag4 = torch.from_numpy((np.abs(rs.randn(40, 129, 6000)) * 3).astype(np.float32))
-    assert methods._pipeline_chunks(mag4, 0.0, False) == 4
-    y_host = S.griffin_lim(mag4.pin_memory(), max_iter=3, tol=0, verbose=False, eva_iter=2, window=w, hop_length=64)
-    y_dev = S.griffin_lim(mag4.cuda(), max_iter=3, tol=0, verbose=False, eva_iter=2, window=w.cuda(), hop_length=64)
-    assert torch.equal(y_host, y_dev.cpu())
 
 
 def test_cuda_graph_replay_of_plain_iterations_is_identical(monkeypatch):
