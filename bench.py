@@ -17,8 +17,9 @@ its own B=512 batch; the path needs no collective).
                  step, median / p95 / max beside it
   roofline     : fused GL-iteration kernel, algorithmic bytes 20*B*F*T + 8*B*L per launch / event-timed average
                  launch duration, against MEASURED_PEAKS.json hbm_gbs
-  cpu_baseline : oracle port (numpy, batch split over all host cores) on a bounded sample of the workload; `parity`
-                 compares the final spectral convergence of the GPU run and the CPU port on that same sample
+  cpu_baseline : the unmodified reference (baseline/_ref) on the host CPUs on a bounded sample of the workload (the
+                 oracle port beside it, or alone when the reference is not installed); `parity` compares the final
+                 spectral convergence of the GPU run, the reference and the CPU port on that same sample
   reference_cuda : the unmodified reference (baseline/_ref) with device='cuda' on the same inputs (cuFFT + cuDNN)
   configs      : cfg1 / cfg3 / cfg4 / cfg5 of BASELINE.json (ms per job, per iteration, audio-s*it/s, roofline
                  fraction); for N > 1: cfg2 STRONG-scaled (B = 512 / N per rank), cfg3 / cfg4 batch-sharded, and cfg5
@@ -651,18 +652,44 @@ def run_ours(args, w):
         ref_cuda = measure_reference_cuda(cx, w, mag, win)
         Bc, threads = cpu_sample_size(w)
         run_cpu, (win_c, a_c, mag_c) = cpu_job(w, Bc, threads)
-        tcpu, y_cpu = run_cpu()
-        cpu = {"value": units(w, Bc) / tcpu, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": f"B={Bc} of {w['B']} signals, full length and iteration count, one run of {tcpu:.1f} s"}
-        # the GPU path on the CPU sample's very magnitudes: final spectral convergence of both results, judged by the
-        # same (GPU) STFT.  north_star: within 1 % (0.0864 dB).
         mag_s = torch.from_numpy(mag_c).to(dev)
+        y_ref = None
+        if reference_available():
+            # the UNMODIFIED reference on the host CPUs, on the sample's very magnitudes
+            try:
+                ref = import_reference()
+                mag_cpu, win_cpu = torch.from_numpy(mag_c), torch.from_numpy(hann(w["n_fft"]))
+                t0 = time.perf_counter()
+                with torch.no_grad():
+                    y_ref = ref.griffin_lim(mag_cpu, max_iter=iters, tol=0, alpha=w["coef"], verbose=False, eva_iter=10,
+                                            hop_length=w["hop"], window=win_cpu)
+                tcpu = time.perf_counter() - t0
+                cpu = {"value": units(w, Bc) / tcpu, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "reference",
+                       "sample": f"B={Bc} of {w['B']} signals, full length and iteration count, one run of {tcpu:.1f} s of "
+                                 "torch_specinv 0.2.1 (baseline/_ref) on the host CPUs"}
+            except Exception as ex:
+                y_ref, cpu = None, {"reference_failed": f"{type(ex).__name__}: {ex}"[:200]}
+        tcpu, y_cpu = run_cpu()
+        port = {"value": units(w, Bc) / tcpu, "unit": UNIT, "cores": threads, "kind": "port",
+                "sample": f"B={Bc} of {w['B']} signals, full length and iteration count, one run of {tcpu:.1f} s"}
+        if y_ref is None:
+            cpu = dict(port, **(cpu or {}))
+        else:
+            cpu["oracle_port"] = port
+        # the GPU path on the CPU sample's very magnitudes: final spectral convergence of all results, judged by the
+        # same (GPU) STFT.  north_star: within 1 % (0.0864 dB) of the reference.
         y_gpu = S.griffin_lim(mag_s, max_iter=iters, tol=0, alpha=w["coef"], verbose=False, eva_iter=10, **kw)
         sc_g = final_sc_db(cx, w, mag_s, win, y_gpu)
         sc_c = final_sc_db(cx, w, mag_s, win, torch.from_numpy(np.ascontiguousarray(y_cpu)).to(dev))
+        one_pct = 20 * math.log10(1.01)
         parity = {"sample": f"the cpu_baseline sample (B={Bc}, seed 0)", "final_sc_db_gpu": sc_g,
-                  "final_sc_db_cpu_port": sc_c, "diff_db": sc_g - sc_c, "one_percent_db": 20 * math.log10(1.01),
-                  "within_1pct": abs(sc_g - sc_c) <= 20 * math.log10(1.01)}
+                  "final_sc_db_cpu_port": sc_c, "diff_db": sc_g - sc_c, "one_percent_db": one_pct,
+                  "within_1pct": abs(sc_g - sc_c) <= one_pct}
+        if y_ref is not None:
+            sc_r = final_sc_db(cx, w, mag_s, win, y_ref.to(dev).contiguous())
+            parity.update({"final_sc_db_reference": sc_r, "diff_db_vs_reference": sc_g - sc_r,
+                           "within_1pct_of_reference": abs(sc_g - sc_r) <= one_pct,
+                           "max_abs_diff_vs_reference": float((y_gpu - y_ref.to(dev)).abs().max())})
         del mag_s, y_gpu
     del mag, yh, mag_host
     torch.cuda.empty_cache()
