@@ -25,3 +25,11 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture(params=["mixed-radix", "legacy"])
+def generic_kernel(request, monkeypatch):
+    """The two generic kernel families of csrc: the mixed-radix team kernel (default) and, with SPECINV_GENERIC_MR=0,
+    the radix-2^2 CTA-wide kernel (powers of two) / the direct DFT (everything else)."""
+    monkeypatch.setenv("SPECINV_GENERIC_MR", "1" if request.param == "mixed-radix" else "0")
+    return request.param

@@ -156,4 +156,14 @@ NONPOW2_CASES = [
     _c("np2_96_twosided_f64", n_fft=96, window="hann", hop_length=24, T=19, B=2, dtype="float64", seed=35, onesided=False),
     _c("np2_1000_nocenter_f32", n_fft=1000, window="hamming", hop_length=250, T=8, B=2, dtype="float32", seed=36,
        center=False),
+    # radices 7, 11, 13, an odd half (250 = 2 * 5^3), large mixed sizes; 34 = 2 * 17 stays on the direct DFT
+    _c("np2_112_hann_f32", n_fft=112, window="hann", hop_length=28, T=21, B=2, dtype="float32", seed=37),
+    _c("np2_220_hamming_f64", n_fft=220, window="hamming", hop_length=55, T=13, B=2, dtype="float64", seed=38),
+    _c("np2_52_hann_f32", n_fft=52, window="hann", hop_length=13, T=33, B=3, dtype="float32", seed=39, pad_mode="replicate"),
+    _c("np2_250_oddhalf_f32", n_fft=250, window="hann", hop_length=50, T=14, B=2, dtype="float32", seed=40),
+    _c("np2_250_oddhalf_twosided_f64", n_fft=250, window="hann", hop_length=125, T=9, B=1, dtype="float64", seed=41,
+       onesided=False),
+    _c("np2_1536_hann_f32", n_fft=1536, window="hann", hop_length=384, T=7, B=1, dtype="float32", seed=42),
+    _c("np2_2000_hann_f32", n_fft=2000, window="hann", hop_length=500, T=6, B=1, dtype="float32", seed=43),
+    _c("np2_34_direct_f64", n_fft=34, window="hann", hop_length=17, T=25, B=2, dtype="float64", seed=44),
 ]

@@ -1,6 +1,7 @@
 """n_fft that is not a power of two (the reference infers n_fft from the bin count, methods.py:65-68; 400 is
-torchaudio's default): the direct-DFT tile kernels of csrc/specinv_generic.cu against outputs of the unmodified
-reference (tests/golden/nonpow2.npz) and single iterations from the oracle's state."""
+torchaudio's default): the mixed-radix team kernels of csrc/specinv_generic_mr.cu (half sizes that factor into 2 .. 13)
+and the direct-DFT tile kernels of csrc/specinv_generic.cu (everything else, and SPECINV_GENERIC_MR=0) against outputs of
+the unmodified reference (tests/golden/nonpow2.npz) and single iterations from the oracle's state."""
 import os
 
 import numpy as np
@@ -27,7 +28,7 @@ def close(a, b, tol, what=""):
 
 
 @pytest.mark.parametrize("case", cases.NONPOW2_CASES, ids=lambda c: c["name"])
-def test_public_api_matches_the_reference(case):
+def test_public_api_matches_the_reference(case, generic_kernel):
     import spectrogram_inversion_b200 as S
     inp = cases.make_case_inputs(case)
     kw = {k: (torch.from_numpy(v).cuda() if isinstance(v, np.ndarray) else v) for k, v in inp["kwargs"].items()}
@@ -44,7 +45,7 @@ def test_public_api_matches_the_reference(case):
 
 
 @pytest.mark.parametrize("case", cases.NONPOW2_CASES, ids=lambda c: c["name"])
-def test_single_iterations_from_the_oracles_state(case):
+def test_single_iterations_from_the_oracles_state(case, generic_kernel):
     from spectrogram_inversion_b200.engine import ADMMSolver, GriffinLimSolver, StftPlan
     from spectrogram_inversion_b200.stft_args import args_helper
     inp = cases.make_case_inputs(case)

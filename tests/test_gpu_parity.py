@@ -54,7 +54,7 @@ def build(case):
 
 
 @pytest.mark.parametrize("case", cases.ITER_CASES, ids=lambda c: c["name"])
-def test_stft_istft_primitives(case):
+def test_stft_istft_primitives(case, generic_kernel):
     inp, C, mag, plan, oa = build(case)
     name = case["name"]
     tol = tol_of(case["dtype"])
@@ -72,7 +72,7 @@ def test_stft_istft_primitives(case):
 
 
 @pytest.mark.parametrize("case", cases.ITER_CASES, ids=lambda c: c["name"])
-def test_griffin_lim_iterations_from_identical_state(case):
+def test_griffin_lim_iterations_from_identical_state(case, generic_kernel):
     from spectrogram_inversion_b200.engine import GriffinLimSolver
     inp, C, mag, plan, oa = build(case)
     tol = tol_of(case["dtype"])
@@ -98,7 +98,7 @@ def test_griffin_lim_iterations_from_identical_state(case):
 
 
 @pytest.mark.parametrize("case", cases.ITER_CASES, ids=lambda c: c["name"])
-def test_griffin_lim_matches_reference_golden(case):
+def test_griffin_lim_matches_reference_golden(case, generic_kernel):
     import spectrogram_inversion_b200 as S
     inp = cases.make_case_inputs(case)
     kw = {k: (torch.from_numpy(v) if isinstance(v, np.ndarray) else v) for k, v in inp["kwargs"].items()}
@@ -112,7 +112,7 @@ def test_griffin_lim_matches_reference_golden(case):
 
 
 @pytest.mark.parametrize("case", cases.ITER_CASES, ids=lambda c: c["name"])
-def test_admm_iterations_and_golden(case):
+def test_admm_iterations_and_golden(case, generic_kernel):
     import spectrogram_inversion_b200 as S
     from spectrogram_inversion_b200.engine import ADMMSolver
     inp, C, mag, plan, oa = build(case)
