@@ -30,39 +30,62 @@ struct BinIO {
     long long fr;   // b*T + t
     __device__ BinIO(const TileArgs& a_, long long fr_) : a(a_), fr(fr_) {}
     __device__ __forceinline__ cx_t<T> ldc(const void* main, const void* nyq, int kk) const {
-        if (a.dm.onesided && kk == a.dm.M) return ((const cx_t<T>*)nyq)[fr];
-        return ((const cx_t<T>*)main)[fr * a.dm.row + kk];
+        // read-only path (ld.global.nc): the inputs are never written by the launch (ping-pong state), and the
+        // compiler may then batch the loads of unrolled iterations ahead of the stores
+        if (a.dm.onesided && kk == a.dm.M) return __ldg((const cx_t<T>*)nyq + fr);
+        return __ldg((const cx_t<T>*)main + fr * a.dm.row + kk);
     }
     __device__ __forceinline__ void stc(void* main, void* nyq, int kk, cx_t<T> v) const {
         if (a.dm.onesided && kk == a.dm.M) ((cx_t<T>*)nyq)[fr] = v;
         else ((cx_t<T>*)main)[fr * a.dm.row + kk] = v;
     }
     __device__ __forceinline__ T ldm(int kk) const {
-        if (a.dm.onesided && kk == a.dm.M) return ((const T*)a.mag_nyq)[fr];
-        return ((const T*)a.mag_main)[fr * a.dm.row + kk];
+        if (a.dm.onesided && kk == a.dm.M) return __ldg((const T*)a.mag_nyq + fr);
+        return __ldg((const T*)a.mag_main + fr * a.dm.row + kk);
     }
 };
 
-// Point-wise stage for one frequency bin.  s = STFT bin of the current signal estimate.
-// Returns the spectrum value that goes into the inverse transform.
+// Point-wise stage for one frequency bin, split into its global loads (`bin_load`: issued early / batched by the
+// callers that pipeline) and the arithmetic + stores (`bin_apply`).  s = STFT bin of the current signal estimate;
+// bin_apply returns the spectrum value that goes into the inverse transform.
+template <typename T>
+struct BinIn {
+    cx_t<T> s0, s1;   // GL: q_prev / ADMM: X, U / ISTFT: spectrum
+    T m;              // target magnitude
+};
+
 template <typename T, int OP>
-__device__ __forceinline__ cx_t<T> bin_update(const TileArgs& a, const BinIO<T>& io, int kk, cx_t<T> s,
-                                              bool owned, bool want_sums, T& dsum, T& esum) {
+__device__ __forceinline__ BinIn<T> bin_load(const TileArgs& a, const BinIO<T>& io, int kk) {
+    BinIn<T> in;
+    in.s0 = mk<T>(T(0), T(0)); in.s1 = in.s0; in.m = T(0);
+    if constexpr (OP == OP_ISTFT) {
+        in.s0 = io.ldc(a.s0_in_main, a.s0_in_nyq, kk);
+    } else if constexpr (OP == OP_GL) {
+        in.m = io.ldm(kk);
+        if (a.s0_in_main != nullptr) in.s0 = io.ldc(a.s0_in_main, a.s0_in_nyq, kk);
+    } else if constexpr (OP == OP_ADMM) {
+        in.s0 = io.ldc(a.s0_in_main, a.s0_in_nyq, kk);
+        in.s1 = io.ldc(a.s1_in_main, a.s1_in_nyq, kk);
+        in.m = io.ldm(kk);
+    }
+    return in;
+}
+
+template <typename T, int OP>
+__device__ __forceinline__ cx_t<T> bin_apply(const TileArgs& a, const BinIO<T>& io, int kk, cx_t<T> s, const BinIn<T>& in,
+                                             bool owned, bool want_sums, T& dsum, T& esum) {
     if constexpr (OP == OP_STFT) {
         io.stc(a.s0_out_main, a.s0_out_nyq, kk, s);
         return s;
     } else if constexpr (OP == OP_ISTFT) {
-        return io.ldc(a.s0_in_main, a.s0_in_nyq, kk);
+        return in.s0;
     } else if constexpr (OP == OP_GL) {
         // methods.py:243-247
         const T lr = (T)a.coef;
         const bool momentum = a.s0_in_main != nullptr;     // NULL state: plain Griffin-Lim (lr == 0), q_n = s
-        T m = io.ldm(kk);
+        const T m = in.m;
         cx_t<T> q = s;
-        if (momentum) {
-            cx_t<T> qp = io.ldc(a.s0_in_main, a.s0_in_nyq, kk);
-            q = mk<T>(s.x - qp.x * lr, s.y - qp.y * lr);
-        }
+        if (momentum) q = mk<T>(s.x - in.s0.x * lr, s.y - in.s0.y * lr);
         if (owned) {
             if (momentum) io.stc(a.s0_out_main, a.s0_out_nyq, kk, q);
             if (want_sums) {
@@ -76,9 +99,8 @@ __device__ __forceinline__ cx_t<T> bin_update(const TileArgs& a, const BinIO<T>&
         // methods.py:467-475 with Y = X + U
         const T rho = (T)a.coef;
         const T inv = T(1) / (T(1) + rho);
-        cx_t<T> X = io.ldc(a.s0_in_main, a.s0_in_nyq, kk);
-        cx_t<T> U = io.ldc(a.s1_in_main, a.s1_in_nyq, kk);
-        T m = io.ldm(kk);
+        const cx_t<T> X = in.s0, U = in.s1;
+        const T m = in.m;
         cx_t<T> Z = mk<T>((rho * (X.x + U.x) + s.x) * inv, (rho * (X.y + U.y) + s.y) * inv);
         cx_t<T> Un = mk<T>(U.x + X.x - Z.x, U.y + X.y - Z.y);
         cx_t<T> Xn = project<T>(mk<T>(Z.x - Un.x, Z.y - Un.y), m);
@@ -93,6 +115,13 @@ __device__ __forceinline__ cx_t<T> bin_update(const TileArgs& a, const BinIO<T>&
         }
         return mk<T>(Xn.x + Un.x, Xn.y + Un.y);
     }
+}
+
+template <typename T, int OP>
+__device__ __forceinline__ cx_t<T> bin_update(const TileArgs& a, const BinIO<T>& io, int kk, cx_t<T> s,
+                                              bool owned, bool want_sums, T& dsum, T& esum) {
+    const BinIn<T> in = bin_load<T, OP>(a, io, kk);
+    return bin_apply<T, OP>(a, io, kk, s, in, owned, want_sums, dsum, esum);
 }
 
 // implemented in specinv_generic_mr.cu: SPECINV_ERR_UNSUPPORTED when M = n_fft / 2 has a prime factor > 13

@@ -89,6 +89,13 @@ SPX_HD int mr_position(const Plan& p, int k) {
     return pos;
 }
 
+template <typename C> SPX_HD C ldro(const C* p) {      // read-only table load (ld.global.nc on the device)
+#ifdef __CUDA_ARCH__
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
 template <typename C> SPX_HD C add(C a, C b) { a.x += b.x; a.y += b.y; return a; }
 template <typename C> SPX_HD C sub(C a, C b) { a.x -= b.x; a.y -= b.y; return a; }
 template <typename C> SPX_HD C mul(C a, C b) { C r; r.x = a.x * b.x - a.y * b.y; r.y = a.x * b.y + a.y * b.x; return r; }
@@ -170,12 +177,12 @@ SPX_HD void pass_r(C* wb, int nf, int Mp, const Plan& p, int s, const C* __restr
         });
         if (INV && span > 1) {
             const int tj = twstep * j;
-            static_for<R - 1>([&](auto qq) { x[qq + 1] = mul(x[qq + 1], tw[tj * (qq + 1)]); });
+            static_for<R - 1>([&](auto qq) { x[qq + 1] = mul(x[qq + 1], ldro(tw + tj * (qq + 1))); });
         }
         Dft<R, T, C>::run(x);
         if (!INV && span > 1) {
             const int tj = twstep * j;
-            static_for<R - 1>([&](auto qq) { x[qq + 1] = mul(x[qq + 1], tw[tj * (qq + 1)]); });
+            static_for<R - 1>([&](auto qq) { x[qq + 1] = mul(x[qq + 1], ldro(tw + tj * (qq + 1))); });
         }
         static_for<R>([&](auto m) {
             C t;

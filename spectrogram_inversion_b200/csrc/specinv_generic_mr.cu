@@ -61,19 +61,20 @@ __global__ void __launch_bounds__(512, 2) mr_tile_kernel(const TileArgs a, const
         const long long base = (long long)f0 * hop;
         const bool interior = base >= dm.P && base + (long long)(nfr - 1) * hop + N <= dm.P + dm.L;
         const int total = nfr * M;
+#pragma unroll 4
         for (int idx = tid; idx < total; idx += NT) {
             const int f = mr::fdiv(idx, ml.magic_M), n = idx - f * M;
             const long long pp = base + (long long)f * hop + 2 * n;
             T v0, v1;
             if (interior) {
-                v0 = x[pp - dm.P]; v1 = x[pp - dm.P + 1];
+                v0 = __ldg(x + (pp - dm.P)); v1 = __ldg(x + (pp - dm.P + 1));
             } else {
                 const long long i0 = pad_index(pp, dm.P, dm.L, dm.pad_mode);
                 const long long i1 = pad_index(pp + 1, dm.P, dm.L, dm.pad_mode);
-                v0 = i0 >= 0 ? x[i0] : T(0);
-                v1 = i1 >= 0 ? x[i1] : T(0);
+                v0 = i0 >= 0 ? __ldg(x + i0) : T(0);
+                v1 = i1 >= 0 ? __ldg(x + i1) : T(0);
             }
-            wb[f * Mp + mr::padidx(n)] = mk<T>(v0 * wa[2 * n], v1 * wa[2 * n + 1]);
+            wb[f * Mp + mr::padidx(n)] = mk<T>(v0 * __ldg(wa + 2 * n), v1 * __ldg(wa + 2 * n + 1));
         }
     }
     __syncthreads();
@@ -99,52 +100,86 @@ __global__ void __launch_bounds__(512, 2) mr_tile_kernel(const TileArgs a, const
     }
 
     // ---- C: real-FFT post-process, point-wise update, inverse pre-process (pairs k, M-k) ------------------------
+    // Two pairs per thread and trip: the global loads of both (state rows, magnitudes: up to 10 per pair) are issued
+    // before any arithmetic, so a thread keeps ~20 loads in flight instead of stalling pair after pair (fp32).
     T dsum = T(0), esum = T(0);
     const bool want_sums = a.sums != nullptr;
     {
         const int npair = M / 2 + 1;
         const int total = nf * npair;
-        for (int idx = ttid; idx < total; idx += tnt) {
-            const int f = mr::fdiv(idx, ml.magic_npair), k = idx - f * npair;
+        struct Pair { int k, pA, pB; bool owned; long long fr; C* v; };
+        auto locate = [&](int idx) {
+            Pair p;
+            const int f = mr::fdiv(idx, ml.magic_npair);
+            p.k = idx - f * npair;
             const int t = f0 + fa + f;
-            const bool owned = t >= t0;
-            C* v = tb + (size_t)f * Mp;
-            const int kA = k, kB = M - k;
-            const int pA = perm[kA], pB = perm[kB == M ? 0 : kB];
-            const C w = twr[k];
-            C sA = mk<T>(T(0), T(0)), sB = sA;
-            if constexpr (OP != OP_ISTFT) {
-                rfft_post_pair<T>(v[pA], v[pB], w, sA, sB);
+            p.owned = t >= t0;
+            p.fr = (long long)b * dm.T + t;
+            p.v = tb + (size_t)f * Mp;
+            const int kB = M - p.k;
+            p.pA = perm[p.k]; p.pB = perm[kB == M ? 0 : kB];
+            return p;
+        };
+        auto finish = [&](const Pair& p, C hA, C hB, C w) {
+            if constexpr (OP != OP_STFT) {
+                if (p.k == 0) { hA.y = T(0); hB.y = T(0); }  // C2R ignores Im(DC), Im(Nyquist)
+                C zA, zB;
+                irfft_pre_pair<T>(hA, hB, w, zA, zB);
+                p.v[p.pA] = zA;
+                if (M - p.k != p.k && p.k != 0) p.v[p.pB] = zB;
             }
-            const BinIO<T> io(a, (long long)b * dm.T + t);
-            C hA, hB;
-            if (dm.onesided) {
-                hA = bin_update<T, OP>(a, io, kA, sA, owned, want_sums, dsum, esum);
-                hB = (kB != kA) ? bin_update<T, OP>(a, io, kB, sB, owned, want_sums, dsum, esum) : hA;
-            } else {
-                // two-sided: bins kA, kB and their mirrors N-kA, N-kB (= conj of the real-input STFT);
-                // ifft(...).real (methods.py:145-146) == irfft of the Hermitian part (p[k]+conj p[N-k])/2
-                hA = bin_update<T, OP>(a, io, kA, sA, owned, want_sums, dsum, esum);
+        };
+        if (dm.onesided) {
+            constexpr bool TWO = sizeof(T) == 4;        // fp64: one pair (two would spill the 64-register budget)
+            for (int idx = ttid; idx < total; idx += TWO ? 2 * tnt : tnt) {
+                const bool two = TWO && idx + tnt < total;
+                const Pair p0 = locate(idx), p1 = locate(two ? idx + tnt : idx);
+                const BinIO<T> io0(a, p0.fr), io1(a, p1.fr);
+                const BinIn<T> a0 = bin_load<T, OP>(a, io0, p0.k), b0 = bin_load<T, OP>(a, io0, M - p0.k);
+                const BinIn<T> a1 = bin_load<T, OP>(a, io1, p1.k), b1 = bin_load<T, OP>(a, io1, M - p1.k);
+                const C w0 = __ldg(twr + p0.k), w1 = __ldg(twr + p1.k);
+                {
+                    C sA = mk<T>(T(0), T(0)), sB = sA;
+                    if constexpr (OP != OP_ISTFT) rfft_post_pair<T>(p0.v[p0.pA], p0.v[p0.pB], w0, sA, sB);
+                    const C hA = bin_apply<T, OP>(a, io0, p0.k, sA, a0, p0.owned, want_sums, dsum, esum);
+                    const C hB = (M - p0.k != p0.k) ? bin_apply<T, OP>(a, io0, M - p0.k, sB, b0, p0.owned, want_sums, dsum, esum) : hA;
+                    finish(p0, hA, hB, w0);
+                }
+                if (two) {
+                    C sA = mk<T>(T(0), T(0)), sB = sA;
+                    if constexpr (OP != OP_ISTFT) rfft_post_pair<T>(p1.v[p1.pA], p1.v[p1.pB], w1, sA, sB);
+                    const C hA = bin_apply<T, OP>(a, io1, p1.k, sA, a1, p1.owned, want_sums, dsum, esum);
+                    const C hB = (M - p1.k != p1.k) ? bin_apply<T, OP>(a, io1, M - p1.k, sB, b1, p1.owned, want_sums, dsum, esum) : hA;
+                    finish(p1, hA, hB, w1);
+                }
+            }
+        } else {
+            // two-sided: bins kA, kB and their mirrors N-kA, N-kB (= conj of the real-input STFT);
+            // ifft(...).real (methods.py:145-146) == irfft of the Hermitian part (p[k]+conj p[N-k])/2
+            for (int idx = ttid; idx < total; idx += tnt) {
+                const Pair p = locate(idx);
+                const int kA = p.k, kB = M - p.k;
+                const BinIO<T> io(a, p.fr);
+                const BinIn<T> iA = bin_load<T, OP>(a, io, kA), iB = bin_load<T, OP>(a, io, kB);
+                const BinIn<T> jA = bin_load<T, OP>(a, io, kA != 0 ? N - kA : kA), jB = bin_load<T, OP>(a, io, kB != M ? N - kB : kB);
+                const C w = __ldg(twr + p.k);
+                C sA = mk<T>(T(0), T(0)), sB = sA;
+                if constexpr (OP != OP_ISTFT) rfft_post_pair<T>(p.v[p.pA], p.v[p.pB], w, sA, sB);
+                C hA = bin_apply<T, OP>(a, io, kA, sA, iA, p.owned, want_sums, dsum, esum), hB;
                 if (kA != 0) {
-                    C m = bin_update<T, OP>(a, io, N - kA, mk<T>(sA.x, -sA.y), owned, want_sums, dsum, esum);
+                    C m = bin_apply<T, OP>(a, io, N - kA, mk<T>(sA.x, -sA.y), jA, p.owned, want_sums, dsum, esum);
                     hA = mk<T>(T(0.5) * (hA.x + m.x), T(0.5) * (hA.y - m.y));
                 }
                 if (kB != kA) {
-                    hB = bin_update<T, OP>(a, io, kB, sB, owned, want_sums, dsum, esum);
+                    hB = bin_apply<T, OP>(a, io, kB, sB, iB, p.owned, want_sums, dsum, esum);
                     if (kB != M) {
-                        C m = bin_update<T, OP>(a, io, N - kB, mk<T>(sB.x, -sB.y), owned, want_sums, dsum, esum);
+                        C m = bin_apply<T, OP>(a, io, N - kB, mk<T>(sB.x, -sB.y), jB, p.owned, want_sums, dsum, esum);
                         hB = mk<T>(T(0.5) * (hB.x + m.x), T(0.5) * (hB.y - m.y));
                     }
                 } else {
                     hB = hA;
                 }
-            }
-            if constexpr (OP != OP_STFT) {
-                if (k == 0) { hA.y = T(0); hB.y = T(0); }  // C2R ignores Im(DC), Im(Nyquist)
-                C zA, zB;
-                irfft_pre_pair<T>(hA, hB, w, zA, zB);
-                v[pA] = zA;
-                if (kB != kA && k != 0) v[pB] = zB;
+                finish(p, hA, hB, w);
             }
         }
     }
@@ -178,17 +213,19 @@ __global__ void __launch_bounds__(512, 2) mr_tile_kernel(const TileArgs a, const
         T* xo = (T*)a.x_out + (long long)b * dm.L;
         const T* __restrict__ ienv = (const T*)a.inv_env;
         const T* wbf = reinterpret_cast<const T*>(wb);
+#pragma unroll 2
         for (int i = tid; i < span; i += NT) {
             const long long m = o0 + i - dm.P;
             if (m < 0 || m >= dm.L) continue;
+            const T ie = __ldg(ienv + m);
             const int u = lead + i;
             int fl = u / hop;                       // newest frame that covers the sample
             int off = u - fl * hop;
             if (fl > nfr - 1) { off += (fl - (nfr - 1)) * hop; fl = nfr - 1; }
             T acc = T(0);
             for (; fl >= 0 && off < N; --fl, off += hop)
-                acc += wbf[2 * ((size_t)fl * Mp + mr::padidx(off >> 1)) + (off & 1)] * ws[off];
-            xo[m] = acc * ienv[m];
+                acc += wbf[2 * ((size_t)fl * Mp + mr::padidx(off >> 1)) + (off & 1)] * __ldg(ws + off);
+            xo[m] = acc * ie;
         }
     }
 }

@@ -18,6 +18,7 @@
 
 #include "specinv_common.cuh"
 #include "generic_fft.cuh"
+#include "mixed_radix.cuh"
 
 namespace specinv {
 
@@ -47,6 +48,8 @@ struct RtisiArgs {
     int step_begin, step_end;                 // outer steps [step_begin, step_end) of the T + LA steps of a run
     void* state;                              // per-signal sliding state in / out (rtisi_state_elems), or nullptr
     size_t state_elems;
+    int use_mr;                               // mixed-radix passes (any n_fft whose half factors into 2 .. 13)
+    mr::Plan mp;
 };
 
 template <typename T>
@@ -64,6 +67,7 @@ __global__ void __launch_bounds__(256) rtisi_kernel(const RtisiArgs a) {
     T* y = kept + (size_t)K * N;                              // [ylen] overlap-add of the current buffer
     T* ykept = y + ylen;                                      // [ylen] part of y that comes from kept frames
     T* carry = ykept + ylen;                                  // [N] output overlap-add carry
+    unsigned short* perm = reinterpret_cast<unsigned short*>(carry + N);   // [M] padded position of bin k after the forward passes
 
     const int tid = threadIdx.x, NT = blockDim.x;
     const int b = blockIdx.x;
@@ -78,8 +82,25 @@ __global__ void __launch_bounds__(256) rtisi_kernel(const RtisiArgs a) {
     const T* ienv = (const T*)a.inv_env;
     T* xo = (T*)a.x_out + (long long)b * dm.L;
     const T coef = (T)a.synth_coeff, lr = (T)a.lr;
-    const int sh = 32 - dm.logM;
     T* workf = reinterpret_cast<T*>(work);
+    for (int k = tid; k < M; k += NT)
+        perm[k] = (unsigned short)padidx(a.use_mr ? mr::mr_position(a.mp, k) : (int)(__brev((unsigned)k) >> (32 - dm.logM)));
+    // the transforms of `nf` frames at v: mixed-radix passes (mixed_radix.cuh) or the radix-2^2 passes (generic_fft.cuh);
+    // both end with __syncthreads()
+    auto forward = [&](C* v, int nf) {
+        if (a.use_mr) {
+            for (int s = 0; s < a.mp.nst; ++s) { mr::pass<T, false>(v, nf, Mp, a.mp, s, tw, tid, NT); __syncthreads(); }
+        } else {
+            fft_forward_inplace<T>(v, nf, M, Mp, tw);
+        }
+    };
+    auto inverse = [&](C* v, int nf) {
+        if (a.use_mr) {
+            for (int s = a.mp.nst - 1; s >= 0; --s) { mr::pass<T, true>(v, nf, Mp, a.mp, s, tw, tid, NT); __syncthreads(); }
+        } else {
+            fft_inverse_inplace<T>(v, nf, M, dm.logM, Mp, tw);
+        }
+    };
 
     // magnitude of bin kk of spectrogram frame t (zero outside [0, T): the reference pads with zeros, :339)
     auto mag_of = [&](int t, int kk) -> T {
@@ -119,8 +140,7 @@ __global__ void __launch_bounds__(256) rtisi_kernel(const RtisiArgs a) {
         C* v = work + (size_t)LA * Mp;
         for (int k = tid; k <= M / 2; k += NT) {
             const int kA = k, kB = M - k;
-            const int pA = padidx((int)(__brev((unsigned)kA) >> sh));
-            const int pB = padidx((int)(__brev((unsigned)(kB & (M - 1))) >> sh));
+            const int pA = perm[kA], pB = perm[kB == M ? 0 : kB];
             C hA = mk<T>(mag_of(0, kA), T(0)), hB = mk<T>(mag_of(0, kB), T(0));
             if (!dm.onesided) {   // Hermitian part of a real two-sided spectrum: (m[k] + m[N-k]) / 2
                 if (kA != 0) hA.x = T(0.5) * (hA.x + mag_of(0, N - kA));
@@ -132,7 +152,7 @@ __global__ void __launch_bounds__(256) rtisi_kernel(const RtisiArgs a) {
             if (kB != kA && k != 0) v[pB] = zB;
         }
         __syncthreads();
-        fft_inverse_inplace<T>(v, 1, M, dm.logM, Mp, tw);
+        inverse(v, 1);
     }
 
     int kslot = 0;   // kept ring: logical kept frame f (0 = oldest) lives in slot (kslot + f) % K
@@ -169,7 +189,7 @@ __global__ void __launch_bounds__(256) rtisi_kernel(const RtisiArgs a) {
                     mk<T>(y[aa * hop + 2 * n] * win[2 * n], y[aa * hop + 2 * n + 1] * win[2 * n + 1]);
             }
             __syncthreads();
-            fft_forward_inplace<T>(work, NA, M, Mp, tw);
+            forward(work, NA);
             // ---- momentum, projection (:387-396), real-FFT post / pre-processing
             const int npair = M / 2 + 1;
             for (int idx = tid; idx < NA * npair; idx += NT) {
@@ -180,8 +200,7 @@ __global__ void __launch_bounds__(256) rtisi_kernel(const RtisiArgs a) {
                 const int t = i + aa - LA;                  // spectrogram frame of this active frame
                 const bool mom = j > 0 || (i > 0 && aa < LA);
                 const int kA = k, kB = M - k;
-                const int pA = padidx((int)(__brev((unsigned)kA) >> sh));
-                const int pB = padidx((int)(__brev((unsigned)(kB & (M - 1))) >> sh));
+                const int pA = perm[kA], pB = perm[kB == M ? 0 : kB];
                 const C w = twr[k];
                 C sA, sB;
                 rfft_post_pair<T>(v[pA], v[pB], w, sA, sB);
@@ -217,7 +236,7 @@ __global__ void __launch_bounds__(256) rtisi_kernel(const RtisiArgs a) {
                 if (kB != kA && k != 0) v[pB] = zB;
             }
             __syncthreads();
-            fft_inverse_inplace<T>(work, NA, M, dm.logM, Mp, tw);    // ends with __syncthreads()
+            inverse(work, NA);                                       // ends with __syncthreads()
         }
 
         // ---- commit the oldest active frame (:401-404) and fuse the final overlap-add (:406-408)
@@ -306,7 +325,15 @@ static int rtisi_t(const specinv_desc* d, const Dims& dm, const void* plan, cons
     a.max_iter = max_iter; a.asymmetric = asymmetric;
     a.synth_coeff = synth_coeff; a.lr = alpha / (1.0 + alpha);
     a.mag_main = mag_main; a.mag_nyq = mag_nyq; a.x_out = x_out;
-    a.Mp = dm.M + (dm.M >> 4);
+    a.Mp = mr::padded_len(dm.M);
+    {
+        // mixed-radix passes whenever the half size factors into 2 .. 13 (the only path for a non-power-of-two n_fft,
+        // whose root table is W_N); SPECINV_GENERIC_MR=0 keeps the radix-2^2 passes for the powers of two
+        const char* e = getenv("SPECINV_GENERIC_MR");
+        const bool want = !(e && e[0] == '0') || !dm.pow2;
+        a.use_mr = want && dm.M <= 4096 && mr::make_plan(dm.M, dm.pow2 ? dm.M : dm.N, &a.mp) ? 1 : 0;
+        if (!a.use_mr && !dm.pow2) return SPECINV_ERR_UNSUPPORTED;    // a prime factor > 13: no RTISI-LA kernel
+    }
     a.step_begin = step_begin; a.step_end = step_end; a.state = state; a.state_elems = rtisi_state_elems(dm, a.LA);
     T* asym = (T*)scratch;
     a.asym1 = asym; a.asym2 = asym + dm.N;
@@ -324,7 +351,7 @@ static int rtisi_t(const specinv_desc* d, const Dims& dm, const void* plan, cons
     }
     const int NA = a.LA + 1, F = dm.onesided ? dm.M + 1 : dm.N, ylen = a.LA * dm.hop + dm.N;
     const size_t smem = ((size_t)NA * a.Mp + (size_t)NA * F) * 2 * sizeof(T) +
-                        ((size_t)dm.K * dm.N + 2 * (size_t)ylen + dm.N) * sizeof(T);
+                        ((size_t)dm.K * dm.N + 2 * (size_t)ylen + dm.N) * sizeof(T) + (size_t)dm.M * 2;
     int dev = 0, optin = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
@@ -354,7 +381,6 @@ int specinv_rtisi_la_steps(const specinv_desc* d, const void* plan, const void* 
                            int max_iter, double alpha, double synth_coeff, int step_begin, int step_end, void* state,
                            void* stream) {
     Dims dm; int rc = make_dims(d, &dm); if (rc) return rc;
-    if (!dm.pow2) return SPECINV_ERR_UNSUPPORTED;      // the RTISI-LA kernels are built on the power-of-two FFTs
     if (!plan || !window || !mag_main || !x_out || !scratch || (dm.onesided && !mag_nyq)) return SPECINV_ERR_INVALID;
     if (max_iter < 1 || alpha < 0) return SPECINV_ERR_INVALID;
     const int steps = dm.T + (look_ahead < 0 ? dm.K : look_ahead);

@@ -167,3 +167,19 @@ NONPOW2_CASES = [
     _c("np2_2000_hann_f32", n_fft=2000, window="hann", hop_length=500, T=6, B=1, dtype="float32", seed=43),
     _c("np2_34_direct_f64", n_fft=34, window="hann", hop_length=17, T=25, B=2, dtype="float64", seed=44),
 ]
+
+# RTISI-LA at n_fft that is not a power of two (mixed-radix passes in csrc/specinv_rtisi.cu)
+NONPOW2_RTISI_CASES = [
+    dict(_c("np2_rtisi_400_f64", n_fft=400, window="hann", hop_length=100, T=9, B=2, dtype="float64", seed=51),
+         look_ahead=-1, asym=False, max_iter=3, alpha=0.99),
+    dict(_c("np2_rtisi_120_asym_f64", n_fft=120, window="hann", hop_length=30, T=11, B=2, dtype="float64", seed=52),
+         look_ahead=2, asym=True, max_iter=2, alpha=0.5),
+    dict(_c("np2_rtisi_250_oddhalf_f64", n_fft=250, window="hamming", hop_length=50, T=9, B=1, dtype="float64", seed=53),
+         look_ahead=1, asym=False, max_iter=2, alpha=0.99),
+    dict(_c("np2_rtisi_600_f32", n_fft=600, window="hann", hop_length=150, T=8, B=2, dtype="float32", seed=54),
+         look_ahead=3, asym=False, max_iter=2, alpha=0.99),
+    dict(_c("np2_rtisi_96_twosided_f64", n_fft=96, window="hann", hop_length=24, T=9, B=2, dtype="float64", seed=55,
+            onesided=False), look_ahead=-1, asym=False, max_iter=2, alpha=0.99),
+    dict(_c("np2_rtisi_112_nocenter_f64", n_fft=112, window="hann", hop_length=28, T=10, B=1, dtype="float64", seed=56,
+            center=False), look_ahead=0, asym=False, max_iter=3, alpha=0.99),
+]

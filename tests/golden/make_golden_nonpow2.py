@@ -40,6 +40,13 @@ def main():
             x0, _ = ref._istft(C, n_fft, ref._get_ola_weight(pa["window"]), **pa)
             out[f"{name}/istft_x"] = x0.numpy()
             print(name, n_fft, out[f"{name}/gl_k1"].shape)
+        for case in cases.NONPOW2_RTISI_CASES:
+            inp = cases.make_case_inputs(case)
+            kw = {k: (torch.from_numpy(v) if isinstance(v, np.ndarray) else v) for k, v in inp["kwargs"].items()}
+            y = ref.RTISI_LA(torch.from_numpy(inp["mag"]), look_ahead=case["look_ahead"], asymmetric_window=case["asym"],
+                             max_iter=case["max_iter"], alpha=case["alpha"], verbose=0, **kw)
+            out[f"{case['name']}/rtisi"] = y.numpy()
+            print(case["name"], y.shape)
     np.savez_compressed(os.path.join(HERE, "nonpow2.npz"), **out)
 
 

@@ -85,7 +85,24 @@ def test_single_iterations_from_the_oracles_state(case, generic_kernel):
         close(solver.signal, st.x, tol * 2, f"ADMM x step {k}")
 
 
-def test_rtisi_la_declines_non_power_of_two():
+@pytest.mark.parametrize("case", cases.NONPOW2_RTISI_CASES, ids=lambda c: c["name"])
+def test_rtisi_la_matches_the_reference(case):
+    """Whole RTISI-LA runs (small T, few inner iterations) at n_fft that is not a power of two -- the generic
+    persistent kernel on the mixed-radix passes -- against the unmodified reference's output and the oracle's."""
+    import spectrogram_inversion_b200 as S
+    inp = cases.make_case_inputs(case)
+    kw = {k: (torch.from_numpy(v) if isinstance(v, np.ndarray) else v) for k, v in inp["kwargs"].items()}
+    y = S.RTISI_LA(torch.from_numpy(inp["mag"]).cuda(), look_ahead=case["look_ahead"], asymmetric_window=case["asym"],
+                   max_iter=case["max_iter"], alpha=case["alpha"], verbose=0, **kw)
+    f32 = case["dtype"] == "float32"
+    close(y, NP2[f"{case['name']}/rtisi"], 5e-3 if f32 else 1e-7, "vs reference")
+    yo = O.RTISI_LA(inp["mag"], look_ahead=case["look_ahead"], asymmetric_window=case["asym"], max_iter=case["max_iter"],
+                    alpha=case["alpha"], **inp["kwargs"])
+    close(y, yo, 5e-3 if f32 else 1e-7, "vs oracle")
+
+
+def test_rtisi_la_declines_a_large_prime_factor():
+    """n_fft = 2 * 17: Griffin-Lim / ADMM run on the direct DFT, RTISI-LA has no kernel for it."""
     import spectrogram_inversion_b200 as S
     with pytest.raises(NotImplementedError):
-        S.RTISI_LA(torch.rand(2, 201, 12).cuda(), max_iter=2, verbose=0, window=torch.hann_window(400).cuda(), hop_length=100)
+        S.RTISI_LA(torch.rand(2, 18, 12).cuda(), max_iter=2, verbose=0, window=torch.hann_window(34).cuda(), hop_length=17)

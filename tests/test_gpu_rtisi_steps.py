@@ -61,11 +61,14 @@ CUT_CASES = [
     dict(n_fft=1024, B=2, T=10, la=3, asym=False, it=2, dtype="float32", generic=True),
     dict(n_fft=256, B=3, T=15, la=-1, asym=False, it=3, dtype="float64"),
     dict(n_fft=256, B=2, T=11, la=1, asym=True, it=2, dtype="float32", center=False, win="hamming"),
+    dict(n_fft=400, B=2, T=11, la=-1, asym=False, it=2, dtype="float32"),           # mixed-radix passes (200 = 8 * 5 * 5)
+    dict(n_fft=256, B=2, T=11, la=2, asym=False, it=2, dtype="float32", legacy=True),   # radix-2^2 passes
 ]
 
 
-@pytest.mark.parametrize("c", CUT_CASES, ids=lambda c: f"n{c['n_fft']}_B{c['B']}_la{c['la']}_{c['dtype']}{'_generic' if c.get('generic') else ''}")
+@pytest.mark.parametrize("c", CUT_CASES, ids=lambda c: f"n{c['n_fft']}_B{c['B']}_la{c['la']}_{c['dtype']}{'_generic' if c.get('generic') else ''}{'_legacy' if c.get('legacy') else ''}")
 def test_cut_runs_are_bit_identical_to_one_run(c, monkeypatch):
+    monkeypatch.setenv("SPECINV_GENERIC_MR", "0" if c.get("legacy") else "1")
     import spectrogram_inversion_b200 as S
     monkeypatch.setenv("SPECINV_FORCE_GENERIC", "1" if c.get("generic") else "0")
     hop = c["n_fft"] // 4
@@ -101,7 +104,7 @@ def _canonical(su, st, dtype):
     kept = st.buf[:, :K].astype(np.float64) * (w * su.synth_coeff)
     carry = np.zeros((B, N))
     out = st.commits[LA:]                                                       # committed output frames so far
-    for back, fr in enumerate(reversed(out[-3:] if len(out) else [])):          # back = 0: the last one
+    for back, fr in enumerate(reversed(out[-K:] if (len(out) and K) else [])):  # back = 0: the last one
         sh = (back + 1) * a.hop_length
         if sh < N:
             carry[:, :N - sh] += (fr.astype(np.float64) * w)[:, sh:]
@@ -119,15 +122,21 @@ STEP_CASES = [
     dict(n_fft=2048, B=2, T=10, la=3, asym=False, dtype="float32"),
     dict(n_fft=1024, B=2, T=12, la=3, asym=False, dtype="float32", generic=True),
     dict(n_fft=256, B=3, T=14, la=-1, asym=True, dtype="float64"),
+    dict(n_fft=256, B=3, T=14, la=-1, asym=True, dtype="float64", legacy=True),     # radix-2^2 passes (SPECINV_GENERIC_MR=0)
+    dict(n_fft=400, B=2, T=12, la=3, asym=False, dtype="float32"),                  # mixed radix: 200 = 8 * 5 * 5
+    dict(n_fft=600, B=2, T=10, la=-1, asym=True, dtype="float64"),                  # 300 = 4 * 5 * 5 * 3
+    dict(n_fft=250, B=2, T=10, la=1, asym=False, dtype="float64"),                  # odd half 125 = 5^3, hop 62
+    dict(n_fft=1144, B=1, T=8, la=2, asym=False, dtype="float32"),                  # 572 = 4 * 13 * 11
 ]
 
 
-@pytest.mark.parametrize("c", STEP_CASES, ids=lambda c: f"n{c['n_fft']}_B{c['B']}_la{c['la']}_asym{int(c['asym'])}_{c['dtype']}{'_generic' if c.get('generic') else ''}{'_two_warps' if c.get('two_warps') else ''}")
+@pytest.mark.parametrize("c", STEP_CASES, ids=lambda c: f"n{c['n_fft']}_B{c['B']}_la{c['la']}_asym{int(c['asym'])}_{c['dtype']}{'_generic' if c.get('generic') else ''}{'_legacy' if c.get('legacy') else ''}{'_two_warps' if c.get('two_warps') else ''}")
 def test_one_outer_step_from_the_oracles_state(c, monkeypatch):
     """Outer step i (its max_iter inner iterations j = 0 .. max_iter-1 and the commit) from the ORACLE's state, for
     several i (start-up, steady state, tail where the look-ahead runs past the spectrogram) and max_iter = 1, 2:
     frames to 1e-5 absolute (unit-scale signals) x 4 per extra inner iteration, spectra relative to their scale."""
     monkeypatch.setenv("SPECINV_FORCE_GENERIC", "1" if c.get("generic") else "0")
+    monkeypatch.setenv("SPECINV_GENERIC_MR", "0" if c.get("legacy") else "1")
     monkeypatch.setenv("SPECINV_RTISI_TWO_WARPS", "1" if c.get("two_warps") else "0")
     dtype = np.dtype(c["dtype"])
     f32 = dtype == np.float32
@@ -145,7 +154,7 @@ def test_one_outer_step_from_the_oracles_state(c, monkeypatch):
                 st = O.rtisi_inner(su, st, j)
             st = O.rtisi_commit(su, st)
         states.append(st)
-        for i in (1, 2, LA + 2, c["T"] // 2, c["T"], steps - 2):
+        for i in sorted({1, 2, LA + 2, c["T"] // 2, min(c["T"], steps - 2), steps - 2}):   # (the last step saves no state)
             flat, _ = _canonical(su, states[i], dtype)
             state = torch.from_numpy(np.ascontiguousarray(flat)).cuda().view(torch.uint8).reshape(-1)
             assert state.numel() == nbytes
