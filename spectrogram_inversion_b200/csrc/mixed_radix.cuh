@@ -1,5 +1,5 @@
 // Mixed-radix in-place complex FFT passes in shared memory, for ANY transform length M whose prime factors are
-// <= 13 (radices 8, 4, 2, 3, 5, 7, 11, 13).  Used by the generic tile kernels (specinv_generic.cu) for n_fft that is
+// <= 13 (radices 16 (fp32), 8, 4, 2, 3, 5, 7, 11, 13).  Used by the generic tile kernels (specinv_generic.cu) for n_fft that is
 // not a power of two (the reference infers n_fft from the bin count, methods.py:65-68: 400, 600, 1000 ...), and as
 // the faster path for the power-of-two sizes the specialised kernels do not cover.
 //
@@ -37,15 +37,25 @@ struct Plan {
 
 inline unsigned magic_of(int d) { return d <= 1 ? 0u : (unsigned)((0x100000000ull + (unsigned)d - 1) / (unsigned)d); }
 
-// Host: factor M into the supported radices.  Returns false when a prime factor > 13 remains.
-inline bool make_plan(int M, int tw_n, Plan* p) {
+// Host: factor M into the supported radices.  Returns false when a prime factor > 13 remains.  `allow16`: radix-16
+// stages (fp32: the packed 16-point butterfly of fft_regs.cuh) where they save a pass over shared memory.
+inline bool make_plan(int M, int tw_n, Plan* p, bool allow16 = false) {
     if (M < 1 || tw_n % M != 0) return false;
     int rad[32]; int n = 0, m = M;
     int twos = 0;
     while (m % 2 == 0) { m /= 2; ++twos; }
-    while (twos >= 3) { rad[n++] = 8; twos -= 3; }
-    if (twos == 2) rad[n++] = 4;
-    if (twos == 1) rad[n++] = 2;
+    {
+        // the fewest power-of-two stages, and among those the fewest radix-16 ones
+        const int per = allow16 ? 4 : 3;
+        const int stages = (twos + per - 1) / per;
+        int n16 = 0;
+        if (allow16) while (twos - 4 * n16 > 3 * (stages - n16)) ++n16;
+        for (int i = 0; i < n16; ++i) rad[n++] = 16;
+        int r = twos - 4 * n16;
+        while (r >= 3) { rad[n++] = 8; r -= 3; }
+        if (r == 2) rad[n++] = 4;
+        if (r == 1) rad[n++] = 2;
+    }
     const int odd[5] = {3, 5, 7, 11, 13};
     // largest odd radices first: the last stages (span 1, r) then have the small odd strides
     for (int i = 4; i >= 0; --i)
@@ -100,6 +110,13 @@ template <typename C> SPX_HD C add(C a, C b) { a.x += b.x; a.y += b.y; return a;
 template <typename C> SPX_HD C sub(C a, C b) { a.x -= b.x; a.y -= b.y; return a; }
 template <typename C> SPX_HD C mul(C a, C b) { C r; r.x = a.x * b.x - a.y * b.y; r.y = a.x * b.y + a.y * b.x; return r; }
 template <typename C> SPX_HD C mul_mi(C a) { C r; r.x = a.y; r.y = -a.x; return r; }     // * (-i)
+// c + s * a (real s)
+template <typename C, typename T> SPX_HD C axpy(C c, T s, C a) { c.x += s * a.x; c.y += s * a.y; return c; }
+// fp32: one packed FP32x2 instruction per complex add / real scale, two per complex product (fft_regs.cuh)
+SPX_HD float2 add(float2 a, float2 b) { return padd(a, b); }
+SPX_HD float2 sub(float2 a, float2 b) { return psub(a, b); }
+SPX_HD float2 mul(float2 a, float2 b) { return cmul2(a, b); }
+SPX_HD float2 axpy(float2 c, float s, float2 a) { return pfma(f2(s, s), a, c); }
 
 // ---- in-register forward DFTs (roots exp(-2 pi i / R)) -----------------------------------------------------
 template <int R, typename T, typename C> struct Dft;
@@ -131,6 +148,8 @@ template <typename T, typename C> struct Dft<8, T, C> {
         x[3] = add(e[3], o3);   x[7] = sub(e[3], o3);
     }
 };
+template <> struct Dft<8, float, float2> { SPX_HD static void run(float2* x) { fft8<false>(x); } };
+template <> struct Dft<16, float, float2> { SPX_HD static void run(float2* x) { fft16<false>(x); } };
 // odd prime R: with a_m = x[m] + x[R-m], b_m = x[m] - x[R-m] (m = 1 .. h = (R-1)/2)
 //   y[q]   = x0 + sum_m cos(2 pi m q / R) a_m - i sum_m sin(2 pi m q / R) b_m,   y[R-q] = conj-side (+ i ...)
 template <int R, typename T, typename C> struct Dft {
@@ -149,8 +168,8 @@ template <int R, typename T, typename C> struct Dft {
             static_for<H>([&](auto mm) {
                 constexpr int m = decltype(mm)::value + 1;
                 constexpr T cs = (T)cx_cos2pi(m * q, R), sn = (T)cx_sin2pi(m * q, R);
-                c.x += cs * a[mm].x; c.y += cs * a[mm].y;
-                d.x += sn * b[mm].x; d.y += sn * b[mm].y;
+                c = axpy(c, cs, a[mm]);
+                d = axpy(d, sn, b[mm]);
             });
             // -i d = (d.y, -d.x)
             x[q].x = c.x + d.y;     x[q].y = c.y - d.x;
@@ -194,6 +213,9 @@ SPX_HD void pass_r(C* wb, int nf, int Mp, const Plan& p, int s, const C* __restr
 
 template <typename T, bool INV, typename C>
 SPX_HD void pass(C* wb, int nf, int Mp, const Plan& p, int s, const C* __restrict__ tw, int tid, int nt) {
+    if constexpr (sizeof(T) == 4) {
+        if (p.radix[s] == 16) { pass_r<T, 16, INV>(wb, nf, Mp, p, s, tw, tid, nt); return; }
+    }
     switch (p.radix[s]) {
         case 8:  pass_r<T, 8, INV>(wb, nf, Mp, p, s, tw, tid, nt); break;
         case 4:  pass_r<T, 4, INV>(wb, nf, Mp, p, s, tw, tid, nt); break;

@@ -308,7 +308,7 @@ int mr_tile_launch(int dtype, int op, TileArgs& a, cudaStream_t st) {
     if (dm.M > 4096) return SPECINV_ERR_UNSUPPORTED;           // positions are 16-bit
     mr::Plan mp;
     // the plan's root table: W_M^j (M entries) for a power of two, W_N^j (N entries) otherwise (specinv_common.cuh)
-    if (!mr::make_plan(dm.M, dm.pow2 ? dm.M : dm.N, &mp)) return SPECINV_ERR_UNSUPPORTED;
+    if (!mr::make_plan(dm.M, dm.pow2 ? dm.M : dm.N, &mp, dtype == SPECINV_F32)) return SPECINV_ERR_UNSUPPORTED;
     return dtype == SPECINV_F64 ? launch_mr_op<double>(op, a, mp, st) : launch_mr_op<float>(op, a, mp, st);
 }
 

@@ -11,7 +11,7 @@ using namespace specinv;
 template <typename T, typename C>
 double run(int M, int tw_n, int nt) {
     mr::Plan p;
-    if (!mr::make_plan(M, tw_n, &p)) { printf("M=%d: no plan\n", M); return 1e9; }
+    if (!mr::make_plan(M, tw_n, &p, sizeof(T) == 4)) { printf("M=%d: no plan\n", M); return 1e9; }
     const int nf = 3, Mp = mr::padded_len(M);
     std::vector<C> tw(tw_n), wb((size_t)nf * Mp);
     for (int j = 0; j < tw_n; ++j) { tw[j].x = (T)cos(2 * M_PI * j / tw_n); tw[j].y = (T)(-sin(2 * M_PI * j / tw_n)); }

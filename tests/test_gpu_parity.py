@@ -400,7 +400,8 @@ def test_rtisi_fast_kernel_1024_against_oracle(rc, monkeypatch):
     """The register-FFT RTISI-LA kernel (n_fft = 1024 / hop = 256, 512 / 128, 2048 / 512) against the oracle in float64.  fp32 trajectories of
     RTISI-LA drift apart quickly (the projection divides by |S|; SURVEY.md section 7: fp32 vs fp64 of the REFERENCE
     decorrelate over a full run), so the yardstick is the drift of two other fp32 implementations from the same fp64
-    run -- the oracle in float32 and the generic shared-memory kernel: an indexing mistake gives O(1) errors."""
+    run -- the oracle in float32 and the generic shared-memory kernel on either of its two FFTs: an indexing mistake
+    gives O(1) errors."""
     import spectrogram_inversion_b200 as S
     rs = np.random.RandomState(rc["T"])
     n_fft = rc.get("n_fft", 1024)
@@ -421,14 +422,16 @@ def test_rtisi_fast_kernel_1024_against_oracle(rc, monkeypatch):
     y64 = O.RTISI_LA(mag.astype(np.float64), **run, **kw64)
     tkw = {k: (torch.from_numpy(v).cuda() if isinstance(v, np.ndarray) else v) for k, v in kw.items()}
     outs = {}
-    for force in ("0", "1"):
-        monkeypatch.setenv("SPECINV_FORCE_GENERIC", force)
+    # "1": the generic kernel on the mixed-radix passes, "1b": on the radix-2^2 passes (SPECINV_GENERIC_MR=0)
+    for force in ("0", "1", "1b"):
+        monkeypatch.setenv("SPECINV_FORCE_GENERIC", force[0])
+        monkeypatch.setenv("SPECINV_GENERIC_MR", "0" if force.endswith("b") else "1")
         outs[force] = S.RTISI_LA(torch.from_numpy(mag).cuda(), verbose=0, **run, **tkw).cpu().numpy()
 
     def rel_l2(a, b):
         return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
     assert outs["0"].shape == y64.shape and np.isfinite(outs["0"]).all()
-    drift = max(rel_l2(y32, y64), rel_l2(outs["1"], y64))
+    drift = max(rel_l2(y32, y64), rel_l2(outs["1"], y64), rel_l2(outs["1b"], y64))
     assert drift < 0.1, drift                              # the horizon is short enough for the comparison to mean something
     assert rel_l2(outs["0"], y64) <= 4 * drift + 1e-5, (rel_l2(outs["0"], y64), drift)
     assert rel_l2(outs["0"], outs["1"]) <= 4 * drift + 1e-5
