@@ -31,6 +31,16 @@ struct MrLaunch {
     unsigned magic_npair;  // ceil(2^32 / (M/2 + 1))
 };
 
+// L2 prefetch of the 128-byte lines of [p, p + bytes) by `nt` threads (thread `tid`): the rows a later phase loads are
+// known long before (state / magnitude rows of the team's frames, 1/envelope of the tile's output range), so their
+// DRAM latency is paid under the butterflies instead of in front of the point-wise arithmetic.
+__device__ __forceinline__ void prefetch_l2(const void* p, size_t bytes, int tid, int nt) {
+    if (!p || bytes == 0) return;
+    const uintptr_t lo = (uintptr_t)p & ~(uintptr_t)127, hi = (uintptr_t)p + bytes;
+    for (uintptr_t q = lo + (uintptr_t)tid * 128; q < hi; q += (uintptr_t)nt * 128)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+}
+
 template <typename T, int OP>
 __global__ void __launch_bounds__(512, 2) mr_tile_kernel(const TileArgs a, const mr::Plan mp, const MrLaunch ml) {
     using C = cx_t<T>;
@@ -54,6 +64,13 @@ __global__ void __launch_bounds__(512, 2) mr_tile_kernel(const TileArgs a, const
 
     // padded position of bin k after the forward passes
     for (int k = tid; k < M; k += NT) perm[k] = (unsigned short)mr::padidx(mr::mr_position(mp, k));
+
+    if constexpr (OP != OP_STFT) {   // 1/envelope of the samples this tile will write (phase E)
+        long long m0 = (long long)t0 * hop - dm.P, m1 = ((t1 == dm.T) ? dm.Lp : (long long)t1 * hop) - dm.P;
+        if (m0 < 0) m0 = 0;
+        if (m1 > dm.L) m1 = dm.L;
+        if (m1 > m0) prefetch_l2((const T*)a.inv_env + m0, (size_t)(m1 - m0) * sizeof(T), tid, NT);
+    }
 
     // ---- A: frame + analysis window: z[n] = x[2n] w[2n] + i x[2n+1] w[2n+1] ----------------------------------
     if constexpr (OP != OP_ISTFT) {
@@ -90,6 +107,14 @@ __global__ void __launch_bounds__(512, 2) mr_tile_kernel(const TileArgs a, const
         if (G == 1) __syncwarp();
         else asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "r"(tnt) : "memory");
     };
+
+    if constexpr (OP != OP_STFT) {   // the rows of the team's frames that the point-wise stage (C) will load
+        const size_t fr0 = (size_t)b * dm.T + f0 + fa;
+        const size_t rc = (size_t)dm.row * sizeof(C), rm = (size_t)dm.row * sizeof(T);
+        if (a.s0_in_main) prefetch_l2((const char*)a.s0_in_main + fr0 * rc, (size_t)nf * rc, ttid, tnt);
+        if (a.s1_in_main) prefetch_l2((const char*)a.s1_in_main + fr0 * rc, (size_t)nf * rc, ttid, tnt);
+        if (a.mag_main) prefetch_l2((const char*)a.mag_main + fr0 * rm, (size_t)nf * rm, ttid, tnt);
+    }
 
     // ---- B: forward passes (natural -> digit-reversed) ---------------------------------------------------------
     if constexpr (OP != OP_ISTFT) {
@@ -254,8 +279,14 @@ static int launch_mr(TileArgs& a, const mr::Plan& mp, cudaStream_t st) {
     const int optin = mr_smem_optin();
     if (optin <= 0) return SPECINV_ERR_NO_DEVICE;
     const size_t big = (size_t)optin - 1024 - perm_bytes;
-    // two CTAs per SM when a reasonable tile fits half of the SM's shared memory (228 KB, 1 KB reserved per CTA)
-    size_t budget = (size_t)(228 * 1024 / 2 - 1024) - 1024 - perm_bytes;
+    // Two CTAs of 16 warps per SM (1024 threads at 64 registers), each with half of the SM's shared memory (228 KB,
+    // 1 KB reserved per CTA).  SPECINV_MR_CTAS_PER_SM=4 launches four CTAs of 8 warps with a quarter each: measured
+    // within +-6 % of the default (0.305 vs 0.326 ms at 400/100, 1.09 vs 1.05 ms at 256/64, 1.29 vs 0.75 ms at 1536/384
+    // where the smaller tile pays more halo frames), so it stays an experiment switch.
+    static int forced_ctas = -1;
+    if (forced_ctas < 0) { const char* e = getenv("SPECINV_MR_CTAS_PER_SM"); forced_ctas = e ? atoi(e) : 0; }
+    const int ctas = forced_ctas == 4 ? 4 : 2;
+    size_t budget = (size_t)(228 * 1024 / ctas - 1024) - 256 - perm_bytes;
     if (budget > big) budget = big;
     int cap = (int)(budget / frame_bytes);
     if (cap - halo < (halo > 1 ? 2 * halo : 2)) cap = (int)(big / frame_bytes);   // poor owned / halo ratio: one fat CTA
@@ -264,9 +295,9 @@ static int launch_mr(TileArgs& a, const mr::Plan& mp, cudaStream_t st) {
     // small problems: prefer enough tiles to cover the 148 SMs twice
     while (cap - halo > 4 * (halo > 0 ? halo : 1) && (long long)dm.B * ((dm.T + cap - halo - 1) / (cap - halo)) < 2 * 148)
         cap = halo + (cap - halo + 1) / 2;
-    // teams: 16 warps dealt to 16, 8, 4, 2 or 1 teams; the tile holds a multiple of the team count (even load), and a
-    // bigger team pays ~3 % per doubling in barriers
-    const int warps = 16;
+    // teams: the CTA's warps dealt to 16, 8, 4, 2 or 1 teams; the tile holds a multiple of the team count (even load),
+    // and a bigger team pays ~3 % per doubling in barriers
+    const int warps = 32 / ctas;
     int best_teams = 1, best_nfr = cap; double best_score = -1.0;
     for (int teams = warps; teams >= 1; teams >>= 1) {
         int nfr = cap / teams * teams;
