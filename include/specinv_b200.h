@@ -42,7 +42,7 @@ extern "C" {
 
 enum {
     SPECINV_OK = 0,
-    SPECINV_ERR_INVALID = -1,      /* bad argument (null pointer, non power-of-two n_fft, ...) */
+    SPECINV_ERR_INVALID = -1,      /* bad argument (null pointer, n_fft out of range, ...) */
     SPECINV_ERR_UNSUPPORTED = -2,  /* valid in the reference but not implemented by these kernels */
     SPECINV_ERR_NO_DEVICE = -3     /* no sm_100 device / kernel image not loadable */
 };
@@ -55,7 +55,7 @@ enum { SPECINV_PAD_REFLECT = 0, SPECINV_PAD_CONSTANT = 1, SPECINV_PAD_REPLICATE 
 /* Normalised STFT description == the output of the reference's _args_helper
  * (methods.py:21-91) plus the problem size. */
 typedef struct specinv_desc {
-    int32_t n_fft;       /* power of two, 16..8192 */
+    int32_t n_fft;       /* even, 16..8192 (RTISI-LA: n_fft/2 must factor into 2 .. 13) */
     int32_t hop;         /* hop_length, 1..n_fft */
     int32_t n_frames;    /* T */
     int32_t batch;       /* B */
