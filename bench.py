@@ -24,7 +24,8 @@ its own B=512 batch; the path needs no collective).
   configs      : cfg1 / cfg3 / cfg4 / cfg5 of BASELINE.json (ms per job, per iteration, audio-s*it/s, roofline
                  fraction); for N > 1: cfg2 STRONG-scaled (B = 512 / N per rank), cfg3 / cfg4 batch-sharded, and cfg5
                  FRAME-SHARDED over the N ranks through the NVLink peer-memory halo exchange (ms / iteration, speed-up
-                 over one GPU, exchange time, boundary checks)
+                 over one GPU, exchange time, boundary checks); `generic400`: the generic (mixed-radix) path at
+                 torchaudio's default transform, with the reference's CUDA path on the same inputs beside it
 """
 from __future__ import annotations
 
@@ -60,6 +61,11 @@ WORKLOADS = {
                  desc="ADMM B=128 x 20 s @ 44.1 kHz, n_fft=2048 hop=512 hann, 100 iters, rho=0.1"),
     "cfg5": dict(algo="gl", B=1, N=172800000, sr=48000, n_fft=4096, hop=1024, iters=100, coef=0.99,
                  desc="griffin_lim one 1 h @ 48 kHz signal, n_fft=4096 hop=1024 hann, 100 iters, alpha=0.99"),
+    # not a BASELINE config: the GENERIC path (mixed-radix team kernels, csrc/specinv_generic_mr.cu) at torchaudio's
+    # default transform (n_fft=400, hop=200), reported beside the reference's own CUDA path on the same inputs
+    "generic400": dict(algo="gl", B=64, N=160000, sr=16000, n_fft=400, hop=200, iters=32, coef=0.99,
+                       desc="GENERIC path: griffin_lim B=64 x 10 s @ 16 kHz, n_fft=400 hop=200 hann (torchaudio's "
+                            "default transform), 32 iters, alpha=0.99"),
 }
 
 
@@ -349,7 +355,7 @@ def final_sc_db(cx, w, mag, win, y):
     return float(S.sc(est, mag))
 
 
-def measure_config(cx, name, w, B, n_jobs, n_warm, seed):
+def measure_config(cx, name, w, B, n_jobs, n_warm, seed, with_reference_cuda=False):
     """Device-resident timing of one BASELINE config at B signals per rank: n_warm untimed + n_jobs timed whole
     public calls, barrier + synchronize on both sides, max over ranks."""
     torch = cx.torch
@@ -390,6 +396,8 @@ def measure_config(cx, name, w, B, n_jobs, n_warm, seed):
             out["final_sc_db"] = final_sc_db(cx, w, mag, win, y)
         except Exception as ex:   # never let a diagnostic kill the line
             out["final_sc_db"] = f"unavailable: {ex}"
+    if with_reference_cuda:
+        out["reference_cuda"] = measure_reference_cuda(cx, w, mag, win)
     del mag, y
     torch.cuda.empty_cache()
     return out
@@ -697,7 +705,7 @@ def run_ours(args, w):
     # ---- the other configs (device-resident, bounded: 2 warm-up + 3 timed whole calls each)
     configs = {}
     if args.configs != "none":
-        want = ["cfg1", "cfg3", "cfg4", "cfg5"] if args.configs == "all" else \
+        want = ["cfg1", "cfg3", "cfg4", "cfg5", "generic400"] if args.configs == "all" else \
             [c for c in args.configs.split(",") if c in WORKLOADS]
         for name in want:
             wc = WORKLOADS[name]
@@ -706,7 +714,8 @@ def run_ours(args, w):
                     configs["cfg5_frame_sharded"] = measure_cfg5_sharded(cx, wc)
                     continue
                 Bc = wc["B"] if wc["B"] == 1 else max(1, wc["B"] // world)      # batch configs: strong scaling
-                r = measure_config(cx, name, wc, Bc, 3, 2, 77 + rank)
+                r = measure_config(cx, name, wc, Bc, 3, 2, 77 + rank,
+                                   with_reference_cuda=(name == "generic400" and world == 1 and not args.no_cpu))
                 if wc["B"] == 1 and world > 1:
                     r["note"] = "a single signal does not shard by batch: every rank ran its own replica"
                 elif world > 1:
