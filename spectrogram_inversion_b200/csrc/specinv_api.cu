@@ -387,6 +387,8 @@ int specinv_fill_padding(int dtype, void* x, int64_t ld, int rows, int64_t padde
                          int64_t signal_len, int pad_mode, void* stream) {
     if (!x || rows < 1 || pad < 0 || local_len < 1 || signal_len < 1) return SPECINV_ERR_INVALID;
     if (pad == 0) return SPECINV_OK;
+    // an interior range of a frame-sharded signal holds no padding sample at all: nothing to launch
+    if (padded_offset >= pad && padded_offset + local_len <= pad + signal_len) return SPECINV_OK;
     // A buffer that holds padding samples must also hold their sources: reflect padding mirrors sample P + k onto
     // P - k (and L + P - 1 - k onto L + P - 1 + k), so an edge range needs 2 * pad + 1 samples; otherwise the kernel
     // would have to leave stale padding behind (the source lives on the neighbouring rank).

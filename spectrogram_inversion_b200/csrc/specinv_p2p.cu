@@ -53,6 +53,10 @@ __host__ __device__ inline size_t flags_off(int rows, long long ov, size_t es) {
 
 template <typename T>
 __global__ void __launch_bounds__(1024) halo_exchange_kernel(const HaloArgs a) {
+    // The next iteration's kernel is launched with programmatic stream serialization (specinv_fastw_kernel.cuh): let
+    // its prologue (tensor-memory allocation, table fill from the plan -- nothing this kernel writes) run under the
+    // exchange; its griddepcontrol.wait still blocks until this grid has completed and its stores are visible.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int side = blockIdx.x;                 // 0: exchange with the left neighbour, 1: with the right one
     char* peer = a.recv_peer[side];
     if (!peer) return;
