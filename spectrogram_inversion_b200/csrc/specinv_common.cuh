@@ -45,7 +45,7 @@ template <typename T> __device__ __forceinline__ cx_t<T> project(cx_t<T> q, T ma
 // Dimensions derived from a specinv_desc (host side and kernels share it).
 struct Dims {
     int N;        // n_fft
-    int M;        // N/2: size of the complex FFT used for the real transform
+    int M;        // N/2 (floor): size of the complex FFT used for the real transform; top bin of the half spectrum
     int logM;
     int pow2;     // n_fft is a power of two (FFT kernels); otherwise the direct-DFT tile kernel of specinv_generic.cu
     int hop;
@@ -77,7 +77,7 @@ inline int make_dims(const specinv_desc* d, Dims* o) {
     if (!d) return SPECINV_ERR_INVALID;
     const int N = d->n_fft;
     if (N < 16 || N > 8192) return SPECINV_ERR_INVALID;
-    if (N & 1) return SPECINV_ERR_UNSUPPORTED;     // odd n_fft (two-sided spectra with an odd bin count only)
+    if ((N & 1) && d->onesided) return SPECINV_ERR_INVALID;   // an odd n_fft only exists two-sided (bin count = n_fft): direct DFT
     if (d->hop < 1 || d->hop > N) return SPECINV_ERR_INVALID;
     if (d->n_frames < 1 || d->batch < 1) return SPECINV_ERR_INVALID;
     if (d->dtype != SPECINV_F32 && d->dtype != SPECINV_F64) return SPECINV_ERR_INVALID;

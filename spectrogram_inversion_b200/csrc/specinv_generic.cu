@@ -161,9 +161,9 @@ __global__ void __launch_bounds__(1024) tile_kernel(const TileArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------
-// Any EVEN n_fft that is not a power of two (the reference infers n_fft from the bin count, methods.py:65-68; 400 is
-// torchaudio's default): the same tile structure with the transforms done as direct DFTs on the W_N table of the
-// plan.  O(N^2) per frame instead of O(N log N) -- a coverage path (about 4x the generic FFT kernel's time at
+// Any n_fft the mixed-radix kernels (specinv_generic_mr.cu) do not take -- a half with a prime factor > 13, or an ODD
+// n_fft (two-sided spectra only: the reference infers n_fft = bin count, methods.py:65-68) --: the same tile structure
+// with the transforms done as direct DFTs on the W_N table of the plan.  O(N^2) per frame instead of O(N log N) -- a coverage path (about 4x the generic FFT kernel's time at
 // N = 400), never a fallback to another library.  Shared memory per frame: N time samples and N/2+1 bins.
 //   forward : s[k] = sum_n fr[n] W_N^(kn), k <= N/2               (fr = frame * analysis window)
 //   inverse : x[n] = Re h[0] + (-1)^n Re h[N/2] + 2 sum_{0<k<N/2} Re(h[k] conj(W_N^(kn)))   (C2R, unnormalised:
@@ -217,9 +217,10 @@ __global__ void __launch_bounds__(512) dft_tile_kernel(const TileArgs a) {
         }
         const BinIO<T> io(a, (long long)b * dm.T + t);
         C h = bin_update<T, OP>(a, io, k, s, owned, want_sums, dsum, esum);
-        if (!dm.onesided && k != 0 && k != dm.M) {
+        if (!dm.onesided && k != 0 && (k != dm.M || (N & 1))) {
             // two-sided: the mirrored bin N-k holds conj(s) of the real-input STFT; ifft(...).real (methods.py:145-146)
-            // is the C2R transform of the Hermitian part (p[k] + conj p[N-k]) / 2
+            // is the C2R transform of the Hermitian part (p[k] + conj p[N-k]) / 2  (odd N: no Nyquist bin, k = M = (N-1)/2
+            // has a mirror like every other bin)
             const C m = bin_update<T, OP>(a, io, N - k, mk<T>(s.x, -s.y), owned, want_sums, dsum, esum);
             h = mk<T>(T(0.5) * (h.x + m.x), T(0.5) * (h.y - m.y));
         }
@@ -249,10 +250,12 @@ __global__ void __launch_bounds__(512) dft_tile_kernel(const TileArgs a) {
     for (int idx = tid; idx < nfr * N; idx += NT) {
         const int f = idx / N, n = idx - f * N;
         const C* h = hb + (size_t)f * H;
-        T acc = h[0].x + ((n & 1) ? -h[dm.M].x : h[dm.M].x);
+        const bool oddN = N & 1;
+        T acc = oddN ? h[0].x : h[0].x + ((n & 1) ? -h[dm.M].x : h[dm.M].x);
         T part = T(0);
         int j = n;                                                   // (k n) mod N for k = 1
-        for (int k = 1; k < dm.M; ++k) {
+        const int kend = oddN ? dm.M + 1 : dm.M;
+        for (int k = 1; k < kend; ++k) {
             const C w = tw[j];
             part += h[k].x * w.x + h[k].y * w.y;                     // Re(h conj(W))
             j += n; if (j >= N) j -= N;

@@ -336,7 +336,7 @@ static int launch_mr_op(int op, TileArgs& a, const mr::Plan& mp, cudaStream_t st
 
 int mr_tile_launch(int dtype, int op, TileArgs& a, cudaStream_t st) {
     const Dims& dm = a.dm;
-    if (dm.M > 4096) return SPECINV_ERR_UNSUPPORTED;           // positions are 16-bit
+    if (dm.M > 4096 || (dm.N & 1)) return SPECINV_ERR_UNSUPPORTED;   // positions are 16-bit; the N/2-point trick needs an even N
     mr::Plan mp;
     // the plan's root table: W_M^j (M entries) for a power of two, W_N^j (N entries) otherwise (specinv_common.cuh)
     if (!mr::make_plan(dm.M, dm.pow2 ? dm.M : dm.N, &mp, dtype == SPECINV_F32)) return SPECINV_ERR_UNSUPPORTED;

@@ -331,7 +331,7 @@ static int rtisi_t(const specinv_desc* d, const Dims& dm, const void* plan, cons
         // whose root table is W_N); SPECINV_GENERIC_MR=0 keeps the radix-2^2 passes for the powers of two
         const char* e = getenv("SPECINV_GENERIC_MR");
         const bool want = !(e && e[0] == '0') || !dm.pow2;
-        a.use_mr = want && dm.M <= 4096 && mr::make_plan(dm.M, dm.pow2 ? dm.M : dm.N, &a.mp, sizeof(T) == 4) ? 1 : 0;
+        a.use_mr = want && dm.M <= 4096 && !(dm.N & 1) && mr::make_plan(dm.M, dm.pow2 ? dm.M : dm.N, &a.mp, sizeof(T) == 4) ? 1 : 0;
         if (!a.use_mr && !dm.pow2) return SPECINV_ERR_UNSUPPORTED;    // a prime factor > 13: no RTISI-LA kernel
     }
     a.step_begin = step_begin; a.step_end = step_end; a.state = state; a.state_elems = rtisi_state_elems(dm, a.LA);

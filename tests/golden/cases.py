@@ -166,6 +166,12 @@ NONPOW2_CASES = [
     _c("np2_1536_hann_f32", n_fft=1536, window="hann", hop_length=384, T=7, B=1, dtype="float32", seed=42),
     _c("np2_2000_hann_f32", n_fft=2000, window="hann", hop_length=500, T=6, B=1, dtype="float32", seed=43),
     _c("np2_34_direct_f64", n_fft=34, window="hann", hop_length=17, T=25, B=2, dtype="float64", seed=44),
+    # ODD n_fft: two-sided spectra only (n_fft = bin count, methods.py:65-68); direct DFT
+    _c("odd_255_twosided_f64", n_fft=255, window="hann", hop_length=64, T=9, B=2, dtype="float64", seed=61, onesided=False),
+    _c("odd_75_twosided_f32", n_fft=75, window="hamming", hop_length=25, T=14, B=3, dtype="float32", seed=62, onesided=False,
+       center=False),
+    _c("odd_129_shortwin_twosided_f32", n_fft=129, win_length=100, window="hann", hop_length=32, T=11, B=1, dtype="float32",
+       seed=63, onesided=False, pad_mode="constant", normalized=True),
 ]
 
 # RTISI-LA at n_fft that is not a power of two (mixed-radix passes in csrc/specinv_rtisi.cu)

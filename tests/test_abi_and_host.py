@@ -58,8 +58,10 @@ def test_host_only_entry_points(lib):
         assert nbytes.value > 2 * L.value * mag.dtype.itemsize
     ok = lib.make_desc(1000, 250, 10, 1, True, 0, False, True, lib.F32)       # not a power of two: direct-DFT kernels
     assert handle.specinv_signal_length(C.byref(ok), C.byref(L)) == 0 and L.value == 9 * 250
-    bad = lib.make_desc(1001, 250, 10, 1, True, 0, False, False, lib.F32)     # odd n_fft
-    assert handle.specinv_signal_length(C.byref(bad), C.byref(L)) == lib.ERR_UNSUPPORTED
+    odd = lib.make_desc(1001, 250, 10, 1, True, 0, False, False, lib.F32)     # odd n_fft: two-sided only, direct DFT
+    assert handle.specinv_signal_length(C.byref(odd), C.byref(L)) == 0 and L.value == 9 * 250 + 1
+    bad = lib.make_desc(1001, 250, 10, 1, True, 0, False, True, lib.F32)      # an odd n_fft has no onesided spectrum
+    assert handle.specinv_signal_length(C.byref(bad), C.byref(L)) == -1
     bad = lib.make_desc(1024, 0, 10, 1, True, 0, False, True, lib.F32)
     assert handle.specinv_signal_length(C.byref(bad), C.byref(L)) == -1
 
