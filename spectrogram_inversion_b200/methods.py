@@ -3,6 +3,8 @@
 from __future__ import annotations
 
 import math
+import os
+
 import torch
 from tqdm import tqdm
 
@@ -87,7 +89,8 @@ def _pipeline_chunks(spec: torch.Tensor, tol: float, verbose, state_arrays: int 
     if spec.is_cuda or len(spec.shape) != 3 or tol != 0 or verbose:
         return 1
     B, F, T = spec.shape
-    n = int(max(1, min(4, B, (B * T) // 60000)))
+    cap = int(os.environ.get("SPECINV_HOST_CHUNKS", "4"))         # measured: tools/e2e_chunks.py
+    n = int(max(1, min(cap, B, (B * T) // 60000)))
     # ... and small enough for the device: a chunk holds its input, the magnitudes, the ping-pong state (two complex
     # arrays for Griffin-Lim, four for ADMM) and two signals; keep that within 80 % of the free memory
     per_signal = F * T * spec.element_size() * (2 if not spec.is_complex() else 1) * (1 + 0.5 + 2 * state_arrays + 1)
