@@ -147,9 +147,39 @@ __global__ void convert_kernel(Dims dm, int F, V* main, V* nyq, V* ext, long lon
     }
 }
 
+// The external tensor is frame-major itself (frequency stride 1: what torch.stft returns and what `abs()` of it keeps):
+// no transpose, every (signal, frame) row of F bins is one contiguous run on both sides -- a warp copies a row with
+// coalesced accesses (main <- the first `row` bins, nyq <- the last one when onesided).
+template <typename V, bool TO_INTERNAL>
+__global__ void __launch_bounds__(256) rowcopy_kernel(Dims dm, int F, V* __restrict__ main, V* __restrict__ nyq,
+                                                      V* __restrict__ ext, long long sb, long long st) {
+    const int lane = threadIdx.x & 31;
+    const long long rows = (long long)dm.B * dm.T;
+    const long long wstride = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < rows; r += wstride) {
+        const long long b = r / dm.T, t = r - b * dm.T;
+        V* e = ext + b * sb + t * st;
+        V* m = main + r * dm.row;
+#pragma unroll 4
+        for (int k = lane; k < dm.row; k += 32) {
+            if (TO_INTERNAL) m[k] = e[k]; else e[k] = m[k];
+        }
+        if (dm.onesided && lane == 0) {
+            if (TO_INTERNAL) nyq[r] = e[dm.M]; else e[dm.M] = nyq[r];
+        }
+    }
+}
+
 template <typename V, bool TO_INTERNAL>
 static int convert(const Dims& dm, V* main, V* nyq, V* ext, long long sb, long long sf, long long st, cudaStream_t s) {
     const int F = dm.onesided ? dm.M + 1 : dm.N;
+    if (sf == 1) {
+        const long long rows = (long long)dm.B * dm.T;
+        long long blocks = (rows + 7) / 8;                       // 8 warps per block, one row per warp and trip
+        if (blocks > 148 * 32) blocks = 148 * 32;
+        rowcopy_kernel<V, TO_INTERNAL><<<(unsigned)blocks, 256, 0, s>>>(dm, F, main, nyq, ext, sb, st);
+        return (int)cudaGetLastError();
+    }
     dim3 grid((F + 31) / 32, (dm.T + 31) / 32, dm.B), block(32, 8);
     if (grid.y > 65535 || grid.z > 65535) return SPECINV_ERR_UNSUPPORTED;
     convert_kernel<V, TO_INTERNAL><<<grid, block, 0, s>>>(dm, F, main, nyq, ext, sb, sf, st);

@@ -640,6 +640,38 @@ def test_specialised_kernels_match_the_reference_itself(case):
         close(y, FASTREF[f"{name}/rtisi_la3_k1"], 5e-3, "RTISI-LA vs reference")
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+@pytest.mark.parametrize("onesided", [True, False])
+def test_layout_conversion_is_exact_for_every_stride_pattern(dtype, onesided):
+    """pack / unpack between the reference's (B, F, T) tensors and the split frame-major layout: contiguous input (32 x 32
+    tile transposes), frame-major input = what torch.stft returns (the row-copy kernel), a strided view of a larger
+    tensor, real and complex; all bit-exact."""
+    from spectrogram_inversion_b200.engine import StftPlan
+    from spectrogram_inversion_b200.stft_args import StftArgs
+    dev = torch.device("cuda")
+    n_fft, B, T = 128, 3, 45
+    F = n_fft // 2 + 1 if onesided else n_fft
+    plan = StftPlan(StftArgs(n_fft, 32, n_fft, torch.hann_window(n_fft, device=dev, dtype=dtype), True, "reflect", False,
+                             onesided), T, B, dtype, dev)
+    g = torch.Generator(device=dev).manual_seed(5)
+    for cplx in (False, True):
+        base = torch.randn(B, F, T, device=dev, dtype=dtype, generator=g)
+        if cplx:
+            base = torch.complex(base, torch.randn(B, F, T, device=dev, dtype=dtype, generator=g))
+        frame_major = base.transpose(1, 2).contiguous().transpose(1, 2)            # strides (F*T, 1, F)
+        wide = torch.zeros(B, F + 3, 2 * T, device=dev, dtype=base.dtype)
+        wide[:, 1:F + 1, ::2] = base
+        views = {"contiguous": base, "frame-major": frame_major, "strided view": wide[:, 1:F + 1, ::2]}
+        assert frame_major.stride() == (F * T, 1, F)
+        ref = None
+        for name, v in views.items():
+            s = plan.pack(v)
+            got = torch.cat([s.main, s.nyq.unsqueeze(-1)], dim=-1) if onesided else s.main      # (B, T, F)
+            assert torch.equal(got, base.transpose(1, 2)), name
+            if cplx:
+                assert torch.equal(plan.unpack(s), base), name
+
+
 def test_random_configurations_specialised_vs_fp64_generic():
     """tools/fuzz_fast_vs_generic.py: random (n_fft, hop, B, T, padding, window length, algorithm) draws; the specialised
     fp32 kernels must stay within 4x the generic fp32 kernel's distance (+1e-5) from the generic fp64 result."""
