@@ -262,6 +262,29 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def bind_to_gpu_numa(torch, index):
+    """Pin this process (and the pinned host buffers it allocates afterwards: first touch) to the CPUs NVML reports as
+    local to its GPU.  Under torchrun eight ranks otherwise float over both sockets and the e2e leg's host <-> device
+    copies (1.48 GB per step and rank) cross the socket interconnect.  SPECINV_BENCH_NUMA_BIND=0 switches it off.
+    Returns a short description for the JSON line."""
+    if os.environ.get("SPECINV_BENCH_NUMA_BIND", "1") == "0":
+        return "off"
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        uuid = str(torch.cuda.get_device_properties(index).uuid)
+        h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * i + b for i, wd in enumerate(words) for b in range(64) if (wd >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        cpus = (cpus & allowed) or allowed
+        os.sched_setaffinity(0, cpus)
+        return f"{len(cpus)} cpus local to the GPU"
+    except Exception as ex:      # no NVML / not permitted: run unbound
+        return f"unbound ({type(ex).__name__})"
+
+
 class Ctx:
     """torch / distributed plumbing shared by the measurement functions."""
 
@@ -276,6 +299,7 @@ class Ctx:
             raise RuntimeError("bench.py needs a CUDA device: the product path has no CPU fallback")
         torch.cuda.set_device(self.local)
         self.dev = torch.device("cuda", self.local)
+        self.numa = bind_to_gpu_numa(torch, self.local)
         if self.world > 1:
             dist.init_process_group("nccl", device_id=self.dev)
         self.peak, self.peak_src = measured_peak()
@@ -757,7 +781,8 @@ def run_ours(args, w):
                         "ms_per_step_max": srt[-1], "ms_per_step_all": e2e_steps,
                         "timing": f"value from the MEAN of {len(e2e_steps)} steps (rank 0's steps listed in call order; "
                                   "the mean is the max over ranks)"},
-                "gpu_launches": launches, "clocks": clocks, "configs": configs}
+                "gpu_launches": launches, "clocks": clocks, "host_binding": cx.numa,
+                "configs": configs}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -178,9 +178,12 @@ template <int R, typename T, typename C> struct Dft {
     }
 };
 
-// One pass of stage `s` over `nf` frames by a team of `nt` threads (this thread is `tid`).
+// One pass of stage `s` over `nf` frames by a team of `nt` threads (this thread is `tid`).  `scale` (or nullptr): 2 M
+// reals, element n of the result is multiplied by (scale[2n], scale[2n+1]) component-wise on the way out -- the last
+// inverse pass applies the synthesis window to the sample pairs it holds in registers anyway.
 template <typename T, int R, bool INV, typename C>
-SPX_HD void pass_r(C* wb, int nf, int Mp, const Plan& p, int s, const C* __restrict__ tw, int tid, int nt) {
+SPX_HD void pass_r(C* wb, int nf, int Mp, const Plan& p, int s, const C* __restrict__ tw, int tid, int nt,
+                   const T* __restrict__ scale) {
     const int nb = p.M / R, span = p.span[s], twstep = p.tw_step[s];
     const unsigned mg_span = p.span_magic[s], mg_nb = p.nb_magic[s];
     const int total = nf * nb;
@@ -206,25 +209,30 @@ SPX_HD void pass_r(C* wb, int nf, int Mp, const Plan& p, int s, const C* __restr
         static_for<R>([&](auto m) {
             C t;
             if (INV) { t.x = x[m].y; t.y = x[m].x; } else t = x[m];
+            if (scale) {
+                const C w = ldro(reinterpret_cast<const C*>(scale) + (e0 + m * span));
+                t.x *= w.x; t.y *= w.y;
+            }
             v[padidx(e0 + m * span)] = t;
         });
     }
 }
 
 template <typename T, bool INV, typename C>
-SPX_HD void pass(C* wb, int nf, int Mp, const Plan& p, int s, const C* __restrict__ tw, int tid, int nt) {
+SPX_HD void pass(C* wb, int nf, int Mp, const Plan& p, int s, const C* __restrict__ tw, int tid, int nt,
+                 const T* __restrict__ scale = nullptr) {
     if constexpr (sizeof(T) == 4) {
-        if (p.radix[s] == 16) { pass_r<T, 16, INV>(wb, nf, Mp, p, s, tw, tid, nt); return; }
+        if (p.radix[s] == 16) { pass_r<T, 16, INV>(wb, nf, Mp, p, s, tw, tid, nt, scale); return; }
     }
     switch (p.radix[s]) {
-        case 8:  pass_r<T, 8, INV>(wb, nf, Mp, p, s, tw, tid, nt); break;
-        case 4:  pass_r<T, 4, INV>(wb, nf, Mp, p, s, tw, tid, nt); break;
-        case 2:  pass_r<T, 2, INV>(wb, nf, Mp, p, s, tw, tid, nt); break;
-        case 3:  pass_r<T, 3, INV>(wb, nf, Mp, p, s, tw, tid, nt); break;
-        case 5:  pass_r<T, 5, INV>(wb, nf, Mp, p, s, tw, tid, nt); break;
-        case 7:  pass_r<T, 7, INV>(wb, nf, Mp, p, s, tw, tid, nt); break;
-        case 11: pass_r<T, 11, INV>(wb, nf, Mp, p, s, tw, tid, nt); break;
-        case 13: pass_r<T, 13, INV>(wb, nf, Mp, p, s, tw, tid, nt); break;
+        case 8:  pass_r<T, 8, INV>(wb, nf, Mp, p, s, tw, tid, nt, scale); break;
+        case 4:  pass_r<T, 4, INV>(wb, nf, Mp, p, s, tw, tid, nt, scale); break;
+        case 2:  pass_r<T, 2, INV>(wb, nf, Mp, p, s, tw, tid, nt, scale); break;
+        case 3:  pass_r<T, 3, INV>(wb, nf, Mp, p, s, tw, tid, nt, scale); break;
+        case 5:  pass_r<T, 5, INV>(wb, nf, Mp, p, s, tw, tid, nt, scale); break;
+        case 7:  pass_r<T, 7, INV>(wb, nf, Mp, p, s, tw, tid, nt, scale); break;
+        case 11: pass_r<T, 11, INV>(wb, nf, Mp, p, s, tw, tid, nt, scale); break;
+        case 13: pass_r<T, 13, INV>(wb, nf, Mp, p, s, tw, tid, nt, scale); break;
         default: break;
     }
 }

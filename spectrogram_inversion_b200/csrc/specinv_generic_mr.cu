@@ -29,6 +29,7 @@ struct MrLaunch {
     int Mp;                // padded complex elements per frame
     unsigned magic_M;      // ceil(2^32 / M)
     unsigned magic_npair;  // ceil(2^32 / (M/2 + 1))
+    unsigned magic_hop;    // ceil(2^32 / hop), or 0: divide (hop == 1, or tile positions * hop would overflow 32 bits)
 };
 
 // L2 prefetch of the 128-byte lines of [p, p + bytes) by `nt` threads (thread `tid`): the rows a later phase loads are
@@ -78,6 +79,19 @@ __global__ void __launch_bounds__(512, 2) mr_tile_kernel(const TileArgs a, const
         const long long base = (long long)f0 * hop;
         const bool interior = base >= dm.P && base + (long long)(nfr - 1) * hop + N <= dm.P + dm.L;
         const int total = nfr * M;
+        // interior tile, even hop, aligned rows: a sample pair and its window pair are one vector load each
+        const bool vec = interior && (hop & 1) == 0 && (((uintptr_t)(x + (base - dm.P))) & (2 * sizeof(T) - 1)) == 0;
+        if (vec) {
+            const C* __restrict__ x2 = reinterpret_cast<const C*>(x + (base - dm.P));
+            const C* __restrict__ wa2 = reinterpret_cast<const C*>(wa);
+            const int hop2 = hop >> 1;
+#pragma unroll 4
+            for (int idx = tid; idx < total; idx += NT) {
+                const int f = mr::fdiv(idx, ml.magic_M), n = idx - f * M;
+                const C v = __ldg(x2 + (size_t)f * hop2 + n), w = __ldg(wa2 + n);
+                wb[f * Mp + mr::padidx(n)] = mk<T>(v.x * w.x, v.y * w.y);
+            }
+        } else
 #pragma unroll 4
         for (int idx = tid; idx < total; idx += NT) {
             const int f = mr::fdiv(idx, ml.magic_M), n = idx - f * M;
@@ -224,12 +238,12 @@ __global__ void __launch_bounds__(512, 2) mr_tile_kernel(const TileArgs a, const
 
     // ---- D: inverse passes (digit-reversed -> natural) -----------------------------------------------------------
     for (int s = mp.nst - 1; s >= 0; --s) {
-        mr::pass<T, true>(tb, nf, Mp, mp, s, tw, ttid, tnt);
+        mr::pass<T, true>(tb, nf, Mp, mp, s, tw, ttid, tnt, s == 0 ? ws : (const T*)nullptr);   // last pass: x synthesis window
         team_sync();
     }
     __syncthreads();
 
-    // ---- E: windowed overlap-add of the owned output range (gather), times 1/envelope -------------------------
+    // ---- E: overlap-add of the owned output range (gather over the windowed frames), times 1/envelope -----------
     {
         const long long o0 = (long long)t0 * hop;
         const long long o1 = (t1 == dm.T) ? dm.Lp : (long long)t1 * hop;
@@ -237,20 +251,41 @@ __global__ void __launch_bounds__(512, 2) mr_tile_kernel(const TileArgs a, const
         const int lead = (t0 - f0) * hop;           // tile-local position of o0 (frame f0 starts at 0)
         T* xo = (T*)a.x_out + (long long)b * dm.L;
         const T* __restrict__ ienv = (const T*)a.inv_env;
-        const T* wbf = reinterpret_cast<const T*>(wb);
-#pragma unroll 2
-        for (int i = tid; i < span; i += NT) {
-            const long long m = o0 + i - dm.P;
-            if (m < 0 || m >= dm.L) continue;
-            const T ie = __ldg(ienv + m);
-            const int u = lead + i;
-            int fl = u / hop;                       // newest frame that covers the sample
-            int off = u - fl * hop;
+        auto newest = [&](int u, int& fl, int& off) {   // newest frame of the tile that covers position u, offset in it
+            fl = ml.magic_hop ? (int)__umulhi((unsigned)u, ml.magic_hop) : u / hop;
+            off = u - fl * hop;
             if (fl > nfr - 1) { off += (fl - (nfr - 1)) * hop; fl = nfr - 1; }
-            T acc = T(0);
-            for (; fl >= 0 && off < N; --fl, off += hop)
-                acc += wbf[2 * ((size_t)fl * Mp + mr::padidx(off >> 1)) + (off & 1)] * __ldg(ws + off);
-            xo[m] = acc * ie;
+        };
+        if ((hop & 1) == 0) {
+            // even hop: two consecutive samples sit in ONE complex element of every frame that covers them
+            for (int i = 2 * tid; i < span; i += 2 * NT) {
+                const long long m = o0 + i - dm.P;
+                if (m + 1 < 0 || m >= dm.L) continue;
+                const bool ok0 = m >= 0, ok1 = m + 1 < dm.L;
+                const T ie0 = ok0 ? __ldg(ienv + m) : T(0), ie1 = ok1 ? __ldg(ienv + m + 1) : T(0);
+                int fl, off;
+                newest(lead + i, fl, off);
+                C acc = mk<T>(T(0), T(0));
+                for (; fl >= 0 && off < N; --fl, off += hop) {
+                    const C v = wb[fl * Mp + mr::padidx(off >> 1)];
+                    acc.x += v.x; acc.y += v.y;
+                }
+                if (ok0) xo[m] = acc.x * ie0;
+                if (ok1) xo[m + 1] = acc.y * ie1;
+            }
+        } else {
+            const T* wbf = reinterpret_cast<const T*>(wb);
+            for (int i = tid; i < span; i += NT) {
+                const long long m = o0 + i - dm.P;
+                if (m < 0 || m >= dm.L) continue;
+                const T ie = __ldg(ienv + m);
+                int fl, off;
+                newest(lead + i, fl, off);
+                T acc = T(0);
+                for (; fl >= 0 && off < N; --fl, off += hop)
+                    acc += wbf[2 * (fl * Mp + mr::padidx(off >> 1)) + (off & 1)];
+                xo[m] = acc * ie;
+            }
         }
     }
 }
@@ -312,6 +347,7 @@ static int launch_mr(TileArgs& a, const mr::Plan& mp, cudaStream_t st) {
     ml.Mp = Mp;
     ml.magic_M = mr::magic_of(dm.M);
     ml.magic_npair = mr::magic_of(dm.M / 2 + 1);
+    ml.magic_hop = ((long long)(best_nfr + 1) * dm.hop + dm.N) * (long long)dm.hop < (1LL << 32) ? mr::magic_of(dm.hop) : 0u;
     a.tile_frames = best_nfr - halo;
     a.Mp = Mp;
     const size_t smem = (size_t)best_nfr * frame_bytes + perm_bytes;
