@@ -24,24 +24,27 @@ struct TileArgs {
     int Mp;            // padded complex elements per frame in shared memory
 };
 
-template <typename T>
+// Addresses of the bins of one (signal, frame) row.  NYQ = false: the caller guarantees kk != M (every (k, M-k) pair
+// but k = 0), so the onesided layout's separate Nyquist array never enters the address arithmetic.
+template <typename T, bool NYQ = true>
 struct BinIO {
     const TileArgs& a;
-    long long fr;   // b*T + t
-    __device__ BinIO(const TileArgs& a_, long long fr_) : a(a_), fr(fr_) {}
+    long long fr;     // b*T + t
+    long long roff;   // fr * row: element offset of the frame's main row
+    __device__ BinIO(const TileArgs& a_, long long fr_) : a(a_), fr(fr_), roff(fr_ * a_.dm.row) {}
     __device__ __forceinline__ cx_t<T> ldc(const void* main, const void* nyq, int kk) const {
         // read-only path (ld.global.nc): the inputs are never written by the launch (ping-pong state), and the
         // compiler may then batch the loads of unrolled iterations ahead of the stores
-        if (a.dm.onesided && kk == a.dm.M) return __ldg((const cx_t<T>*)nyq + fr);
-        return __ldg((const cx_t<T>*)main + fr * a.dm.row + kk);
+        if (NYQ && a.dm.onesided && kk == a.dm.M) return __ldg((const cx_t<T>*)nyq + fr);
+        return __ldg((const cx_t<T>*)main + roff + kk);
     }
     __device__ __forceinline__ void stc(void* main, void* nyq, int kk, cx_t<T> v) const {
-        if (a.dm.onesided && kk == a.dm.M) ((cx_t<T>*)nyq)[fr] = v;
-        else ((cx_t<T>*)main)[fr * a.dm.row + kk] = v;
+        if (NYQ && a.dm.onesided && kk == a.dm.M) ((cx_t<T>*)nyq)[fr] = v;
+        else ((cx_t<T>*)main)[roff + kk] = v;
     }
     __device__ __forceinline__ T ldm(int kk) const {
-        if (a.dm.onesided && kk == a.dm.M) return __ldg((const T*)a.mag_nyq + fr);
-        return __ldg((const T*)a.mag_main + fr * a.dm.row + kk);
+        if (NYQ && a.dm.onesided && kk == a.dm.M) return __ldg((const T*)a.mag_nyq + fr);
+        return __ldg((const T*)a.mag_main + roff + kk);
     }
 };
 
@@ -54,8 +57,8 @@ struct BinIn {
     T m;              // target magnitude
 };
 
-template <typename T, int OP>
-__device__ __forceinline__ BinIn<T> bin_load(const TileArgs& a, const BinIO<T>& io, int kk) {
+template <typename T, int OP, typename IO>
+__device__ __forceinline__ BinIn<T> bin_load(const TileArgs& a, const IO& io, int kk) {
     BinIn<T> in;
     in.s0 = mk<T>(T(0), T(0)); in.s1 = in.s0; in.m = T(0);
     if constexpr (OP == OP_ISTFT) {
@@ -71,8 +74,8 @@ __device__ __forceinline__ BinIn<T> bin_load(const TileArgs& a, const BinIO<T>& 
     return in;
 }
 
-template <typename T, int OP>
-__device__ __forceinline__ cx_t<T> bin_apply(const TileArgs& a, const BinIO<T>& io, int kk, cx_t<T> s, const BinIn<T>& in,
+template <typename T, int OP, typename IO>
+__device__ __forceinline__ cx_t<T> bin_apply(const TileArgs& a, const IO& io, int kk, cx_t<T> s, const BinIn<T>& in,
                                              bool owned, bool want_sums, T& dsum, T& esum) {
     if constexpr (OP == OP_STFT) {
         io.stc(a.s0_out_main, a.s0_out_nyq, kk, s);
@@ -117,8 +120,8 @@ __device__ __forceinline__ cx_t<T> bin_apply(const TileArgs& a, const BinIO<T>& 
     }
 }
 
-template <typename T, int OP>
-__device__ __forceinline__ cx_t<T> bin_update(const TileArgs& a, const BinIO<T>& io, int kk, cx_t<T> s,
+template <typename T, int OP, typename IO>
+__device__ __forceinline__ cx_t<T> bin_update(const TileArgs& a, const IO& io, int kk, cx_t<T> s,
                                               bool owned, bool want_sums, T& dsum, T& esum) {
     const BinIn<T> in = bin_load<T, OP>(a, io, kk);
     return bin_apply<T, OP>(a, io, kk, s, in, owned, want_sums, dsum, esum);

@@ -6,9 +6,9 @@
 // Forward: decimation in frequency, stage s = 0 .. nst-1 with radix r_s on blocks of S_s = r_s * span_s points:
 //     y[q] = (sum_m v[e0 + m span] W_r^(mq)) * W_S^(jq),   stored back at e0 + q span        (e0 = blk S + j)
 // which leaves bin k = q_0 + r_0 (q_1 + r_1 (q_2 + ...)) at position q_0 span_0 + q_1 span_1 + ... (mixed-radix digit
-// reversal, `mr_position`).  Inverse: the transposed flow graph, stages nst-1 .. 0, twiddle BEFORE the butterfly, with
-// conjugated roots; implemented as the forward arithmetic on (im, re)-swapped values (swap(a conj(w)) = swap(a) w), so
-// there is one butterfly per radix.  Digit-reversed input -> natural order, unnormalised.
+// reversal, `mr_position`).  Inverse: the transposed flow graph, stages nst-1 .. 0, conjugated twiddle BEFORE the
+// butterfly; the conjugated R-point DFT is the forward one with its outputs renamed (m -> (R - m) mod R, free in the
+// unrolled code), so there is one butterfly per radix.  Digit-reversed input -> natural order, unnormalised.
 //
 // A pass is executed by a TEAM of `nt` threads (a warp, a few warps, or a whole CTA) over `nf` frames that live at
 // wb + f * Mp with the padded index padidx(n); the caller synchronises the team between passes.  Everything is
@@ -109,6 +109,8 @@ template <typename C> SPX_HD C ldro(const C* p) {      // read-only table load (
 template <typename C> SPX_HD C add(C a, C b) { a.x += b.x; a.y += b.y; return a; }
 template <typename C> SPX_HD C sub(C a, C b) { a.x -= b.x; a.y -= b.y; return a; }
 template <typename C> SPX_HD C mul(C a, C b) { C r; r.x = a.x * b.x - a.y * b.y; r.y = a.x * b.y + a.y * b.x; return r; }
+template <typename C> SPX_HD C mulc(C a, C b) { C r; r.x = a.x * b.x + a.y * b.y; r.y = a.y * b.x - a.x * b.y; return r; }   // a conj(b)
+template <typename C> SPX_HD C cwise(C a, C b) { a.x *= b.x; a.y *= b.y; return a; }                 // component-wise
 template <typename C> SPX_HD C mul_mi(C a) { C r; r.x = a.y; r.y = -a.x; return r; }     // * (-i)
 // c + s * a (real s)
 template <typename C, typename T> SPX_HD C axpy(C c, T s, C a) { c.x += s * a.x; c.y += s * a.y; return c; }
@@ -116,6 +118,8 @@ template <typename C, typename T> SPX_HD C axpy(C c, T s, C a) { c.x += s * a.x;
 SPX_HD float2 add(float2 a, float2 b) { return padd(a, b); }
 SPX_HD float2 sub(float2 a, float2 b) { return psub(a, b); }
 SPX_HD float2 mul(float2 a, float2 b) { return cmul2(a, b); }
+SPX_HD float2 mulc(float2 a, float2 b) { return cmulc2(a, b); }
+SPX_HD float2 cwise(float2 a, float2 b) { return pmul(a, b); }
 SPX_HD float2 axpy(float2 c, float s, float2 a) { return pfma(f2(s, s), a, c); }
 
 // ---- in-register forward DFTs (roots exp(-2 pi i / R)) -----------------------------------------------------
@@ -193,25 +197,22 @@ SPX_HD void pass_r(C* wb, int nf, int Mp, const Plan& p, int s, const C* __restr
         C* v = wb + f * Mp;
         const int e0 = blk * span * R + j;
         C x[R];
-        static_for<R>([&](auto m) {
-            const C t = v[padidx(e0 + m * span)];
-            if (INV) { x[m].x = t.y; x[m].y = t.x; } else x[m] = t;
-        });
-        if (INV && span > 1) {
+        static_for<R>([&](auto m) { x[m] = v[padidx(e0 + m * span)]; });
+        if (INV && span > 1) {      // inverse: conjugated stage twiddles BEFORE the butterfly
             const int tj = twstep * j;
-            static_for<R - 1>([&](auto qq) { x[qq + 1] = mul(x[qq + 1], ldro(tw + tj * (qq + 1))); });
+            static_for<R - 1>([&](auto qq) { x[qq + 1] = mulc(x[qq + 1], ldro(tw + tj * (qq + 1))); });
         }
         Dft<R, T, C>::run(x);
         if (!INV && span > 1) {
             const int tj = twstep * j;
             static_for<R - 1>([&](auto qq) { x[qq + 1] = mul(x[qq + 1], ldro(tw + tj * (qq + 1))); });
         }
-        static_for<R>([&](auto m) {
-            C t;
-            if (INV) { t.x = x[m].y; t.y = x[m].x; } else t = x[m];
+        // inverse: sum_q y[q] conj(W_R^(mq)) is output (R - m) mod R of the FORWARD butterfly -- a compile-time renaming
+        static_for<R>([&](auto mm) {
+            constexpr int m = decltype(mm)::value;
+            C t = x[INV ? (R - m) % R : m];
             if (scale) {
-                const C w = ldro(reinterpret_cast<const C*>(scale) + (e0 + m * span));
-                t.x *= w.x; t.y *= w.y;
+                t = cwise(t, ldro(reinterpret_cast<const C*>(scale) + (e0 + m * span)));
             }
             v[padidx(e0 + m * span)] = t;
         });

@@ -29,6 +29,7 @@ struct MrLaunch {
     int Mp;                // padded complex elements per frame
     unsigned magic_M;      // ceil(2^32 / M)
     unsigned magic_npair;  // ceil(2^32 / (M/2 + 1))
+    unsigned magic_np1;    // ceil(2^32 / (M/2)): the pairs k = 1 .. M/2
     unsigned magic_hop;    // ceil(2^32 / hop), or 0: divide (hop == 1, or tile positions * hop would overflow 32 bits)
 };
 
@@ -169,11 +170,27 @@ __global__ void __launch_bounds__(512, 2) mr_tile_kernel(const TileArgs a, const
             }
         };
         if (dm.onesided) {
+            // pairs k = 1 .. M/2: never the Nyquist bin (BinIO<T, false>: one row offset per frame, no select between the
+            // main and the Nyquist arrays); the (0, M) pair of every frame follows
             constexpr bool TWO = sizeof(T) == 4;        // fp64: one pair (two would spill the 64-register budget)
-            for (int idx = ttid; idx < total; idx += TWO ? 2 * tnt : tnt) {
-                const bool two = TWO && idx + tnt < total;
-                const Pair p0 = locate(idx), p1 = locate(two ? idx + tnt : idx);
-                const BinIO<T> io0(a, p0.fr), io1(a, p1.fr);
+            const int np1 = npair - 1, total1 = nf * np1;
+            const unsigned magic_np1 = ml.magic_np1;
+            auto locate1 = [&](int idx) {
+                Pair p;
+                const int f = mr::fdiv(idx, magic_np1);
+                p.k = idx - f * np1 + 1;
+                const int t = f0 + fa + f;
+                p.owned = t >= t0;
+                p.fr = (long long)b * dm.T + t;
+                p.v = tb + (size_t)f * Mp;
+                p.pA = perm[p.k]; p.pB = perm[M - p.k];
+                return p;
+            };
+            using IO1 = BinIO<T, false>;
+            for (int idx = ttid; idx < total1; idx += TWO ? 2 * tnt : tnt) {
+                const bool two = TWO && idx + tnt < total1;
+                const Pair p0 = locate1(idx), p1 = locate1(two ? idx + tnt : idx);
+                const IO1 io0(a, p0.fr), io1(a, p1.fr);
                 const BinIn<T> a0 = bin_load<T, OP>(a, io0, p0.k), b0 = bin_load<T, OP>(a, io0, M - p0.k);
                 const BinIn<T> a1 = bin_load<T, OP>(a, io1, p1.k), b1 = bin_load<T, OP>(a, io1, M - p1.k);
                 const C w0 = __ldg(twr + p0.k), w1 = __ldg(twr + p1.k);
@@ -191,6 +208,17 @@ __global__ void __launch_bounds__(512, 2) mr_tile_kernel(const TileArgs a, const
                     const C hB = (M - p1.k != p1.k) ? bin_apply<T, OP>(a, io1, M - p1.k, sB, b1, p1.owned, want_sums, dsum, esum) : hA;
                     finish(p1, hA, hB, w1);
                 }
+            }
+            for (int f = ttid; f < nf; f += tnt) {      // DC and Nyquist: both read Z[0]
+                const Pair p = locate(f * npair);
+                const BinIO<T> io(a, p.fr);
+                const BinIn<T> iA = bin_load<T, OP>(a, io, 0), iB = bin_load<T, OP>(a, io, M);
+                const C w = __ldg(twr);
+                C sA = mk<T>(T(0), T(0)), sB = sA;
+                if constexpr (OP != OP_ISTFT) rfft_post_pair<T>(p.v[p.pA], p.v[p.pB], w, sA, sB);
+                const C hA = bin_apply<T, OP>(a, io, 0, sA, iA, p.owned, want_sums, dsum, esum);
+                const C hB = bin_apply<T, OP>(a, io, M, sB, iB, p.owned, want_sums, dsum, esum);
+                finish(p, hA, hB, w);
             }
         } else {
             // two-sided: bins kA, kB and their mirrors N-kA, N-kB (= conj of the real-input STFT);
@@ -347,6 +375,7 @@ static int launch_mr(TileArgs& a, const mr::Plan& mp, cudaStream_t st) {
     ml.Mp = Mp;
     ml.magic_M = mr::magic_of(dm.M);
     ml.magic_npair = mr::magic_of(dm.M / 2 + 1);
+    ml.magic_np1 = mr::magic_of(dm.M / 2);
     ml.magic_hop = ((long long)(best_nfr + 1) * dm.hop + dm.N) * (long long)dm.hop < (1LL << 32) ? mr::magic_of(dm.hop) : 0u;
     a.tile_frames = best_nfr - halo;
     a.Mp = Mp;
