@@ -406,8 +406,18 @@ def measure_config(cx, name, w, B, n_jobs, n_warm, seed, with_reference_cuda=Fal
     if w["algo"] == "rtisi":
         steps = (T + w["look_ahead"]) * w["iters"]
         flops = B * steps * (w["look_ahead"] + 1) * frame_flops(w["n_fft"])
+        fp32_peak, fp32_src = None, None
+        try:
+            with open(os.path.join(ROOT, "profiles", "fp32_peak.json")) as f:
+                pk = json.load(f)
+            fp32_peak, fp32_src = float(pk["fp32_fma_tflops"]), pk["source"]
+        except Exception:
+            pass
+        tfl = flops / (job_ms / 1e3) / 1e12
         out.update({"us_per_inner_iteration": 1e3 * job_ms / steps, "bound": "latency / fp32 (HBM traffic negligible)",
-                    "tflops_achieved": flops / (job_ms / 1e3) / 1e12,
+                    "tflops_achieved": tfl, "fp32_peak_tflops": fp32_peak,
+                    "fp32_frac": (tfl / fp32_peak) if fp32_peak else None,      # per GPU: B signals of this rank
+                    "fp32_peak_source": fp32_src,
                     "flops_convention": "SURVEY.md 8d: B x (T+LA) x max_iter x (LA+1) frames x frame_flops(n_fft)",
                     "hbm_bytes_per_job": iter_bytes(w, B)})
     else:
