@@ -44,7 +44,7 @@ __device__ __forceinline__ void prefetch_l2(const void* p, size_t bytes, int tid
 }
 
 template <typename T, int OP>
-__global__ void __launch_bounds__(512, 2) mr_tile_kernel(const TileArgs a, const mr::Plan mp, const MrLaunch ml) {
+__global__ void __launch_bounds__(sizeof(T) == 8 ? 256 : 512, 2) mr_tile_kernel(const TileArgs a, const mr::Plan mp, const MrLaunch ml) {
     using C = cx_t<T>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     C* wb = reinterpret_cast<C*>(smem_raw);
@@ -360,7 +360,9 @@ static int launch_mr(TileArgs& a, const mr::Plan& mp, cudaStream_t st) {
         cap = halo + (cap - halo + 1) / 2;
     // teams: the CTA's warps dealt to 16, 8, 4, 2 or 1 teams; the tile holds a multiple of the team count (even load),
     // and a bigger team pays ~3 % per doubling in barriers
-    const int warps = 32 / ctas;
+    // fp64: 8 warps per CTA (two CTAs per SM at up to 128 registers: the double-precision butterflies of radix 8 / 11 /
+    // 13 do not fit 64 registers without spilling)
+    const int warps = (sizeof(T) == 8 ? 16 : 32) / ctas;
     int best_teams = 1, best_nfr = cap; double best_score = -1.0;
     for (int teams = warps; teams >= 1; teams >>= 1) {
         int nfr = cap / teams * teams;
