@@ -33,16 +33,6 @@ struct MrLaunch {
     unsigned magic_hop;    // ceil(2^32 / hop), or 0: divide (hop == 1, or tile positions * hop would overflow 32 bits)
 };
 
-// L2 prefetch of the 128-byte lines of [p, p + bytes) by `nt` threads (thread `tid`): the rows a later phase loads are
-// known long before (state / magnitude rows of the team's frames, 1/envelope of the tile's output range), so their
-// DRAM latency is paid under the butterflies instead of in front of the point-wise arithmetic.
-__device__ __forceinline__ void prefetch_l2(const void* p, size_t bytes, int tid, int nt) {
-    if (!p || bytes == 0) return;
-    const uintptr_t lo = (uintptr_t)p & ~(uintptr_t)127, hi = (uintptr_t)p + bytes;
-    for (uintptr_t q = lo + (uintptr_t)tid * 128; q < hi; q += (uintptr_t)nt * 128)
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
-}
-
 template <typename T, int OP>
 __global__ void __launch_bounds__(sizeof(T) == 8 ? 256 : 512, 2) mr_tile_kernel(const TileArgs a, const mr::Plan mp, const MrLaunch ml) {
     using C = cx_t<T>;
@@ -66,13 +56,6 @@ __global__ void __launch_bounds__(sizeof(T) == 8 ? 256 : 512, 2) mr_tile_kernel(
 
     // padded position of bin k after the forward passes
     for (int k = tid; k < M; k += NT) perm[k] = (unsigned short)mr::padidx(mr::mr_position(mp, k));
-
-    if constexpr (OP != OP_STFT) {   // 1/envelope of the samples this tile will write (phase E)
-        long long m0 = (long long)t0 * hop - dm.P, m1 = ((t1 == dm.T) ? dm.Lp : (long long)t1 * hop) - dm.P;
-        if (m0 < 0) m0 = 0;
-        if (m1 > dm.L) m1 = dm.L;
-        if (m1 > m0) prefetch_l2((const T*)a.inv_env + m0, (size_t)(m1 - m0) * sizeof(T), tid, NT);
-    }
 
     // ---- A: frame + analysis window: z[n] = x[2n] w[2n] + i x[2n+1] w[2n+1] ----------------------------------
     if constexpr (OP != OP_ISTFT) {
@@ -122,14 +105,6 @@ __global__ void __launch_bounds__(sizeof(T) == 8 ? 256 : 512, 2) mr_tile_kernel(
         if (G == 1) __syncwarp();
         else asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "r"(tnt) : "memory");
     };
-
-    if constexpr (OP != OP_STFT) {   // the rows of the team's frames that the point-wise stage (C) will load
-        const size_t fr0 = (size_t)b * dm.T + f0 + fa;
-        const size_t rc = (size_t)dm.row * sizeof(C), rm = (size_t)dm.row * sizeof(T);
-        if (a.s0_in_main) prefetch_l2((const char*)a.s0_in_main + fr0 * rc, (size_t)nf * rc, ttid, tnt);
-        if (a.s1_in_main) prefetch_l2((const char*)a.s1_in_main + fr0 * rc, (size_t)nf * rc, ttid, tnt);
-        if (a.mag_main) prefetch_l2((const char*)a.mag_main + fr0 * rm, (size_t)nf * rm, ttid, tnt);
-    }
 
     // ---- B: forward passes (natural -> digit-reversed) ---------------------------------------------------------
     if constexpr (OP != OP_ISTFT) {
