@@ -26,7 +26,14 @@ def stats():
             h.get("host_alloc_time.total", 0), h.get("reserved_bytes.current", 0) >> 20)
 
 
+smi = None
+if len(sys.argv) > 2 and sys.argv[2] == "smi":      # the clock sampler of bench.py beside the calls
+    import subprocess
+    smi = subprocess.Popen(["nvidia-smi", "--query-gpu=clocks.sm,power.draw", "--format=csv,noheader,nounits", "-lms", "200"],
+                           stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
 y = None
+for _ in range(4):
+    y = S.griffin_lim(mag_host, max_iter=64, tol=0, verbose=False, **kw)
 prev = stats()
 for k in range(n_calls):
     torch.cuda.synchronize()
@@ -39,3 +46,5 @@ for k in range(n_calls):
           f"reserved {cur[3]} MiB | pinned alloc +{cur[4] - prev[4]} free +{cur[5] - prev[5]} alloc_time {cur[6]} reserved {cur[7]} MiB",
           flush=True)
     prev = cur
+if smi is not None:
+    smi.terminate()
