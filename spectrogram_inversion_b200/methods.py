@@ -141,6 +141,15 @@ def _run_host_pipelined(spec, n_chunks, make_solver, max_iter, eva_iter, metric,
     s_in.wait_stream(cur)
     B = spec.shape[0]
     bounds = [(B * k) // n_chunks for k in range(n_chunks + 1)]
+    split = os.environ.get("SPECINV_HOST_SPLIT")          # experiment: relative chunk sizes, e.g. "1,3,3,1"
+    if split:
+        wts = [float(v) for v in split.split(",")]
+        acc, bounds = 0.0, [0]
+        for v in wts:
+            acc += v
+            bounds.append(min(B, max(bounds[-1] + 1, int(round(B * acc / sum(wts))))))
+        bounds[-1] = B
+        n_chunks = len(wts)
 
     trace = PIPELINE_TRACE
     marks = {}
