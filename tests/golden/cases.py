@@ -125,6 +125,9 @@ GRAD_CASES = [
     dict(_c("grad_nocenter", n_fft=64, window="hamming", hop_length=16, T=7, B=2, center=False), look_ahead=2, asym=True),
     dict(_c("grad_twosided", n_fft=32, window="hann", hop_length=8, T=6, B=1, onesided=False), look_ahead=1),
     dict(_c("grad_rect_default", n_fft=32, T=6, B=2), asym=True),
+    # n_fft that is not a power of two (mixed-radix kernels) and an odd two-sided one (direct DFT; no RTISI-LA kernel)
+    dict(_c("grad_np2_120", n_fft=120, window="hann", hop_length=30, T=7, B=2, seed=71), look_ahead=2),
+    dict(_c("grad_odd_75_twosided", n_fft=75, window="hamming", hop_length=25, T=6, B=1, onesided=False, seed=72), rtisi=False),
 ]
 
 
